@@ -1,0 +1,231 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) on torch-CPU.
+
+Run in the build container only (the reference checkout does not travel):
+    python tests/golden/make_golden.py
+Each file holds the inputs and the reference's outputs for one scenario; tests compare the
+oracle (tests/test_oracle_golden.py, CPU) and the CUDA path (tests/test_parity_gpu.py) to them.
+
+Regime note.  The reference delegates `R^T @ (xyz - t)` to torch.bmm, i.e. MKL sgemm with K=3.
+MKL picks different kernels (different fp32 summation orders) depending on thread count and
+N: with >= 2 threads and N >= ~50 000 voxels it is the left-to-right fma chain (also what a GPU
+computes); single-threaded or tiny N it is (a0 x0 + a2 x2) + a1 x1 without fma.  Real scenes
+(0.2 M - 24 M voxels, multi-core) are in the first regime, so every golden grid has >= 60 000
+voxels and this script asserts the regime it ran in.
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+import _ref_loader  # noqa: E402
+from spatially_aware_ai_b200 import synth  # noqa: E402
+
+clipfusion, clip_seem_fusion, handy_utils = _ref_loader.load_reference()
+
+
+class FakeClip(torch.nn.Module):
+    """Duck-typed stand-in for clipfusion.Clip: returns the pre-generated feature image."""
+
+    def __init__(self, feature_dim):
+        super().__init__()
+        self.feature_dim = feature_dim
+        self.next_table = None
+
+    def img_inference_tiled(self, rgb_imgs, patch_size, patch_stride):
+        return self.next_table
+
+
+class FakeSeg:
+    def __init__(self):
+        self.queue = []
+
+    def run_on_image(self, img):
+        return self.queue.pop(0)
+
+
+def assert_fma_regime(n_voxels):
+    torch.manual_seed(1)
+    A = torch.randn(1, 3, 3)
+    X = (torch.randn(n_voxels, 3)[None] - torch.randn(1, 1, 3)).transpose(1, 2)
+    Y = (A.transpose(1, 2) @ X)[0].numpy()
+    At, Xn = A.transpose(1, 2)[0].numpy().astype(np.float64), X[0].numpy().astype(np.float64)
+    acc = (At[:, 0:1] * Xn[0]).astype(np.float32).astype(np.float64)
+    acc = (At[:, 1:2] * Xn[1] + acc).astype(np.float32).astype(np.float64)
+    acc = (At[:, 2:3] * Xn[2] + acc).astype(np.float32)
+    mism = int((acc != Y).sum())
+    assert mism <= 2, "torch.bmm is not in the fma-chain regime here (%d mismatches)" % mism
+
+
+SCENES = {
+    # name: (SceneConfig kwargs, class, batch, n_calls, special)
+    "seem_a": dict(cfg=dict(extent=(2.2, 2.0, 1.6), voxel_size=0.05, height=48, width=64, patch_size=32,
+                            patch_stride=16, feature_dim=8, frames=8, missing_fraction=0.05, seg_block=8,
+                            seed=11, name="seem_a"),
+                   cls="ClipSeemFusion", batch=1, calls=8),
+    "fusion_a": dict(cfg=dict(extent=(2.2, 2.0, 1.6), voxel_size=0.05, height=48, width=64, patch_size=32,
+                              patch_stride=16, feature_dim=8, frames=6, missing_fraction=0.05, seg_block=8,
+                              seed=12, name="fusion_a"),
+                     cls="ClipFusion", batch=1, calls=6),
+    "fusion_b2": dict(cfg=dict(extent=(2.2, 2.0, 1.6), voxel_size=0.05, height=48, width=64, patch_size=32,
+                               patch_stride=16, feature_dim=8, frames=6, missing_fraction=0.05, seg_block=8,
+                               seed=13, name="fusion_b2"),
+                      cls="ClipFusion", batch=2, calls=3),
+    # odd image size (not a power of two), denser patch grid, trunc 3 voxels, plus degenerate frames
+    "seem_edge": dict(cfg=dict(extent=(2.4, 1.8, 1.5), voxel_size=0.05, trunc_vox=3, height=44, width=60,
+                               patch_size=20, patch_stride=8, feature_dim=12, frames=7, missing_fraction=0.1,
+                               seg_block=4, seed=14, name="seem_edge"),
+                      cls="ClipSeemFusion", batch=1, calls=7, edge=True),
+}
+
+
+def scene_frames(spec):
+    cfg = synth.SceneConfig(**spec["cfg"])
+    rng = np.random.default_rng(cfg.seed + 1000)
+    frames = []
+    for i in range(cfg.frames):
+        fr = synth.make_frame(cfg, i, table_layout="hwc" if i % 3 == 2 else "chw")
+        if i % 2 == 1:
+            fr["pose"] = synth.perturbed_pose(cfg, i, rng)
+            fr["depth"] = synth.render_depth(cfg, fr["pose"], fr["K"])
+            fr["depth"][rng.random(fr["depth"].shape) < cfg.missing_fraction] = 0.0
+        if spec.get("edge"):
+            if i == 2:      # all depth missing: sdf = -z/trunc, only voxels within trunc of the camera
+                fr["depth"][:] = 0.0
+            elif i == 3:    # camera far outside the grid looking away: nothing valid
+                fr["pose"][:3, 3] += np.array([30.0, 0.0, 0.0], np.float32)
+            elif i == 4:    # surface far beyond the grid: tsdf_valid everywhere in view, valid nowhere
+                fr["depth"][:] = 50.0
+            elif i == 5:    # anisotropic / off-centre intrinsics
+                fr["K"] = np.array([[70.0, 0.0, 20.0], [0.0, 40.0, 30.0], [0.0, 0.0, 1.0]], np.float32)
+            elif i == 6:    # camera inside the grid volume's margin, steep roll
+                fr["pose"] = synth.perturbed_pose(cfg, i, rng)
+        frames.append(fr)
+    return cfg, frames
+
+
+def run_scene(name, spec):
+    cfg, frames = scene_frames(spec)
+    origin, nvox = cfg.grid()
+    assert int(np.prod(nvox)) >= 60000
+    assert_fma_regime(int(np.prod(nvox)))
+    fake_clip = FakeClip(cfg.feature_dim)
+    fake_seg = FakeSeg()
+    t_origin, t_nvox = torch.from_numpy(origin), torch.from_numpy(nvox)
+    if spec["cls"] == "ClipSeemFusion":
+        vol = clip_seem_fusion.ClipSeemFusion(t_origin, cfg.voxel_size, t_nvox, cfg.trunc, False,
+                                              cfg.patch_size, cfg.patch_stride, fake_clip, fake_seg)
+    else:
+        real_clip = clipfusion.Clip
+        clipfusion.Clip = lambda model, pretraining: fake_clip
+        try:
+            vol = clipfusion.ClipFusion(t_origin, cfg.voxel_size, t_nvox, cfg.trunc, False, "fake", "fake",
+                                        cfg.patch_size, cfg.patch_stride)
+        finally:
+            clipfusion.Clip = real_clip
+    B = spec["batch"]
+    counts = []
+    mid_state = None
+    for call in range(spec["calls"]):
+        batch = frames[call * B:(call + 1) * B]
+        fake_clip.next_table = torch.stack([torch.from_numpy(f["table"]) for f in batch])
+        fake_seg.queue = [torch.from_numpy(f["seg"].astype(np.int64)) for f in batch]
+        w0, tw0 = vol.weight.clone(), vol.tsdf_weight.clone()
+        vol.integrate(torch.stack([torch.from_numpy(f["depth"]) for f in batch]),
+                      torch.stack([torch.from_numpy(f["rgb"]) for f in batch]),
+                      torch.stack([torch.from_numpy(f["pose"]) for f in batch]),
+                      torch.stack([torch.from_numpy(f["K"]) for f in batch]))
+        counts.append([int((vol.weight - w0).sum()), int((vol.tsdf_weight - tw0).sum())])
+        if call == spec["calls"] // 2 - 1:
+            mid_state = dict(mid_tsdf=vol.tsdf.numpy().copy(), mid_weight=vol.weight.numpy().copy(),
+                             mid_tsdf_weight=vol.tsdf_weight.numpy().copy())
+    out = dict(
+        origin=origin, nvox=nvox, voxel_size=np.float64(cfg.voxel_size), trunc=np.float64(cfg.trunc),
+        feature_dim=np.int64(cfg.feature_dim), batch=np.int64(B), cls=np.array(spec["cls"]),
+        depth=np.stack([f["depth"] for f in frames]), rgb=np.stack([f["rgb"] for f in frames]),
+        seg=np.stack([f["seg"] for f in frames]),
+        table=np.stack([np.ascontiguousarray(f["table"]) for f in frames]),
+        table_hwc=np.array([not f["table"].flags["C_CONTIGUOUS"] for f in frames]),
+        pose=np.stack([f["pose"] for f in frames]), K=np.stack([f["K"] for f in frames]),
+        counts=np.array(counts, np.int64),   # per call: sum of weight / tsdf_weight increments
+        tsdf=vol.tsdf.numpy(), weight=vol.weight.numpy(), tsdf_weight=vol.tsdf_weight.numpy(),
+        rgb_state=vol.rgb.numpy(), clip_feat=vol.clip_feat.numpy(),
+        xyz_world_sha256=np.array(hashlib.sha256(vol.xyz_world.numpy().tobytes()).hexdigest()),
+        torch_version=np.array(torch.__version__), torch_threads=np.int64(torch.get_num_threads()),
+    )
+    out.update(mid_state)
+    if spec["cls"] == "ClipSeemFusion":
+        lab = vol.labels_one_hot.numpy()
+        nz = np.flatnonzero(lab)
+        out["labels_nz_index"] = nz.astype(np.int64)
+        out["labels_nz_value"] = lab.reshape(-1)[nz].astype(np.int32)
+        out["n_classes"] = np.int64(lab.shape[1])
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(name, "voxels", int(np.prod(nvox)), "counts", counts, "->", os.path.getsize(path) // 1024, "KiB")
+
+
+def run_query_golden():
+    rng = np.random.default_rng(77)
+    M, C, T = 257, 32, 7
+    F = rng.standard_normal((M, C)).astype(np.float32)
+    F[5] = 0.0                      # an unobserved voxel: zero feature row
+    Fn = torch.from_numpy(F)
+    Fn = Fn / Fn.norm(dim=-1, keepdim=True)
+    Fn = torch.nan_to_num(Fn)       # clip_seem_fusion.py:507-511
+    X = rng.standard_normal((T, C)).astype(np.float32)
+    X /= np.linalg.norm(X, axis=-1, keepdims=True)
+    Xt = torch.from_numpy(X)
+
+    class _Self:
+        def text_inference(self, labels):
+            return Xt
+
+    relevance = clipfusion.Clip.run_query(_Self(), Fn, ["x"] * T)
+    surgery = clipfusion.Clip.clip_feature_surgery(Fn[None], Xt)
+    red = torch.from_numpy(rng.standard_normal((1, C)).astype(np.float32))
+    surgery_red = clipfusion.Clip.clip_feature_surgery(Fn[None], Xt, redundant_feats=red)
+    # row 0 all-zero variant (w == 1): clipfusion.py:913-915 reads row 0 only
+    F0 = Fn.clone()
+    F0[0] = 0
+    surgery_row0_zero = clipfusion.Clip.clip_feature_surgery(F0[None], Xt)
+
+    # extract_mesh_by_object (handy_utils.py:585-611) on a small random mesh
+    V, Fc = 60, 90
+    verts = rng.standard_normal((V, 3)).astype(np.float32)
+    faces = rng.integers(0, V, size=(Fc, 3)).astype(np.int64)
+    colors = rng.random((V, 3)).astype(np.float32)
+    vidx = rng.integers(0, 3, size=V).astype(np.int64)
+    import open3d as o3d  # stub module from _ref_loader
+
+    class _Mesh:
+        pass
+
+    o3d.geometry = type("g", (), {"TriangleMesh": _Mesh})
+    o3d.utility = type("u", (), {"Vector3dVector": staticmethod(lambda a: a), "Vector3iVector": staticmethod(lambda a: a)})
+    handy_utils.o3d = o3d
+    ov, of, oc, _ = handy_utils.extract_mesh_by_object(verts, faces.copy(), colors, vidx, 1)
+
+    path = os.path.join(HERE, "query.npz")
+    np.savez_compressed(path, F_raw=F, F=Fn.numpy(), X=X, relevance=relevance.numpy(), surgery=surgery.numpy(),
+                        redundant=red.numpy(), surgery_red=surgery_red.numpy(),
+                        surgery_row0_zero=surgery_row0_zero.numpy(),
+                        mesh_verts=verts, mesh_faces=faces, mesh_colors=colors, mesh_vidx=vidx,
+                        obj1_verts=ov, obj1_faces=of, obj1_colors=oc)
+    print("query ->", os.path.getsize(path) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    only = sys.argv[1:]
+    for name, spec in SCENES.items():
+        if not only or name in only:
+            run_scene(name, spec)
+    if not only or "query" in only:
+        run_query_golden()
