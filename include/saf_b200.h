@@ -1,0 +1,219 @@
+/*
+ * saf_b200.h -- C ABI of libsaf_b200.so: the B200 (sm_100a) implementation of the
+ * spatially_aware_AI RGB-D fusion + language-query hot path.
+ *
+ * The reference has no FFI of its own for this path: its boundary is the Python class surface
+ * (SURVEY.md section 8b).  Each entry point below names the reference code it replaces; the
+ * Python classes in spatially_aware_ai_b200/ (same names/signatures as the reference's) are
+ * thin ctypes callers of these functions.  INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, POD structs; no torch / C++ types.
+ *   - every pointer marked "device" is a CUDA device pointer valid on the current device;
+ *     `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - all functions are asynchronous w.r.t. the host unless stated otherwise, allocate no
+ *     device memory (the caller owns the workspace) and keep no global mutable state, so
+ *     one workspace per (volume, stream) is safe.  A volume must not be integrated from two
+ *     streams at once (the reference's integrate() is not re-entrant either).
+ *   - return value: 0 = ok, >0 = cudaError_t of a failed CUDA call, <0 = SAF_ERR_* argument error.
+ *   - layouts follow the reference buffers (clip_seem_fusion.py:640-672): voxel (x,y,z) of the
+ *     grid lives at flat index (x*ny + y)*nz + z; an x-slab [x_begin,x_end) is the contiguous
+ *     flat range starting at x_begin*ny*nz, and slab-local buffers start at that voxel.
+ */
+#ifndef SAF_B200_H
+#define SAF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SAF_ABI_VERSION 1
+#define SAF_MAX_BATCH 8          /* frames per integrate() call; every reference caller uses 1 */
+#define SAF_BLOCK_EDGE 8         /* voxel blocks are 8x8x8 */
+
+/* argument errors */
+#define SAF_ERR_NULL        (-1)
+#define SAF_ERR_BATCH       (-2)
+#define SAF_ERR_GRID        (-3)
+#define SAF_ERR_WORKSPACE   (-4)  /* workspace too small for this grid / batch / table */
+#define SAF_ERR_SHAPE       (-5)
+#define SAF_ERR_DTYPE       (-6)
+#define SAF_ERR_ALIGNMENT   (-7)
+#define SAF_ERR_UNSUPPORTED (-8)
+#define SAF_ERR_DEVICE      (-9)  /* not an sm_100 device */
+
+/* class-map element types accepted for saf_frame.seg (the reference passes an int tensor and
+ * converts with .float(), clip_seem_fusion.py:755-760) */
+#define SAF_SEG_NONE 0
+#define SAF_SEG_U8   1
+#define SAF_SEG_I16  2
+#define SAF_SEG_I32  3
+#define SAF_SEG_I64  4
+#define SAF_SEG_F32  5
+
+/* rgb sampling: clipfusion.py:701-706 (nearest) / clip_seem_fusion.py:793-798 (bilinear) */
+#define SAF_RGB_NEAREST  0
+#define SAF_RGB_BILINEAR 1
+
+/* bits of saf_stats.error_flags */
+#define SAF_FLAG_BAD_CLASS_ID 1u  /* a sampled class id was outside [0,n_classes): torch one_hot raises */
+
+/* Voxel grid geometry.  ClipSeemFusion.__init__ arguments origin / voxel_size / nvox
+ * (clip_seem_fusion.py:612-672); x_begin/x_end select the x-slab the buffers hold
+ * (0 / nvox[0] for the whole grid).  Voxel centres are fl(fl(i)*voxel_size)+origin with the
+ * GLOBAL index i, exactly as clip_seem_fusion.py:664-669 computes xyz_world. */
+typedef struct saf_grid_desc {
+    float   origin[3];
+    float   voxel_size;
+    int32_t nvox[3];
+    int32_t x_begin;
+    int32_t x_end;
+} saf_grid_desc;
+
+/* Device buffers of one slab; names, dtypes and shapes are the reference's registered buffers
+ * (clip_seem_fusion.py:640-659).  labels_one_hot may be NULL (ClipFusion has none). */
+typedef struct saf_volume {
+    float   *tsdf;            /* [N]            */
+    int32_t *tsdf_weight;     /* [N]            */
+    int32_t *weight;          /* [N]            */
+    float   *rgb;             /* [N,3]          */
+    float   *clip_feat;       /* [N,feature_dim]*/
+    int32_t *labels_one_hot;  /* [N,n_classes] or NULL */
+    int32_t  feature_dim;
+    int32_t  n_classes;       /* 143 in the reference (133 + 10) */
+} saf_volume;
+
+/* One RGB-D frame plus the two producer outputs integrate() pulls in
+ * (clip_seem_fusion.py:691-695 feature image, :755 class map). */
+typedef struct saf_frame {
+    const float *depth;       /* device [H,W] metres, 0 = missing                                  */
+    const float *rgb;         /* device [H,W,3] in [0,1] (the reference's rgb_imgs[b], HWC)          */
+    const void  *seg;         /* device [H,W] class ids of type seg_dtype, or NULL                   */
+    const float *table;       /* device feature image: element (c, py, px) at                        */
+    int64_t      table_stride_c;  /*   table[c*stride_c + (py*npx+px)*stride_r]  (elements)          */
+    int64_t      table_stride_r;
+    int32_t      npy, npx;    /* patch grid (clipfusion.py:795-796)                                  */
+    int32_t      seg_dtype;   /* SAF_SEG_*                                                           */
+    int32_t      reserved;
+    float        pose[16];    /* camera->world, row-major 4x4 (clipfusion.py:308-312 axes)           */
+    float        K[9];        /* intrinsics, row-major 3x3                                           */
+    int32_t      reserved2;
+    const float *pose_device; /* optional device copies of pose[16] / K[9]: when non-NULL the kernels  */
+    const float *K_device;    /* read these instead (the reference's callers hand integrate() CUDA     */
+                              /* tensors, clip_seem_fusion.py:308-311; no host sync needed this way)   */
+} saf_frame;
+
+/* Counters kept in the workspace (device) and copied out by saf_read_stats. */
+typedef struct saf_stats {
+    uint64_t total_frames;       /* frames integrated since saf_workspace_init                       */
+    uint64_t total_valid;        /* sum over frames of #voxels with `valid` (feature updates)         */
+    uint64_t total_tsdf_valid;   /* sum over frames of #voxels with `tsdf_valid`                      */
+    uint64_t total_blocks;       /* sum over calls of visible 8^3 blocks                              */
+    uint32_t last_blocks;        /* visible blocks of the most recent call                            */
+    uint32_t last_valid[SAF_MAX_BATCH];
+    uint32_t last_tsdf_valid[SAF_MAX_BATCH];
+    uint32_t error_flags;        /* SAF_FLAG_* (sticky)                                               */
+} saf_stats;
+
+/* Caller-owned device scratch.  `base` is a device allocation of `bytes` (>= saf_workspace_bytes
+ * for the same grid / max_batch / max_table_elems), 256-byte aligned. */
+typedef struct saf_workspace {
+    void    *base;
+    uint64_t bytes;
+    int32_t  max_batch;         /* largest batch integrate() will be called with (<= SAF_MAX_BATCH) */
+    int32_t  reserved;
+    int64_t  max_table_elems;   /* largest npy*npx*feature_dim of a feature image                    */
+} saf_workspace;
+
+int         saf_abi_version(void);
+const char *saf_error_string(int code);
+
+/* ---- workspace -------------------------------------------------------------------------- */
+
+/* Bytes of device scratch needed to integrate batches of up to max_batch frames with feature
+ * images of up to max_table_elems (= npy*npx*C) elements into this slab. */
+int saf_workspace_bytes(const saf_grid_desc *grid, int32_t max_batch, int64_t max_table_elems,
+                        uint64_t *bytes_out);
+/* Zero the counters and record the layout; call once after allocating. */
+int saf_workspace_init(const saf_workspace *ws, const saf_grid_desc *grid, void *stream);
+/* Copy the counters to host memory.  Synchronises `stream`. */
+int saf_read_stats(const saf_workspace *ws, saf_stats *out_host, void *stream);
+
+/* ---- fusion: ClipSeemFusion.integrate (clip_seem_fusion.py:676-822) and
+ *              ClipFusion.integrate     (clipfusion.py:627-721) ------------------------------ */
+
+/* K1  frame set-up: conservative frustum test of every 8^3 voxel block against the B camera
+ * frusta -> compact visible-block list in the workspace; repacks channel-major feature images
+ * to [R,C] rows.  Replaces nothing in the reference (it projects all N voxels,
+ * clip_seem_fusion.py:698-712); it bounds the work of K2. */
+int saf_frustum_cull(const saf_grid_desc *grid, const saf_frame *frames, int32_t batch,
+                     int32_t height, int32_t width, float trunc, const saf_workspace *ws, void *stream);
+
+/* K2  projection + nearest depth sample + sdf/masks + TSDF and tsdf_weight running average
+ * (clip_seem_fusion.py:698-744) for the voxels of the visible blocks; appends every `valid`
+ * voxel (index, gx, gy) to the per-frame list in the workspace.
+ * valid_out / tsdf_valid_out: optional device [batch, N] uint8 masks (0/1), must be zeroed by
+ * the caller (only visited voxels are written). */
+int saf_tsdf_update(const saf_grid_desc *grid, const saf_volume *vol, const saf_frame *frames,
+                    int32_t batch, int32_t height, int32_t width, float trunc, const saf_workspace *ws,
+                    uint8_t *valid_out, uint8_t *tsdf_valid_out, void *stream);
+
+/* K3  for every listed voxel of frame `frame_index`: nearest class id -> one histogram counter,
+ * rgb sample, bilinear feature sample from the [R,C] table (staged in shared memory by TMA),
+ * running averages of rgb and clip_feat, weight += 1  (clip_seem_fusion.py:751-822). */
+int saf_feature_accumulate(const saf_grid_desc *grid, const saf_volume *vol, const saf_frame *frames,
+                           int32_t batch, int32_t frame_index, int32_t height, int32_t width,
+                           int32_t rgb_mode, const saf_workspace *ws, void *stream);
+
+/* One reference integrate() call: K1, K2, then K3 for each frame of the batch in order. */
+int saf_integrate(const saf_grid_desc *grid, const saf_volume *vol, const saf_frame *frames,
+                  int32_t batch, int32_t height, int32_t width, float trunc, int32_t rgb_mode,
+                  const saf_workspace *ws, void *stream);
+
+/* n_frames successive single-frame integrate() calls (the reference's frame loop,
+ * clip_seem_fusion.py:305-313) issued from one host call. */
+int saf_integrate_sequence(const saf_grid_desc *grid, const saf_volume *vol, const saf_frame *frames,
+                           int32_t n_frames, int32_t height, int32_t width, float trunc,
+                           int32_t rgb_mode, const saf_workspace *ws, void *stream);
+
+/* argmax_with_check_2d_efficient (clip_seem_fusion.py:315-325): per-voxel argmax of the label
+ * histogram (first maximum), -1 where the histogram is all zero.  out: device int64 [n]. */
+int saf_label_argmax(const int32_t *labels_one_hot, int64_t n, int32_t n_classes, int64_t *out,
+                     void *stream);
+
+/* ---- query: Clip.run_query / Clip.clip_feature_surgery (clipfusion.py:899-934) and the
+ *             callers' normalisation (clip_seem_fusion.py:507-511) ---------------------------- */
+
+#define SAF_NORM_NONE        0   /* rows already unit length                                          */
+#define SAF_NORM_NAN_TO_NUM  1   /* f/|f|, zero rows -> 0        (clip_seem_fusion.py:507-511)        */
+#define SAF_NORM_CLAMP_MIN   2   /* f/max(|f|, 0.1)              (hypersim_eval.py:50-51)             */
+
+#define SAF_SCORE_DOT        0   /* S = F X^T                                                         */
+#define SAF_SCORE_SOFTMAX100 1   /* softmax(100*S) over texts    (clipfusion.py:902-903)              */
+#define SAF_SCORE_SURGERY    2   /* w_t S[m,t] - mean_s(w_s S[m,s])  (clipfusion.py:913-932)          */
+
+/* Scores of M feature rows against T text embeddings.
+ *   feats  device [M, ldf] f32 (first C columns used), text device [T,C] f32,
+ *   surgery_w device [T] f32: the class weights w (required for SAF_SCORE_SURGERY),
+ *   out    device [M,T] f32.
+ * precision: 0 = fp32 CUDA-core FMA, 1 = tf32 tensor cores (tcgen05), 2 = 3xTF32 split (tcgen05). */
+int saf_query_scores(const float *feats, int64_t M, int32_t C, int64_t ldf, const float *text, int32_t T,
+                     int32_t norm_mode, int32_t score_mode, const float *surgery_w, int32_t precision,
+                     float *out, void *stream);
+
+/* Top-k rows per text without materialising [M,T]: out_scores/out_index device [T,k]
+ * (descending score, ties to the lower row); row indices are offset by index_base
+ * (the slab's first global voxel).  ws: device scratch of saf_query_topk_workspace_bytes. */
+int saf_query_topk_workspace_bytes(int64_t M, int32_t T, int32_t k, uint64_t *bytes_out);
+int saf_query_topk(const float *feats, int64_t M, int32_t C, int64_t ldf, const float *text, int32_t T,
+                   int32_t norm_mode, int32_t score_mode, const float *surgery_w, int32_t precision,
+                   int32_t k, int64_t index_base, float *out_scores, int64_t *out_index, void *ws,
+                   uint64_t ws_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAF_B200_H */

@@ -1,0 +1,150 @@
+// saf_internal.cuh -- workspace layout and small device helpers shared by the kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "saf_b200.h"
+
+#define SAF_CUDA_TRY(expr)                         \
+    do {                                           \
+        cudaError_t _e = (expr);                   \
+        if (_e != cudaSuccess) return (int)_e;     \
+    } while (0)
+
+namespace saf {
+
+constexpr uint64_t kWsMagic = 0x5341465f42323030ull;  // "SAF_B200"
+constexpr int kBlockEdge = SAF_BLOCK_EDGE;
+constexpr int kBlockVoxels = kBlockEdge * kBlockEdge * kBlockEdge;
+
+// Device-resident workspace header (512 bytes).  Per-call counters are reset by the kernels
+// themselves: K1 zeroes n_valid/n_tsdf_valid before K2 runs, K2's last CTA folds the call into the
+// totals and zeroes n_blocks / k2_done for the next call.
+struct WsHeader {
+    uint32_t n_blocks;                      // visible blocks of the call in flight
+    uint32_t k2_done;                       // CTA completion ticket of K2
+    uint32_t error_flags;
+    uint32_t last_blocks;
+    uint32_t n_valid[SAF_MAX_BATCH];
+    uint32_t n_tsdf_valid[SAF_MAX_BATCH];
+    unsigned long long total_frames;
+    unsigned long long total_valid;
+    unsigned long long total_tsdf_valid;
+    unsigned long long total_blocks;
+    // immutable after saf_workspace_init
+    uint64_t magic;
+    uint64_t bytes;
+    uint64_t list_cap;                      // entries per per-frame valid list (= slab voxels)
+    uint64_t max_table_elems;
+    uint64_t off_blocks, off_lists, off_tables;
+    uint32_t nblocks_total;
+    uint32_t max_batch;
+    uint32_t nb[3];                         // blocks per axis of the slab
+    uint32_t pad_[1];
+};
+static_assert(sizeof(WsHeader) <= 512, "workspace header grew past its slot");
+
+// One `valid` voxel of one frame: slab-local flat index and the normalised image coordinates
+// the reference reuses for all three samplers (clip_seem_fusion.py:752).
+struct __align__(16) ValidEntry {
+    uint32_t voxel;
+    float gx, gy;
+    uint32_t pad;
+};
+
+struct WsLayout {
+    uint64_t bytes;
+    uint64_t list_cap;
+    uint64_t off_blocks, off_lists, off_tables;
+    uint32_t nblocks_total;
+    uint32_t nb[3];
+};
+
+inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+inline int compute_layout(const saf_grid_desc* g, int32_t max_batch, int64_t max_table_elems, WsLayout* L)
+{
+    if (!g || !L) return SAF_ERR_NULL;
+    if (max_batch < 1 || max_batch > SAF_MAX_BATCH) return SAF_ERR_BATCH;
+    if (g->nvox[0] <= 0 || g->nvox[1] <= 0 || g->nvox[2] <= 0 || g->x_begin < 0 || g->x_end > g->nvox[0] ||
+        g->x_begin >= g->x_end || !(g->voxel_size > 0.f))
+        return SAF_ERR_GRID;
+    if (max_table_elems < 0) return SAF_ERR_SHAPE;
+    const uint64_t nxs = (uint64_t)(g->x_end - g->x_begin);
+    const uint64_t n = nxs * (uint64_t)g->nvox[1] * (uint64_t)g->nvox[2];
+    if (n >= (1ull << 32)) return SAF_ERR_GRID;  // voxel indices are 32-bit
+    L->nb[0] = (uint32_t)((nxs + kBlockEdge - 1) / kBlockEdge);
+    L->nb[1] = (uint32_t)((g->nvox[1] + kBlockEdge - 1) / kBlockEdge);
+    L->nb[2] = (uint32_t)((g->nvox[2] + kBlockEdge - 1) / kBlockEdge);
+    L->nblocks_total = L->nb[0] * L->nb[1] * L->nb[2];
+    L->list_cap = n;
+    L->off_blocks = 512;
+    L->off_lists = align_up(L->off_blocks + 4ull * L->nblocks_total, 256);
+    L->off_tables = align_up(L->off_lists + (uint64_t)max_batch * n * sizeof(ValidEntry), 256);
+    L->bytes = align_up(L->off_tables + (uint64_t)max_batch * (uint64_t)max_table_elems * 4ull, 256);
+    return 0;
+}
+
+// ---- device helpers ------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// streaming 128-bit accesses for the once-per-frame feature rows
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p)
+{
+    float4 v;
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream_f4(float4* p, const float4& v)
+{
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+
+int device_sm_count(int* sms, int* smem_optin);
+
+}  // namespace saf

@@ -1,0 +1,312 @@
+// saf_topk.cu -- top-k feature rows per text embedding without keeping the [M,T] score matrix.
+//
+// The reference ranks with torch.argsort over the whole score matrix
+// (/root/reference/eval_scannet_segmentation.py:546-561) or thresholds it
+// (query_mesh.py:59-73); at M = 24 M voxels x T = 256 texts that matrix is 24.6 GB, so scores are
+// produced in row chunks and reduced on the fly:
+//   topk_scan_kernel   each CTA owns 8 texts x one row split and keeps their k best (score, row)
+//                      in shared memory; a score is inserted only if it beats the current k-th
+//                      best, which after warm-up is rare (~k ln(M/k) times per text)
+//   topk_merge_kernel  one CTA per text ranks the splits' candidates -> final sorted top-k
+// Order: descending score, ties to the lower row index (a total order, so the result does not
+// depend on the insertion order).
+#include <math.h>
+
+#include "saf_internal.cuh"
+
+namespace saf {
+
+constexpr int kScanThreads = 256;
+constexpr int kTextsPerCta = 8;
+
+__device__ __forceinline__ bool beats(float s, long long i, float s2, long long i2)
+{
+    return s > s2 || (s == s2 && i < i2);
+}
+
+struct Partial {  // [splits][T][k]
+    float* score;
+    long long* index;
+};
+
+// S: [rows, T] scores of rows [row0, row0 + rows) (global row = index_base + row0 + r)
+__global__ void __launch_bounds__(kScanThreads) topk_scan_kernel(const float* __restrict__ S, int64_t rows, int T,
+                                                                 int64_t row_id0, int k, Partial part, int first_chunk)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    long long* best_i = reinterpret_cast<long long*>(smem);                    // [8][k]
+    float* best_s = reinterpret_cast<float*>(best_i + (size_t)kTextsPerCta * k);  // [8][k]
+    __shared__ float thr_s[kTextsPerCta];
+    __shared__ long long thr_i[kTextsPerCta];
+    __shared__ int thr_pos[kTextsPerCta];
+    __shared__ int count[kTextsPerCta];
+    __shared__ int lock[kTextsPerCta];
+
+    const int t0 = blockIdx.x * kTextsPerCta;
+    const int split = blockIdx.y, splits = gridDim.y;
+    const int lane = threadIdx.x & 31;
+
+    // load this (split, text) partial list from the previous chunk
+    for (int e = threadIdx.x; e < kTextsPerCta * k; e += kScanThreads) {
+        const int j = e / k, q = e - j * k;
+        const int t = t0 + j;
+        float s = -INFINITY;
+        long long i = -1;
+        if (!first_chunk && t < T) {
+            s = part.score[((size_t)split * T + t) * k + q];
+            i = part.index[((size_t)split * T + t) * k + q];
+        }
+        best_s[e] = s;
+        best_i[e] = i;
+    }
+    __syncthreads();
+    if (threadIdx.x < kTextsPerCta) {
+        const int j = threadIdx.x;
+        int c = 0, wp = 0;
+        float ws = INFINITY;
+        long long wi = -1;
+        for (int q = 0; q < k; ++q) {
+            if (best_i[j * k + q] >= 0) {
+                ++c;
+                if (beats(ws, wi, best_s[j * k + q], best_i[j * k + q])) {
+                    ws = best_s[j * k + q];
+                    wi = best_i[j * k + q];
+                    wp = q;
+                }
+            }
+        }
+        // lists are kept packed: valid entries occupy [0, count)
+        count[j] = c;
+        thr_s[j] = (c == k) ? ws : -INFINITY;
+        thr_i[j] = (c == k) ? wi : (long long)0x7fffffffffffffffll;
+        thr_pos[j] = wp;
+        lock[j] = 0;
+    }
+    __syncthreads();
+
+    const int64_t per_split = (rows + splits - 1) / splits;
+    const int64_t r_begin = (int64_t)split * per_split;
+    const int64_t r_end = min(rows, r_begin + per_split);
+    for (int64_t rb = r_begin; rb < r_end; rb += kScanThreads) {
+        const int64_t r = rb + threadIdx.x;
+        const bool in = r < r_end;
+        float sc[kTextsPerCta];
+#pragma unroll
+        for (int j = 0; j < kTextsPerCta; ++j) sc[j] = (in && t0 + j < T) ? S[r * T + t0 + j] : -INFINITY;
+        const long long gid = row_id0 + r;
+#pragma unroll
+        for (int j = 0; j < kTextsPerCta; ++j) {
+            const bool cand = in && (t0 + j < T) && !(sc[j] != sc[j]) &&
+                              beats(sc[j], gid, *(volatile float*)&thr_s[j], *(volatile long long*)&thr_i[j]);
+            unsigned mask = __ballot_sync(0xffffffffu, cand);
+            while (mask) {
+                const int src = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const float s = __shfl_sync(0xffffffffu, sc[j], src);
+                const long long i = __shfl_sync(0xffffffffu, gid, src);
+                if (lane == 0) {
+                    while (atomicCAS(&lock[j], 0, 1) != 0) {
+                    }
+                }
+                __syncwarp();
+                __threadfence_block();
+                float* ls = best_s + (size_t)j * k;
+                long long* li = best_i + (size_t)j * k;
+                const int c = *(volatile int*)&count[j];
+                if (c < k) {
+                    if (lane == 0) {
+                        ls[c] = s;
+                        li[c] = i;
+                        *(volatile int*)&count[j] = c + 1;
+                    }
+                    __syncwarp();
+                    if (c + 1 == k) {
+                        // list just became full: find its worst element
+                        float ws = INFINITY;
+                        long long wi = -1;
+                        int wp = 0;
+                        for (int q = lane; q < k; q += 32) {
+                            const float qs = *(volatile float*)&ls[q];
+                            const long long qi = *(volatile long long*)&li[q];
+                            if (beats(ws, wi, qs, qi)) {
+                                ws = qs;
+                                wi = qi;
+                                wp = q;
+                            }
+                        }
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            const float os = __shfl_xor_sync(0xffffffffu, ws, o);
+                            const long long oi = __shfl_xor_sync(0xffffffffu, wi, o);
+                            const int op = __shfl_xor_sync(0xffffffffu, wp, o);
+                            if (beats(ws, wi, os, oi)) {
+                                ws = os;
+                                wi = oi;
+                                wp = op;
+                            }
+                        }
+                        if (lane == 0) {
+                            *(volatile float*)&thr_s[j] = ws;
+                            *(volatile long long*)&thr_i[j] = wi;
+                            thr_pos[j] = wp;
+                        }
+                    }
+                } else if (beats(s, i, *(volatile float*)&thr_s[j], *(volatile long long*)&thr_i[j])) {
+                    const int wp0 = *(volatile int*)&thr_pos[j];
+                    if (lane == 0) {
+                        ls[wp0] = s;
+                        li[wp0] = i;
+                    }
+                    __syncwarp();
+                    float ws = INFINITY;
+                    long long wi = -1;
+                    int wp = 0;
+                    for (int q = lane; q < k; q += 32) {
+                        const float qs = *(volatile float*)&ls[q];
+                        const long long qi = *(volatile long long*)&li[q];
+                        if (beats(ws, wi, qs, qi)) {
+                            ws = qs;
+                            wi = qi;
+                            wp = q;
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const float os = __shfl_xor_sync(0xffffffffu, ws, o);
+                        const long long oi = __shfl_xor_sync(0xffffffffu, wi, o);
+                        const int op = __shfl_xor_sync(0xffffffffu, wp, o);
+                        if (beats(ws, wi, os, oi)) {
+                            ws = os;
+                            wi = oi;
+                            wp = op;
+                        }
+                    }
+                    if (lane == 0) {
+                        *(volatile float*)&thr_s[j] = ws;
+                        *(volatile long long*)&thr_i[j] = wi;
+                        *(volatile int*)&thr_pos[j] = wp;
+                    }
+                }
+                __syncwarp();
+                __threadfence_block();
+                if (lane == 0) atomicExch(&lock[j], 0);
+                __syncwarp();
+            }
+        }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < kTextsPerCta * k; e += kScanThreads) {
+        const int j = e / k, q = e - j * k;
+        const int t = t0 + j;
+        if (t < T) {
+            part.score[((size_t)split * T + t) * k + q] = best_s[e];
+            part.index[((size_t)split * T + t) * k + q] = best_i[e];
+        }
+    }
+}
+
+// one CTA per text: rank every candidate among the splits' lists; ranks < k are the answer
+__global__ void __launch_bounds__(256) topk_merge_kernel(Partial part, int splits, int T, int k, int64_t index_base,
+                                                         float* __restrict__ out_s, long long* __restrict__ out_i)
+{
+    const int t = blockIdx.x;
+    const int n = splits * k;
+    for (int q = threadIdx.x; q < k; q += blockDim.x) {
+        out_s[(size_t)t * k + q] = -INFINITY;
+        out_i[(size_t)t * k + q] = -1;
+    }
+    __syncthreads();
+    for (int a = threadIdx.x; a < n; a += blockDim.x) {
+        const int sa = a / k, qa = a - sa * k;
+        const float s = part.score[((size_t)sa * T + t) * k + qa];
+        const long long i = part.index[((size_t)sa * T + t) * k + qa];
+        if (i < 0) continue;
+        int rank = 0;
+        for (int b = 0; b < n; ++b) {
+            const int sb = b / k, qb = b - sb * k;
+            const long long i2 = part.index[((size_t)sb * T + t) * k + qb];
+            if (i2 < 0) continue;
+            rank += beats(part.score[((size_t)sb * T + t) * k + qb], i2, s, i) ? 1 : 0;
+        }
+        if (rank < k) {
+            out_s[(size_t)t * k + rank] = s;
+            out_i[(size_t)t * k + rank] = i + index_base;
+        }
+    }
+}
+
+constexpr int kTopkSplits = 32;
+constexpr int64_t kTopkChunkRows = 1 << 19;
+
+struct TopkLayout {
+    uint64_t off_scores, off_part_s, off_part_i, bytes;
+    int64_t chunk_rows;
+};
+
+static int topk_layout(int64_t M, int T, int k, TopkLayout* L)
+{
+    if (M < 0 || T <= 0 || k <= 0 || k > 2048) return SAF_ERR_SHAPE;
+    L->chunk_rows = M < kTopkChunkRows ? (M > 0 ? M : 1) : kTopkChunkRows;
+    L->off_scores = 0;
+    L->off_part_s = align_up((uint64_t)L->chunk_rows * T * 4, 256);
+    L->off_part_i = align_up(L->off_part_s + (uint64_t)kTopkSplits * T * k * 4, 256);
+    L->bytes = align_up(L->off_part_i + (uint64_t)kTopkSplits * T * k * 8, 256);
+    return 0;
+}
+
+}  // namespace saf
+
+using namespace saf;
+
+extern "C" {
+
+int saf_query_topk_workspace_bytes(int64_t M, int32_t T, int32_t k, uint64_t* bytes_out)
+{
+    if (!bytes_out) return SAF_ERR_NULL;
+    TopkLayout L;
+    int rc = topk_layout(M, T, k, &L);
+    if (rc) return rc;
+    *bytes_out = L.bytes;
+    return 0;
+}
+
+int saf_query_topk(const float* feats, int64_t M, int32_t C, int64_t ldf, const float* text, int32_t T,
+                   int32_t norm_mode, int32_t score_mode, const float* surgery_w, int32_t precision, int32_t k,
+                   int64_t index_base, float* out_scores, int64_t* out_index, void* ws, uint64_t ws_bytes, void* stream)
+{
+    int sms = 0, smem_optin = 0;
+    int rc = device_sm_count(&sms, &smem_optin);
+    if (rc) return rc;
+    if (!feats || !text || !out_scores || !out_index || !ws) return SAF_ERR_NULL;
+    if (((uintptr_t)ws & 255u) != 0) return SAF_ERR_ALIGNMENT;
+    TopkLayout L;
+    rc = topk_layout(M, T, k, &L);
+    if (rc) return rc;
+    if (ws_bytes < L.bytes) return SAF_ERR_WORKSPACE;
+    const size_t smem = (size_t)kTextsPerCta * k * 12;
+    if (smem + 1024 > (size_t)smem_optin) return SAF_ERR_SHAPE;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char* base = (unsigned char*)ws;
+    float* scores = (float*)(base + L.off_scores);
+    Partial part;
+    part.score = (float*)(base + L.off_part_s);
+    part.index = (long long*)(base + L.off_part_i);
+    SAF_CUDA_TRY(cudaFuncSetAttribute(topk_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const dim3 grid((T + kTextsPerCta - 1) / kTextsPerCta, kTopkSplits);
+    int first = 1;
+    for (int64_t r0 = 0; r0 < M || first; r0 += L.chunk_rows) {
+        const int64_t rows = M - r0 < L.chunk_rows ? M - r0 : L.chunk_rows;
+        if (rows > 0) {
+            rc = saf_query_scores(feats + r0 * ldf, rows, C, ldf, text, T, norm_mode, score_mode, surgery_w, precision,
+                                  scores, stream);
+            if (rc) return rc;
+        }
+        topk_scan_kernel<<<grid, kScanThreads, smem, st>>>(scores, rows > 0 ? rows : 0, T, r0, k, part, first);
+        SAF_CUDA_TRY(cudaGetLastError());
+        first = 0;
+    }
+    topk_merge_kernel<<<T, 256, 0, st>>>(part, kTopkSplits, T, k, index_base, out_scores, (long long*)out_index);
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -1,0 +1,302 @@
+"""Drop-in fusion volumes: same constructor / integrate / buffer surface as the reference's
+``ClipSeemFusion`` (/root/reference/clip_seem_fusion.py:611-888) and ``ClipFusion``
+(/root/reference/clipfusion.py:575-763), with the per-frame work done by the sm_100a kernels in
+libsaf_b200.so.  PyTorch is only the owner of device memory and streams here.
+
+Differences a caller can observe:
+  * tensors must live on a CUDA device (sm_100); there is no CPU path - it raises instead.
+  * ``xyz_world`` is not stored (12 B/voxel re-read every frame in the reference); voxel centres
+    are recomputed in-kernel with the reference's exact roundings.  The attribute still exists
+    as a lazily computed property.
+  * optional ``x_begin`` / ``x_end`` keyword arguments hold only an x-slab of the grid
+    (multi-GPU partitioning); buffers then cover that slab, coordinates stay global.
+  * class ids outside [0, n_classes) cannot raise inside a kernel; they set a sticky flag that
+    ``check_errors()`` (and ``stats()``) turn into the RuntimeError torch's one_hot would raise.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_SEG_DTYPES = {torch.uint8: _lib.SAF_SEG_U8, torch.int16: _lib.SAF_SEG_I16, torch.int32: _lib.SAF_SEG_I32,
+               torch.int64: _lib.SAF_SEG_I64, torch.float32: _lib.SAF_SEG_F32}
+
+
+def _as_int_list(nvox):
+    if isinstance(nvox, torch.Tensor):
+        return [int(v) for v in nvox.tolist()]
+    return [int(v) for v in np.asarray(nvox).tolist()]
+
+
+class _FusionVolume(torch.nn.Module):
+    """State layout of clip_seem_fusion.py:640-672 plus the kernel plumbing shared by both classes."""
+
+    _with_labels = True
+    _rgb_mode = _lib.SAF_RGB_BILINEAR
+
+    def _init_volume(self, origin, voxel_size, nvox, trunc, feature_dim, x_begin=0, x_end=None):
+        self.origin = origin
+        self.voxel_size = voxel_size
+        self.nvox = nvox
+        self.trunc = trunc
+        self.n_clip_feats = int(feature_dim)
+        dims = _as_int_list(nvox)
+        self.x_begin = int(x_begin)
+        self.x_end = dims[0] if x_end is None else int(x_end)
+        if not (0 <= self.x_begin < self.x_end <= dims[0]):
+            raise ValueError("x-slab [%d,%d) outside the grid" % (self.x_begin, self.x_end))
+        self._dims = dims
+        n = (self.x_end - self.x_begin) * dims[1] * dims[2]
+        self.register_buffer("tsdf", torch.zeros(n, dtype=torch.float32))
+        self.register_buffer("rgb", torch.zeros((n, 3), dtype=torch.float32))
+        self.register_buffer("clip_feat", torch.zeros((n, self.n_clip_feats), dtype=torch.float32))
+        self.register_buffer("weight", torch.zeros(n, dtype=torch.int32))
+        self.register_buffer("tsdf_weight", torch.zeros(n, dtype=torch.int32))
+        if self._with_labels:
+            # 133 + 10 spare classes, clip_seem_fusion.py:653-659
+            self.n_classes = 133 + 10
+            self.register_buffer("labels_one_hot", torch.zeros((n, self.n_classes), dtype=torch.int32))
+        self._ws_tensor = None
+        self._ws = None
+        self._ws_key = None
+        self._grid = None
+
+    # -- geometry ------------------------------------------------------------------------------
+
+    def _grid_desc(self):
+        if self._grid is None:
+            g = _lib.GridDesc()
+            origin = self.origin.detach().cpu().to(torch.float32).tolist() if isinstance(self.origin, torch.Tensor) \
+                else np.asarray(self.origin, dtype=np.float32).tolist()
+            g.origin[:] = origin
+            g.voxel_size = float(self.voxel_size)
+            g.nvox[:] = self._dims
+            g.x_begin, g.x_end = self.x_begin, self.x_end
+            self._grid = g
+        return self._grid
+
+    @property
+    def xyz_world(self):
+        """World coordinates of the slab's voxel centres, computed like clip_seem_fusion.py:664-669."""
+        dev = self.tsdf.device
+        x = torch.arange(self.x_begin, self.x_end, device=dev)
+        y = torch.arange(self._dims[1], device=dev)
+        z = torch.arange(self._dims[2], device=dev)
+        xx, yy, zz = torch.meshgrid(x, y, z, indexing="ij")
+        xyz_idx = torch.stack((xx, yy, zz), dim=-1).view(-1, 3)
+        origin = self.origin if isinstance(self.origin, torch.Tensor) else torch.as_tensor(self.origin)
+        return xyz_idx * self.voxel_size + origin.to(dev)
+
+    # -- kernel plumbing -----------------------------------------------------------------------
+
+    def _volume_desc(self):
+        v = _lib.Volume()
+        v.tsdf = self.tsdf.data_ptr()
+        v.tsdf_weight = self.tsdf_weight.data_ptr()
+        v.weight = self.weight.data_ptr()
+        v.rgb = self.rgb.data_ptr()
+        v.clip_feat = self.clip_feat.data_ptr()
+        v.labels_one_hot = self.labels_one_hot.data_ptr() if self._with_labels else None
+        v.feature_dim = self.n_clip_feats
+        v.n_classes = self.n_classes if self._with_labels else 0
+        return v
+
+    def _workspace(self, batch, table_elems):
+        dev = self.tsdf.device
+        key = self._ws_key
+        if key is not None and key[0] == dev and key[1] >= batch and key[2] >= table_elems:
+            return self._ws
+        lib = _lib.load()
+        old_stats = self.stats(check=False) if self._ws is not None else None
+        max_batch = max(batch, key[1] if key else 1)
+        max_table = max(table_elems, key[2] if key else 0)
+        nbytes = ctypes.c_uint64()
+        _lib.check(lib.saf_workspace_bytes(ctypes.byref(self._grid_desc()), max_batch, max_table,
+                                           ctypes.byref(nbytes)), "saf_workspace_bytes")
+        self._ws_tensor = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=dev)
+        base = (self._ws_tensor.data_ptr() + 255) // 256 * 256
+        ws = _lib.Workspace()
+        ws.base, ws.bytes, ws.max_batch, ws.max_table_elems = base, nbytes.value, max_batch, max_table
+        _lib.check(lib.saf_workspace_init(ctypes.byref(ws), ctypes.byref(self._grid_desc()),
+                                          torch.cuda.current_stream(dev).cuda_stream), "saf_workspace_init")
+        self._ws, self._ws_key = ws, (dev, max_batch, max_table)
+        self._stats_carry = old_stats
+        return ws
+
+    def _make_frames(self, depth_imgs, rgb_imgs, poses, K, clip_feat_img, seg_maps):
+        B, H, W, _ = rgb_imgs.shape
+        dev = self.tsdf.device
+        for name, t in (("depth_imgs", depth_imgs), ("rgb_imgs", rgb_imgs), ("clip feature image", clip_feat_img)):
+            if t.device != dev:
+                raise RuntimeError("%s is on %s but the volume is on %s" % (name, t.device, dev))
+        depth = depth_imgs.to(torch.float32).contiguous()
+        rgb = rgb_imgs.to(torch.float32).contiguous()
+        table = clip_feat_img[:, : self.n_clip_feats]
+        if table.dtype != torch.float32:
+            table = table.to(torch.float32)
+        if table.shape[1] != self.n_clip_feats:
+            raise RuntimeError("feature image has %d channels, volume needs %d" % (table.shape[1], self.n_clip_feats))
+        _, _, npy, npx = table.shape
+        sb, sc, sy, sx = table.stride()
+        if npy > 1 and npx > 1 and sy != sx * npx:
+            table = table.contiguous()
+            sb, sc, sy, sx = table.stride()
+        sr = sx if npx > 1 else (sy if npy > 1 else max(1, self.n_clip_feats if sc == 1 else 1))
+        poses_dev = K_dev = None
+        if poses.is_cuda:
+            poses_dev = poses.to(torch.float32).contiguous()
+            K_dev = K.to(device=dev, dtype=torch.float32).contiguous()
+        else:
+            poses_host = poses.to(torch.float32).contiguous().view(B, 16)
+            K_host = K.detach().cpu().to(torch.float32).contiguous().view(B, 9)
+        frames = (_lib.Frame * B)()
+        keep = [depth, rgb, table, poses_dev, K_dev]
+        for b in range(B):
+            f = frames[b]
+            f.depth = depth[b].data_ptr()
+            f.rgb = rgb[b].data_ptr()
+            f.table = table[b].data_ptr()
+            f.table_stride_c, f.table_stride_r = sc, sr
+            f.npy, f.npx = npy, npx
+            if seg_maps is not None:
+                seg = seg_maps[b]
+                if seg.device != dev:
+                    raise RuntimeError("segmentation map is on %s but the volume is on %s" % (seg.device, dev))
+                if seg.dtype not in _SEG_DTYPES:
+                    seg = seg.to(torch.int64)
+                seg = seg.contiguous()
+                if tuple(seg.shape) != (H, W):
+                    raise RuntimeError("segmentation map shape %s != image %s" % (tuple(seg.shape), (H, W)))
+                keep.append(seg)
+                f.seg = seg.data_ptr()
+                f.seg_dtype = _SEG_DTYPES[seg.dtype]
+            if poses_dev is not None:
+                f.pose_device = poses_dev[b].data_ptr()
+                f.K_device = K_dev[b].data_ptr()
+            else:
+                f.pose[:] = poses_host[b].tolist()
+                f.K[:] = K_host[b].tolist()
+        return frames, keep, (B, H, W, npy * npx * self.n_clip_feats)
+
+    def _integrate_frames(self, depth_imgs, rgb_imgs, poses, K, clip_feat_img, seg_maps):
+        if not self.tsdf.is_cuda:
+            raise RuntimeError("spatially_aware_ai_b200 volumes run on a CUDA (sm_100) device only; "
+                               "call .to('cuda') - there is no CPU path")
+        frames, keep, (B, H, W, table_elems) = self._make_frames(depth_imgs, rgb_imgs, poses, K, clip_feat_img, seg_maps)
+        if B > _lib.SAF_MAX_BATCH:
+            raise RuntimeError("batch of %d frames exceeds SAF_MAX_BATCH=%d" % (B, _lib.SAF_MAX_BATCH))
+        ws = self._workspace(B, table_elems)
+        vol = self._volume_desc()
+        stream = torch.cuda.current_stream(self.tsdf.device).cuda_stream
+        rc = _lib.load().saf_integrate(ctypes.byref(self._grid_desc()), ctypes.byref(vol), frames, B, H, W,
+                                       float(self.trunc), self._rgb_mode, ctypes.byref(ws), stream)
+        _lib.check(rc, "saf_integrate")
+        del keep
+
+    # -- bookkeeping ---------------------------------------------------------------------------
+
+    def stats(self, check=True):
+        """Counters kept by the kernels: frames, sum of valid / tsdf_valid voxels, visible blocks."""
+        if self._ws is None:
+            return dict(total_frames=0, total_valid=0, total_tsdf_valid=0, total_blocks=0, last_blocks=0,
+                        last_valid=[], last_tsdf_valid=[], error_flags=0)
+        st = _lib.Stats()
+        stream = torch.cuda.current_stream(self.tsdf.device).cuda_stream
+        _lib.check(_lib.load().saf_read_stats(ctypes.byref(self._ws), ctypes.byref(st), stream), "saf_read_stats")
+        out = dict(total_frames=st.total_frames, total_valid=st.total_valid, total_tsdf_valid=st.total_tsdf_valid,
+                   total_blocks=st.total_blocks, last_blocks=st.last_blocks, last_valid=list(st.last_valid),
+                   last_tsdf_valid=list(st.last_tsdf_valid), error_flags=st.error_flags)
+        carry = getattr(self, "_stats_carry", None)
+        if carry:
+            for k in ("total_frames", "total_valid", "total_tsdf_valid", "total_blocks"):
+                out[k] += carry[k]
+            out["error_flags"] |= carry["error_flags"]
+        if check and out["error_flags"] & _lib.SAF_FLAG_BAD_CLASS_ID:
+            raise RuntimeError("Class values must be smaller than num_classes.")
+        return out
+
+    def check_errors(self):
+        self.stats(check=True)
+
+    def label_argmax(self):
+        """argmax_with_check_2d_efficient (clip_seem_fusion.py:315-325): int64 [N], -1 where unobserved."""
+        out = torch.empty(self.labels_one_hot.shape[0], dtype=torch.int64, device=self.tsdf.device)
+        stream = torch.cuda.current_stream(self.tsdf.device).cuda_stream
+        _lib.check(_lib.load().saf_label_argmax(self.labels_one_hot.data_ptr(), out.numel(), self.n_classes,
+                                                out.data_ptr(), stream), "saf_label_argmax")
+        return out
+
+
+class ClipSeemFusion(_FusionVolume):
+    """clip_seem_fusion.py:611-888."""
+
+    _with_labels = True
+    _rgb_mode = _lib.SAF_RGB_BILINEAR
+
+    def __init__(self, origin, voxel_size, nvox, trunc, scale_patches_by_depth, clip_patch_size, clip_patch_stride,
+                 clip_model, seg_model, x_begin=0, x_end=None):
+        super().__init__()
+        self.clip = clip_model
+        self.clip_patch_size = clip_patch_size
+        self.clip_patch_stride = clip_patch_stride
+        self.scale_patches_by_depth = scale_patches_by_depth
+        self.segmentation_model = seg_model
+        self._init_volume(origin, voxel_size, nvox, trunc, self.clip.feature_dim, x_begin, x_end)
+        self.debug_counter = 0
+
+    def integrate(self, depth_imgs, rgb_imgs, poses, K):
+        """clip_seem_fusion.py:676-822.  depth [B,H,W], rgb [B,H,W,3] in [0,1], poses [B,4,4], K [B,3,3]."""
+        batch_size = rgb_imgs.shape[0]
+        rgb_chw = rgb_imgs.permute(0, 3, 1, 2)
+        if self.scale_patches_by_depth:
+            clip_feat_img = self.clip.img_inference_tiled_depthscaled(rgb_chw, depth_imgs, K,
+                                                                      patch_stride=self.clip_patch_stride)
+        else:
+            clip_feat_img = self.clip.img_inference_tiled(rgb_chw, patch_size=self.clip_patch_size,
+                                                          patch_stride=self.clip_patch_stride)
+        seg_maps = [self.segmentation_model.run_on_image(rgb_chw[i]) for i in range(batch_size)]
+        self._integrate_frames(depth_imgs, rgb_imgs, poses, K, clip_feat_img, seg_maps)
+
+    def extract_mesh(self):
+        from .mesh import extract_mesh_seem
+        return extract_mesh_seem(self)
+
+
+class ClipFusion(_FusionVolume):
+    """clipfusion.py:575-763.  `clip_model` may be an open_clip model name (as in the reference) or an
+    already constructed object with feature_dim / img_inference_tiled (what the tests inject)."""
+
+    _with_labels = False
+    _rgb_mode = _lib.SAF_RGB_NEAREST
+
+    def __init__(self, origin, voxel_size, nvox, trunc, scale_patches_by_depth, clip_model, clip_pretraining,
+                 clip_patch_size, clip_patch_stride, x_begin=0, x_end=None):
+        super().__init__()
+        if isinstance(clip_model, str):
+            from .query import Clip
+            self.clip = Clip(clip_model, clip_pretraining)
+            self.clip.requires_grad_(False)
+            self.clip.eval()
+        else:
+            self.clip = clip_model
+        self.clip_patch_size = clip_patch_size
+        self.clip_patch_stride = clip_patch_stride
+        self.scale_patches_by_depth = scale_patches_by_depth
+        self._init_volume(origin, voxel_size, nvox, trunc, self.clip.feature_dim, x_begin, x_end)
+
+    def integrate(self, depth_imgs, rgb_imgs, poses, K):
+        """clipfusion.py:627-721."""
+        rgb_chw = rgb_imgs.permute(0, 3, 1, 2)
+        if self.scale_patches_by_depth:
+            clip_feat_img = self.clip.img_inference_tiled_depthscaled(rgb_chw, depth_imgs, K,
+                                                                      patch_stride=self.clip_patch_stride)
+        else:
+            clip_feat_img = self.clip.img_inference_tiled(rgb_chw, patch_size=self.clip_patch_size,
+                                                          patch_stride=self.clip_patch_stride)
+        self._integrate_frames(depth_imgs, rgb_imgs, poses, K, clip_feat_img, None)
+
+    def extract_mesh(self):
+        from .mesh import extract_mesh_fusion
+        return extract_mesh_fusion(self)

@@ -66,3 +66,65 @@ def cosine_rows(a, b):
     nzm = den > 0
     out[nzm] = num[nzm] / den[nzm]
     return out
+
+
+# ---- GPU-side replay through the drop-in classes ------------------------------------------------
+
+class FakeClip:
+    """Duck-typed producer: returns the pre-generated tiled-patch feature image
+    (stands in for clipfusion.py:808-839)."""
+
+    def __init__(self, feature_dim):
+        self.feature_dim = feature_dim
+        self.next_table = None
+
+    def img_inference_tiled(self, rgb_imgs, patch_size, patch_stride):
+        return self.next_table
+
+
+class FakeSeg:
+    """Duck-typed kMaX stand-in (handy_utils.py:103-161): returns the pre-generated class map."""
+
+    def __init__(self):
+        self.queue = []
+
+    def run_on_image(self, img):
+        return self.queue.pop(0)
+
+
+def make_gpu_volume(g, device="cuda", x_begin=0, x_end=None):
+    import torch
+    import spatially_aware_ai_b200 as saf
+    clip, seg = FakeClip(g["feature_dim"]), FakeSeg()
+    origin, nvox = torch.from_numpy(g["origin"]), torch.from_numpy(g["nvox"])
+    if g["cls"] == "ClipSeemFusion":
+        vol = saf.ClipSeemFusion(origin, g["voxel_size"], nvox, g["trunc"], False, 0, 0, clip, seg,
+                                 x_begin=x_begin, x_end=x_end)
+    else:
+        vol = saf.ClipFusion(origin, g["voxel_size"], nvox, g["trunc"], False, clip, None, 0, 0,
+                             x_begin=x_begin, x_end=x_end)
+    return vol.to(device), clip, seg
+
+
+def replay_gpu(g, device="cuda", x_begin=0, x_end=None, upto=None, seg_dtype=None, pose_on_device=True):
+    import torch
+    vol, clip, seg = make_gpu_volume(g, device, x_begin, x_end)
+    counts = []
+    for c, (depth, rgb, segs, tables, pose, K) in enumerate(golden_calls(g)):
+        if upto is not None and c >= upto:
+            break
+        clip.next_table = torch.stack([torch.from_numpy(np.ascontiguousarray(t)) for t in tables]).to(device)
+        # keep the generator's memory layout (hwc-backed views) per frame when the batch is 1
+        if len(tables) == 1 and not tables[0].flags["C_CONTIGUOUS"]:
+            t = torch.from_numpy(np.ascontiguousarray(tables[0].transpose(1, 2, 0))).to(device)
+            clip.next_table = t.permute(2, 0, 1)[None]
+        dt = seg_dtype or torch.int64
+        seg.queue = [torch.from_numpy(s.astype(np.int64)).to(device=device, dtype=dt) for s in segs]
+        p, k = torch.from_numpy(pose), torch.from_numpy(K)
+        if pose_on_device:
+            p, k = p.to(device), k.to(device)
+        vol.integrate(torch.from_numpy(depth).to(device), torch.from_numpy(rgb).to(device), p, k)
+        st = vol.stats()
+        B = len(tables)
+        counts.append([sum(st["last_valid"][:B]), sum(st["last_tsdf_valid"][:B])])
+    return vol, np.array(counts)
