@@ -1,7 +1,10 @@
 // saf_abi.cu -- version and error strings of the C ABI.
 #include <cuda_runtime.h>
 
-#include "saf_b200.h"
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "saf_internal.cuh"
 
 extern "C" {
 
@@ -25,3 +28,29 @@ const char* saf_error_string(int code)
     }
 }
 }
+
+namespace saf {
+
+int debug_check_launch(const char* what, cudaStream_t st)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        fprintf(stderr, "[saf] launch of %s failed: %s\n", what, cudaGetErrorString(e));
+        return (int)e;
+    }
+    static int debug = -1;
+    if (debug < 0) {
+        const char* v = getenv("SAF_DEBUG_SYNC");
+        debug = (v && v[0] == '1') ? 1 : 0;
+    }
+    if (debug) {
+        e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            fprintf(stderr, "[saf] kernel %s faulted: %s\n", what, cudaGetErrorString(e));
+            return (int)e;
+        }
+    }
+    return 0;
+}
+
+}  // namespace saf

@@ -147,4 +147,13 @@ __device__ __forceinline__ void st_stream_f4(float4* p, const float4& v)
 
 int device_sm_count(int* sms, int* smem_optin);
 
+// SAF_DEBUG_SYNC=1 in the environment: synchronise after every launch and name the kernel that
+// faulted on stderr (compute-sanitizer is not available on every pool).
+int debug_check_launch(const char* what, cudaStream_t st);
+#define SAF_CHECK_LAUNCH(what, st)                          \
+    do {                                                    \
+        int _rc = saf::debug_check_launch(what, st);        \
+        if (_rc) return _rc;                                \
+    } while (0)
+
 }  // namespace saf

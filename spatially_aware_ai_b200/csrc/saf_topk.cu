@@ -5,8 +5,9 @@
 // (query_mesh.py:59-73); at M = 24 M voxels x T = 256 texts that matrix is 24.6 GB, so scores are
 // produced in row chunks and reduced on the fly:
 //   topk_scan_kernel   each CTA owns 8 texts x one row split and keeps their k best (score, row)
-//                      in shared memory; a score is inserted only if it beats the current k-th
-//                      best, which after warm-up is rare (~k ln(M/k) times per text)
+//                      in shared memory, one warp per text; a score is queued for insertion only
+//                      if it beats the current k-th best, which after warm-up is rare
+//                      (~k ln(M/k) times per text)
 //   topk_merge_kernel  one CTA per text ranks the splits' candidates -> final sorted top-k
 // Order: descending score, ties to the lower row index (a total order, so the result does not
 // depend on the insertion order).
@@ -29,58 +30,85 @@ struct Partial {  // [splits][T][k]
     long long* index;
 };
 
-// S: [rows, T] scores of rows [row0, row0 + rows) (global row = index_base + row0 + r)
+// warp-wide argmin under `beats` of a packed list (the element every other one beats)
+__device__ __forceinline__ void find_worst(const float* ls, const long long* li, int k, int lane, float& ws,
+                                           long long& wi, int& wp)
+{
+    ws = INFINITY;
+    wi = -1;
+    wp = 0;
+    for (int q = lane; q < k; q += 32) {
+        const float qs = ls[q];
+        const long long qi = li[q];
+        if (beats(ws, wi, qs, qi)) {
+            ws = qs;
+            wi = qi;
+            wp = q;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float os = __shfl_xor_sync(0xffffffffu, ws, o);
+        const long long oi = __shfl_xor_sync(0xffffffffu, wi, o);
+        const int op = __shfl_xor_sync(0xffffffffu, wp, o);
+        if (beats(ws, wi, os, oi)) {
+            ws = os;
+            wi = oi;
+            wp = op;
+        }
+    }
+}
+
+// S: [rows, T] scores of rows [row0, row0 + rows) (global row = index_base + row0 + r).
+// 256 threads = 8 warps; the CTA owns 8 texts and warp w is the only writer of text w's list, so
+// no locks: per block of 256 rows every thread pushes its candidates (score beats the current
+// k-th best) into the text's queue, then warp w drains queue w.
 __global__ void __launch_bounds__(kScanThreads) topk_scan_kernel(const float* __restrict__ S, int64_t rows, int T,
                                                                  int64_t row_id0, int k, Partial part, int first_chunk)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    long long* best_i = reinterpret_cast<long long*>(smem);                    // [8][k]
+    long long* best_i = reinterpret_cast<long long*>(smem);                       // [8][k]
     float* best_s = reinterpret_cast<float*>(best_i + (size_t)kTextsPerCta * k);  // [8][k]
+    __shared__ long long q_i[kTextsPerCta][kScanThreads];
+    __shared__ float q_s[kTextsPerCta][kScanThreads];
+    __shared__ int q_n[kTextsPerCta];
     __shared__ float thr_s[kTextsPerCta];
     __shared__ long long thr_i[kTextsPerCta];
-    __shared__ int thr_pos[kTextsPerCta];
-    __shared__ int count[kTextsPerCta];
-    __shared__ int lock[kTextsPerCta];
 
     const int t0 = blockIdx.x * kTextsPerCta;
     const int split = blockIdx.y, splits = gridDim.y;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    // load this (split, text) partial list from the previous chunk
+    // load this (split, text) partial list from the previous chunk; lists are packed: valid entries
+    // (index >= 0) occupy [0, count)
     for (int e = threadIdx.x; e < kTextsPerCta * k; e += kScanThreads) {
         const int j = e / k, q = e - j * k;
         const int t = t0 + j;
-        float s = -INFINITY;
-        long long i = -1;
+        float sv = -INFINITY;
+        long long iv = -1;
         if (!first_chunk && t < T) {
-            s = part.score[((size_t)split * T + t) * k + q];
-            i = part.index[((size_t)split * T + t) * k + q];
+            sv = part.score[((size_t)split * T + t) * k + q];
+            iv = part.index[((size_t)split * T + t) * k + q];
         }
-        best_s[e] = s;
-        best_i[e] = i;
+        best_s[e] = sv;
+        best_i[e] = iv;
     }
+    if (threadIdx.x < kTextsPerCta) q_n[threadIdx.x] = 0;
     __syncthreads();
-    if (threadIdx.x < kTextsPerCta) {
-        const int j = threadIdx.x;
-        int c = 0, wp = 0;
-        float ws = INFINITY;
-        long long wi = -1;
-        for (int q = 0; q < k; ++q) {
-            if (best_i[j * k + q] >= 0) {
-                ++c;
-                if (beats(ws, wi, best_s[j * k + q], best_i[j * k + q])) {
-                    ws = best_s[j * k + q];
-                    wi = best_i[j * k + q];
-                    wp = q;
-                }
-            }
-        }
-        // lists are kept packed: valid entries occupy [0, count)
-        count[j] = c;
-        thr_s[j] = (c == k) ? ws : -INFINITY;
-        thr_i[j] = (c == k) ? wi : (long long)0x7fffffffffffffffll;
-        thr_pos[j] = wp;
-        lock[j] = 0;
+    // warp-private state of text `warp`
+    float* ls = best_s + (size_t)warp * k;
+    long long* li = best_i + (size_t)warp * k;
+    int count = 0;
+    for (int q = lane; q < k; q += 32) count += (li[q] >= 0) ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
+    float ws;
+    long long wi;
+    int wp;
+    find_worst(ls, li, k, lane, ws, wi, wp);
+    if (lane == 0) {
+        thr_s[warp] = (count == k) ? ws : -INFINITY;
+        thr_i[warp] = (count == k) ? wi : (long long)0x7fffffffffffffffll;
     }
     __syncthreads();
 
@@ -90,111 +118,48 @@ __global__ void __launch_bounds__(kScanThreads) topk_scan_kernel(const float* __
     for (int64_t rb = r_begin; rb < r_end; rb += kScanThreads) {
         const int64_t r = rb + threadIdx.x;
         const bool in = r < r_end;
-        float sc[kTextsPerCta];
-#pragma unroll
-        for (int j = 0; j < kTextsPerCta; ++j) sc[j] = (in && t0 + j < T) ? S[r * T + t0 + j] : -INFINITY;
         const long long gid = row_id0 + r;
 #pragma unroll
         for (int j = 0; j < kTextsPerCta; ++j) {
-            const bool cand = in && (t0 + j < T) && !(sc[j] != sc[j]) &&
-                              beats(sc[j], gid, *(volatile float*)&thr_s[j], *(volatile long long*)&thr_i[j]);
-            unsigned mask = __ballot_sync(0xffffffffu, cand);
-            while (mask) {
-                const int src = __ffs(mask) - 1;
-                mask &= mask - 1;
-                const float s = __shfl_sync(0xffffffffu, sc[j], src);
-                const long long i = __shfl_sync(0xffffffffu, gid, src);
-                if (lane == 0) {
-                    while (atomicCAS(&lock[j], 0, 1) != 0) {
-                    }
-                }
-                __syncwarp();
-                __threadfence_block();
-                float* ls = best_s + (size_t)j * k;
-                long long* li = best_i + (size_t)j * k;
-                const int c = *(volatile int*)&count[j];
-                if (c < k) {
-                    if (lane == 0) {
-                        ls[c] = s;
-                        li[c] = i;
-                        *(volatile int*)&count[j] = c + 1;
-                    }
-                    __syncwarp();
-                    if (c + 1 == k) {
-                        // list just became full: find its worst element
-                        float ws = INFINITY;
-                        long long wi = -1;
-                        int wp = 0;
-                        for (int q = lane; q < k; q += 32) {
-                            const float qs = *(volatile float*)&ls[q];
-                            const long long qi = *(volatile long long*)&li[q];
-                            if (beats(ws, wi, qs, qi)) {
-                                ws = qs;
-                                wi = qi;
-                                wp = q;
-                            }
-                        }
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) {
-                            const float os = __shfl_xor_sync(0xffffffffu, ws, o);
-                            const long long oi = __shfl_xor_sync(0xffffffffu, wi, o);
-                            const int op = __shfl_xor_sync(0xffffffffu, wp, o);
-                            if (beats(ws, wi, os, oi)) {
-                                ws = os;
-                                wi = oi;
-                                wp = op;
-                            }
-                        }
-                        if (lane == 0) {
-                            *(volatile float*)&thr_s[j] = ws;
-                            *(volatile long long*)&thr_i[j] = wi;
-                            thr_pos[j] = wp;
-                        }
-                    }
-                } else if (beats(s, i, *(volatile float*)&thr_s[j], *(volatile long long*)&thr_i[j])) {
-                    const int wp0 = *(volatile int*)&thr_pos[j];
-                    if (lane == 0) {
-                        ls[wp0] = s;
-                        li[wp0] = i;
-                    }
-                    __syncwarp();
-                    float ws = INFINITY;
-                    long long wi = -1;
-                    int wp = 0;
-                    for (int q = lane; q < k; q += 32) {
-                        const float qs = *(volatile float*)&ls[q];
-                        const long long qi = *(volatile long long*)&li[q];
-                        if (beats(ws, wi, qs, qi)) {
-                            ws = qs;
-                            wi = qi;
-                            wp = q;
-                        }
-                    }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        const float os = __shfl_xor_sync(0xffffffffu, ws, o);
-                        const long long oi = __shfl_xor_sync(0xffffffffu, wi, o);
-                        const int op = __shfl_xor_sync(0xffffffffu, wp, o);
-                        if (beats(ws, wi, os, oi)) {
-                            ws = os;
-                            wi = oi;
-                            wp = op;
-                        }
-                    }
-                    if (lane == 0) {
-                        *(volatile float*)&thr_s[j] = ws;
-                        *(volatile long long*)&thr_i[j] = wi;
-                        *(volatile int*)&thr_pos[j] = wp;
-                    }
-                }
-                __syncwarp();
-                __threadfence_block();
-                if (lane == 0) atomicExch(&lock[j], 0);
-                __syncwarp();
+            const float sc = (in && t0 + j < T) ? S[r * T + t0 + j] : -INFINITY;
+            if (in && (t0 + j < T) && !(sc != sc) && beats(sc, gid, thr_s[j], thr_i[j])) {
+                const int pos = atomicAdd(&q_n[j], 1);
+                q_s[j][pos] = sc;
+                q_i[j][pos] = gid;
             }
         }
+        __syncthreads();
+        const int nq = q_n[warp];
+        for (int e = 0; e < nq; ++e) {
+            const float s = q_s[warp][e];
+            const long long i = q_i[warp][e];
+            if (count < k) {
+                if (lane == 0) {
+                    ls[count] = s;
+                    li[count] = i;
+                }
+                ++count;
+                __syncwarp();
+                if (count == k) find_worst(ls, li, k, lane, ws, wi, wp);
+            } else if (beats(s, i, ws, wi)) {
+                if (lane == 0) {
+                    ls[wp] = s;
+                    li[wp] = i;
+                }
+                __syncwarp();
+                find_worst(ls, li, k, lane, ws, wi, wp);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            q_n[warp] = 0;
+            if (count == k) {
+                thr_s[warp] = ws;
+                thr_i[warp] = wi;
+            }
+        }
+        __syncthreads();
     }
-    __syncthreads();
     for (int e = threadIdx.x; e < kTextsPerCta * k; e += kScanThreads) {
         const int j = e / k, q = e - j * k;
         const int t = t0 + j;
@@ -284,7 +249,7 @@ int saf_query_topk(const float* feats, int64_t M, int32_t C, int64_t ldf, const 
     if (rc) return rc;
     if (ws_bytes < L.bytes) return SAF_ERR_WORKSPACE;
     const size_t smem = (size_t)kTextsPerCta * k * 12;
-    if (smem + 1024 > (size_t)smem_optin) return SAF_ERR_SHAPE;
+    if (smem + 32 * 1024 > (size_t)smem_optin) return SAF_ERR_SHAPE;
     cudaStream_t st = (cudaStream_t)stream;
     unsigned char* base = (unsigned char*)ws;
     float* scores = (float*)(base + L.off_scores);
@@ -301,12 +266,14 @@ int saf_query_topk(const float* feats, int64_t M, int32_t C, int64_t ldf, const 
                                   scores, stream);
             if (rc) return rc;
         }
+        SAF_CHECK_LAUNCH("query_scores (top-k chunk)", st);
         topk_scan_kernel<<<grid, kScanThreads, smem, st>>>(scores, rows > 0 ? rows : 0, T, r0, k, part, first);
-        SAF_CUDA_TRY(cudaGetLastError());
+        SAF_CHECK_LAUNCH("topk_scan_kernel", st);
         first = 0;
     }
     topk_merge_kernel<<<T, 256, 0, st>>>(part, kTopkSplits, T, k, index_base, out_scores, (long long*)out_index);
-    return (int)cudaGetLastError();
+    SAF_CHECK_LAUNCH("topk_merge_kernel", st);
+    return 0;
 }
 
 }  // extern "C"
