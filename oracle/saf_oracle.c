@@ -153,7 +153,7 @@ int saf_oracle_integrate(const float *origin, float voxel_size, const int *nvox,
     (void)num_threads;
 #endif
 
-#pragma omp parallel for schedule(static) reduction(| : bad_label) reduction(+ : cnt_valid[:SAF_ORACLE_MAX_BATCH], cnt_tv[:SAF_ORACLE_MAX_BATCH])
+#pragma omp parallel for schedule(dynamic, 2048) reduction(| : bad_label) reduction(+ : cnt_valid[:SAF_ORACLE_MAX_BATCH], cnt_tv[:SAF_ORACLE_MAX_BATCH])
     for (int64_t v = 0; v < nslab; ++v) {
         const int iz = (int)(v % nz);
         const int iy = (int)((v / nz) % ny);

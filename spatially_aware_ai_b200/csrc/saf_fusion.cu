@@ -2,13 +2,19 @@
 //
 // Replaces ClipSeemFusion.integrate (/root/reference/clip_seem_fusion.py:676-822) and
 // ClipFusion.integrate (/root/reference/clipfusion.py:627-721).  Three kernels per call:
-//   K1 frame_setup_kernel      conservative frustum test of 8^3 voxel blocks -> compact block list
-//                              (+ repack of channel-major feature images to [R,C] rows)
+//   K1 frame_setup_kernel      conservative frustum test of 8^3 voxel blocks -> ascending list of
+//                              visible blocks (+ repack of channel-major feature images to [R,C])
 //   K2 tsdf_update_kernel      exact per-voxel projection / depth sample / masks / TSDF running
-//                              average for the listed blocks; emits the list of `valid` voxels
-//   K3 feature_accumulate_*    one warp per listed voxel: 128-bit streaming read-modify-write of
-//                              the C-float feature row, table rows read from shared memory
-//                              (staged by TMA bulk copies), rgb + label counter + weight
+//                              average for the listed blocks; emits each block's `valid` voxels in
+//                              voxel order plus per-block counts and their prefix sums
+//   K3 feature_accumulate_*    one warp per listed voxel: the voxel's C-float feature row is pulled
+//                              into a per-warp shared-memory ring by TMA bulk copies, blended with
+//                              the bilinear sample of the frame's [R,C] table (also TMA-staged in
+//                              shared memory) and streamed back with 128-bit stores; rgb, label
+//                              counter and weight are handled one lane per voxel.
+// The lists are deterministic and spatially ordered (ascending block, then voxel) so that K3 can
+// walk them forwards on even frames and backwards on odd frames: the rows a frame wrote last are
+// the first ones the next frame reads, which turns the 126 MB L2 into a cross-frame cache.
 // All decisions that feed masks use explicitly rounded intrinsics in the reference's op order;
 // this file is compiled with -fmad=false so nothing is contracted behind our back.
 #include <limits.h>
@@ -35,9 +41,14 @@ struct FusionParams {
     uint64_t nslab;
     uint64_t list_cap;
     uint64_t max_table_elems;
+    uint32_t n_k1;             // number of K1 cull CTAs (segments of block_seg)
     WsHeader* hdr;
-    uint32_t* block_list;
-    ValidEntry* lists;
+    uint32_t* cta_count;       // [n_k1]              visible blocks found by each K1 CTA
+    uint32_t* block_seg;       // [n_k1*256]          per-CTA ordered segments
+    uint32_t* block_list;      // [nblocks_total]     dense, ascending block ids (K1's last CTA)
+    uint32_t* blk_count;       // [batch][nblocks_total]   valid voxels per visible block (by rank)
+    uint32_t* blk_offset;      // [batch][nblocks_total+1] exclusive prefix of blk_count
+    ValidEntry* lists;         // [batch][nblocks_total*512] rank r's entries start at r*512
     float* tables;
     uint8_t* valid_out;
     uint8_t* tsdf_valid_out;
@@ -150,8 +161,6 @@ __device__ __forceinline__ float load_class_id(const void* seg, int dtype, int p
 // K1: frame set-up (frustum cull of voxel blocks + feature-image repack)
 // ---------------------------------------------------------------------------------------------
 
-constexpr int kK1Threads = 256;
-
 __device__ __forceinline__ bool block_maybe_visible(const Geom& g, float cx, float cy, float cz, float r, float fW,
                                                     float fH)
 {
@@ -185,6 +194,45 @@ __device__ __forceinline__ bool block_maybe_visible(const Geom& g, float cx, flo
     return !cull;
 }
 
+// exclusive prefix sum of n values (global, read through L2) by one CTA (blockDim.x a multiple of 32,
+// at most 1024); returns the total to every thread.  scratch: 33 uint32 in shared memory.
+__device__ uint32_t cta_exclusive_scan(const uint32_t* src, uint32_t* dst, uint32_t n, uint32_t* scratch)
+{
+    const uint32_t nt = blockDim.x, t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarp = nt >> 5;
+    const uint32_t per = (n + nt - 1) / nt;
+    const uint32_t lo = min(n, t * per), hi = min(n, lo + per);
+    uint32_t sum = 0;
+    for (uint32_t i = lo; i < hi; ++i) sum += __ldcg(src + i);
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += up;
+    }
+    if (lane == 31) scratch[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t ws = lane < nwarp ? scratch[lane] : 0u;
+        uint32_t wi = ws;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= (uint32_t)o) wi += up;
+        }
+        if (lane < nwarp) scratch[lane] = wi - ws;  // exclusive warp base
+        if (lane == 31) scratch[32] = wi;           // grand total
+    }
+    __syncthreads();
+    uint32_t base = scratch[warp] + incl - sum;
+    const uint32_t total = scratch[32];
+    for (uint32_t i = lo; i < hi; ++i) {
+        dst[i] = base;
+        base += __ldcg(src + i);
+    }
+    __syncthreads();
+    return total;
+}
+
 __global__ void __launch_bounds__(kK1Threads) frame_setup_kernel(const FusionParams p, uint32_t cull_ctas)
 {
     if (blockIdx.x >= cull_ctas) {
@@ -204,14 +252,9 @@ __global__ void __launch_bounds__(kK1Threads) frame_setup_kernel(const FusionPar
         }
         return;
     }
+    __shared__ uint32_t s_warp[kK1Threads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t blk = blockIdx.x * kK1Threads + threadIdx.x;
-    if (blk == 0) {
-#pragma unroll
-        for (int b = 0; b < SAF_MAX_BATCH; ++b) {
-            p.hdr->n_valid[b] = 0;
-            p.hdr->n_tsdf_valid[b] = 0;
-        }
-    }
     bool vis = false;
     if (blk < p.nblocks_total) {
         const uint32_t bz = blk % p.nb[2];
@@ -233,15 +276,18 @@ __global__ void __launch_bounds__(kK1Threads) frame_setup_kernel(const FusionPar
             vis |= block_maybe_visible(g, cx, cy, cz, r, fW, fH);
         }
     }
+    // ordered compaction inside the CTA: this CTA's visible blocks, ascending, into its own segment
     const unsigned m = __ballot_sync(0xffffffffu, vis);
-    if (m) {
-        const int lane = threadIdx.x & 31;
-        const int leader = __ffs(m) - 1;
-        uint32_t base = 0;
-        if (lane == leader) base = atomicAdd(&p.hdr->n_blocks, (uint32_t)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (vis) p.block_list[base + __popc(m & ((1u << lane) - 1u))] = blk;
+    if (lane == 0) s_warp[warp] = (uint32_t)__popc(m);
+    __syncthreads();
+    uint32_t base = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kK1Threads / 32; ++w) {
+        if (w < warp) base += s_warp[w];
+        total += s_warp[w];
     }
+    if (vis) p.block_seg[(size_t)blockIdx.x * kK1Threads + base + __popc(m & ((1u << lane) - 1u))] = blk;
+    if (threadIdx.x == 0) p.cta_count[blockIdx.x] = total;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -249,13 +295,19 @@ __global__ void __launch_bounds__(kK1Threads) frame_setup_kernel(const FusionPar
 // ---------------------------------------------------------------------------------------------
 
 constexpr int kK2Threads = 128;
+constexpr int kK2Iter = kBlockVoxels / kK2Threads;  // voxels per thread per block
 
-template <int BATCH1>
+template <bool BATCH1>
 __global__ void __launch_bounds__(kK2Threads) tsdf_update_kernel(const FusionParams p)
 {
+    __shared__ uint32_t s_cnt[kK2Iter][kK2Threads / 32];
+    __shared__ uint32_t s_scan[33];
+    __shared__ uint32_t s_off[kMaxK1Ctas];
+    __shared__ bool is_last;
     WsHeader* hdr = p.hdr;
-    const uint32_t n_blocks = hdr->n_blocks;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // K1 left one ordered segment of visible blocks per cull CTA: rank -> (segment, position)
+    const uint32_t n_blocks = cta_exclusive_scan(p.cta_count, s_off, p.n_k1, s_scan);
     const int B = BATCH1 ? 1 : p.batch;
     const float fW = (float)p.W, fH = (float)p.H;
     const int ny = p.grid.nvox[1], nz = p.grid.nvox[2];
@@ -266,68 +318,100 @@ __global__ void __launch_bounds__(kK2Threads) tsdf_update_kernel(const FusionPar
     if (BATCH1) load_geom(p.frames[0], g);
 
     for (uint32_t bi = blockIdx.x; bi < n_blocks; bi += gridDim.x) {
-        const uint32_t blk = p.block_list[bi];
+        uint32_t lo = 0, hi = p.n_k1;  // s_off[lo] <= bi < s_off[hi] (with s_off[n_k1] = n_blocks)
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (s_off[mid] <= bi)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        const uint32_t blk = p.block_seg[(size_t)lo * kK1Threads + (bi - s_off[lo])];
         const uint32_t bz = blk % p.nb[2];
         const uint32_t by = (blk / p.nb[2]) % p.nb[1];
         const uint32_t bx = blk / (p.nb[2] * p.nb[1]);
+        float xw[kK2Iter], yw[kK2Iter], zw[kK2Iter], t_old[kK2Iter], bt[kK2Iter];
+        uint32_t v[kK2Iter];
+        int tw[kK2Iter], bw[kK2Iter];
+        bool inside[kK2Iter];
+        // voxel centres, and the voxel's TSDF state fetched up front (one latency instead of two)
 #pragma unroll
-        for (int j = 0; j < kBlockVoxels / kK2Threads; ++j) {
+        for (int j = 0; j < kK2Iter; ++j) {
             const int local = threadIdx.x + j * kK2Threads;
-            const int lx = (int)bx * kBlockEdge + (local >> 6);          // slab-local x
+            const int lx = (int)bx * kBlockEdge + (local >> 6);  // slab-local x
             const int iy = (int)by * kBlockEdge + ((local >> 3) & 7);
             const int iz = (int)bz * kBlockEdge + (local & 7);
-            const bool inside = lx < (int)p.nxs && iy < ny && iz < nz;
-            const uint32_t v = inside ? (uint32_t)(((uint64_t)lx * ny + iy) * nz + iz) : 0u;
-            const float xw = voxel_centre(lx + p.grid.x_begin, p.grid.voxel_size, p.grid.origin[0]);
-            const float yw = voxel_centre(iy, p.grid.voxel_size, p.grid.origin[1]);
-            const float zw = voxel_centre(iz, p.grid.voxel_size, p.grid.origin[2]);
-            int bw = 0;
-            float bt = 0.0f;
-            for (int b = 0; b < B; ++b) {
-                const saf_frame& f = p.frames[b];
-                if (!BATCH1) load_geom(f, g);
-                float gx, gy, z;
-                project(g.P, g.K, xw, yw, zw, fW, fH, gx, gy, z);
-                const int px = nearest_index(gx, p.W), py = nearest_index(gy, p.H);
-                const float d = (inside && px >= 0 && py >= 0) ? __ldg(f.depth + (size_t)py * p.W + px) : 0.0f;
-                const float sdf = __fdiv_rn(__fsub_rn(d, z), p.trunc);
-                const bool in_view = inside && (fabsf(gx) <= 1.0f) && (fabsf(gy) <= 1.0f) && (z > 0.0f);
-                const bool valid = in_view && (fabsf(sdf) <= 1.0f);
+            inside[j] = lx < (int)p.nxs && iy < ny && iz < nz;
+            v[j] = inside[j] ? (uint32_t)(((uint64_t)lx * ny + iy) * nz + iz) : 0u;
+            xw[j] = voxel_centre(lx + p.grid.x_begin, p.grid.voxel_size, p.grid.origin[0]);
+            yw[j] = voxel_centre(iy, p.grid.voxel_size, p.grid.origin[1]);
+            zw[j] = voxel_centre(iz, p.grid.voxel_size, p.grid.origin[2]);
+            t_old[j] = inside[j] ? p.vol.tsdf[v[j]] : 0.0f;
+            tw[j] = inside[j] ? p.vol.tsdf_weight[v[j]] : 0;
+            bw[j] = 0;
+            bt[j] = 0.0f;
+        }
+        for (int b = 0; b < B; ++b) {
+            const saf_frame& f = p.frames[b];
+            if (!BATCH1) load_geom(f, g);
+            float gx[kK2Iter], gy[kK2Iter], z[kK2Iter], d[kK2Iter];
+#pragma unroll
+            for (int j = 0; j < kK2Iter; ++j) {
+                project(g.P, g.K, xw[j], yw[j], zw[j], fW, fH, gx[j], gy[j], z[j]);
+                const int px = nearest_index(gx[j], p.W), py = nearest_index(gy[j], p.H);
+                d[j] = (inside[j] && px >= 0 && py >= 0) ? __ldg(f.depth + (size_t)py * p.W + px) : 0.0f;
+            }
+            bool valid[kK2Iter];
+            unsigned vmask[kK2Iter];
+#pragma unroll
+            for (int j = 0; j < kK2Iter; ++j) {
+                const float sdf = __fdiv_rn(__fsub_rn(d[j], z[j]), p.trunc);
+                const bool in_view = inside[j] && (fabsf(gx[j]) <= 1.0f) && (fabsf(gy[j]) <= 1.0f) && (z[j] > 0.0f);
+                valid[j] = in_view && (fabsf(sdf) <= 1.0f);
                 const bool tv = in_view && (sdf > -1.0f);
                 if (tv) {
-                    bw += 1;
-                    bt = __fadd_rn(bt, fminf(fmaxf(sdf, -1.0f), 1.0f));
+                    bw[j] += 1;
+                    bt[j] = __fadd_rn(bt[j], fminf(fmaxf(sdf, -1.0f), 1.0f));
                     tv_count[BATCH1 ? 0 : b] += 1;
                 }
-                if (p.valid_out && inside) {
-                    if (valid) p.valid_out[(uint64_t)b * p.nslab + v] = 1;
-                    if (tv) p.tsdf_valid_out[(uint64_t)b * p.nslab + v] = 1;
+                if (p.valid_out && inside[j]) {
+                    if (valid[j]) p.valid_out[(uint64_t)b * p.nslab + v[j]] = 1;
+                    if (tv) p.tsdf_valid_out[(uint64_t)b * p.nslab + v[j]] = 1;
                 }
-                // append (voxel, gx, gy) to frame b's list: one atomic per warp
-                const unsigned m = __ballot_sync(0xffffffffu, valid);
-                if (m) {
-                    const int leader = __ffs(m) - 1;
-                    uint32_t base = 0;
-                    if (lane == leader) base = atomicAdd(&hdr->n_valid[b], (uint32_t)__popc(m));
-                    base = __shfl_sync(0xffffffffu, base, leader);
-                    if (valid) {
+                vmask[j] = __ballot_sync(0xffffffffu, valid[j]);
+                if (lane == 0) s_cnt[j][warp] = (uint32_t)__popc(vmask[j]);
+            }
+            __syncthreads();
+            // entries in voxel order: rank = (# valid with a smaller local index)
+            uint32_t run = 0;
+            ValidEntry* seg = p.lists + (uint64_t)b * p.list_cap + (uint64_t)bi * kBlockVoxels;
+#pragma unroll
+            for (int j = 0; j < kK2Iter; ++j) {
+#pragma unroll
+                for (int w = 0; w < kK2Threads / 32; ++w) {
+                    if (w == warp && valid[j]) {
                         ValidEntry e;
-                        e.voxel = v;
-                        e.gx = gx;
-                        e.gy = gy;
+                        e.voxel = v[j];
+                        e.gx = gx[j];
+                        e.gy = gy[j];
                         e.pad = 0;
-                        p.lists[(uint64_t)b * p.list_cap + base + __popc(m & ((1u << lane) - 1u))] = e;
+                        seg[run + __popc(vmask[j] & ((1u << lane) - 1u))] = e;
                     }
+                    run += s_cnt[j][w];
                 }
             }
-            if (bw > 0) {
+            if (threadIdx.x == 0) p.blk_count[(uint64_t)b * p.nblocks_total + bi] = run;
+            __syncthreads();
+        }
+#pragma unroll
+        for (int j = 0; j < kK2Iter; ++j) {
+            if (bw[j] > 0) {
                 // clip_seem_fusion.py:736-744: three separately rounded fp32 ops
-                const int tw = p.vol.tsdf_weight[v];
-                const int nw = tw + bw;
+                const int nw = tw[j] + bw[j];
                 const float fnw = __int2float_rn(nw);
-                const float t_old = p.vol.tsdf[v];
-                p.vol.tsdf[v] = __fadd_rn(__fdiv_rn(bt, fnw), __fmul_rn(t_old, __fdiv_rn(__int2float_rn(tw), fnw)));
-                p.vol.tsdf_weight[v] = nw;
+                p.vol.tsdf[v[j]] =
+                    __fadd_rn(__fdiv_rn(bt[j], fnw), __fmul_rn(t_old[j], __fdiv_rn(__int2float_rn(tw[j]), fnw)));
+                p.vol.tsdf_weight[v[j]] = nw;
             }
         }
     }
@@ -340,25 +424,33 @@ __global__ void __launch_bounds__(kK2Threads) tsdf_update_kernel(const FusionPar
         for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
         if (lane == 0 && c) atomicAdd(&hdr->n_tsdf_valid[b], c);
     }
-    // last CTA folds this call into the totals and re-arms the block counter for the next K1
-    __shared__ bool is_last;
+    // the last CTA turns the per-block counts into list offsets and folds the call into the totals
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) is_last = (atomicAdd(&hdr->k2_done, 1u) == gridDim.x - 1);
     __syncthreads();
-    if (is_last && threadIdx.x == 0) {
-        __threadfence();
-        unsigned long long sv = 0, stv = 0;
-        for (int b = 0; b < B; ++b) {
-            sv += atomicAdd(&hdr->n_valid[b], 0u);
-            stv += atomicAdd(&hdr->n_tsdf_valid[b], 0u);
+    if (!is_last) return;
+    __threadfence();
+    unsigned long long sv = 0, stv = 0;
+    for (int b = 0; b < B; ++b) {
+        uint32_t* off = p.blk_offset + (uint64_t)b * (p.nblocks_total + 1);
+        const uint32_t total = cta_exclusive_scan(p.blk_count + (uint64_t)b * p.nblocks_total, off, n_blocks, s_scan);
+        if (threadIdx.x == 0) {
+            off[n_blocks] = total;
+            hdr->n_valid[b] = total;
+            const uint32_t t = atomicExch(&hdr->n_tsdf_valid[b], 0u);
+            hdr->last_tsdf_valid[b] = t;
+            sv += total;
+            stv += t;
         }
+    }
+    if (threadIdx.x == 0) {
         hdr->total_valid += sv;
         hdr->total_tsdf_valid += stv;
         hdr->total_blocks += n_blocks;
         hdr->total_frames += (unsigned long long)B;
         hdr->last_blocks = n_blocks;
-        hdr->n_blocks = 0;
+        hdr->n_blocks = n_blocks;
         hdr->k2_done = 0;
     }
 }
@@ -367,45 +459,58 @@ __global__ void __launch_bounds__(kK2Threads) tsdf_update_kernel(const FusionPar
 // K3: per-voxel feature / rgb / label accumulation (clip_seem_fusion.py:751-822)
 // ---------------------------------------------------------------------------------------------
 
-constexpr int kK3Threads = 512;
+constexpr int kK3Warps = 16;
+constexpr int kK3Threads = kK3Warps * 32;
 
-struct VoxelScalars {
-    float a, b;        // a = 1/(w+1), b = w * a
-    int w;
-};
-
-// rgb (lanes 0-2), label counter (lane 3) and weight (lane 4) of one voxel
-__device__ __forceinline__ void update_small_state(const FusionParams& p, const saf_frame& f, const ValidEntry& e,
-                                                   const VoxelScalars& s, int lane)
+// flat list position -> entry: position i lives in visible block r = upper_bound(offset, i) - 1
+__device__ __forceinline__ ValidEntry fetch_entry(const ValidEntry* __restrict__ list, const uint32_t* __restrict__ off,
+                                                  uint32_t n_blocks, uint32_t i)
 {
-    if (lane < 3) {
-        float smp;
-        if (p.rgb_mode == SAF_RGB_NEAREST) {
-            const int px = nearest_index(e.gx, p.W), py = nearest_index(e.gy, p.H);
-            smp = (px >= 0 && py >= 0) ? __ldg(f.rgb + ((size_t)py * p.W + px) * 3 + lane) : 0.0f;
-        } else {
-            Taps t;
-            bilinear_setup(e.gx, e.gy, p.W, p.H, t);
-            float v[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) v[k] = t.idx[k] >= 0 ? __ldg(f.rgb + (size_t)t.idx[k] * 3 + lane) : 0.0f;
-            smp = bilinear_mix(v[0], v[1], v[2], v[3], t.w);
-        }
-        float* dst = p.vol.rgb + (size_t)e.voxel * 3 + lane;
-        *dst = __fadd_rn(__fmul_rn(smp, s.a), __fmul_rn(*dst, s.b));
-    } else if (lane == 3) {
-        if (p.vol.labels_one_hot && f.seg) {
-            const int px = nearest_index(e.gx, p.W), py = nearest_index(e.gy, p.H);
-            const float lf = (px >= 0 && py >= 0) ? load_class_id(f.seg, f.seg_dtype, py * p.W + px) : 0.0f;
-            const long long id = (long long)lf;
-            if (id >= 0 && id < p.vol.n_classes)
-                p.vol.labels_one_hot[(size_t)e.voxel * p.vol.n_classes + id] += 1;
-            else
-                atomicOr(&p.hdr->error_flags, SAF_FLAG_BAD_CLASS_ID);
-        }
-    } else if (lane == 4) {
-        p.vol.weight[e.voxel] = s.w + 1;
+    uint32_t lo = 0, hi = n_blocks;  // invariant: off[lo] <= i < off[hi]
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(off + mid) <= i)
+            lo = mid;
+        else
+            hi = mid;
     }
+    return list[(uint64_t)lo * kBlockVoxels + (i - __ldg(off + lo))];
+}
+
+// rgb running average, label counter and weight of ONE voxel, done by one lane
+// (clip_seem_fusion.py:786-798, 808-822; nearest rgb: clipfusion.py:701-706)
+__device__ __forceinline__ void update_small_state(const FusionParams& p, const saf_frame& f, const ValidEntry& e, int w)
+{
+    const float a = __frcp_rn(__int2float_rn(w + 1));
+    const float b = __fmul_rn(__int2float_rn(w), a);
+    float smp[3];
+    const int px = nearest_index(e.gx, p.W), py = nearest_index(e.gy, p.H);
+    if (p.rgb_mode == SAF_RGB_NEAREST) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) smp[c] = (px >= 0 && py >= 0) ? __ldg(f.rgb + ((size_t)py * p.W + px) * 3 + c) : 0.0f;
+    } else {
+        Taps t;
+        bilinear_setup(e.gx, e.gy, p.W, p.H, t);
+        float val[4][3];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) val[k][c] = t.idx[k] >= 0 ? __ldg(f.rgb + (size_t)t.idx[k] * 3 + c) : 0.0f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) smp[c] = bilinear_mix(val[0][c], val[1][c], val[2][c], val[3][c], t.w);
+    }
+    float* dst = p.vol.rgb + (size_t)e.voxel * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) dst[c] = __fadd_rn(__fmul_rn(smp[c], a), __fmul_rn(dst[c], b));
+    if (p.vol.labels_one_hot && f.seg) {
+        const float lf = (px >= 0 && py >= 0) ? load_class_id(f.seg, f.seg_dtype, py * p.W + px) : 0.0f;
+        const long long id = (long long)lf;
+        if (id >= 0 && id < p.vol.n_classes)
+            p.vol.labels_one_hot[(size_t)e.voxel * p.vol.n_classes + id] += 1;
+        else
+            atomicOr(&p.hdr->error_flags, SAF_FLAG_BAD_CLASS_ID);
+    }
+    p.vol.weight[e.voxel] = w + 1;
 }
 
 __device__ __forceinline__ float4 mix4(const float4& t0, const float4& t1, const float4& t2, const float4& t3,
@@ -429,89 +534,107 @@ __device__ __forceinline__ float4 blend4(const float4& smp, const float4& old, f
     return r;
 }
 
-// Stage the [R,C] table into shared memory: one TMA bulk copy per row when 16-byte rules allow,
-// plain loads otherwise.  Returns after the copies are ISSUED; wait with mbar_wait(bar, 0).
-__device__ __forceinline__ void stage_table(float* tab, const float* src, int64_t src_stride_r, int R, int C,
-                                            uint64_t* bar, bool use_tma)
-{
-    if (use_tma) {
-        if (threadIdx.x == 0) {
-            mbar_init(bar, 1);
-            fence_mbar_init();
-        }
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            if (threadIdx.x == 0) mbar_arrive_expect_tx(bar, (uint32_t)R * (uint32_t)C * 4u);
-            __syncwarp();
-            for (int r = threadIdx.x; r < R; r += 32)
-                tma_bulk_g2s(tab + (size_t)r * C, src + (size_t)r * src_stride_r, (uint32_t)C * 4u, bar);
-        }
-    } else {
-        for (int64_t e = threadIdx.x; e < (int64_t)R * C; e += blockDim.x) {
-            const int64_t r = e / C, c = e - r * C;
-            tab[e] = src[r * src_stride_r + c];
-        }
-        __syncthreads();
-    }
-}
-
-// CHUNKS = C/128 float4 per lane (compile time), VPW voxels in flight per warp.
-template <int CHUNKS, int VPW, bool TABLE_SMEM>
+// Shared-memory plan of feature_accumulate_kernel:
+//   [ table: R*C floats (TABLE_SMEM) ][ ring: kK3Warps * NST rows of C floats ][ mbarriers ]
+// CHUNKS = C/128 float4 per lane; NST = ring stages per warp (rows in flight per warp).
+template <int CHUNKS, int NST, bool TABLE_SMEM>
 __global__ void __launch_bounds__(kK3Threads, 1)
-feature_accumulate_kernel(const FusionParams p, const float* __restrict__ table, int64_t table_stride_r, int use_tma)
+feature_accumulate_kernel(const FusionParams p, const float* __restrict__ table, int64_t table_stride_r, int table_tma)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ uint64_t bar;
-    float* tab = reinterpret_cast<float*>(smem_raw);
     constexpr int C = CHUNKS * 128;
     const saf_frame& f = p.frames[p.frame_index];
     const int R = f.npy * f.npx;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t n = p.hdr->n_valid[p.frame_index];
     if (n == 0) return;
+    const uint32_t n_blocks = p.hdr->last_blocks;
 
-    if (TABLE_SMEM) stage_table(tab, table, table_stride_r, R, C, &bar, use_tma != 0);
+    float* tab = reinterpret_cast<float*>(smem_raw);
+    float* ring = tab + (TABLE_SMEM ? (size_t)R * C : 0);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)kK3Warps * NST * C);  // [0] table, then [warp][stage]
+    float* my_ring = ring + (size_t)warp * NST * C;
+    uint64_t* my_bars = bars + 1 + warp * NST;
 
-    const uint32_t nwarps = gridDim.x * (kK3Threads / 32);
-    const uint32_t gwarp = blockIdx.x * (kK3Threads / 32) + (threadIdx.x >> 5);
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        for (int i = 0; i < kK3Warps * NST; ++i) mbar_init(&bars[1 + i], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (TABLE_SMEM) {
+        if (table_tma) {
+            if (warp == 0) {
+                if (lane == 0) mbar_arrive_expect_tx(&bars[0], (uint32_t)R * (uint32_t)C * 4u);
+                __syncwarp();
+                for (int r = lane; r < R; r += 32)
+                    tma_bulk_g2s(tab + (size_t)r * C, table + (size_t)r * table_stride_r, (uint32_t)C * 4u, &bars[0]);
+            }
+        } else {
+            for (int64_t e = threadIdx.x; e < (int64_t)R * C; e += kK3Threads) {
+                const int64_t r = e / C, c = e - r * C;
+                tab[e] = table[r * table_stride_r + c];
+            }
+            __syncthreads();
+        }
+    }
+    bool table_ready = !(TABLE_SMEM && table_tma);
+
+    const uint32_t nwarps = gridDim.x * kK3Warps;
+    const uint32_t gwarp = blockIdx.x * kK3Warps + warp;
+    const uint32_t k_total = n > gwarp ? (n - gwarp + nwarps - 1) / nwarps : 0;  // entries this warp owns
+    // odd frames walk the list backwards (see the header comment)
+    const bool reverse = ((p.hdr->total_frames + (unsigned long long)p.frame_index) & 1ull) != 0;
     const ValidEntry* __restrict__ list = p.lists + (uint64_t)p.frame_index * p.list_cap;
+    const uint32_t* __restrict__ off = p.blk_offset + (uint64_t)p.frame_index * (p.nblocks_total + 1);
     const float4* tab4 = reinterpret_cast<const float4*>(TABLE_SMEM ? tab : table);
     const int64_t tab_row4 = TABLE_SMEM ? (C / 4) : (table_stride_r / 4);
+    uint32_t t_use = 0;  // rows this warp has pushed through the ring (stage = t % NST, parity = (t / NST) & 1)
 
-    bool table_ready = !(TABLE_SMEM && use_tma);
-    for (uint64_t i0 = gwarp; i0 < n; i0 += (uint64_t)nwarps * VPW) {
-        ValidEntry e[VPW];
-        float4 old[VPW][CHUNKS];
-        VoxelScalars sc[VPW];
-        bool act[VPW];
-#pragma unroll
-        for (int v = 0; v < VPW; ++v) {
-            const uint64_t i = i0 + (uint64_t)v * nwarps;
-            act[v] = i < n;
-            if (act[v]) e[v] = list[i];
+    for (uint32_t kb = 0; kb < k_total; kb += 32) {
+        const uint32_t cnt = min(32u, k_total - kb);
+        // lane l owns entry kb + l of this batch: fetch it, then do its small state
+        ValidEntry mine;
+        mine.voxel = 0;
+        mine.gx = mine.gy = 0.0f;
+        int my_w = 0;
+        if (lane < cnt) {
+            uint32_t i = gwarp + (kb + lane) * nwarps;
+            if (reverse) i = n - 1 - i;
+            mine = fetch_entry(list, off, n_blocks, i);
+            my_w = p.vol.weight[mine.voxel];
         }
-#pragma unroll
-        for (int v = 0; v < VPW; ++v) {
-            if (!act[v]) continue;
-            const float4* row = reinterpret_cast<const float4*>(p.vol.clip_feat + (size_t)e[v].voxel * C);
-#pragma unroll
-            for (int j = 0; j < CHUNKS; ++j) old[v][j] = ld_stream_f4(row + j * 32 + lane);
-            sc[v].w = p.vol.weight[e[v].voxel];
+        // start the first rows of the batch before spending time on the small state
+        const uint32_t pre = min((uint32_t)NST, cnt);
+        for (uint32_t q = 0; q < pre; ++q) {
+            const uint32_t vq = __shfl_sync(0xffffffffu, mine.voxel, q);
+            if (lane == 0) {
+                const uint32_t s = (t_use + q) % NST;
+                mbar_arrive_expect_tx(&my_bars[s], (uint32_t)C * 4u);
+                tma_bulk_g2s(my_ring + (size_t)s * C, p.vol.clip_feat + (size_t)vq * C, (uint32_t)C * 4u, &my_bars[s]);
+            }
         }
+        if (lane < cnt) update_small_state(p, f, mine, my_w);
         if (!table_ready) {
-            mbar_wait(&bar, 0);
+            mbar_wait(&bars[0], 0);
             table_ready = true;
         }
-#pragma unroll
-        for (int v = 0; v < VPW; ++v) {
-            if (!act[v]) continue;
+        for (uint32_t q = 0; q < cnt; ++q) {
+            const uint32_t s = t_use % NST;
+            const uint32_t parity = (t_use / NST) & 1u;
+            const uint32_t vq = __shfl_sync(0xffffffffu, mine.voxel, q);
+            const float gx = __shfl_sync(0xffffffffu, mine.gx, q);
+            const float gy = __shfl_sync(0xffffffffu, mine.gy, q);
+            const int w = __shfl_sync(0xffffffffu, my_w, q);
             // clip_seem_fusion.py:808-810
-            sc[v].a = __frcp_rn(__int2float_rn(sc[v].w + 1));
-            sc[v].b = __fmul_rn(__int2float_rn(sc[v].w), sc[v].a);
+            const float a = __frcp_rn(__int2float_rn(w + 1));
+            const float b = __fmul_rn(__int2float_rn(w), a);
             Taps t;
-            bilinear_setup(e[v].gx, e[v].gy, f.npx, f.npy, t);
-            float4* row = reinterpret_cast<float4*>(p.vol.clip_feat + (size_t)e[v].voxel * C);
+            bilinear_setup(gx, gy, f.npx, f.npy, t);
+            float4* row = reinterpret_cast<float4*>(p.vol.clip_feat + (size_t)vq * C);
+            const float4* old4 = reinterpret_cast<const float4*>(my_ring + (size_t)s * C);
             const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+            mbar_wait(&my_bars[s], parity);
 #pragma unroll
             for (int j = 0; j < CHUNKS; ++j) {
                 const int col = j * 32 + lane;
@@ -519,12 +642,20 @@ feature_accumulate_kernel(const FusionParams p, const float* __restrict__ table,
                 const float4 t1 = t.idx[1] >= 0 ? tab4[t.idx[1] * tab_row4 + col] : zero;
                 const float4 t2 = t.idx[2] >= 0 ? tab4[t.idx[2] * tab_row4 + col] : zero;
                 const float4 t3 = t.idx[3] >= 0 ? tab4[t.idx[3] * tab_row4 + col] : zero;
-                st_stream_f4(row + col, blend4(mix4(t0, t1, t2, t3, t.w), old[v][j], sc[v].a, sc[v].b));
+                st_stream_f4(row + col, blend4(mix4(t0, t1, t2, t3, t.w), old4[col], a, b));
             }
-            update_small_state(p, f, e[v], sc[v], lane);
+            __syncwarp();  // every lane has consumed stage s
+            if (q + NST < cnt) {
+                const uint32_t vn = __shfl_sync(0xffffffffu, mine.voxel, q + NST);
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(&my_bars[s], (uint32_t)C * 4u);
+                    tma_bulk_g2s(my_ring + (size_t)s * C, p.vol.clip_feat + (size_t)vn * C, (uint32_t)C * 4u, &my_bars[s]);
+                }
+            }
+            ++t_use;
         }
     }
-    if (!table_ready) mbar_wait(&bar, 0);  // never leave a bulk copy in flight at exit
+    if (!table_ready) mbar_wait(&bars[0], 0);  // never leave a bulk copy in flight at exit
 }
 
 // Any feature_dim: VEC = 4 (C % 4 == 0, 16-byte aligned rows) or 1.  Table rows read from global.
@@ -537,15 +668,16 @@ __global__ void __launch_bounds__(kK3Threads) feature_accumulate_generic_kernel(
     const int C = p.vol.feature_dim;
     const int lane = threadIdx.x & 31;
     const uint32_t n = p.hdr->n_valid[p.frame_index];
-    const uint32_t nwarps = gridDim.x * (kK3Threads / 32);
-    const uint32_t gwarp = blockIdx.x * (kK3Threads / 32) + (threadIdx.x >> 5);
+    const uint32_t n_blocks = p.hdr->last_blocks;
+    const uint32_t nwarps = gridDim.x * kK3Warps;
+    const uint32_t gwarp = blockIdx.x * kK3Warps + (threadIdx.x >> 5);
     const ValidEntry* __restrict__ list = p.lists + (uint64_t)p.frame_index * p.list_cap;
+    const uint32_t* __restrict__ off = p.blk_offset + (uint64_t)p.frame_index * (p.nblocks_total + 1);
     for (uint64_t i = gwarp; i < n; i += nwarps) {
-        const ValidEntry e = list[i];
-        VoxelScalars sc;
-        sc.w = p.vol.weight[e.voxel];
-        sc.a = __frcp_rn(__int2float_rn(sc.w + 1));
-        sc.b = __fmul_rn(__int2float_rn(sc.w), sc.a);
+        const ValidEntry e = fetch_entry(list, off, n_blocks, (uint32_t)i);
+        const int w = p.vol.weight[e.voxel];
+        const float a = __frcp_rn(__int2float_rn(w + 1));
+        const float b = __fmul_rn(__int2float_rn(w), a);
         Taps t;
         bilinear_setup(e.gx, e.gy, f.npx, f.npy, t);
         float* row = p.vol.clip_feat + (size_t)e.voxel * C;
@@ -558,7 +690,7 @@ __global__ void __launch_bounds__(kK3Threads) feature_accumulate_generic_kernel(
                 for (int k = 0; k < 4; ++k)
                     tv[k] = t.idx[k] >= 0 ? __ldg(reinterpret_cast<const float4*>(table + t.idx[k] * table_stride_r) + col)
                                           : zero;
-                st_stream_f4(reinterpret_cast<float4*>(row) + col, blend4(mix4(tv[0], tv[1], tv[2], tv[3], t.w), o, sc.a, sc.b));
+                st_stream_f4(reinterpret_cast<float4*>(row) + col, blend4(mix4(tv[0], tv[1], tv[2], tv[3], t.w), o, a, b));
             }
         } else {
             for (int c = lane; c < C; c += 32) {
@@ -566,10 +698,11 @@ __global__ void __launch_bounds__(kK3Threads) feature_accumulate_generic_kernel(
 #pragma unroll
                 for (int k = 0; k < 4; ++k) tv[k] = t.idx[k] >= 0 ? __ldg(table + t.idx[k] * table_stride_r + c) : 0.0f;
                 const float smp = bilinear_mix(tv[0], tv[1], tv[2], tv[3], t.w);
-                row[c] = __fadd_rn(__fmul_rn(smp, sc.a), __fmul_rn(row[c], sc.b));
+                row[c] = __fadd_rn(__fmul_rn(smp, a), __fmul_rn(row[c], b));
             }
         }
-        update_small_state(p, f, e, sc, lane);
+        __syncwarp();
+        if (lane == 0) update_small_state(p, f, e, w);
     }
 }
 
@@ -652,13 +785,18 @@ static int build_params(const saf_grid_desc* grid, const saf_volume* vol, const 
     p->nb[1] = L.nb[1];
     p->nb[2] = L.nb[2];
     p->nblocks_total = L.nblocks_total;
+    p->n_k1 = L.n_k1;
     p->nxs = (uint32_t)(grid->x_end - grid->x_begin);
-    p->nslab = L.list_cap;
+    p->nslab = (uint64_t)p->nxs * (uint64_t)grid->nvox[1] * (uint64_t)grid->nvox[2];
     p->list_cap = L.list_cap;
     p->max_table_elems = (uint64_t)ws->max_table_elems;
     unsigned char* base = (unsigned char*)ws->base;
     p->hdr = (WsHeader*)base;
+    p->cta_count = (uint32_t*)(base + L.off_cta_count);
+    p->block_seg = (uint32_t*)(base + L.off_block_seg);
     p->block_list = (uint32_t*)(base + L.off_blocks);
+    p->blk_count = (uint32_t*)(base + L.off_blk_count);
+    p->blk_offset = (uint32_t*)(base + L.off_blk_offset);
     p->lists = (ValidEntry*)(base + L.off_lists);
     p->tables = (float*)(base + L.off_tables);
     return 0;
@@ -688,30 +826,49 @@ static int check_feature_args(const saf_volume* vol, const saf_frame* frames, in
 
 static int launch_k1(const FusionParams& p, cudaStream_t st)
 {
-    const uint32_t cull_ctas = (p.nblocks_total + kK1Threads - 1) / kK1Threads;
     const uint32_t pack_ctas = p.pack_mask ? 64u : 0u;
-    frame_setup_kernel<<<cull_ctas + pack_ctas, kK1Threads, 0, st>>>(p, cull_ctas);
-    return (int)cudaGetLastError();
+    frame_setup_kernel<<<p.n_k1 + pack_ctas, kK1Threads, 0, st>>>(p, p.n_k1);
+    SAF_CHECK_LAUNCH("frame_setup_kernel (K1)", st);
+    return 0;
 }
 
 static int launch_k2(const FusionParams& p, int sms, cudaStream_t st)
 {
-    const uint32_t grid = (uint32_t)min((uint64_t)p.nblocks_total, (uint64_t)sms * 16u);
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)p.nblocks_total, (uint64_t)sms * 16u);
     if (p.batch == 1)
-        tsdf_update_kernel<1><<<grid, kK2Threads, 0, st>>>(p);
+        tsdf_update_kernel<true><<<grid, kK2Threads, 0, st>>>(p);
     else
-        tsdf_update_kernel<0><<<grid, kK2Threads, 0, st>>>(p);
-    return (int)cudaGetLastError();
+        tsdf_update_kernel<false><<<grid, kK2Threads, 0, st>>>(p);
+    SAF_CHECK_LAUNCH("tsdf_update_kernel (K2)", st);
+    return 0;
 }
 
-template <int CHUNKS, int VPW, bool SMEM>
-static int launch_k3_fixed(const FusionParams& p, const float* table, int64_t stride_r, int use_tma, size_t smem,
+template <int CHUNKS, int NST, bool SMEM>
+static int launch_k3_fixed(const FusionParams& p, const float* table, int64_t stride_r, int table_tma, size_t smem,
                            int sms, cudaStream_t st)
 {
-    auto kern = feature_accumulate_kernel<CHUNKS, VPW, SMEM>;
-    if (smem > 48 * 1024) SAF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<sms, kK3Threads, smem, st>>>(p, table, stride_r, use_tma);
-    return (int)cudaGetLastError();
+    auto kern = feature_accumulate_kernel<CHUNKS, NST, SMEM>;
+    SAF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<sms, kK3Threads, smem, st>>>(p, table, stride_r, table_tma);
+    SAF_CHECK_LAUNCH("feature_accumulate_kernel (K3)", st);
+    return 0;
+}
+
+template <int CHUNKS>
+static int launch_k3_chunks(const FusionParams& p, const float* table, int64_t stride_r, int R, int sms,
+                            int smem_optin, cudaStream_t st)
+{
+    constexpr size_t row = (size_t)CHUNKS * 128 * 4;
+    const size_t tab = (size_t)R * row;
+    const size_t budget = (size_t)smem_optin - 256;
+    auto need = [&](int nst, bool smem_tab) { return (smem_tab ? tab : 0) + (size_t)kK3Warps * nst * row + 8 * (1 + kK3Warps * nst); };
+    // prefer the table in shared memory with as many ring stages as fit (at most 3)
+    if (need(3, true) <= budget) return launch_k3_fixed<CHUNKS, 3, true>(p, table, stride_r, 1, need(3, true), sms, st);
+    if (need(2, true) <= budget) return launch_k3_fixed<CHUNKS, 2, true>(p, table, stride_r, 1, need(2, true), sms, st);
+    if (need(1, true) <= budget) return launch_k3_fixed<CHUNKS, 1, true>(p, table, stride_r, 1, need(1, true), sms, st);
+    // table too large: read its rows through L1/L2 instead
+    if (need(3, false) <= budget) return launch_k3_fixed<CHUNKS, 3, false>(p, table, stride_r, 0, need(3, false), sms, st);
+    return launch_k3_fixed<CHUNKS, 2, false>(p, table, stride_r, 0, need(2, false), sms, st);
 }
 
 static int launch_k3(FusionParams& p, int frame_index, int sms, int smem_optin, cudaStream_t st)
@@ -725,28 +882,19 @@ static int launch_k3(FusionParams& p, int frame_index, int sms, int smem_optin, 
     const int64_t stride_r = packed ? C : f.table_stride_r;
     const bool rows16 = (C % 4 == 0) && (stride_r % 4 == 0) && (((uintptr_t)table & 15u) == 0) &&
                         (((uintptr_t)p.vol.clip_feat & 15u) == 0);
-    const size_t tab_bytes = (size_t)R * C * 4;
-    const bool fits = tab_bytes + 1024 <= (size_t)smem_optin;
-    if (rows16 && (C == 512 || C == 768 || C == 1024)) {
-        const int use_tma = 1;
-        if (fits) {
-            switch (C) {
-                case 512: return launch_k3_fixed<4, 2, true>(p, table, stride_r, use_tma, tab_bytes, sms, st);
-                case 768: return launch_k3_fixed<6, 2, true>(p, table, stride_r, use_tma, tab_bytes, sms, st);
-                default: return launch_k3_fixed<8, 2, true>(p, table, stride_r, use_tma, tab_bytes, sms, st);
-            }
-        }
+    if (rows16) {
         switch (C) {
-            case 512: return launch_k3_fixed<4, 2, false>(p, table, stride_r, 0, 0, sms, st);
-            case 768: return launch_k3_fixed<6, 2, false>(p, table, stride_r, 0, 0, sms, st);
-            default: return launch_k3_fixed<8, 2, false>(p, table, stride_r, 0, 0, sms, st);
+            case 512: return launch_k3_chunks<4>(p, table, stride_r, R, sms, smem_optin, st);
+            case 768: return launch_k3_chunks<6>(p, table, stride_r, R, sms, smem_optin, st);
+            case 1024: return launch_k3_chunks<8>(p, table, stride_r, R, sms, smem_optin, st);
+            default: break;
         }
-    }
-    if (rows16)
         feature_accumulate_generic_kernel<4><<<sms * 2, kK3Threads, 0, st>>>(p, table, stride_r);
-    else
+    } else {
         feature_accumulate_generic_kernel<1><<<sms * 2, kK3Threads, 0, st>>>(p, table, stride_r);
-    return (int)cudaGetLastError();
+    }
+    SAF_CHECK_LAUNCH("feature_accumulate_generic_kernel (K3)", st);
+    return 0;
 }
 
 }  // namespace saf
@@ -779,9 +927,6 @@ int saf_workspace_init(const saf_workspace* ws, const saf_grid_desc* grid, void*
     h.bytes = L.bytes;
     h.list_cap = L.list_cap;
     h.max_table_elems = (uint64_t)ws->max_table_elems;
-    h.off_blocks = L.off_blocks;
-    h.off_lists = L.off_lists;
-    h.off_tables = L.off_tables;
     h.nblocks_total = L.nblocks_total;
     h.max_batch = (uint32_t)ws->max_batch;
     h.nb[0] = L.nb[0];
@@ -811,7 +956,7 @@ int saf_read_stats(const saf_workspace* ws, saf_stats* out, void* stream)
     out->last_blocks = h.last_blocks;
     for (int b = 0; b < SAF_MAX_BATCH; ++b) {
         out->last_valid[b] = h.n_valid[b];
-        out->last_tsdf_valid[b] = h.n_tsdf_valid[b];
+        out->last_tsdf_valid[b] = h.last_tsdf_valid[b];
     }
     out->error_flags = h.error_flags;
     return 0;
@@ -826,10 +971,7 @@ int saf_frustum_cull(const saf_grid_desc* grid, const saf_frame* frames, int32_t
     FusionParams p;
     rc = build_params(grid, nullptr, frames, batch, H, W, trunc, SAF_RGB_BILINEAR, ws, &p);
     if (rc) return rc;
-    cudaStream_t st = (cudaStream_t)stream;
-    // stand-alone use: do not rely on K2 having re-armed the counter
-    SAF_CUDA_TRY(cudaMemsetAsync(&p.hdr->n_blocks, 0, sizeof(uint32_t), st));
-    return launch_k1(p, st);
+    return launch_k1(p, (cudaStream_t)stream);
 }
 
 int saf_tsdf_update(const saf_grid_desc* grid, const saf_volume* vol, const saf_frame* frames, int32_t batch, int32_t H,
@@ -908,7 +1050,8 @@ int saf_label_argmax(const int32_t* labels, int64_t n, int32_t n_classes, int64_
     const int64_t want = (n + 7) / 8;
     const int grid = (int)std::min<int64_t>(want, (int64_t)sms * 8);
     label_argmax_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(labels, n, n_classes, (long long*)out);
-    return (int)cudaGetLastError();
+    SAF_CHECK_LAUNCH("label_argmax_kernel", (cudaStream_t)stream);
+    return 0;
 }
 
 }  // extern "C"

@@ -18,16 +18,19 @@ constexpr uint64_t kWsMagic = 0x5341465f42323030ull;  // "SAF_B200"
 constexpr int kBlockEdge = SAF_BLOCK_EDGE;
 constexpr int kBlockVoxels = kBlockEdge * kBlockEdge * kBlockEdge;
 
-// Device-resident workspace header (512 bytes).  Per-call counters are reset by the kernels
-// themselves: K1 zeroes n_valid/n_tsdf_valid before K2 runs, K2's last CTA folds the call into the
-// totals and zeroes n_blocks / k2_done for the next call.
+// Device-resident workspace header (512 bytes).  Per-call counters are produced by the kernels
+// themselves (no host memsets): K1's last CTA publishes n_blocks and the dense ordered block list,
+// K2's last CTA publishes the per-block list offsets, n_valid and the running totals.
 struct WsHeader {
-    uint32_t n_blocks;                      // visible blocks of the call in flight
+    uint32_t n_blocks;                      // visible blocks of the call in flight (written by K1's last CTA)
+    uint32_t k1_done;                       // CTA completion ticket of K1
     uint32_t k2_done;                       // CTA completion ticket of K2
     uint32_t error_flags;
     uint32_t last_blocks;
-    uint32_t n_valid[SAF_MAX_BATCH];
-    uint32_t n_tsdf_valid[SAF_MAX_BATCH];
+    uint32_t pad0_[3];
+    uint32_t n_valid[SAF_MAX_BATCH];        // length of each frame's valid list (written by K2's last CTA)
+    uint32_t n_tsdf_valid[SAF_MAX_BATCH];   // per-call accumulators (atomics), folded and zeroed by K2's last CTA
+    uint32_t last_tsdf_valid[SAF_MAX_BATCH];
     unsigned long long total_frames;
     unsigned long long total_valid;
     unsigned long long total_tsdf_valid;
@@ -35,13 +38,12 @@ struct WsHeader {
     // immutable after saf_workspace_init
     uint64_t magic;
     uint64_t bytes;
-    uint64_t list_cap;                      // entries per per-frame valid list (= slab voxels)
+    uint64_t list_cap;                      // entries per per-frame valid list (= nblocks_total * 512)
     uint64_t max_table_elems;
-    uint64_t off_blocks, off_lists, off_tables;
     uint32_t nblocks_total;
     uint32_t max_batch;
     uint32_t nb[3];                         // blocks per axis of the slab
-    uint32_t pad_[1];
+    uint32_t pad1_[1];
 };
 static_assert(sizeof(WsHeader) <= 512, "workspace header grew past its slot");
 
@@ -53,11 +55,19 @@ struct __align__(16) ValidEntry {
     uint32_t pad;
 };
 
+constexpr int kK1Threads = 256;             // blocks tested per K1 CTA (one per thread)
+constexpr uint32_t kMaxK1Ctas = 2048;       // K1's last CTA scans this many per-CTA counts in shared memory
+
+// Workspace layout (all offsets 256-byte aligned):
+//   header | cta_count[n_k1] | block_seg[n_k1*256] | block_list[nblocks_total]
+//   | blk_count[max_batch][nblocks_total] | blk_offset[max_batch][nblocks_total+1]
+//   | lists[max_batch][nblocks_total*512] | tables[max_batch][max_table_elems]
 struct WsLayout {
     uint64_t bytes;
     uint64_t list_cap;
-    uint64_t off_blocks, off_lists, off_tables;
+    uint64_t off_cta_count, off_block_seg, off_blocks, off_blk_count, off_blk_offset, off_lists, off_tables;
     uint32_t nblocks_total;
+    uint32_t n_k1;
     uint32_t nb[3];
 };
 
@@ -73,15 +83,22 @@ inline int compute_layout(const saf_grid_desc* g, int32_t max_batch, int64_t max
     if (max_table_elems < 0) return SAF_ERR_SHAPE;
     const uint64_t nxs = (uint64_t)(g->x_end - g->x_begin);
     const uint64_t n = nxs * (uint64_t)g->nvox[1] * (uint64_t)g->nvox[2];
-    if (n >= (1ull << 32)) return SAF_ERR_GRID;  // voxel indices are 32-bit
+    if (n >= (1ull << 31)) return SAF_ERR_GRID;  // voxel indices are 32-bit
     L->nb[0] = (uint32_t)((nxs + kBlockEdge - 1) / kBlockEdge);
     L->nb[1] = (uint32_t)((g->nvox[1] + kBlockEdge - 1) / kBlockEdge);
     L->nb[2] = (uint32_t)((g->nvox[2] + kBlockEdge - 1) / kBlockEdge);
-    L->nblocks_total = L->nb[0] * L->nb[1] * L->nb[2];
-    L->list_cap = n;
-    L->off_blocks = 512;
-    L->off_lists = align_up(L->off_blocks + 4ull * L->nblocks_total, 256);
-    L->off_tables = align_up(L->off_lists + (uint64_t)max_batch * n * sizeof(ValidEntry), 256);
+    const uint64_t nblocks = (uint64_t)L->nb[0] * L->nb[1] * L->nb[2];
+    L->n_k1 = (uint32_t)((nblocks + kK1Threads - 1) / kK1Threads);
+    if (L->n_k1 > kMaxK1Ctas) return SAF_ERR_GRID;  // > 268 M voxels in one slab: shard it
+    L->nblocks_total = (uint32_t)nblocks;
+    L->list_cap = nblocks * kBlockVoxels;
+    L->off_cta_count = 512;
+    L->off_block_seg = align_up(L->off_cta_count + 4ull * L->n_k1, 256);
+    L->off_blocks = align_up(L->off_block_seg + 4ull * L->n_k1 * kK1Threads, 256);
+    L->off_blk_count = align_up(L->off_blocks + 4ull * nblocks, 256);
+    L->off_blk_offset = align_up(L->off_blk_count + 4ull * max_batch * nblocks, 256);
+    L->off_lists = align_up(L->off_blk_offset + 4ull * max_batch * (nblocks + 1), 256);
+    L->off_tables = align_up(L->off_lists + (uint64_t)max_batch * L->list_cap * sizeof(ValidEntry), 256);
     L->bytes = align_up(L->off_tables + (uint64_t)max_batch * (uint64_t)max_table_elems * 4ull, 256);
     return 0;
 }
