@@ -1,14 +1,298 @@
-// saf_query_tc.cu -- tcgen05 (5th-gen tensor core) kernels for the query GEMM.  Placeholder until
-// the TMA + TMEM pipeline lands: reports "unsupported" so callers fail loudly instead of silently
-// taking another path.
+// saf_query_tc.cu -- the query GEMM S = F X^T on the 5th-gen tensor cores (tcgen05), sm_100a.
+//
+// Replaces the matmul of Clip.run_query / Clip.clip_feature_surgery
+// (/root/reference/clipfusion.py:902, 909, 913-932) for large T.  F[M,C] is the fp32 feature
+// matrix as it sits in HBM (the voxel grid's clip_feat or mesh-vertex features); it is fed to
+// the tensor cores UNCONVERTED with kind::tf32 (the MMA reads the fp32 words and uses their top
+// 19 bits), so the kernel moves every feature byte exactly once: TMA -> swizzled shared memory
+// -> tcgen05.mma -> TMEM.  Row norms (the callers' F/|F|, clip_seem_fusion.py:507-511) are
+// accumulated from the same shared-memory tiles by the epilogue warps while the MMAs run.
+//
+// One CTA per 128-row tile of F, all T (<= 256 per pass) texts at once:
+//   warp 0      TMA producer: A tile [128 x 32 fp32] + B tile [N x 32 fp32] per k-block, 4 stages
+//   warp 1      TMEM allocation, single-thread tcgen05.mma issue (4 x K=8 per k-block), commits
+//   warps 2-5   per-row sum of squares from the A tiles; epilogue tcgen05.ld -> scale -> store
+#include <cuda.h>
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
 #include "saf_internal.cuh"
 
 namespace saf {
 
-int query_scores_tc(const float*, int64_t, int32_t, int64_t, const float*, int32_t, int32_t, int32_t, float*,
-                    cudaStream_t)
+namespace tc {
+
+constexpr int BM = 128;          // rows of F per CTA (UMMA M)
+constexpr int BK = 32;           // fp32 per k-block = one 128-byte swizzle row
+constexpr int UMMA_K = 8;        // tf32 MMA K
+constexpr int STAGES = 4;
+constexpr int THREADS = 192;
+constexpr uint32_t A_BYTES = BM * BK * 4;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
 {
-    return SAF_ERR_UNSUPPORTED;
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, 128-byte swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart
+// (cute::UMMA::SmemDescriptor: LBO = 1, SBO = 64 (x16 B), version = 1, layout = SWIZZLE_128B).
+__device__ __forceinline__ uint64_t umma_desc(const void* smem_tile)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_u32(smem_tile) >> 4) & 0x3FFFu);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)64 << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// cute::UMMA::InstrDescriptor for kind::tf32: D = F32, A = B = TF32, both K-major, M = 128, N = n.
+__device__ __forceinline__ uint32_t umma_idesc_tf32(uint32_t n)
+{
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float row_scale(float norm2, int norm_mode)
+{
+    if (norm_mode == SAF_NORM_NONE) return 1.0f;
+    const float nrm = sqrtf(norm2);
+    if (norm_mode == SAF_NORM_CLAMP_MIN) return 1.0f / fmaxf(nrm, 0.1f);
+    return nrm > 0.0f ? 1.0f / nrm : 0.0f;
+}
+
+// out[m, t0 + t] = scale(m) * sum_c F[m,c] X[t0+t,c]   for the CTA's 128 rows and t < t_valid.
+__global__ void __launch_bounds__(THREADS, 1)
+query_gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int64_t M,
+                       int C, int n_pad, int t_valid, int t0, uint32_t tmem_cols, int norm_mode, float* __restrict__ out,
+                       int64_t ldo)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const uint32_t stage_bytes = A_BYTES + (uint32_t)n_pad * BK * 4;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * stage_bytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + STAGES;
+    uint64_t* tmem_full = bars + 2 * STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_k = (C + BK - 1) / BK;
+    const int64_t m0 = (int64_t)blockIdx.x * BM;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1 + 4);  // MMA commit + one arrive per norm warp
+        }
+        mbar_init(tmem_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ---- TMA producer -------------------------------------------------------------------
+        if (lane == 0) {
+            for (int k = 0; k < num_k; ++k) {
+                const int s = k % STAGES;
+                const uint32_t ph = (uint32_t)(k / STAGES) & 1u;
+                mbar_wait(&empty[s], ph ^ 1u);
+                unsigned char* a_dst = smem + (size_t)s * stage_bytes;
+                mbar_arrive_expect_tx(&full[s], stage_bytes);
+                tma_load_2d(a_dst, &map_a, k * BK, (int)m0, &full[s]);
+                tma_load_2d(a_dst + A_BYTES, &map_b, k * BK, t0, &full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        // ---- MMA issuer ---------------------------------------------------------------------
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32((uint32_t)n_pad);
+            for (int k = 0; k < num_k; ++k) {
+                const int s = k % STAGES;
+                const uint32_t ph = (uint32_t)(k / STAGES) & 1u;
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const unsigned char* a_src = smem + (size_t)s * stage_bytes;
+                const uint64_t adesc = umma_desc(a_src), bdesc = umma_desc(a_src + A_BYTES);
+#pragma unroll
+                for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                    // advance 32 bytes inside the 128-byte swizzle row: +2 in the 16-byte address field
+                    umma_tf32(tmem_base, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
+                              (uint32_t)((k | kk) != 0));
+                }
+                umma_commit(&empty[s]);  // frees the stage once these MMAs have read it
+            }
+            umma_commit(tmem_full);      // accumulator complete
+        }
+    } else {
+        // ---- row norms during the main loop, then the epilogue --------------------------------
+        const int row = (warp & 3) * 32 + lane;  // TMEM lane group of this warp = warp % 4
+        float norm2 = 0.0f;
+        for (int k = 0; k < num_k; ++k) {
+            const int s = k % STAGES;
+            const uint32_t ph = (uint32_t)(k / STAGES) & 1u;
+            mbar_wait(&full[s], ph);
+            if (norm_mode != SAF_NORM_NONE) {
+                const float4* a4 = reinterpret_cast<const float4*>(smem + (size_t)s * stage_bytes) + row * 8;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    // the swizzle only permutes the eight 16-byte chunks inside the row: rotate the
+                    // starting chunk by the row so that a quarter-warp touches all 32 banks
+                    const float4 v = a4[(j + row) & 7];
+                    norm2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, norm2))));
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+        const float scale = row_scale(norm2, norm_mode);
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const int64_t m = m0 + row;
+        const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        for (int c0 = 0; c0 < n_pad; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(lane_base + (uint32_t)c0, r);
+            if (m < M) {
+                float* dst = out + m * ldo + t0 + c0;
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                    if (c0 + c < t_valid) dst[c] = __uint_as_float(r[c]) * scale;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int get_encode_fn(EncodeTiledFn* fn)
+{
+    static EncodeTiledFn cached = nullptr;
+    if (!cached) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        SAF_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !p) return SAF_ERR_DEVICE;
+        cached = (EncodeTiledFn)p;
+    }
+    *fn = cached;
+    return 0;
+}
+
+// 2-D fp32 row-major matrix [rows, cols] with row pitch ld (elements); box = [box_rows, 32 cols], 128B swizzle.
+static int make_map(EncodeTiledFn enc, CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                    uint32_t box_rows)
+{
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld * 4};
+    cuuint32_t box[2] = {BK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : SAF_ERR_SHAPE;
+}
+
+}  // namespace tc
+
+int query_scores_tc(const float* feats, int64_t M, int32_t C, int64_t ldf, const float* text, int32_t T,
+                    int32_t norm_mode, int32_t precision, float* out, cudaStream_t st)
+{
+    using namespace tc;
+    if (precision != 1) return SAF_ERR_UNSUPPORTED;  // 3xTF32 split: not implemented, use precision 0 (fp32)
+    // TMA needs 16-byte aligned bases and row pitches
+    if ((((uintptr_t)feats | (uintptr_t)text) & 15u) != 0 || (ldf % 4) != 0 || (C % 4) != 0) return SAF_ERR_ALIGNMENT;
+    if (M >= (1ll << 31)) return SAF_ERR_SHAPE;
+    EncodeTiledFn enc;
+    int rc = get_encode_fn(&enc);
+    if (rc) return rc;
+    CUtensorMap map_a;
+    rc = make_map(enc, &map_a, feats, (uint64_t)M, (uint64_t)C, (uint64_t)ldf, BM);
+    if (rc) return rc;
+    const int64_t tiles = (M + BM - 1) / BM;
+    for (int t0 = 0; t0 < T; t0 += 256) {
+        const int t_valid = std::min(256, T - t0);
+        const int n_pad = std::max(16, (t_valid + 15) & ~15);
+        uint32_t tmem_cols = 32;
+        while (tmem_cols < (uint32_t)((n_pad + 31) & ~31)) tmem_cols <<= 1;
+        CUtensorMap map_b;
+        rc = make_map(enc, &map_b, text, (uint64_t)T, (uint64_t)C, (uint64_t)C, (uint32_t)n_pad);
+        if (rc) return rc;
+        const size_t stage_bytes = A_BYTES + (size_t)n_pad * BK * 4;
+        const size_t smem = (size_t)STAGES * stage_bytes + (2 * STAGES + 1) * 8 + 16;
+        SAF_CUDA_TRY(cudaFuncSetAttribute(query_gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        query_gemm_tf32_kernel<<<(unsigned)tiles, THREADS, smem, st>>>(map_a, map_b, M, C, n_pad, t_valid, t0, tmem_cols,
+                                                                      norm_mode, out, (int64_t)T);
+        SAF_CHECK_LAUNCH("query_gemm_tf32_kernel", st);
+    }
+    return 0;
 }
 
 }  // namespace saf

@@ -286,3 +286,27 @@ def test_query_topk_matches_oracle(M, C, T, k):
     assert (_np(ti)[:, kk:] == -1).all()
     got_scores = np.take_along_axis(_np(scores).T, want, axis=1)
     assert np.array_equal(_np(ts)[:, :kk], got_scores)
+
+
+@pytest.mark.parametrize("M,C,T", [(1000, 768, 33), (300, 64, 256), (4097, 512, 300), (129, 100, 5), (70000, 768, 64)])
+def test_query_tensor_core_scores(M, C, T):
+    """tcgen05 kind::tf32 GEMM (precision='tf32') against the fp32 kernel and the numpy oracle.
+    tf32 keeps 10 mantissa bits of each operand: |error| <= 2^-9 * |f| * |x| per score."""
+    import spatially_aware_ai_b200 as saf
+    rng = np.random.default_rng(M * 7 + T)
+    F = rng.standard_normal((M, C)).astype(np.float32)
+    F[::17] = 0
+    X = rng.standard_normal((T, C)).astype(np.float32)
+    X /= np.linalg.norm(X, axis=1, keepdims=True)
+    Fd, Xd = torch.from_numpy(F).cuda(), torch.from_numpy(X).cuda()
+    ref = O.normalize_rows(F) @ X.T
+    got = _np(saf.query_scores(Fd, Xd, norm="nan_to_num", mode="dot", precision="tf32"))
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() <= 2.0 ** -9 + 1e-5
+    assert not got[::17].any()
+    # un-normalised dot product and the softmax epilogue on top of the tensor-core scores
+    raw = _np(saf.query_scores(Fd, Xd, norm=None, mode="dot", precision="tf32"))
+    bound = 2.0 ** -9 * np.linalg.norm(F, axis=1, keepdims=True) + 1e-4
+    assert (np.abs(raw - F @ X.T) <= bound).all()
+    sm = _np(saf.query_scores(Fd, Xd, norm="nan_to_num", mode="softmax100", precision="tf32"))
+    assert np.allclose(sm.sum(axis=1), 1.0, atol=1e-4)
