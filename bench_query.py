@@ -1,0 +1,94 @@
+#!/usr/bin/env python
+"""bench_query.py -- language-query scoring throughput (BASELINE.json configs[3]):
+T CLIP text embeddings scored by cosine against an [M, C] fused feature matrix.
+
+    python bench_query.py [--rows M] [--texts T] [--dim C] [--k K] [--precision tf32|fp32]
+
+Prints one JSON line: scores kernel GB/s and TFLOP/s (CUDA events, median of --iters), top-k time,
+and the numpy oracle's time on a bounded row sample for scale.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rows", type=int, default=24_000_000)
+    ap.add_argument("--texts", type=int, default=256)
+    ap.add_argument("--dim", type=int, default=768)
+    ap.add_argument("--k", type=int, default=100)
+    ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--precision", default="tf32")
+    ap.add_argument("--no-topk", action="store_true")
+    ap.add_argument("--cpu-rows", type=int, default=200_000)
+    args = ap.parse_args()
+
+    import torch
+    import spatially_aware_ai_b200 as saf
+    dev = torch.device("cuda:0")
+    M, T, C = args.rows, args.texts, args.dim
+    g = torch.Generator(device=dev).manual_seed(0)
+    F = torch.empty((M, C), dtype=torch.float32, device=dev)
+    step = 1 << 20
+    for r0 in range(0, M, step):
+        F[r0:r0 + step].normal_(generator=g)
+    X = torch.randn((T, C), generator=g, device=dev)
+    X = X / X.norm(dim=1, keepdim=True)
+    out = torch.empty((M, T), dtype=torch.float32, device=dev)
+    peaks = {}
+    ppath = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(ppath):
+        peaks = json.load(open(ppath))
+
+    def timed(fn, iters):
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return float(np.median(ts))
+
+    ms = timed(lambda: saf.query_scores(F, X, norm="nan_to_num", mode="dot", precision=args.precision, out=out), args.iters)
+    read_b = M * C * 4 + T * C * 4
+    write_b = M * T * 4
+    flops = 2.0 * M * C * T
+    res = {"metric": "query_scores", "rows": M, "texts": T, "dim": C, "precision": args.precision,
+           "scores_ms": ms, "read_GBps": read_b / ms / 1e6, "read_plus_write_GBps": (read_b + write_b) / ms / 1e6,
+           "tflops": flops / ms / 1e9, "hbm_peak_GBps": peaks.get("hbm_gbs"),
+           "frac_hbm_rw": (read_b + write_b) / ms / 1e6 / peaks["hbm_gbs"] if peaks else None,
+           "tf32_dense_peak_tflops_nominal": 1125.0, "frac_tensor_nominal": flops / ms / 1e9 / 1125.0}
+    if not args.no_topk:
+        tk = timed(lambda: saf.query_topk(F, X, args.k, norm="nan_to_num", mode="dot", precision=args.precision), 2)
+        res["topk_ms"] = tk
+        res["topk_k"] = args.k
+        res["topk_read_GBps"] = read_b / tk / 1e6
+    # CPU: numpy (MKL/OpenBLAS sgemm, all cores) on a row sample
+    from oracle import oracle as O
+    Fs = F[: args.cpu_rows].cpu().numpy()
+    Xs = X.cpu().numpy()
+    t0 = time.perf_counter()
+    ref = O.normalize_rows(Fs) @ Xs.T
+    cpu_s = time.perf_counter() - t0
+    got = out[: args.cpu_rows].cpu().numpy()
+    res["cpu_rows_per_s"] = args.cpu_rows / cpu_s
+    res["gpu_rows_per_s"] = M / (ms * 1e-3)
+    res["max_abs_err_vs_oracle"] = float(np.abs(got - ref).max())
+    res["cpu_cores"] = os.cpu_count()
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()

@@ -162,6 +162,24 @@ __device__ __forceinline__ void st_stream_f4(float4* p, const float4& v)
                  : "memory");
 }
 
+// ---- exact fp32 scoring helpers shared by the fp32 query kernel and the top-k rescoring kernel, so that
+// both produce bit-identical scores -------------------------------------------------------------------
+__device__ __forceinline__ float row_scale(float norm2, int norm_mode)
+{
+    if (norm_mode == SAF_NORM_NONE) return 1.0f;
+    const float nrm = sqrtf(norm2);
+    if (norm_mode == SAF_NORM_CLAMP_MIN) return 1.0f / fmaxf(nrm, 0.1f);
+    return nrm > 0.0f ? 1.0f / nrm : 0.0f;  // f/|f| then nan_to_num: zero rows stay zero
+}
+__device__ __forceinline__ float dot4_acc(const float4& f, const float4& x, float acc)
+{
+    return fmaf(f.x, x.x, fmaf(f.y, x.y, fmaf(f.z, x.z, fmaf(f.w, x.w, acc))));
+}
+__device__ __forceinline__ float sq4_acc(const float4& f, float acc)
+{
+    return acc + (f.x * f.x + f.y * f.y + f.z * f.z + f.w * f.w);
+}
+
 int device_sm_count(int* sms, int* smem_optin);
 
 // SAF_DEBUG_SYNC=1 in the environment: synchronise after every launch and name the kernel that

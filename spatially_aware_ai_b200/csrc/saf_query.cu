@@ -21,14 +21,6 @@ int query_scores_tc(const float* feats, int64_t M, int32_t C, int64_t ldf, const
 
 constexpr int kQThreads = 256;
 
-__device__ __forceinline__ float row_scale(float norm2, int norm_mode)
-{
-    if (norm_mode == SAF_NORM_NONE) return 1.0f;
-    const float nrm = sqrtf(norm2);
-    if (norm_mode == SAF_NORM_CLAMP_MIN) return 1.0f / fmaxf(nrm, 0.1f);
-    return nrm > 0.0f ? 1.0f / nrm : 0.0f;  // f/|f| then nan_to_num: zero rows stay zero
-}
-
 // out[m, t0 + t] = scale(m) * <F[m,:], X[t0+t,:]>   for t in [0, Tt)
 template <int VEC>
 __global__ void __launch_bounds__(kQThreads) query_scores_fp32_kernel(const float* __restrict__ F, int64_t M, int C,
@@ -55,11 +47,11 @@ __global__ void __launch_bounds__(kQThreads) query_scores_fp32_kernel(const floa
             if (VEC == 4) {
                 for (int c4 = lane; c4 < C / 4; c4 += 32) {
                     const float4 f = __ldg(reinterpret_cast<const float4*>(row) + c4);
-                    if (tb == 0) norm2 += f.x * f.x + f.y * f.y + f.z * f.z + f.w * f.w;
+                    if (tb == 0) norm2 = sq4_acc(f, norm2);
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         const float4 x = reinterpret_cast<const float4*>(xs + (size_t)(tb + i) * C)[c4];
-                        acc[i] = fmaf(f.x, x.x, fmaf(f.y, x.y, fmaf(f.z, x.z, fmaf(f.w, x.w, acc[i]))));
+                        acc[i] = dot4_acc(f, x, acc[i]);
                     }
                 }
             } else {

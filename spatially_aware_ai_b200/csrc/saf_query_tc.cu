@@ -109,19 +109,32 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__device__ __forceinline__ float row_scale(float norm2, int norm_mode)
-{
-    if (norm_mode == SAF_NORM_NONE) return 1.0f;
-    const float nrm = sqrtf(norm2);
-    if (norm_mode == SAF_NORM_CLAMP_MIN) return 1.0f / fmaxf(nrm, 0.1f);
-    return nrm > 0.0f ? 1.0f / nrm : 0.0f;
-}
+// A row that may still belong to a text's top-k: tensor-core score and its error radius.
+struct __align__(16) Candidate {
+    float score;   // tf32 score (scaled)
+    float eps;     // |exact - score| <= eps
+    uint32_t row;  // row of F
+    uint32_t pad;
+};
 
-// out[m, t0 + t] = scale(m) * sum_c F[m,c] X[t0+t,c]   for the CTA's 128 rows and t < t_valid.
+// Filter state of the fused top-k (device arrays indexed by text).
+struct FilterArgs {
+    const float* thr;      // [T] a row is kept iff score + eps >= thr[t]
+    const float* xnorm;    // [T] |X_t|
+    Candidate* buckets;    // [T][cap]
+    uint32_t* counts;      // [T]
+    uint32_t* flags;       // bit 0: a bucket overflowed
+    uint32_t cap;
+};
+
+// FILTER = false: out[m, t0 + t] = scale(m) * sum_c F[m,c] X[t0+t,c] for the CTA's 128 rows, t < t_valid.
+// FILTER = true : nothing is written to `out`; instead every (row, text) whose score may still reach
+//                 the text's current top-k threshold is appended to that text's candidate bucket.
+template <bool FILTER>
 __global__ void __launch_bounds__(THREADS, 1)
 query_gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int64_t M,
                        int C, int n_pad, int t_valid, int t0, uint32_t tmem_cols, int norm_mode, float* __restrict__ out,
-                       int64_t ldo)
+                       int64_t ldo, int64_t tile0, const FilterArgs fa)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t stage_bytes = A_BYTES + (uint32_t)n_pad * BK * 4;
@@ -133,7 +146,7 @@ query_gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_k = (C + BK - 1) / BK;
-    const int64_t m0 = (int64_t)blockIdx.x * BM;
+    const int64_t m0 = ((int64_t)blockIdx.x + tile0) * BM;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -191,7 +204,7 @@ query_gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             const int s = k % STAGES;
             const uint32_t ph = (uint32_t)(k / STAGES) & 1u;
             mbar_wait(&full[s], ph);
-            if (norm_mode != SAF_NORM_NONE) {
+            if (FILTER || norm_mode != SAF_NORM_NONE) {
                 const float4* a4 = reinterpret_cast<const float4*>(smem + (size_t)s * stage_bytes) + row * 8;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -207,18 +220,80 @@ query_gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         const float scale = row_scale(norm2, norm_mode);
         mbar_wait(tmem_full, 0);
         tc_fence_after();
-        const int64_t m = m0 + row;
+        if (FILTER) {
+            // tf32 keeps 10 explicit mantissa bits of each operand (truncation): every product is off by
+            // less than 2^-9 relative, so |exact - tf32| <= 2^-9 |f| |x| (Cauchy-Schwarz) plus fp32 slack.
+            const float eps_row = 0.001953125f * sqrtf(norm2) * scale;
+            const int64_t m = m0 + row;
+            const uint32_t lane_base_f = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+            for (int c0 = 0; c0 < n_pad; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(lane_base_f + (uint32_t)c0, r);
+                if (m < M) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const int t = t0 + c0 + c;
+                        if (c0 + c < t_valid) {
+                            const float sc = __uint_as_float(r[c]) * scale;
+                            const float e = eps_row * __ldg(fa.xnorm + t) + 1e-6f;
+                            if (sc + e >= __ldg(fa.thr + t)) {
+                                const uint32_t pos = atomicAdd(fa.counts + t, 1u);
+                                if (pos < fa.cap) {
+                                    Candidate cd;
+                                    cd.score = sc;
+                                    cd.eps = e;
+                                    cd.row = (uint32_t)m;
+                                    cd.pad = 0;
+                                    fa.buckets[(size_t)t * fa.cap + pos] = cd;
+                                } else {
+                                    atomicOr(fa.flags, 1u);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        } else {
+        // All MMAs have retired, so the stage buffers are free: each warp parks its 32 score rows
+        // there (row pitch n_pad + 4 floats keeps the 128-bit shared stores conflict free) and
+        // then streams them out row by row with fully coalesced global stores.
+        const int pitch = n_pad + 4;
+        float* park = reinterpret_cast<float*>(smem) + (size_t)(warp & 3) * 32 * pitch;
         const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         for (int c0 = 0; c0 < n_pad; c0 += 32) {
             uint32_t r[32];
             tmem_ld32(lane_base + (uint32_t)c0, r);
-            if (m < M) {
-                float* dst = out + m * ldo + t0 + c0;
+            float4* dst = reinterpret_cast<float4*>(park + (size_t)lane * pitch + c0);
 #pragma unroll
-                for (int c = 0; c < 32; ++c)
-                    if (c0 + c < t_valid) dst[c] = __uint_as_float(r[c]) * scale;
+            for (int c = 0; c < 32; c += 4)
+                if (c0 + c < n_pad)
+                    dst[c >> 2] = make_float4(__uint_as_float(r[c]) * scale, __uint_as_float(r[c + 1]) * scale,
+                                              __uint_as_float(r[c + 2]) * scale, __uint_as_float(r[c + 3]) * scale);
+        }
+        __syncwarp();
+        const int64_t row0 = m0 + (warp & 3) * 32;
+        const bool vec_ok = ((ldo | (int64_t)t0) & 3) == 0 && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
+        for (int rr = 0; rr < 32; ++rr) {
+            const int64_t m = row0 + rr;
+            if (m >= M) break;
+            const float* src = park + (size_t)rr * pitch;
+            float* dst = out + m * ldo + t0;
+            if (vec_ok) {
+                for (int c = lane * 4; c < t_valid; c += 128) {
+                    const float4 v = *reinterpret_cast<const float4*>(src + c);
+                    if (c + 3 < t_valid) {
+                        *reinterpret_cast<float4*>(dst + c) = v;
+                    } else {
+                        dst[c] = v.x;
+                        if (c + 1 < t_valid) dst[c + 1] = v.y;
+                        if (c + 2 < t_valid) dst[c + 2] = v.z;
+                    }
+                }
+            } else {
+                for (int c = lane; c < t_valid; c += 32) dst[c] = src[c];
             }
         }
+        }  // !FILTER
     }
     tc_fence_before();
     __syncthreads();
@@ -260,14 +335,13 @@ static int make_map(EncodeTiledFn enc, CUtensorMap* map, const float* base, uint
     return r == CUDA_SUCCESS ? 0 : SAF_ERR_SHAPE;
 }
 
-}  // namespace tc
 
-int query_scores_tc(const float* feats, int64_t M, int32_t C, int64_t ldf, const float* text, int32_t T,
-                    int32_t norm_mode, int32_t precision, float* out, cudaStream_t st)
+
+// Launches the GEMM over rows [row_begin, row_end) (row_begin a multiple of 128) for all T texts.
+static int launch_gemm(bool filter, const float* feats, int64_t M, int32_t C, int64_t ldf, const float* text, int32_t T,
+                       int32_t norm_mode, float* out, int64_t row_begin, int64_t row_end, const FilterArgs& fa,
+                       cudaStream_t st)
 {
-    using namespace tc;
-    if (precision != 1) return SAF_ERR_UNSUPPORTED;  // 3xTF32 split: not implemented, use precision 0 (fp32)
-    // TMA needs 16-byte aligned bases and row pitches
     if ((((uintptr_t)feats | (uintptr_t)text) & 15u) != 0 || (ldf % 4) != 0 || (C % 4) != 0) return SAF_ERR_ALIGNMENT;
     if (M >= (1ll << 31)) return SAF_ERR_SHAPE;
     EncodeTiledFn enc;
@@ -276,7 +350,9 @@ int query_scores_tc(const float* feats, int64_t M, int32_t C, int64_t ldf, const
     CUtensorMap map_a;
     rc = make_map(enc, &map_a, feats, (uint64_t)M, (uint64_t)C, (uint64_t)ldf, BM);
     if (rc) return rc;
-    const int64_t tiles = (M + BM - 1) / BM;
+    const int64_t tile0 = row_begin / BM;
+    const int64_t tiles = (row_end - row_begin + BM - 1) / BM;
+    if (tiles <= 0) return 0;
     for (int t0 = 0; t0 < T; t0 += 256) {
         const int t_valid = std::min(256, T - t0);
         const int n_pad = std::max(16, (t_valid + 15) & ~15);
@@ -287,12 +363,231 @@ int query_scores_tc(const float* feats, int64_t M, int32_t C, int64_t ldf, const
         if (rc) return rc;
         const size_t stage_bytes = A_BYTES + (size_t)n_pad * BK * 4;
         const size_t smem = (size_t)STAGES * stage_bytes + (2 * STAGES + 1) * 8 + 16;
-        SAF_CUDA_TRY(cudaFuncSetAttribute(query_gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        query_gemm_tf32_kernel<<<(unsigned)tiles, THREADS, smem, st>>>(map_a, map_b, M, C, n_pad, t_valid, t0, tmem_cols,
-                                                                      norm_mode, out, (int64_t)T);
+        if (filter) {
+            SAF_CUDA_TRY(cudaFuncSetAttribute(query_gemm_tf32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)smem));
+            query_gemm_tf32_kernel<true><<<(unsigned)tiles, THREADS, smem, st>>>(map_a, map_b, M, C, n_pad, t_valid, t0,
+                                                                                tmem_cols, norm_mode, out, (int64_t)T,
+                                                                                tile0, fa);
+        } else {
+            SAF_CUDA_TRY(cudaFuncSetAttribute(query_gemm_tf32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)smem));
+            query_gemm_tf32_kernel<false><<<(unsigned)tiles, THREADS, smem, st>>>(map_a, map_b, M, C, n_pad, t_valid, t0,
+                                                                                 tmem_cols, norm_mode, out, (int64_t)T,
+                                                                                 tile0, fa);
+        }
         SAF_CHECK_LAUNCH("query_gemm_tf32_kernel", st);
     }
     return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused top-k on the tensor cores: no score matrix, exact result
+// ---------------------------------------------------------------------------------------------
+//
+// Rows are processed in waves (8 K rows, then x8 each).  The GEMM epilogue keeps only (row, text)
+// pairs whose score interval [s - eps, s + eps] can still reach the text's threshold L_t = k-th
+// largest lower bound seen so far; after each wave topk_tc_threshold_kernel raises L_t and compacts
+// the bucket.  A rejected row had s + eps < L_t, and k rows with exact score >= L_t exist, so no
+// rejected row can be in the exact top-k.  topk_tc_final_kernel rescoring the survivors in fp32
+// (same arithmetic as the fp32 query kernel) therefore yields the exact top-k.
+
+constexpr uint32_t kBucketCap = 8192;
+constexpr int kFinalMax = 4096;
+
+__device__ __forceinline__ uint32_t float_key(float f)
+{
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(uint32_t k)
+{
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+__global__ void __launch_bounds__(128) topk_tc_init_kernel(const float* __restrict__ X, int C, float* xnorm, float* thr,
+                                                           uint32_t* counts_a, uint32_t* counts_b, uint32_t* flags)
+{
+    __shared__ float red[4];
+    const int t = blockIdx.x;
+    float acc = 0.0f;
+    for (int c = threadIdx.x; c < C; c += 128) acc = fmaf(X[(size_t)t * C + c], X[(size_t)t * C + c], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        xnorm[t] = sqrtf(red[0] + red[1] + red[2] + red[3]) * 1.0001f;
+        thr[t] = -INFINITY;
+        counts_a[t] = 0;
+        counts_b[t] = 0;
+        if (t == 0) flags[0] = 0;
+    }
+}
+
+// one CTA per text: L = k-th largest lower bound in `src`; survivors (upper bound >= L) -> `dst`
+__global__ void __launch_bounds__(256) topk_tc_threshold_kernel(const Candidate* __restrict__ src_all, uint32_t* src_counts,
+                                                                Candidate* __restrict__ dst_all, uint32_t* dst_counts,
+                                                                float* thr, int k, uint32_t cap)
+{
+    extern __shared__ uint32_t keys[];  // [cap] orderable keys of the lower bounds
+    __shared__ uint32_t s_cnt, s_out;
+    const int t = blockIdx.x;
+    const Candidate* src = src_all + (size_t)t * cap;
+    Candidate* dst = dst_all + (size_t)t * cap;
+    const uint32_t n = min(src_counts[t], cap);
+    for (uint32_t i = threadIdx.x; i < n; i += 256) keys[i] = float_key(src[i].score - src[i].eps);
+    if (threadIdx.x == 0) s_out = 0;
+    __syncthreads();
+    float L = -INFINITY;
+    if (n >= (uint32_t)k) {
+        uint32_t prefix = 0;
+        for (int bit = 31; bit >= 0; --bit) {
+            const uint32_t trial = prefix | (1u << bit);
+            if (threadIdx.x == 0) s_cnt = 0;
+            __syncthreads();
+            uint32_t c = 0;
+            for (uint32_t i = threadIdx.x; i < n; i += 256) c += keys[i] >= trial ? 1u : 0u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_cnt, c);
+            __syncthreads();
+            if (s_cnt >= (uint32_t)k) prefix = trial;
+            __syncthreads();
+        }
+        L = key_float(prefix);
+    }
+    for (uint32_t i = threadIdx.x; i < n; i += 256) {
+        const Candidate c = src[i];
+        if (c.score + c.eps >= L) dst[atomicAdd(&s_out, 1u)] = c;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        dst_counts[t] = s_out;
+        src_counts[t] = 0;
+        thr[t] = L;
+    }
+}
+
+// one CTA per text: exact fp32 score of every survivor, then rank -> top-k (descending, ties to lower row)
+__global__ void __launch_bounds__(256) topk_tc_final_kernel(const Candidate* __restrict__ buckets,
+                                                            const uint32_t* __restrict__ counts, uint32_t cap,
+                                                            const float* __restrict__ F, int C, int64_t ldf,
+                                                            const float* __restrict__ X, int norm_mode, int k,
+                                                            int64_t index_base, float* __restrict__ out_s,
+                                                            long long* __restrict__ out_i, uint32_t* flags)
+{
+    __shared__ float ex_s[kFinalMax];
+    __shared__ uint32_t ex_r[kFinalMax];
+    const int t = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const Candidate* b = buckets + (size_t)t * cap;
+    uint32_t n = min(counts[t], cap);
+    if (n > (uint32_t)kFinalMax) {
+        if (threadIdx.x == 0) atomicOr(flags, 2u);
+        n = kFinalMax;
+    }
+    for (int q = threadIdx.x; q < k; q += 256) {
+        out_s[(size_t)t * k + q] = -INFINITY;
+        out_i[(size_t)t * k + q] = -1;
+    }
+    const float4* x4 = reinterpret_cast<const float4*>(X + (size_t)t * C);
+    for (uint32_t e = warp; e < n; e += 8) {
+        const uint32_t row = b[e].row;
+        const float4* f4 = reinterpret_cast<const float4*>(F + (size_t)row * ldf);
+        float acc = 0.0f, norm2 = 0.0f;
+        for (int c4 = lane; c4 < C / 4; c4 += 32) {
+            const float4 f = __ldg(f4 + c4);
+            norm2 = sq4_acc(f, norm2);
+            acc = dot4_acc(f, __ldg(x4 + c4), acc);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            norm2 += __shfl_xor_sync(0xffffffffu, norm2, o);
+            acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        }
+        if (lane == 0) {
+            ex_s[e] = acc * row_scale(norm2, norm_mode);
+            ex_r[e] = row;
+        }
+    }
+    __syncthreads();
+    for (uint32_t a = threadIdx.x; a < n; a += 256) {
+        const float sa = ex_s[a];
+        const uint32_t ra = ex_r[a];
+        int rank = 0;
+        for (uint32_t j = 0; j < n; ++j) {
+            const float sj = ex_s[j];
+            rank += (sj > sa || (sj == sa && ex_r[j] < ra)) ? 1 : 0;
+        }
+        if (rank < k) {
+            out_s[(size_t)t * k + rank] = sa;
+            out_i[(size_t)t * k + rank] = (long long)ra + index_base;
+        }
+    }
+}
+
+}  // namespace tc
+
+uint64_t query_topk_tc_workspace_bytes(int32_t T)
+{
+    return 2ull * (uint64_t)T * tc::kBucketCap * sizeof(tc::Candidate) + 4ull * (uint64_t)T * 4 + 256;
+}
+
+// returns 0 on success, 1 when the caller must fall back to the exact chunked path (bucket overflow:
+// e.g. millions of exactly tied rows), <0 / CUDA error otherwise.  Synchronises the stream.
+int query_topk_tc(const float* feats, int64_t M, int32_t C, int64_t ldf, const float* text, int32_t T, int32_t norm_mode,
+                  int32_t k, int64_t index_base, float* out_scores, int64_t* out_index, void* ws, cudaStream_t st)
+{
+    using namespace tc;
+    unsigned char* base = (unsigned char*)ws;
+    Candidate* bucket[2] = {(Candidate*)base, (Candidate*)(base + (uint64_t)T * kBucketCap * sizeof(Candidate))};
+    uint32_t* u = (uint32_t*)(base + 2ull * (uint64_t)T * kBucketCap * sizeof(Candidate));
+    uint32_t* counts[2] = {u, u + T};
+    float* thr = (float*)(u + 2 * T);
+    float* xnorm = (float*)(u + 3 * T);
+    uint32_t* flags = u + 4 * T;
+    topk_tc_init_kernel<<<T, 128, 0, st>>>(text, C, xnorm, thr, counts[0], counts[1], flags);
+    SAF_CHECK_LAUNCH("topk_tc_init_kernel", st);
+    SAF_CUDA_TRY(cudaFuncSetAttribute(topk_tc_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(kBucketCap * 4)));
+    int cur = 0;
+    int64_t r0 = 0;
+    int64_t wave = (int64_t)kBucketCap / BM * BM;
+    while (r0 < M) {
+        const int64_t r1 = std::min(M, r0 + wave);
+        FilterArgs fa;
+        fa.thr = thr;
+        fa.xnorm = xnorm;
+        fa.buckets = bucket[cur];
+        fa.counts = counts[cur];
+        fa.flags = flags;
+        fa.cap = kBucketCap;
+        int rc = launch_gemm(true, feats, M, C, ldf, text, T, norm_mode, nullptr, r0, r1, fa, st);
+        if (rc) return rc;
+        topk_tc_threshold_kernel<<<T, 256, kBucketCap * 4, st>>>(bucket[cur], counts[cur], bucket[cur ^ 1], counts[cur ^ 1],
+                                                                 thr, k, kBucketCap);
+        SAF_CHECK_LAUNCH("topk_tc_threshold_kernel", st);
+        cur ^= 1;
+        r0 = r1;
+        wave *= 8;
+    }
+    topk_tc_final_kernel<<<T, 256, 0, st>>>(bucket[cur], counts[cur], kBucketCap, feats, C, ldf, text, norm_mode, k,
+                                            index_base, out_scores, (long long*)out_index, flags);
+    SAF_CHECK_LAUNCH("topk_tc_final_kernel", st);
+    uint32_t h_flags = 0;
+    SAF_CUDA_TRY(cudaMemcpyAsync(&h_flags, flags, 4, cudaMemcpyDeviceToHost, st));
+    SAF_CUDA_TRY(cudaStreamSynchronize(st));
+    return h_flags ? 1 : 0;
+}
+
+int query_scores_tc(const float* feats, int64_t M, int32_t C, int64_t ldf, const float* text, int32_t T,
+                    int32_t norm_mode, int32_t precision, float* out, cudaStream_t st)
+{
+    if (precision != 1) return SAF_ERR_UNSUPPORTED;  // 3xTF32 split: not implemented, use precision 0 (fp32)
+    tc::FilterArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    return tc::launch_gemm(false, feats, M, C, ldf, text, T, norm_mode, out, 0, M, fa, st);
 }
 
 }  // namespace saf

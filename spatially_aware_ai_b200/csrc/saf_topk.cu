@@ -13,9 +13,15 @@
 // depend on the insertion order).
 #include <math.h>
 
+#include <algorithm>
+
 #include "saf_internal.cuh"
 
 namespace saf {
+
+uint64_t query_topk_tc_workspace_bytes(int32_t T);
+int query_topk_tc(const float* feats, int64_t M, int32_t C, int64_t ldf, const float* text, int32_t T, int32_t norm_mode,
+                  int32_t k, int64_t index_base, float* out_scores, int64_t* out_index, void* ws, cudaStream_t st);
 
 constexpr int kScanThreads = 256;
 constexpr int kTextsPerCta = 8;
@@ -201,7 +207,9 @@ __global__ void __launch_bounds__(256) topk_merge_kernel(Partial part, int split
 }
 
 constexpr int kTopkSplits = 32;
-constexpr int64_t kTopkChunkRows = 1 << 19;
+// A chunk's [rows, T] score block is written by the scoring kernel and read straight back by the
+// scan kernel: keep it around 48 MB so that it lives in the 126 MB L2 and never travels to HBM.
+constexpr int64_t kTopkChunkBytes = 48ll << 20;
 
 struct TopkLayout {
     uint64_t off_scores, off_part_s, off_part_i, bytes;
@@ -211,11 +219,14 @@ struct TopkLayout {
 static int topk_layout(int64_t M, int T, int k, TopkLayout* L)
 {
     if (M < 0 || T <= 0 || k <= 0 || k > 2048) return SAF_ERR_SHAPE;
-    L->chunk_rows = M < kTopkChunkRows ? (M > 0 ? M : 1) : kTopkChunkRows;
+    int64_t chunk = kTopkChunkBytes / ((int64_t)T * 4);
+    chunk = std::max<int64_t>(4096, chunk) / 128 * 128;
+    L->chunk_rows = M < chunk ? (M > 0 ? M : 1) : chunk;
     L->off_scores = 0;
     L->off_part_s = align_up((uint64_t)L->chunk_rows * T * 4, 256);
     L->off_part_i = align_up(L->off_part_s + (uint64_t)kTopkSplits * T * k * 4, 256);
     L->bytes = align_up(L->off_part_i + (uint64_t)kTopkSplits * T * k * 8, 256);
+    L->bytes = std::max<uint64_t>(L->bytes, align_up(query_topk_tc_workspace_bytes(T), 256));
     return 0;
 }
 
@@ -251,6 +262,15 @@ int saf_query_topk(const float* feats, int64_t M, int32_t C, int64_t ldf, const 
     const size_t smem = (size_t)kTextsPerCta * k * 12;
     if (smem + 32 * 1024 > (size_t)smem_optin) return SAF_ERR_SHAPE;
     cudaStream_t st = (cudaStream_t)stream;
+    if (precision == 1 && M > 0) {
+        // tensor-core path: exact top-k from tf32 scores + fp32 rescoring; plain dot / cosine only
+        if (score_mode != SAF_SCORE_DOT) return SAF_ERR_UNSUPPORTED;
+        if ((C % 4) != 0 || (ldf % 4) != 0 || (((uintptr_t)feats | (uintptr_t)text) & 15u) != 0)
+            return SAF_ERR_ALIGNMENT;
+        rc = query_topk_tc(feats, M, C, ldf, text, T, norm_mode, k, index_base, out_scores, out_index, ws, st);
+        if (rc != 1) return rc;
+        precision = 0;  // bucket overflow (mass ties): redo exactly with the fp32 chunked path
+    }
     unsigned char* base = (unsigned char*)ws;
     float* scores = (float*)(base + L.off_scores);
     Partial part;

@@ -310,3 +310,36 @@ def test_query_tensor_core_scores(M, C, T):
     assert (np.abs(raw - F @ X.T) <= bound).all()
     sm = _np(saf.query_scores(Fd, Xd, norm="nan_to_num", mode="softmax100", precision="tf32"))
     assert np.allclose(sm.sum(axis=1), 1.0, atol=1e-4)
+
+
+@pytest.mark.parametrize("M,C,T,k", [(50000, 768, 40, 10), (300000, 512, 256, 100), (1000, 64, 3, 5),
+                                     (20000, 768, 8, 2000)])
+def test_query_topk_tensor_core_is_exact(M, C, T, k):
+    """Fused tensor-core top-k (tf32 GEMM + candidate filter + fp32 rescoring) returns exactly the
+    ranking of the fp32 score matrix: same indices, same score bits."""
+    import spatially_aware_ai_b200 as saf
+    rng = np.random.default_rng(M + T)
+    F = rng.standard_normal((M, C)).astype(np.float32)
+    F[rng.integers(0, M, size=M // 20)] = 0
+    F[11] = F[5]                                  # an exact tie
+    X = rng.standard_normal((T, C)).astype(np.float32)
+    X /= np.linalg.norm(X, axis=1, keepdims=True)
+    Fd, Xd = torch.from_numpy(F).cuda(), torch.from_numpy(X).cuda()
+    scores = _np(saf.query_scores(Fd, Xd, norm="nan_to_num", mode="dot", precision="fp32"))
+    ts, ti = saf.query_topk(Fd, Xd, k, norm="nan_to_num", mode="dot", precision="tf32", index_base=7)
+    kk = min(k, M)
+    want = O.topk_indices(scores, kk)
+    assert np.array_equal(_np(ti)[:, :kk], want + 7)
+    assert np.array_equal(_np(ts)[:, :kk], np.take_along_axis(scores.T, want, axis=1))
+
+
+def test_query_topk_tensor_core_falls_back_on_mass_ties():
+    """All-zero features: every row ties at score 0, the candidate buckets overflow and the call must
+    fall back to the exact chunked path (lowest indices win)."""
+    import spatially_aware_ai_b200 as saf
+    M, C, T, k = 40000, 64, 4, 6
+    Fd = torch.zeros((M, C), device="cuda")
+    Xd = torch.randn((T, C), device="cuda")
+    ts, ti = saf.query_topk(Fd, Xd, k, norm="nan_to_num", mode="dot", precision="tf32")
+    assert np.array_equal(_np(ti), np.tile(np.arange(k), (T, 1)))
+    assert not _np(ts).any()
