@@ -1,0 +1,86 @@
+"""CPU, world_size 2 over gloo: the host-side logic of the multi-GPU (x-slab) path."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import oracle as O
+from spatially_aware_ai_b200 import slab
+
+
+def test_slab_bounds_cover_grid():
+    for nx in (1, 7, 304, 400):
+        for world in (1, 2, 3, 8):
+            if world > nx:
+                continue
+            cuts = [slab.slab_bounds(nx, world, r) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == nx
+            assert all(a[1] == b[0] for a, b in zip(cuts[:-1], cuts[1:]))
+            sizes = [b - a for a, b in cuts]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        slab.slab_bounds(10, 2, 2)
+
+
+def test_merge_topk_rule():
+    s = torch.tensor([[[0.5, 0.5, 0.1]], [[0.5, 0.9, float("-inf")]]])       # [ranks=2, T=1, n=3]
+    i = torch.tensor([[[7, 3, 9]], [[1, 20, -1]]])
+    ms, mi = slab.merge_topk(s, i, 4)
+    assert mi.tolist() == [[20, 1, 3, 7]]
+    assert np.allclose(ms.numpy(), [[0.9, 0.5, 0.5, 0.5]])
+    ms, mi = slab.merge_topk(s, i, 6)
+    assert mi.tolist() == [[20, 1, 3, 7, 9, -1]]
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, F, X, k, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        M = F.shape[0]
+        a, b = slab.slab_bounds(M, world, rank)          # rows stand in for voxels of an x-slab
+        local = O.normalize_rows(F[a:b]) @ X.T
+        li = O.topk_indices(local, min(k, b - a)) + a    # global indices
+        ls = np.take_along_axis(local.T, li - a, axis=1)
+        pad = k - li.shape[1]
+        if pad:
+            li = np.pad(li, ((0, 0), (0, pad)), constant_values=-1)
+            ls = np.pad(ls, ((0, 0), (0, pad)), constant_values=-np.inf)
+        gs, gi = slab.gather_topk(torch.from_numpy(ls.astype(np.float32)), torch.from_numpy(li), k)
+        row0 = torch.from_numpy(local[0].copy()) if rank == 0 else torch.zeros(X.shape[0])
+        row0 = slab.broadcast_row0_scores(row0, 0)
+        verts = np.full((rank + 2, 3), float(rank), np.float32)
+        faces = np.arange(3 * (rank + 1), dtype=np.int64).reshape(-1, 3) % (rank + 2)
+        mesh = slab.gather_mesh(verts, faces, dst=0)
+        np.savez(os.path.join(out_dir, "r%d.npz" % rank), gs=gs.numpy(), gi=gi.numpy(), row0=row0.numpy(),
+                 mv=mesh[0] if mesh else np.zeros(0), mf=mesh[1] if mesh else np.zeros(0))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_topk_row0_and_mesh_world2(tmp_path):
+    rng = np.random.default_rng(3)
+    M, C, T, k = 301, 16, 5, 9
+    F = rng.standard_normal((M, C)).astype(np.float32)
+    F[40] = F[250]      # a tie across the two slabs
+    X = rng.standard_normal((T, C)).astype(np.float32)
+    mp.spawn(_worker, args=(2, _free_port(), F, X, k, str(tmp_path)), nprocs=2, join=True)
+    full = O.normalize_rows(F) @ X.T
+    want = O.topk_indices(full, k)
+    for r in range(2):
+        z = np.load(tmp_path / ("r%d.npz" % r))
+        assert np.array_equal(z["gi"], want)
+        assert np.allclose(z["gs"], np.take_along_axis(full.T, want, axis=1), atol=1e-6)
+        assert np.allclose(z["row0"], full[0], atol=1e-6)
+    z0 = np.load(tmp_path / "r0.npz")
+    assert z0["mv"].shape == (2 + 3, 3) and z0["mf"].shape == (1 + 2, 3)
+    assert z0["mf"][1:].min() >= 2      # rank 1's faces re-based past rank 0's vertices
