@@ -42,10 +42,10 @@ struct FusionParams {
     uint64_t list_cap;
     uint64_t max_table_elems;
     uint32_t n_k1;             // number of K1 cull CTAs (segments of block_seg)
+    uint32_t slot;             // which of the two per-call scratch slots this call uses
     WsHeader* hdr;
     uint32_t* cta_count;       // [n_k1]              visible blocks found by each K1 CTA
     uint32_t* block_seg;       // [n_k1*256]          per-CTA ordered segments
-    uint32_t* block_list;      // [nblocks_total]     dense, ascending block ids (K1's last CTA)
     uint32_t* blk_count;       // [batch][nblocks_total]   valid voxels per visible block (by rank)
     uint32_t* blk_offset;      // [batch][nblocks_total+1] exclusive prefix of blk_count
     ValidEntry* lists;         // [batch][nblocks_total*512] rank r's entries start at r*512
@@ -302,9 +302,10 @@ __global__ void __launch_bounds__(kK2Threads) tsdf_update_kernel(const FusionPar
 {
     __shared__ uint32_t s_cnt[kK2Iter][kK2Threads / 32];
     __shared__ uint32_t s_scan[33];
-    __shared__ uint32_t s_off[kMaxK1Ctas];
+    extern __shared__ uint32_t s_off[];  // [n_k1]
     __shared__ bool is_last;
     WsHeader* hdr = p.hdr;
+    SlotCounters* sc = &hdr->slot[p.slot];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // K1 left one ordered segment of visible blocks per cull CTA: rank -> (segment, position)
     const uint32_t n_blocks = cta_exclusive_scan(p.cta_count, s_off, p.n_k1, s_scan);
@@ -422,12 +423,12 @@ __global__ void __launch_bounds__(kK2Threads) tsdf_update_kernel(const FusionPar
         uint32_t c = tv_count[b];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-        if (lane == 0 && c) atomicAdd(&hdr->n_tsdf_valid[b], c);
+        if (lane == 0 && c) atomicAdd(&sc->n_tsdf_valid[b], c);
     }
     // the last CTA turns the per-block counts into list offsets and folds the call into the totals
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) is_last = (atomicAdd(&hdr->k2_done, 1u) == gridDim.x - 1);
+    if (threadIdx.x == 0) is_last = (atomicAdd(&sc->k2_done, 1u) == gridDim.x - 1);
     __syncthreads();
     if (!is_last) return;
     __threadfence();
@@ -437,21 +438,22 @@ __global__ void __launch_bounds__(kK2Threads) tsdf_update_kernel(const FusionPar
         const uint32_t total = cta_exclusive_scan(p.blk_count + (uint64_t)b * p.nblocks_total, off, n_blocks, s_scan);
         if (threadIdx.x == 0) {
             off[n_blocks] = total;
-            hdr->n_valid[b] = total;
-            const uint32_t t = atomicExch(&hdr->n_tsdf_valid[b], 0u);
-            hdr->last_tsdf_valid[b] = t;
+            sc->n_valid[b] = total;
+            const uint32_t t = atomicExch(&sc->n_tsdf_valid[b], 0u);
+            sc->last_tsdf_valid[b] = t;
             sv += total;
             stv += t;
         }
     }
     if (threadIdx.x == 0) {
+        sc->frame_base_parity = (uint32_t)(hdr->total_frames & 1ull);
         hdr->total_valid += sv;
         hdr->total_tsdf_valid += stv;
         hdr->total_blocks += n_blocks;
         hdr->total_frames += (unsigned long long)B;
-        hdr->last_blocks = n_blocks;
-        hdr->n_blocks = n_blocks;
-        hdr->k2_done = 0;
+        hdr->last_slot = p.slot;
+        sc->n_blocks = n_blocks;
+        sc->k2_done = 0;
     }
 }
 
@@ -459,6 +461,9 @@ __global__ void __launch_bounds__(kK2Threads) tsdf_update_kernel(const FusionPar
 // K3: per-voxel feature / rgb / label accumulation (clip_seem_fusion.py:751-822)
 // ---------------------------------------------------------------------------------------------
 
+#ifndef K3_MAXNREG
+#define K3_MAXNREG 64
+#endif
 constexpr int kK3Warps = 16;
 constexpr int kK3Threads = kK3Warps * 32;
 
@@ -538,7 +543,7 @@ __device__ __forceinline__ float4 blend4(const float4& smp, const float4& old, f
 //   [ table: R*C floats (TABLE_SMEM) ][ ring: kK3Warps * NST rows of C floats ][ mbarriers ]
 // CHUNKS = C/128 float4 per lane; NST = ring stages per warp (rows in flight per warp).
 template <int CHUNKS, int NST, bool TABLE_SMEM>
-__global__ void __launch_bounds__(kK3Threads, 1)
+__global__ void __maxnreg__(K3_MAXNREG)
 feature_accumulate_kernel(const FusionParams p, const float* __restrict__ table, int64_t table_stride_r, int table_tma)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -546,9 +551,10 @@ feature_accumulate_kernel(const FusionParams p, const float* __restrict__ table,
     const saf_frame& f = p.frames[p.frame_index];
     const int R = f.npy * f.npx;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t n = p.hdr->n_valid[p.frame_index];
+    const SlotCounters* sc = &p.hdr->slot[p.slot];
+    const uint32_t n = sc->n_valid[p.frame_index];
     if (n == 0) return;
-    const uint32_t n_blocks = p.hdr->last_blocks;
+    const uint32_t n_blocks = sc->n_blocks;
 
     float* tab = reinterpret_cast<float*>(smem_raw);
     float* ring = tab + (TABLE_SMEM ? (size_t)R * C : 0);
@@ -584,7 +590,7 @@ feature_accumulate_kernel(const FusionParams p, const float* __restrict__ table,
     const uint32_t gwarp = blockIdx.x * kK3Warps + warp;
     const uint32_t k_total = n > gwarp ? (n - gwarp + nwarps - 1) / nwarps : 0;  // entries this warp owns
     // odd frames walk the list backwards (see the header comment)
-    const bool reverse = ((p.hdr->total_frames + (unsigned long long)p.frame_index) & 1ull) != 0;
+    const bool reverse = ((sc->frame_base_parity + (uint32_t)p.frame_index) & 1u) != 0;
     const ValidEntry* __restrict__ list = p.lists + (uint64_t)p.frame_index * p.list_cap;
     const uint32_t* __restrict__ off = p.blk_offset + (uint64_t)p.frame_index * (p.nblocks_total + 1);
     const float4* tab4 = reinterpret_cast<const float4*>(TABLE_SMEM ? tab : table);
@@ -667,8 +673,9 @@ __global__ void __launch_bounds__(kK3Threads) feature_accumulate_generic_kernel(
     const saf_frame& f = p.frames[p.frame_index];
     const int C = p.vol.feature_dim;
     const int lane = threadIdx.x & 31;
-    const uint32_t n = p.hdr->n_valid[p.frame_index];
-    const uint32_t n_blocks = p.hdr->last_blocks;
+    const SlotCounters* sc = &p.hdr->slot[p.slot];
+    const uint32_t n = sc->n_valid[p.frame_index];
+    const uint32_t n_blocks = sc->n_blocks;
     const uint32_t nwarps = gridDim.x * kK3Warps;
     const uint32_t gwarp = blockIdx.x * kK3Warps + (threadIdx.x >> 5);
     const ValidEntry* __restrict__ list = p.lists + (uint64_t)p.frame_index * p.list_cap;
@@ -758,7 +765,8 @@ int device_sm_count(int* sms, int* smem_optin)
 }
 
 static int build_params(const saf_grid_desc* grid, const saf_volume* vol, const saf_frame* frames, int32_t batch,
-                        int32_t H, int32_t W, float trunc, int32_t rgb_mode, const saf_workspace* ws, FusionParams* p)
+                        int32_t H, int32_t W, float trunc, int32_t rgb_mode, const saf_workspace* ws, FusionParams* p,
+                        uint32_t slot = 0)
 {
     if (!grid || !frames || !ws || !ws->base) return SAF_ERR_NULL;
     if (batch < 1 || batch > SAF_MAX_BATCH || batch > ws->max_batch) return SAF_ERR_BATCH;
@@ -792,13 +800,14 @@ static int build_params(const saf_grid_desc* grid, const saf_volume* vol, const 
     p->max_table_elems = (uint64_t)ws->max_table_elems;
     unsigned char* base = (unsigned char*)ws->base;
     p->hdr = (WsHeader*)base;
-    p->cta_count = (uint32_t*)(base + L.off_cta_count);
-    p->block_seg = (uint32_t*)(base + L.off_block_seg);
-    p->block_list = (uint32_t*)(base + L.off_blocks);
-    p->blk_count = (uint32_t*)(base + L.off_blk_count);
-    p->blk_offset = (uint32_t*)(base + L.off_blk_offset);
-    p->lists = (ValidEntry*)(base + L.off_lists);
-    p->tables = (float*)(base + L.off_tables);
+    p->slot = slot;
+    unsigned char* sb = base + L.slot0 + (uint64_t)slot * L.slot_stride;
+    p->cta_count = (uint32_t*)(sb + L.off_cta_count);
+    p->block_seg = (uint32_t*)(sb + L.off_block_seg);
+    p->blk_count = (uint32_t*)(sb + L.off_blk_count);
+    p->blk_offset = (uint32_t*)(sb + L.off_blk_offset);
+    p->lists = (ValidEntry*)(sb + L.off_lists);
+    p->tables = (float*)(sb + L.off_tables);
     return 0;
 }
 
@@ -836,9 +845,9 @@ static int launch_k2(const FusionParams& p, int sms, cudaStream_t st)
 {
     const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)p.nblocks_total, (uint64_t)sms * 16u);
     if (p.batch == 1)
-        tsdf_update_kernel<true><<<grid, kK2Threads, 0, st>>>(p);
+        tsdf_update_kernel<true><<<grid, kK2Threads, (size_t)p.n_k1 * 4, st>>>(p);
     else
-        tsdf_update_kernel<false><<<grid, kK2Threads, 0, st>>>(p);
+        tsdf_update_kernel<false><<<grid, kK2Threads, (size_t)p.n_k1 * 4, st>>>(p);
     SAF_CHECK_LAUNCH("tsdf_update_kernel (K2)", st);
     return 0;
 }
@@ -953,10 +962,11 @@ int saf_read_stats(const saf_workspace* ws, saf_stats* out, void* stream)
     out->total_valid = h.total_valid;
     out->total_tsdf_valid = h.total_tsdf_valid;
     out->total_blocks = h.total_blocks;
-    out->last_blocks = h.last_blocks;
+    const SlotCounters& sc = h.slot[h.last_slot & 1u];
+    out->last_blocks = sc.n_blocks;
     for (int b = 0; b < SAF_MAX_BATCH; ++b) {
-        out->last_valid[b] = h.n_valid[b];
-        out->last_tsdf_valid[b] = h.last_tsdf_valid[b];
+        out->last_valid[b] = sc.n_valid[b];
+        out->last_tsdf_valid[b] = sc.last_tsdf_valid[b];
     }
     out->error_flags = h.error_flags;
     return 0;
@@ -1008,6 +1018,29 @@ int saf_feature_accumulate(const saf_grid_desc* grid, const saf_volume* vol, con
     return launch_k3(p, frame_index, sms, smem_optin, (cudaStream_t)stream);
 }
 
+// K1 + K2 of one integrate() call on `st_geo`, then its K3 launches on `st_feat`.
+static int integrate_call(const saf_grid_desc* grid, const saf_volume* vol, const saf_frame* frames, int32_t batch,
+                          int32_t H, int32_t W, float trunc, int32_t rgb_mode, const saf_workspace* ws, uint32_t slot,
+                          int sms, int smem_optin, cudaStream_t st_geo, cudaStream_t st_feat, cudaEvent_t geo_done,
+                          cudaEvent_t feat_done)
+{
+    FusionParams p;
+    int rc = build_params(grid, vol, frames, batch, H, W, trunc, rgb_mode, ws, &p, slot);
+    if (rc) return rc;
+    rc = check_feature_args(vol, frames, batch, rgb_mode, ws, &p.pack_mask);
+    if (rc) return rc;
+    if ((rc = launch_k1(p, st_geo))) return rc;
+    if ((rc = launch_k2(p, sms, st_geo))) return rc;
+    if (geo_done) {
+        SAF_CUDA_TRY(cudaEventRecord(geo_done, st_geo));
+        SAF_CUDA_TRY(cudaStreamWaitEvent(st_feat, geo_done, 0));
+    }
+    for (int b = 0; b < batch; ++b)
+        if ((rc = launch_k3(p, b, sms, smem_optin, st_feat))) return rc;
+    if (feat_done) SAF_CUDA_TRY(cudaEventRecord(feat_done, st_feat));
+    return 0;
+}
+
 int saf_integrate(const saf_grid_desc* grid, const saf_volume* vol, const saf_frame* frames, int32_t batch, int32_t H,
                   int32_t W, float trunc, int32_t rgb_mode, const saf_workspace* ws, void* stream)
 {
@@ -1015,27 +1048,71 @@ int saf_integrate(const saf_grid_desc* grid, const saf_volume* vol, const saf_fr
     int rc = device_sm_count(&sms, &smem_optin);
     if (rc) return rc;
     if (!(trunc > 0.f)) return SAF_ERR_SHAPE;
-    FusionParams p;
-    rc = build_params(grid, vol, frames, batch, H, W, trunc, rgb_mode, ws, &p);
-    if (rc) return rc;
-    rc = check_feature_args(vol, frames, batch, rgb_mode, ws, &p.pack_mask);
-    if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if ((rc = launch_k1(p, st))) return rc;
-    if ((rc = launch_k2(p, sms, st))) return rc;
-    for (int b = 0; b < batch; ++b)
-        if ((rc = launch_k3(p, b, sms, smem_optin, st))) return rc;
-    return 0;
+    return integrate_call(grid, vol, frames, batch, H, W, trunc, rgb_mode, ws, 0, sms, smem_optin, st, st, nullptr, nullptr);
 }
 
+// The reference's frame loop.  Frames are independent except through the volume, and K1/K2 touch only the
+// TSDF state while K3 touches only weight / rgb / features / labels, so K1+K2 of frame i+1 run on a side
+// stream underneath K3 of frame i (the two scratch slots of the workspace alternate).
 int saf_integrate_sequence(const saf_grid_desc* grid, const saf_volume* vol, const saf_frame* frames, int32_t n_frames,
                            int32_t H, int32_t W, float trunc, int32_t rgb_mode, const saf_workspace* ws, void* stream)
 {
     if (n_frames < 0) return SAF_ERR_BATCH;
-    for (int32_t i = 0; i < n_frames; ++i) {
-        int rc = saf_integrate(grid, vol, frames + i, 1, H, W, trunc, rgb_mode, ws, stream);
-        if (rc) return rc;
+    int sms = 0, smem_optin = 0;
+    int rc = device_sm_count(&sms, &smem_optin);
+    if (rc) return rc;
+    if (!(trunc > 0.f)) return SAF_ERR_SHAPE;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_frames < 4) {
+        for (int32_t i = 0; i < n_frames; ++i) {
+            rc = integrate_call(grid, vol, frames + i, 1, H, W, trunc, rgb_mode, ws, 0, sms, smem_optin, st, st, nullptr,
+                                nullptr);
+            if (rc) return rc;
+        }
+        return 0;
     }
+    cudaStream_t side = nullptr;
+    cudaEvent_t fork = nullptr, geo_done[2] = {nullptr, nullptr}, feat_done[2] = {nullptr, nullptr};
+    auto cleanup = [&]() {
+        if (fork) cudaEventDestroy(fork);
+        for (int s = 0; s < 2; ++s) {
+            if (geo_done[s]) cudaEventDestroy(geo_done[s]);
+            if (feat_done[s]) cudaEventDestroy(feat_done[s]);
+        }
+        if (side) cudaStreamDestroy(side);
+    };
+#define SAF_SEQ_TRY(expr)                      \
+    do {                                       \
+        cudaError_t _e = (expr);               \
+        if (_e != cudaSuccess) {               \
+            cleanup();                         \
+            return (int)_e;                    \
+        }                                      \
+    } while (0)
+    SAF_SEQ_TRY(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    SAF_SEQ_TRY(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+    for (int s = 0; s < 2; ++s) {
+        SAF_SEQ_TRY(cudaEventCreateWithFlags(&geo_done[s], cudaEventDisableTiming));
+        SAF_SEQ_TRY(cudaEventCreateWithFlags(&feat_done[s], cudaEventDisableTiming));
+    }
+    // the side stream starts after everything already queued on the caller's stream
+    SAF_SEQ_TRY(cudaEventRecord(fork, st));
+    SAF_SEQ_TRY(cudaStreamWaitEvent(side, fork, 0));
+    for (int32_t i = 0; i < n_frames; ++i) {
+        const uint32_t slot = (uint32_t)(i & 1);
+        // slot reuse: K3 of frame i-2 must have finished reading this slot's lists
+        if (i >= 2) SAF_SEQ_TRY(cudaStreamWaitEvent(side, feat_done[slot], 0));
+        rc = integrate_call(grid, vol, frames + i, 1, H, W, trunc, rgb_mode, ws, slot, sms, smem_optin, side, st,
+                            geo_done[slot], feat_done[slot]);
+        if (rc) {
+            cleanup();
+            return rc;
+        }
+    }
+#undef SAF_SEQ_TRY
+    // the caller's stream already waits on the last K2 through geo_done; nothing else runs on `side`
+    cleanup();
     return 0;
 }
 

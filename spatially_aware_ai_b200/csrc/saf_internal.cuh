@@ -18,19 +18,25 @@ constexpr uint64_t kWsMagic = 0x5341465f42323030ull;  // "SAF_B200"
 constexpr int kBlockEdge = SAF_BLOCK_EDGE;
 constexpr int kBlockVoxels = kBlockEdge * kBlockEdge * kBlockEdge;
 
-// Device-resident workspace header (512 bytes).  Per-call counters are produced by the kernels
-// themselves (no host memsets): K1's last CTA publishes n_blocks and the dense ordered block list,
-// K2's last CTA publishes the per-block list offsets, n_valid and the running totals.
-struct WsHeader {
-    uint32_t n_blocks;                      // visible blocks of the call in flight (written by K1's last CTA)
-    uint32_t k1_done;                       // CTA completion ticket of K1
+// Per-call counters.  There are two slots so that K1/K2 of frame i+1 (side stream) can run while K3 of
+// frame i (main stream) is still consuming frame i's lists (saf_integrate_sequence).  They are produced
+// by the kernels themselves (no host memsets): K2's last CTA publishes the per-block list offsets,
+// n_valid, the frame parity K3 uses for its zig-zag walk, and folds the call into the running totals.
+struct SlotCounters {
+    uint32_t n_blocks;                      // visible blocks of the call (written by K2's last CTA)
     uint32_t k2_done;                       // CTA completion ticket of K2
-    uint32_t error_flags;
-    uint32_t last_blocks;
-    uint32_t pad0_[3];
-    uint32_t n_valid[SAF_MAX_BATCH];        // length of each frame's valid list (written by K2's last CTA)
-    uint32_t n_tsdf_valid[SAF_MAX_BATCH];   // per-call accumulators (atomics), folded and zeroed by K2's last CTA
+    uint32_t frame_base_parity;             // total_frames before this call, & 1
+    uint32_t pad_;
+    uint32_t n_valid[SAF_MAX_BATCH];        // length of each frame's valid list
+    uint32_t n_tsdf_valid[SAF_MAX_BATCH];   // accumulators (atomics), folded and zeroed by K2's last CTA
     uint32_t last_tsdf_valid[SAF_MAX_BATCH];
+};
+
+// Device-resident workspace header (512 bytes).
+struct WsHeader {
+    SlotCounters slot[2];
+    uint32_t error_flags;
+    uint32_t last_slot;                     // slot of the most recent call (for saf_read_stats)
     unsigned long long total_frames;
     unsigned long long total_valid;
     unsigned long long total_tsdf_valid;
@@ -59,13 +65,14 @@ constexpr int kK1Threads = 256;             // blocks tested per K1 CTA (one per
 constexpr uint32_t kMaxK1Ctas = 2048;       // K1's last CTA scans this many per-CTA counts in shared memory
 
 // Workspace layout (all offsets 256-byte aligned):
-//   header | cta_count[n_k1] | block_seg[n_k1*256] | block_list[nblocks_total]
-//   | blk_count[max_batch][nblocks_total] | blk_offset[max_batch][nblocks_total+1]
-//   | lists[max_batch][nblocks_total*512] | tables[max_batch][max_table_elems]
+//   header | slot 0 | slot 1        with, per slot,
+//   cta_count[n_k1] | block_seg[n_k1*256] | blk_count[max_batch][nblocks_total]
+//   | blk_offset[max_batch][nblocks_total+1] | lists[max_batch][nblocks_total*512] | tables[max_batch][max_table_elems]
 struct WsLayout {
     uint64_t bytes;
     uint64_t list_cap;
-    uint64_t off_cta_count, off_block_seg, off_blocks, off_blk_count, off_blk_offset, off_lists, off_tables;
+    uint64_t slot0, slot_stride;            // byte offset of slot 0 and distance to slot 1
+    uint64_t off_cta_count, off_block_seg, off_blk_count, off_blk_offset, off_lists, off_tables;  // within a slot
     uint32_t nblocks_total;
     uint32_t n_k1;
     uint32_t nb[3];
@@ -92,14 +99,15 @@ inline int compute_layout(const saf_grid_desc* g, int32_t max_batch, int64_t max
     if (L->n_k1 > kMaxK1Ctas) return SAF_ERR_GRID;  // > 268 M voxels in one slab: shard it
     L->nblocks_total = (uint32_t)nblocks;
     L->list_cap = nblocks * kBlockVoxels;
-    L->off_cta_count = 512;
+    L->off_cta_count = 0;
     L->off_block_seg = align_up(L->off_cta_count + 4ull * L->n_k1, 256);
-    L->off_blocks = align_up(L->off_block_seg + 4ull * L->n_k1 * kK1Threads, 256);
-    L->off_blk_count = align_up(L->off_blocks + 4ull * nblocks, 256);
+    L->off_blk_count = align_up(L->off_block_seg + 4ull * L->n_k1 * kK1Threads, 256);
     L->off_blk_offset = align_up(L->off_blk_count + 4ull * max_batch * nblocks, 256);
     L->off_lists = align_up(L->off_blk_offset + 4ull * max_batch * (nblocks + 1), 256);
     L->off_tables = align_up(L->off_lists + (uint64_t)max_batch * L->list_cap * sizeof(ValidEntry), 256);
-    L->bytes = align_up(L->off_tables + (uint64_t)max_batch * (uint64_t)max_table_elems * 4ull, 256);
+    L->slot_stride = align_up(L->off_tables + (uint64_t)max_batch * (uint64_t)max_table_elems * 4ull, 256);
+    L->slot0 = 512;
+    L->bytes = L->slot0 + 2 * L->slot_stride;
     return 0;
 }
 
