@@ -8,7 +8,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsaf_b200.so")
+# SAF_LIB_PATH: load another build of the same ABI (A/B timing of kernel variants)
+LIB_PATH = os.environ.get("SAF_LIB_PATH") or os.path.join(HERE, "libsaf_b200.so")
 
 SAF_ABI_VERSION = 1
 SAF_MAX_BATCH = 8
