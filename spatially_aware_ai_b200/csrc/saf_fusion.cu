@@ -12,9 +12,9 @@
 //                              the bilinear sample of the frame's [R,C] table (also TMA-staged in
 //                              shared memory) and streamed back with 128-bit stores; rgb, label
 //                              counter and weight are handled one lane per voxel.
-// The lists are deterministic and spatially ordered (ascending block, then voxel) so that K3 can
-// walk them forwards on even frames and backwards on odd frames: the rows a frame wrote last are
-// the first ones the next frame reads, which turns the 126 MB L2 into a cross-frame cache.
+// The lists are deterministic and spatially ordered (ascending block, then voxel): each K3 warp takes a
+// contiguous run of them, i.e. neighbouring voxels, which keeps its feature rows close together in DRAM
+// and lets the per-voxel 4-byte accesses (weight, rgb, label counter) of its lanes share sectors.
 // All decisions that feed masks use explicitly rounded intrinsics in the reference's op order;
 // this file is compiled with -fmad=false so nothing is contracted behind our back.
 #include <limits.h>
@@ -586,11 +586,13 @@ feature_accumulate_kernel(const FusionParams p, const float* __restrict__ table,
     }
     bool table_ready = !(TABLE_SMEM && table_tma);
 
+    // each warp owns a contiguous run of the (spatially ordered) list: its voxels are neighbours, so the
+    // rows it streams are close in memory and the lanes' small-state accesses share sectors
     const uint32_t nwarps = gridDim.x * kK3Warps;
     const uint32_t gwarp = blockIdx.x * kK3Warps + warp;
-    const uint32_t k_total = n > gwarp ? (n - gwarp + nwarps - 1) / nwarps : 0;  // entries this warp owns
-    // odd frames walk the list backwards (see the header comment)
-    const bool reverse = ((sc->frame_base_parity + (uint32_t)p.frame_index) & 1u) != 0;
+    const uint32_t per_warp = (n + nwarps - 1) / nwarps;
+    const uint32_t first = min(n, gwarp * per_warp);
+    const uint32_t k_total = min(n, first + per_warp) - first;  // entries this warp owns
     const ValidEntry* __restrict__ list = p.lists + (uint64_t)p.frame_index * p.list_cap;
     const uint32_t* __restrict__ off = p.blk_offset + (uint64_t)p.frame_index * (p.nblocks_total + 1);
     const float4* tab4 = reinterpret_cast<const float4*>(TABLE_SMEM ? tab : table);
@@ -605,9 +607,7 @@ feature_accumulate_kernel(const FusionParams p, const float* __restrict__ table,
         mine.gx = mine.gy = 0.0f;
         int my_w = 0;
         if (lane < cnt) {
-            uint32_t i = gwarp + (kb + lane) * nwarps;
-            if (reverse) i = n - 1 - i;
-            mine = fetch_entry(list, off, n_blocks, i);
+            mine = fetch_entry(list, off, n_blocks, first + kb + lane);
             my_w = p.vol.weight[mine.voxel];
         }
         // start the first rows of the batch before spending time on the small state
