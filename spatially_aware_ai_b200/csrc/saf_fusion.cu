@@ -426,9 +426,12 @@ __global__ void __launch_bounds__(kK2Threads) tsdf_update_kernel(const FusionPar
         if (lane == 0 && c) atomicAdd(&sc->n_tsdf_valid[b], c);
     }
     // the last CTA turns the per-block counts into list offsets and folds the call into the totals
-    __threadfence();
+    // (one fence by the ticket-taking thread after the CTA barrier publishes the whole CTA's writes)
     __syncthreads();
-    if (threadIdx.x == 0) is_last = (atomicAdd(&sc->k2_done, 1u) == gridDim.x - 1);
+    if (threadIdx.x == 0) {
+        __threadfence();
+        is_last = (atomicAdd(&sc->k2_done, 1u) == gridDim.x - 1);
+    }
     __syncthreads();
     if (!is_last) return;
     __threadfence();
@@ -843,7 +846,7 @@ static int launch_k1(const FusionParams& p, cudaStream_t st)
 
 static int launch_k2(const FusionParams& p, int sms, cudaStream_t st)
 {
-    const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)p.nblocks_total, (uint64_t)sms * 16u);
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)p.nblocks_total, (uint64_t)sms * 8u);
     if (p.batch == 1)
         tsdf_update_kernel<true><<<grid, kK2Threads, (size_t)p.n_k1 * 4, st>>>(p);
     else
