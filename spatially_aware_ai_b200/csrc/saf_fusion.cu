@@ -45,6 +45,7 @@ struct FusionParams {
     uint32_t slot;             // which of the two per-call scratch slots this call uses
     WsHeader* hdr;
     uint32_t* cta_count;       // [n_k1]              visible blocks found by each K1 CTA
+    float* cta_dmax;           // [batch][n_k1]       largest depth in each K1 CTA's slice of the depth image
     uint32_t* block_seg;       // [n_k1*256]          per-CTA ordered segments
     uint32_t* blk_count;       // [batch][nblocks_total]   valid voxels per visible block (by rank)
     uint32_t* blk_offset;      // [batch][nblocks_total+1] exclusive prefix of blk_count
@@ -194,6 +195,34 @@ __device__ __forceinline__ bool block_maybe_visible(const Geom& g, float cx, flo
     return !cull;
 }
 
+// bounding sphere (world centre, radius) of the voxel centres of block (bx,by,bz) of the slab
+__device__ __forceinline__ void block_sphere(const FusionParams& p, uint32_t bx, uint32_t by, uint32_t bz, float& cx,
+                                             float& cy, float& cz, float& r)
+{
+    const int x0 = (int)bx * kBlockEdge, y0 = (int)by * kBlockEdge, z0 = (int)bz * kBlockEdge;
+    const int ex = min(kBlockEdge, (int)p.nxs - x0), ey = min(kBlockEdge, p.grid.nvox[1] - y0),
+              ez = min(kBlockEdge, p.grid.nvox[2] - z0);
+    const float vs = p.grid.voxel_size;
+    const float hx = 0.5f * vs * (float)(ex - 1), hy = 0.5f * vs * (float)(ey - 1), hz = 0.5f * vs * (float)(ez - 1);
+    cx = p.grid.origin[0] + vs * (float)(p.grid.x_begin + x0) + hx;
+    cy = p.grid.origin[1] + vs * (float)y0 + hy;
+    cz = p.grid.origin[2] + vs * (float)z0 + hz;
+    r = sqrtf(hx * hx + hy * hy + hz * hz) + 0.01f * vs;
+}
+
+// smallest camera-space z = K[2,:] . R^T (x - t) over the block's bounding sphere, minus rounding slack
+__device__ __forceinline__ float block_z_min(const Geom& g, float cx, float cy, float cz, float r)
+{
+    const float d0 = cx - g.P[3], d1 = cy - g.P[7], d2 = cz - g.P[11];
+    float pc[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) pc[k] = g.P[k] * d0 + g.P[4 + k] * d1 + g.P[8 + k] * d2;
+    const float plen = sqrtf(pc[0] * pc[0] + pc[1] * pc[1] + pc[2] * pc[2]) + r;
+    const float dot = g.K[6] * pc[0] + g.K[7] * pc[1] + g.K[8] * pc[2];
+    const float nlen = sqrtf(g.K[6] * g.K[6] + g.K[7] * g.K[7] + g.K[8] * g.K[8]);
+    return dot - nlen * r - 1e-3f * nlen * plen - 1e-6f;
+}
+
 // exclusive prefix sum of n values (global, read through L2) by one CTA (blockDim.x a multiple of 32,
 // at most 1024); returns the total to every thread.  scratch: 33 uint32 in shared memory.
 __device__ uint32_t cta_exclusive_scan(const uint32_t* src, uint32_t* dst, uint32_t n, uint32_t* scratch)
@@ -260,21 +289,33 @@ __global__ void __launch_bounds__(kK1Threads) frame_setup_kernel(const FusionPar
         const uint32_t bz = blk % p.nb[2];
         const uint32_t by = (blk / p.nb[2]) % p.nb[1];
         const uint32_t bx = blk / (p.nb[2] * p.nb[1]);
-        const int x0 = (int)bx * kBlockEdge, y0 = (int)by * kBlockEdge, z0 = (int)bz * kBlockEdge;
-        const int ex = min(kBlockEdge, (int)p.nxs - x0), ey = min(kBlockEdge, p.grid.nvox[1] - y0),
-                  ez = min(kBlockEdge, p.grid.nvox[2] - z0);
-        const float vs = p.grid.voxel_size;
-        const float hx = 0.5f * vs * (float)(ex - 1), hy = 0.5f * vs * (float)(ey - 1), hz = 0.5f * vs * (float)(ez - 1);
-        const float cx = p.grid.origin[0] + vs * (float)(p.grid.x_begin + x0) + hx;
-        const float cy = p.grid.origin[1] + vs * (float)y0 + hy;
-        const float cz = p.grid.origin[2] + vs * (float)z0 + hz;
-        const float r = sqrtf(hx * hx + hy * hy + hz * hz) + 0.01f * vs;
+        float cx, cy, cz, r;
+        block_sphere(p, bx, by, bz, cx, cy, cz, r);
         const float fW = (float)p.W, fH = (float)p.H;
         for (int b = 0; b < p.batch; ++b) {
             Geom g;
             load_geom(p.frames[b], g);
             vis |= block_maybe_visible(g, cx, cy, cz, r, fW, fH);
         }
+    }
+    // this CTA's share of the frames' depth maxima (K2 combines the shares; used for its depth cull)
+    __shared__ float s_dmax[kK1Threads / 32];
+    for (int b = 0; b < (p.hdr->depth_cull ? p.batch : 0); ++b) {
+        const int npix = p.H * p.W;
+        const int per = (npix + (int)cull_ctas - 1) / (int)cull_ctas;
+        const int lo = min(npix, (int)blockIdx.x * per), hi = min(npix, lo + per);
+        float dm = 0.0f;
+        for (int i = lo + threadIdx.x; i < hi; i += kK1Threads) dm = fmaxf(dm, __ldg(p.frames[b].depth + i));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dm = fmaxf(dm, __shfl_xor_sync(0xffffffffu, dm, o));
+        if (lane == 0) s_dmax[warp] = dm;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int w = 1; w < kK1Threads / 32; ++w) dm = fmaxf(dm, s_dmax[w]);
+            p.cta_dmax[(size_t)b * p.n_k1 + blockIdx.x] = dm;
+        }
+        __syncthreads();
     }
     // ordered compaction inside the CTA: this CTA's visible blocks, ascending, into its own segment
     const unsigned m = __ballot_sync(0xffffffffu, vis);
@@ -309,6 +350,23 @@ __global__ void __launch_bounds__(kK2Threads) tsdf_update_kernel(const FusionPar
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // K1 left one ordered segment of visible blocks per cull CTA: rank -> (segment, position)
     const uint32_t n_blocks = cta_exclusive_scan(p.cta_count, s_off, p.n_k1, s_scan);
+    // farthest surface of each frame: a voxel is tsdf_valid only if z < depth + trunc <= dmax + trunc
+    // (clip_seem_fusion.py:722-728), so blocks entirely behind that are skipped.  NaN depths never win fmaxf.
+    __shared__ float s_zfar[SAF_MAX_BATCH];
+    const bool depth_cull = hdr->depth_cull != 0;
+    uint32_t processed = 0;
+    if (threadIdx.x < SAF_MAX_BATCH) s_zfar[threadIdx.x] = INFINITY;  // lanes of warp 0
+    __syncwarp();
+    if (warp == 0 && depth_cull) {
+        for (int b = 0; b < (BATCH1 ? 1 : p.batch); ++b) {
+            float dm = 0.0f;
+            for (uint32_t c = lane; c < p.n_k1; c += 32) dm = fmaxf(dm, __ldcg(p.cta_dmax + (size_t)b * p.n_k1 + c));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) dm = fmaxf(dm, __shfl_xor_sync(0xffffffffu, dm, o));
+            if (lane == 0) s_zfar[b] = (dm + p.trunc) * 1.001f + 1e-5f;
+        }
+    }
+    __syncthreads();
     const int B = BATCH1 ? 1 : p.batch;
     const float fW = (float)p.W, fH = (float)p.H;
     const int ny = p.grid.nvox[1], nz = p.grid.nvox[2];
@@ -331,6 +389,20 @@ __global__ void __launch_bounds__(kK2Threads) tsdf_update_kernel(const FusionPar
         const uint32_t bz = blk % p.nb[2];
         const uint32_t by = (blk / p.nb[2]) % p.nb[1];
         const uint32_t bx = blk / (p.nb[2] * p.nb[1]);
+        if (depth_cull) {
+            float cx, cy, cz, r;
+            block_sphere(p, bx, by, bz, cx, cy, cz, r);
+            bool reachable = false;
+            for (int b = 0; b < B; ++b) {
+                if (!BATCH1) load_geom(p.frames[b], g);
+                reachable |= !(block_z_min(g, cx, cy, cz, r) > s_zfar[b]);  // NaN -> keep
+            }
+            if (!reachable) {  // CTA-uniform: the whole block lies behind every frame's farthest surface
+                if (threadIdx.x < B) p.blk_count[(uint64_t)threadIdx.x * p.nblocks_total + bi] = 0;
+                continue;
+            }
+        }
+        processed += 1;
         float xw[kK2Iter], yw[kK2Iter], zw[kK2Iter], t_old[kK2Iter], bt[kK2Iter];
         uint32_t v[kK2Iter];
         int tw[kK2Iter], bw[kK2Iter];
@@ -429,6 +501,7 @@ __global__ void __launch_bounds__(kK2Threads) tsdf_update_kernel(const FusionPar
     // (one fence by the ticket-taking thread after the CTA barrier publishes the whole CTA's writes)
     __syncthreads();
     if (threadIdx.x == 0) {
+        if (processed) atomicAdd(&sc->n_processed, processed);
         __threadfence();
         is_last = (atomicAdd(&sc->k2_done, 1u) == gridDim.x - 1);
     }
@@ -449,6 +522,17 @@ __global__ void __launch_bounds__(kK2Threads) tsdf_update_kernel(const FusionPar
         }
     }
     if (threadIdx.x == 0) {
+        // depth-cull policy for the next calls: on while fewer than a quarter of the visited voxels were
+        // tsdf_valid (many blocks behind the surfaces), off again (with a cool-down) if it removes < 1/8
+        const uint32_t n_proc = atomicExch(&sc->n_processed, 0u);
+        if (!depth_cull) {
+            if (hdr->depth_cull_cooldown) hdr->depth_cull_cooldown -= 1;
+            else if (n_blocks >= 64 && stv * 4ull < (unsigned long long)n_proc * kBlockVoxels * (unsigned long long)B)
+                hdr->depth_cull = 1;
+        } else if ((n_blocks - n_proc) * 8u < n_blocks) {
+            hdr->depth_cull = 0;
+            hdr->depth_cull_cooldown = 64;
+        }
         sc->frame_base_parity = (uint32_t)(hdr->total_frames & 1ull);
         hdr->total_valid += sv;
         hdr->total_tsdf_valid += stv;
@@ -806,6 +890,7 @@ static int build_params(const saf_grid_desc* grid, const saf_volume* vol, const 
     p->slot = slot;
     unsigned char* sb = base + L.slot0 + (uint64_t)slot * L.slot_stride;
     p->cta_count = (uint32_t*)(sb + L.off_cta_count);
+    p->cta_dmax = (float*)(sb + L.off_cta_dmax);
     p->block_seg = (uint32_t*)(sb + L.off_block_seg);
     p->blk_count = (uint32_t*)(sb + L.off_blk_count);
     p->blk_offset = (uint32_t*)(sb + L.off_blk_offset);

@@ -30,6 +30,8 @@ struct SlotCounters {
     uint32_t n_valid[SAF_MAX_BATCH];        // length of each frame's valid list
     uint32_t n_tsdf_valid[SAF_MAX_BATCH];   // accumulators (atomics), folded and zeroed by K2's last CTA
     uint32_t last_tsdf_valid[SAF_MAX_BATCH];
+    uint32_t n_processed;                   // blocks K2 did not skip by the depth test (atomic, zeroed like above)
+    uint32_t pad2_[3];
 };
 
 // Device-resident workspace header (512 bytes).
@@ -37,6 +39,10 @@ struct WsHeader {
     SlotCounters slot[2];
     uint32_t error_flags;
     uint32_t last_slot;                     // slot of the most recent call (for saf_read_stats)
+    // Depth-aware block culling costs two extra L2 round trips on the K1 -> K2 critical path, so it is only
+    // switched on (by K2's last CTA, for the following calls) while it pays: see tsdf_update_kernel.
+    uint32_t depth_cull;
+    uint32_t depth_cull_cooldown;
     unsigned long long total_frames;
     unsigned long long total_valid;
     unsigned long long total_tsdf_valid;
@@ -66,13 +72,13 @@ constexpr uint32_t kMaxK1Ctas = 2048;       // K1's last CTA scans this many per
 
 // Workspace layout (all offsets 256-byte aligned):
 //   header | slot 0 | slot 1        with, per slot,
-//   cta_count[n_k1] | block_seg[n_k1*256] | blk_count[max_batch][nblocks_total]
+//   cta_count[n_k1] | cta_dmax[max_batch][n_k1] | block_seg[n_k1*256] | blk_count[max_batch][nblocks_total]
 //   | blk_offset[max_batch][nblocks_total+1] | lists[max_batch][nblocks_total*512] | tables[max_batch][max_table_elems]
 struct WsLayout {
     uint64_t bytes;
     uint64_t list_cap;
     uint64_t slot0, slot_stride;            // byte offset of slot 0 and distance to slot 1
-    uint64_t off_cta_count, off_block_seg, off_blk_count, off_blk_offset, off_lists, off_tables;  // within a slot
+    uint64_t off_cta_count, off_cta_dmax, off_block_seg, off_blk_count, off_blk_offset, off_lists, off_tables;  // within a slot
     uint32_t nblocks_total;
     uint32_t n_k1;
     uint32_t nb[3];
@@ -100,7 +106,8 @@ inline int compute_layout(const saf_grid_desc* g, int32_t max_batch, int64_t max
     L->nblocks_total = (uint32_t)nblocks;
     L->list_cap = nblocks * kBlockVoxels;
     L->off_cta_count = 0;
-    L->off_block_seg = align_up(L->off_cta_count + 4ull * L->n_k1, 256);
+    L->off_cta_dmax = align_up(L->off_cta_count + 4ull * L->n_k1, 256);
+    L->off_block_seg = align_up(L->off_cta_dmax + 4ull * max_batch * L->n_k1, 256);
     L->off_blk_count = align_up(L->off_block_seg + 4ull * L->n_k1 * kK1Threads, 256);
     L->off_blk_offset = align_up(L->off_blk_count + 4ull * max_batch * nblocks, 256);
     L->off_lists = align_up(L->off_blk_offset + 4ull * max_batch * (nblocks + 1), 256);

@@ -343,3 +343,30 @@ def test_query_topk_tensor_core_falls_back_on_mass_ties():
     ts, ti = saf.query_topk(Fd, Xd, k, norm="nan_to_num", mode="dot", precision="tf32")
     assert np.array_equal(_np(ti), np.tile(np.arange(k), (T, 1)))
     assert not _np(ts).any()
+
+
+def test_depth_aware_block_culling_keeps_results():
+    """Near occluders (depth clipped to 0.6 m in a 2 m room) leave most frustum blocks behind the surface:
+    K2's adaptive depth cull switches on after the first frames and must not change any result."""
+    cfg = synth.SceneConfig(extent=(2.2, 2.0, 1.6), voxel_size=0.05, height=48, width=64, patch_size=32,
+                            patch_stride=16, feature_dim=8, frames=8, seed=31)
+    origin, nvox = cfg.grid()
+    g = dict(cls="ClipSeemFusion", feature_dim=8, origin=origin, nvox=nvox, voxel_size=cfg.voxel_size, trunc=cfg.trunc)
+    vol, clip, seg = Hh.make_gpu_volume(g)
+    orc = O.OracleVolume(origin, cfg.voxel_size, nvox, cfg.trunc, 8, num_threads=4)
+    blocks = []
+    for i in range(cfg.frames):
+        fr = synth.make_frame(cfg, i)
+        fr["depth"] = np.minimum(fr["depth"], np.float32(0.6))
+        if i == 5:
+            fr["depth"][:4] = np.nan          # NaN depths must neither crash the cull nor be used as the maximum
+        clip.next_table = torch.from_numpy(fr["table"]).cuda()[None]
+        seg.queue = [torch.from_numpy(fr["seg"]).cuda()]
+        vol.integrate(torch.from_numpy(fr["depth"]).cuda()[None], torch.from_numpy(fr["rgb"]).cuda()[None],
+                      torch.from_numpy(fr["pose"]).cuda()[None], torch.from_numpy(fr["K"]).cuda()[None])
+        orc.integrate(fr["depth"][None], fr["rgb"][None], fr["pose"][None], fr["K"][None], fr["table"][None],
+                      fr["seg"][None], want_masks=False)
+        st = vol.stats()
+        blocks.append(st["last_blocks"])
+        assert st["last_valid"][0] == orc.last_counts[0, 0] and st["last_tsdf_valid"][0] == orc.last_counts[0, 1]
+    _check_against(vol, orc.tsdf, orc.weight, orc.tsdf_weight, orc.rgb, orc.clip_feat, orc.labels_one_hot, exact=True)
