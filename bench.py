@@ -55,6 +55,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--ref-frames-per-step", type=int, default=4)
+    ap.add_argument("--rooms", type=int, default=0, help="debug: emulate the N-room multi-GPU workload on this rank only")
     return ap.parse_args()
 
 
@@ -72,7 +73,7 @@ def workload_name(cfg, n_rooms):
         cfg.name, cfg.width, cfg.height, cfg.voxel_size * 100, cfg.extent[0], cfg.extent[1], cfg.extent[2],
         nv[0], nv[1], nv[2], np.prod(nv) / 1e6, cfg.feature_dim, cfg.npatches[0], cfg.npatches[1])
     if n_rooms > 1:
-        s += "; %d rooms side by side along x, one x-slab per rank" % n_rooms
+        s += "; %d rooms side by side along x (20 cm partition walls), one x-slab per rank" % n_rooms
     return s
 
 
@@ -228,13 +229,17 @@ def run_native_arm(args):
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
-    n_rooms = world
+    n_rooms = args.rooms if (args.rooms and world == 1) else world
     cfg = scene_config(args, n_rooms)
     origin, nvox_room = cfg.grid()
+    # multi-room scans: each slab is one room plus a 20 cm partition wall towards the next room
+    wall_vox = int(round(0.2 / cfg.voxel_size)) if n_rooms > 1 else 0
+    slab_nx = int(nvox_room[0]) + wall_vox
     nvox = nvox_room.copy()
-    nvox[0] = nvox_room[0] * n_rooms
-    room_dx = nvox_room[0] * cfg.voxel_size       # world-space width of one room slab
-    x_begin, x_end = rank * int(nvox_room[0]), (rank + 1) * int(nvox_room[0])
+    nvox[0] = slab_nx * n_rooms
+    room_dx = slab_nx * cfg.voxel_size            # world-space pitch of the rooms
+    own = rank if world > 1 else 0
+    x_begin, x_end = own * slab_nx, (own + 1) * slab_nx
     lib = _lib.load()
 
     clip, seg = FakeClip(cfg.feature_dim), FakeSeg()

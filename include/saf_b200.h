@@ -116,6 +116,8 @@ typedef struct saf_stats {
     uint32_t last_valid[SAF_MAX_BATCH];
     uint32_t last_tsdf_valid[SAF_MAX_BATCH];
     uint32_t error_flags;        /* SAF_FLAG_* (sticky)                                               */
+    uint32_t last_processed;     /* visible blocks of the last call that survived K2's depth test     */
+    uint32_t depth_cull_on;      /* 1 while the adaptive depth-aware block cull is switched on        */
 } saf_stats;
 
 /* Caller-owned device scratch.  `base` is a device allocation of `bytes` (>= saf_workspace_bytes

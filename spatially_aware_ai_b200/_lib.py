@@ -47,7 +47,8 @@ class Stats(ctypes.Structure):
     _fields_ = [("total_frames", c_uint64), ("total_valid", c_uint64), ("total_tsdf_valid", c_uint64),
                 ("total_blocks", c_uint64), ("last_blocks", ctypes.c_uint32),
                 ("last_valid", ctypes.c_uint32 * SAF_MAX_BATCH), ("last_tsdf_valid", ctypes.c_uint32 * SAF_MAX_BATCH),
-                ("error_flags", ctypes.c_uint32)]
+                ("error_flags", ctypes.c_uint32), ("last_processed", ctypes.c_uint32),
+                ("depth_cull_on", ctypes.c_uint32)]
 
 
 class Workspace(ctypes.Structure):

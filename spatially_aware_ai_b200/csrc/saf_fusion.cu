@@ -45,7 +45,8 @@ struct FusionParams {
     uint32_t slot;             // which of the two per-call scratch slots this call uses
     WsHeader* hdr;
     uint32_t* cta_count;       // [n_k1]              visible blocks found by each K1 CTA
-    float* cta_dmax;           // [batch][n_k1]       largest depth in each K1 CTA's slice of the depth image
+    float* tile_dmax;          // [batch][kMaxDepthTiles] largest depth in each (1 << tile_shift)^2 tile of the depth image
+    int32_t tile_shift, ntx, nty;
     uint32_t* block_seg;       // [n_k1*256]          per-CTA ordered segments
     uint32_t* blk_count;       // [batch][nblocks_total]   valid voxels per visible block (by rank)
     uint32_t* blk_offset;      // [batch][nblocks_total+1] exclusive prefix of blk_count
@@ -197,7 +198,7 @@ __device__ __forceinline__ bool block_maybe_visible(const Geom& g, float cx, flo
 
 // bounding sphere (world centre, radius) of the voxel centres of block (bx,by,bz) of the slab
 __device__ __forceinline__ void block_sphere(const FusionParams& p, uint32_t bx, uint32_t by, uint32_t bz, float& cx,
-                                             float& cy, float& cz, float& r)
+                                             float& cy, float& cz, float& r, float* half = nullptr)
 {
     const int x0 = (int)bx * kBlockEdge, y0 = (int)by * kBlockEdge, z0 = (int)bz * kBlockEdge;
     const int ex = min(kBlockEdge, (int)p.nxs - x0), ey = min(kBlockEdge, p.grid.nvox[1] - y0),
@@ -208,19 +209,76 @@ __device__ __forceinline__ void block_sphere(const FusionParams& p, uint32_t bx,
     cy = p.grid.origin[1] + vs * (float)y0 + hy;
     cz = p.grid.origin[2] + vs * (float)z0 + hz;
     r = sqrtf(hx * hx + hy * hy + hz * hz) + 0.01f * vs;
+    if (half) {
+        half[0] = hx + 0.01f * vs;
+        half[1] = hy + 0.01f * vs;
+        half[2] = hz + 0.01f * vs;
+    }
 }
 
-// smallest camera-space z = K[2,:] . R^T (x - t) over the block's bounding sphere, minus rounding slack
-__device__ __forceinline__ float block_z_min(const Geom& g, float cx, float cy, float cz, float r)
+// smallest camera-space z = K[2,:] . R^T (x - t) over the block's box of voxel centres (exact minimum of a
+// linear function over an axis-aligned box), minus rounding slack
+__device__ __forceinline__ float block_z_min(const Geom& g, float cx, float cy, float cz, const float* half)
 {
+    const float d[3] = {cx - g.P[3], cy - g.P[7], cz - g.P[11]};
+    float zc = 0.0f, ext = 0.0f, mag = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        // world-space gradient of z: n_i = sum_k R[i][k] K[2][k]
+        const float n = g.P[4 * i] * g.K[6] + g.P[4 * i + 1] * g.K[7] + g.P[4 * i + 2] * g.K[8];
+        zc += n * d[i];
+        ext += fabsf(n) * half[i];
+        mag += fabsf(n) * (fabsf(d[i]) + half[i]);
+    }
+    return zc - ext - 1e-3f * mag - 1e-6f;
+}
+
+// Largest depth any voxel of the block can sample: the maximum over the depth tiles its projected bounding
+// sphere can touch (interval arithmetic on x/z, y/z), or the whole-image maximum when that is not cheap to
+// bound (sphere reaches z <= 0, general intrinsics, footprint of more than 64 tiles).
+__device__ __forceinline__ float block_depth_bound(const FusionParams& p, const Geom& g, float cx, float cy, float cz,
+                                                   float r, const float* tiles_smem, const float* tiles_gmem,
+                                                   float image_max)
+{
+    if (g.K[6] != 0.0f || g.K[7] != 0.0f || g.K[8] != 1.0f) return image_max;
     const float d0 = cx - g.P[3], d1 = cy - g.P[7], d2 = cz - g.P[11];
     float pc[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) pc[k] = g.P[k] * d0 + g.P[4 + k] * d1 + g.P[8 + k] * d2;
-    const float plen = sqrtf(pc[0] * pc[0] + pc[1] * pc[1] + pc[2] * pc[2]) + r;
-    const float dot = g.K[6] * pc[0] + g.K[7] * pc[1] + g.K[8] * pc[2];
-    const float nlen = sqrtf(g.K[6] * g.K[6] + g.K[7] * g.K[7] + g.K[8] * g.K[8]);
-    return dot - nlen * r - 1e-3f * nlen * plen - 1e-6f;
+    const float rr = r * 1.01f + 1e-4f * (fabsf(pc[0]) + fabsf(pc[1]) + fabsf(pc[2]));
+    const float z0 = pc[2] - rr, z1 = pc[2] + rr;
+    if (!(z0 > 1e-4f)) return image_max;
+    float lo[2], hi[2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        const float x0 = pc[a] - rr, x1 = pc[a] + rr;
+        lo[a] = fminf(x0 / z0, x0 / z1);
+        hi[a] = fmaxf(x1 / z0, x1 / z1);
+    }
+    // u = K00 ax + K01 ay + K02,  v = K10 ax + K11 ay + K12
+    float uv_lo[2], uv_hi[2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        const float k0 = g.K[3 * a], k1 = g.K[3 * a + 1], k2 = g.K[3 * a + 2];
+        uv_lo[a] = fminf(k0 * lo[0], k0 * hi[0]) + fminf(k1 * lo[1], k1 * hi[1]) + k2;
+        uv_hi[a] = fmaxf(k0 * lo[0], k0 * hi[0]) + fmaxf(k1 * lo[1], k1 * hi[1]) + k2;
+        const float pad = 1.5f + 1e-3f * fmaxf(fabsf(uv_lo[a]), fabsf(uv_hi[a]));  // nearest-pixel rounding + fp slack
+        uv_lo[a] -= pad;
+        uv_hi[a] += pad;
+    }
+    if (!(uv_lo[0] == uv_lo[0]) || !(uv_hi[0] == uv_hi[0]) || !(uv_lo[1] == uv_lo[1]) || !(uv_hi[1] == uv_hi[1]))
+        return image_max;
+    const int tx0 = max(0, (int)floorf(fmaxf(uv_lo[0], -1.0f))) >> p.tile_shift;
+    const int ty0 = max(0, (int)floorf(fmaxf(uv_lo[1], -1.0f))) >> p.tile_shift;
+    const int tx1 = min(p.ntx - 1, (int)floorf(fminf(uv_hi[0], (float)p.W)) >> p.tile_shift);
+    const int ty1 = min(p.nty - 1, (int)floorf(fminf(uv_hi[1], (float)p.H)) >> p.tile_shift);
+    if (uv_hi[0] < 0.0f || uv_hi[1] < 0.0f || tx0 > tx1 || ty0 > ty1) return 0.0f;  // only out-of-image pixels: depth 0
+    if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > 64) return image_max;
+    float m = 0.0f;
+    for (int ty = ty0; ty <= ty1; ++ty)
+        for (int tx = tx0; tx <= tx1; ++tx)
+            m = fmaxf(m, tiles_smem ? tiles_smem[ty * p.ntx + tx] : __ldcg(tiles_gmem + ty * p.ntx + tx));
+    return m;
 }
 
 // exclusive prefix sum of n values (global, read through L2) by one CTA (blockDim.x a multiple of 32,
@@ -298,24 +356,24 @@ __global__ void __launch_bounds__(kK1Threads) frame_setup_kernel(const FusionPar
             vis |= block_maybe_visible(g, cx, cy, cz, r, fW, fH);
         }
     }
-    // this CTA's share of the frames' depth maxima (K2 combines the shares; used for its depth cull)
-    __shared__ float s_dmax[kK1Threads / 32];
-    for (int b = 0; b < (p.hdr->depth_cull ? p.batch : 0); ++b) {
-        const int npix = p.H * p.W;
-        const int per = (npix + (int)cull_ctas - 1) / (int)cull_ctas;
-        const int lo = min(npix, (int)blockIdx.x * per), hi = min(npix, lo + per);
-        float dm = 0.0f;
-        for (int i = lo + threadIdx.x; i < hi; i += kK1Threads) dm = fmaxf(dm, __ldg(p.frames[b].depth + i));
+    // depth-tile maxima for K2's depth cull (only while the cull is switched on): one warp per tile, each
+    // lane walks one pixel row of the tile
+    if (p.hdr->depth_cull) {
+        const int ts = 1 << p.tile_shift, ntiles = p.ntx * p.nty;
+        const int gw = (int)blockIdx.x * (kK1Threads / 32) + warp, nw = (int)cull_ctas * (kK1Threads / 32);
+        for (int b = 0; b < p.batch; ++b) {
+            const float* __restrict__ dimg = p.frames[b].depth;
+            for (int t = gw; t < ntiles; t += nw) {
+                const int x0 = (t % p.ntx) * ts, y0 = (t / p.ntx) * ts;
+                const int x1 = min(p.W, x0 + ts);
+                float dm = 0.0f;
+                for (int y = y0 + lane; y < min(p.H, y0 + ts); y += 32)
+                    for (int x = x0; x < x1; ++x) dm = fmaxf(dm, __ldg(dimg + (size_t)y * p.W + x));
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) dm = fmaxf(dm, __shfl_xor_sync(0xffffffffu, dm, o));
-        if (lane == 0) s_dmax[warp] = dm;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-#pragma unroll
-            for (int w = 1; w < kK1Threads / 32; ++w) dm = fmaxf(dm, s_dmax[w]);
-            p.cta_dmax[(size_t)b * p.n_k1 + blockIdx.x] = dm;
+                for (int o = 16; o > 0; o >>= 1) dm = fmaxf(dm, __shfl_xor_sync(0xffffffffu, dm, o));
+                if (lane == 0) p.tile_dmax[(size_t)b * kMaxDepthTiles + t] = dm;
+            }
         }
-        __syncthreads();
     }
     // ordered compaction inside the CTA: this CTA's visible blocks, ascending, into its own segment
     const unsigned m = __ballot_sync(0xffffffffu, vis);
@@ -350,23 +408,13 @@ __global__ void __launch_bounds__(kK2Threads) tsdf_update_kernel(const FusionPar
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // K1 left one ordered segment of visible blocks per cull CTA: rank -> (segment, position)
     const uint32_t n_blocks = cta_exclusive_scan(p.cta_count, s_off, p.n_k1, s_scan);
-    // farthest surface of each frame: a voxel is tsdf_valid only if z < depth + trunc <= dmax + trunc
-    // (clip_seem_fusion.py:722-728), so blocks entirely behind that are skipped.  NaN depths never win fmaxf.
-    __shared__ float s_zfar[SAF_MAX_BATCH];
+    // Depth cull: a voxel is tsdf_valid only if z < depth + trunc (clip_seem_fusion.py:722-728), so a block whose
+    // nearest z lies behind (largest depth over the image tiles its projection can touch) + trunc is skipped.
+    // NaN depths never win fmaxf; pixels outside the image sample depth 0.
+    __shared__ float s_tile[kMaxDepthTiles];   // frame 0's tile maxima (batch-1 fast path)
+    __shared__ float s_zfar[SAF_MAX_BATCH];    // whole-image bound per frame (fallback)
     const bool depth_cull = hdr->depth_cull != 0;
-    uint32_t processed = 0;
-    if (threadIdx.x < SAF_MAX_BATCH) s_zfar[threadIdx.x] = INFINITY;  // lanes of warp 0
-    __syncwarp();
-    if (warp == 0 && depth_cull) {
-        for (int b = 0; b < (BATCH1 ? 1 : p.batch); ++b) {
-            float dm = 0.0f;
-            for (uint32_t c = lane; c < p.n_k1; c += 32) dm = fmaxf(dm, __ldcg(p.cta_dmax + (size_t)b * p.n_k1 + c));
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) dm = fmaxf(dm, __shfl_xor_sync(0xffffffffu, dm, o));
-            if (lane == 0) s_zfar[b] = (dm + p.trunc) * 1.001f + 1e-5f;
-        }
-    }
-    __syncthreads();
+    __shared__ uint32_t s_rank;                // list segment claimed for the block being processed
     const int B = BATCH1 ? 1 : p.batch;
     const float fW = (float)p.W, fH = (float)p.H;
     const int ny = p.grid.nvox[1], nz = p.grid.nvox[2];
@@ -375,7 +423,26 @@ __global__ void __launch_bounds__(kK2Threads) tsdf_update_kernel(const FusionPar
     for (int b = 0; b < (BATCH1 ? 1 : SAF_MAX_BATCH); ++b) tv_count[b] = 0;
     Geom g;
     if (BATCH1) load_geom(p.frames[0], g);
-
+    if (depth_cull) {
+        const int ntiles = p.ntx * p.nty;
+        for (int b = 0; b < B; ++b) {
+            float dm = 0.0f;
+            for (int t = threadIdx.x; t < ntiles; t += kK2Threads) {
+                const float v = __ldcg(p.tile_dmax + (size_t)b * kMaxDepthTiles + t);
+                if (b == 0) s_tile[t] = v;
+                dm = fmaxf(dm, v);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) dm = fmaxf(dm, __shfl_xor_sync(0xffffffffu, dm, o));
+            if (lane == 0) s_scan[warp] = dm;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                for (int w = 1; w < kK2Threads / 32; ++w) dm = fmaxf(dm, s_scan[w]);
+                s_zfar[b] = dm;
+            }
+            __syncthreads();
+        }
+    }
     for (uint32_t bi = blockIdx.x; bi < n_blocks; bi += gridDim.x) {
         uint32_t lo = 0, hi = p.n_k1;  // s_off[lo] <= bi < s_off[hi] (with s_off[n_k1] = n_blocks)
         while (hi - lo > 1) {
@@ -390,19 +457,20 @@ __global__ void __launch_bounds__(kK2Threads) tsdf_update_kernel(const FusionPar
         const uint32_t by = (blk / p.nb[2]) % p.nb[1];
         const uint32_t bx = blk / (p.nb[2] * p.nb[1]);
         if (depth_cull) {
-            float cx, cy, cz, r;
-            block_sphere(p, bx, by, bz, cx, cy, cz, r);
+            float cx, cy, cz, r, half[3];
+            block_sphere(p, bx, by, bz, cx, cy, cz, r, half);
             bool reachable = false;
             for (int b = 0; b < B; ++b) {
                 if (!BATCH1) load_geom(p.frames[b], g);
-                reachable |= !(block_z_min(g, cx, cy, cz, r) > s_zfar[b]);  // NaN -> keep
+                const float* tiles = (b == 0) ? s_tile : nullptr;
+                const float dfar = block_depth_bound(p, g, cx, cy, cz, r, tiles, p.tile_dmax + (size_t)b * kMaxDepthTiles,
+                                                     s_zfar[b]);
+                reachable |= !(block_z_min(g, cx, cy, cz, half) > (dfar + p.trunc) * 1.001f + 1e-5f);  // NaN -> keep
             }
-            if (!reachable) {  // CTA-uniform: the whole block lies behind every frame's farthest surface
-                if (threadIdx.x < B) p.blk_count[(uint64_t)threadIdx.x * p.nblocks_total + bi] = 0;
-                continue;
-            }
+            if (!reachable) continue;  // CTA-uniform: the whole block lies behind the surfaces it could see
         }
-        processed += 1;
+        // claim the next list segment (arrival order; the list order does not affect any result)
+        if (threadIdx.x == 0) s_rank = atomicAdd(&sc->n_processed, 1u);
         float xw[kK2Iter], yw[kK2Iter], zw[kK2Iter], t_old[kK2Iter], bt[kK2Iter];
         uint32_t v[kK2Iter];
         int tw[kK2Iter], bw[kK2Iter];
@@ -457,7 +525,8 @@ __global__ void __launch_bounds__(kK2Threads) tsdf_update_kernel(const FusionPar
             __syncthreads();
             // entries in voxel order: rank = (# valid with a smaller local index)
             uint32_t run = 0;
-            ValidEntry* seg = p.lists + (uint64_t)b * p.list_cap + (uint64_t)bi * kBlockVoxels;
+            const uint32_t rank = s_rank;  // written before the barrier above
+            ValidEntry* seg = p.lists + (uint64_t)b * p.list_cap + (uint64_t)rank * kBlockVoxels;
 #pragma unroll
             for (int j = 0; j < kK2Iter; ++j) {
 #pragma unroll
@@ -473,7 +542,7 @@ __global__ void __launch_bounds__(kK2Threads) tsdf_update_kernel(const FusionPar
                     run += s_cnt[j][w];
                 }
             }
-            if (threadIdx.x == 0) p.blk_count[(uint64_t)b * p.nblocks_total + bi] = run;
+            if (threadIdx.x == 0) p.blk_count[(uint64_t)b * p.nblocks_total + rank] = run;
             __syncthreads();
         }
 #pragma unroll
@@ -501,7 +570,6 @@ __global__ void __launch_bounds__(kK2Threads) tsdf_update_kernel(const FusionPar
     // (one fence by the ticket-taking thread after the CTA barrier publishes the whole CTA's writes)
     __syncthreads();
     if (threadIdx.x == 0) {
-        if (processed) atomicAdd(&sc->n_processed, processed);
         __threadfence();
         is_last = (atomicAdd(&sc->k2_done, 1u) == gridDim.x - 1);
     }
@@ -509,11 +577,12 @@ __global__ void __launch_bounds__(kK2Threads) tsdf_update_kernel(const FusionPar
     if (!is_last) return;
     __threadfence();
     unsigned long long sv = 0, stv = 0;
+    const uint32_t n_proc = atomicAdd(&sc->n_processed, 0u);
     for (int b = 0; b < B; ++b) {
         uint32_t* off = p.blk_offset + (uint64_t)b * (p.nblocks_total + 1);
-        const uint32_t total = cta_exclusive_scan(p.blk_count + (uint64_t)b * p.nblocks_total, off, n_blocks, s_scan);
+        const uint32_t total = cta_exclusive_scan(p.blk_count + (uint64_t)b * p.nblocks_total, off, n_proc, s_scan);
         if (threadIdx.x == 0) {
-            off[n_blocks] = total;
+            off[n_proc] = total;
             sc->n_valid[b] = total;
             const uint32_t t = atomicExch(&sc->n_tsdf_valid[b], 0u);
             sc->last_tsdf_valid[b] = t;
@@ -523,15 +592,25 @@ __global__ void __launch_bounds__(kK2Threads) tsdf_update_kernel(const FusionPar
     }
     if (threadIdx.x == 0) {
         // depth-cull policy for the next calls: on while fewer than a quarter of the visited voxels were
-        // tsdf_valid (many blocks behind the surfaces), off again (with a cool-down) if it removes < 1/8
-        const uint32_t n_proc = atomicExch(&sc->n_processed, 0u);
+        // tsdf_valid (many blocks behind the surfaces), off again (with a cool-down) once it removes < 1/8
+        // (depth_cull_cooldown counts idle calls while on, remaining cool-down calls while off)
+        sc->n_processed = 0;
+        sc->last_processed = n_proc;
         if (!depth_cull) {
             if (hdr->depth_cull_cooldown) hdr->depth_cull_cooldown -= 1;
-            else if (n_blocks >= 64 && stv * 4ull < (unsigned long long)n_proc * kBlockVoxels * (unsigned long long)B)
+            else if (n_blocks >= 64 && stv * 4ull < (unsigned long long)n_proc * kBlockVoxels * (unsigned long long)B) {
                 hdr->depth_cull = 1;
+                hdr->depth_cull_cooldown = 0;
+            }
         } else if ((n_blocks - n_proc) * 8u < n_blocks) {
-            hdr->depth_cull = 0;
-            hdr->depth_cull_cooldown = 64;
+            // ineffective on this call; give up only after 16 such calls in a row (cameras may alternate
+            // between views where it helps and views where it does not)
+            if (++hdr->depth_cull_cooldown >= 16) {
+                hdr->depth_cull = 0;
+                hdr->depth_cull_cooldown = 32;
+            }
+        } else {
+            hdr->depth_cull_cooldown = 0;
         }
         sc->frame_base_parity = (uint32_t)(hdr->total_frames & 1ull);
         hdr->total_valid += sv;
@@ -539,7 +618,8 @@ __global__ void __launch_bounds__(kK2Threads) tsdf_update_kernel(const FusionPar
         hdr->total_blocks += n_blocks;
         hdr->total_frames += (unsigned long long)B;
         hdr->last_slot = p.slot;
-        sc->n_blocks = n_blocks;
+        sc->n_blocks = n_proc;      // list segments K3 searches
+        sc->n_frustum_blocks = n_blocks;
         sc->k2_done = 0;
     }
 }
@@ -890,7 +970,14 @@ static int build_params(const saf_grid_desc* grid, const saf_volume* vol, const 
     p->slot = slot;
     unsigned char* sb = base + L.slot0 + (uint64_t)slot * L.slot_stride;
     p->cta_count = (uint32_t*)(sb + L.off_cta_count);
-    p->cta_dmax = (float*)(sb + L.off_cta_dmax);
+    p->tile_dmax = (float*)(sb + L.off_cta_dmax);
+    p->tile_shift = 5;
+    for (;;) {
+        p->ntx = (W + (1 << p->tile_shift) - 1) >> p->tile_shift;
+        p->nty = (H + (1 << p->tile_shift) - 1) >> p->tile_shift;
+        if ((uint32_t)p->ntx * (uint32_t)p->nty <= kMaxDepthTiles) break;
+        p->tile_shift += 1;
+    }
     p->block_seg = (uint32_t*)(sb + L.off_block_seg);
     p->blk_count = (uint32_t*)(sb + L.off_blk_count);
     p->blk_offset = (uint32_t*)(sb + L.off_blk_offset);
@@ -1051,12 +1138,14 @@ int saf_read_stats(const saf_workspace* ws, saf_stats* out, void* stream)
     out->total_tsdf_valid = h.total_tsdf_valid;
     out->total_blocks = h.total_blocks;
     const SlotCounters& sc = h.slot[h.last_slot & 1u];
-    out->last_blocks = sc.n_blocks;
+    out->last_blocks = sc.n_frustum_blocks;
     for (int b = 0; b < SAF_MAX_BATCH; ++b) {
         out->last_valid[b] = sc.n_valid[b];
         out->last_tsdf_valid[b] = sc.last_tsdf_valid[b];
     }
     out->error_flags = h.error_flags;
+    out->last_processed = sc.last_processed;
+    out->depth_cull_on = h.depth_cull;
     return 0;
 }
 

@@ -23,7 +23,7 @@ constexpr int kBlockVoxels = kBlockEdge * kBlockEdge * kBlockEdge;
 // by the kernels themselves (no host memsets): K2's last CTA publishes the per-block list offsets,
 // n_valid, the frame parity K3 uses for its zig-zag walk, and folds the call into the running totals.
 struct SlotCounters {
-    uint32_t n_blocks;                      // visible blocks of the call (written by K2's last CTA)
+    uint32_t n_blocks;                      // list segments (blocks K2 processed) of the call, written by K2's last CTA
     uint32_t k2_done;                       // CTA completion ticket of K2
     uint32_t frame_base_parity;             // total_frames before this call, & 1
     uint32_t pad_;
@@ -31,7 +31,9 @@ struct SlotCounters {
     uint32_t n_tsdf_valid[SAF_MAX_BATCH];   // accumulators (atomics), folded and zeroed by K2's last CTA
     uint32_t last_tsdf_valid[SAF_MAX_BATCH];
     uint32_t n_processed;                   // blocks K2 did not skip by the depth test (atomic, zeroed like above)
-    uint32_t pad2_[3];
+    uint32_t last_processed;
+    uint32_t n_frustum_blocks;              // blocks K1 listed for the call
+    uint32_t pad2_[1];
 };
 
 // Device-resident workspace header (512 bytes).
@@ -68,11 +70,12 @@ struct __align__(16) ValidEntry {
 };
 
 constexpr int kK1Threads = 256;             // blocks tested per K1 CTA (one per thread)
+constexpr uint32_t kMaxDepthTiles = 1024;   // depth image tiles (>= 32x32 px) whose maxima K1 publishes for K2's depth cull
 constexpr uint32_t kMaxK1Ctas = 2048;       // K1's last CTA scans this many per-CTA counts in shared memory
 
 // Workspace layout (all offsets 256-byte aligned):
 //   header | slot 0 | slot 1        with, per slot,
-//   cta_count[n_k1] | cta_dmax[max_batch][n_k1] | block_seg[n_k1*256] | blk_count[max_batch][nblocks_total]
+//   cta_count[n_k1] | tile_dmax[max_batch][kMaxDepthTiles] | block_seg[n_k1*256] | blk_count[max_batch][nblocks_total]
 //   | blk_offset[max_batch][nblocks_total+1] | lists[max_batch][nblocks_total*512] | tables[max_batch][max_table_elems]
 struct WsLayout {
     uint64_t bytes;
@@ -107,7 +110,7 @@ inline int compute_layout(const saf_grid_desc* g, int32_t max_batch, int64_t max
     L->list_cap = nblocks * kBlockVoxels;
     L->off_cta_count = 0;
     L->off_cta_dmax = align_up(L->off_cta_count + 4ull * L->n_k1, 256);
-    L->off_block_seg = align_up(L->off_cta_dmax + 4ull * max_batch * L->n_k1, 256);
+    L->off_block_seg = align_up(L->off_cta_dmax + 4ull * max_batch * kMaxDepthTiles, 256);
     L->off_blk_count = align_up(L->off_block_seg + 4ull * L->n_k1 * kK1Threads, 256);
     L->off_blk_offset = align_up(L->off_blk_count + 4ull * max_batch * nblocks, 256);
     L->off_lists = align_up(L->off_blk_offset + 4ull * max_batch * (nblocks + 1), 256);

@@ -207,7 +207,8 @@ class _FusionVolume(torch.nn.Module):
         _lib.check(_lib.load().saf_read_stats(ctypes.byref(self._ws), ctypes.byref(st), stream), "saf_read_stats")
         out = dict(total_frames=st.total_frames, total_valid=st.total_valid, total_tsdf_valid=st.total_tsdf_valid,
                    total_blocks=st.total_blocks, last_blocks=st.last_blocks, last_valid=list(st.last_valid),
-                   last_tsdf_valid=list(st.last_tsdf_valid), error_flags=st.error_flags)
+                   last_tsdf_valid=list(st.last_tsdf_valid), error_flags=st.error_flags,
+                   last_processed=st.last_processed, depth_cull_on=st.depth_cull_on)
         carry = getattr(self, "_stats_carry", None)
         if carry:
             for k in ("total_frames", "total_valid", "total_tsdf_valid", "total_blocks"):
