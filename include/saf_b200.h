@@ -215,6 +215,35 @@ int saf_query_topk(const float *feats, int64_t M, int32_t C, int64_t ldf, const 
                    int32_t k, int64_t index_base, float *out_scores, int64_t *out_index, void *ws,
                    uint64_t ws_bytes, void *stream);
 
+/* ---- mesh: ClipSeemFusion.extract_mesh (clip_seem_fusion.py:824-888) and ClipFusion.extract_mesh
+ *            (clipfusion.py:723-763) ------------------------------------------------------------
+ * The reference masks unobserved voxels (weight == 0) to NaN, runs skimage.measure.marching_cubes
+ * (level 0) on the host, drops faces with a NaN vertex and the vertices no face uses, then samples
+ * rgb / clip_feat (trilinear) and voxel_obj_idx / objects_segmentation_color (nearest) at the
+ * vertices with torch grid_sample.  The three calls below do the same on the device, without the
+ * host round trip; vertices are ordered by (voxel, axis) of their grid edge and faces by cell. */
+
+#define SAF_SAMPLE_TRILINEAR 0   /* grid_sample mode="bilinear" on the 5-D view */
+#define SAF_SAMPLE_NEAREST   1
+
+/* Device scratch for the two calls below: 12 bytes per voxel of the slab (+ small per-CTA arrays). */
+int saf_mesh_workspace_bytes(const saf_grid_desc *grid, uint64_t *bytes_out);
+/* Pass 1: classify cells, count surviving faces and used vertices.  Synchronises `stream` and
+ * returns the counts so that the caller can allocate the outputs.  ws: device, 256-byte aligned. */
+int saf_mesh_count(const saf_grid_desc *grid, const float *tsdf, const int32_t *weight, void *ws,
+                   uint64_t ws_bytes, uint64_t *n_verts_out, uint64_t *n_faces_out, void *stream);
+/* Pass 2 (same inputs and workspace as the saf_mesh_count call before it): vertices in voxel-index
+ * coordinates [V,3] (global x), optionally also verts * voxel_size + origin (clip_seem_fusion.py:880),
+ * and faces [F,3] int64. */
+int saf_mesh_emit(const saf_grid_desc *grid, const float *tsdf, const int32_t *weight, void *ws,
+                  uint64_t ws_bytes, float *verts_out, float *verts_world_out, int64_t *faces_out,
+                  void *stream);
+/* grid_sample of a per-voxel field [N,channels] (slab-local rows) at `verts` (index coordinates):
+ * grid = (verts + 0.5) / nvox * 2 - 1, align_corners=False, zeros padding, mode SAF_SAMPLE_*;
+ * clamp01 != 0 applies .clamp(0, 1) (the colour outputs).  out: device [V,channels]. */
+int saf_mesh_sample(const saf_grid_desc *grid, const float *verts, int64_t n_verts, const float *field,
+                    int32_t channels, int32_t mode, int32_t clamp01, float *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

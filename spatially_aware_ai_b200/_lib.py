@@ -20,6 +20,7 @@ SAF_FLAG_BAD_CLASS_ID = 1
 SAF_NORM_NONE, SAF_NORM_NAN_TO_NUM, SAF_NORM_CLAMP_MIN = 0, 1, 2
 SAF_SCORE_DOT, SAF_SCORE_SOFTMAX100, SAF_SCORE_SURGERY = 0, 1, 2
 SAF_PRECISION_FP32, SAF_PRECISION_TF32, SAF_PRECISION_3XTF32 = 0, 1, 2
+SAF_SAMPLE_TRILINEAR, SAF_SAMPLE_NEAREST = 0, 1
 
 c_void_p, c_int32, c_int64, c_uint64, c_float = (ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64,
                                                  ctypes.c_uint64, ctypes.c_float)
@@ -82,6 +83,13 @@ SIGNATURES = {
     "saf_query_topk": (ctypes.c_int, [c_void_p, c_int64, c_int32, c_int64, c_void_p, c_int32, c_int32, c_int32,
                                       c_void_p, c_int32, c_int32, c_int64, c_void_p, c_void_p, c_void_p, c_uint64,
                                       c_void_p]),
+    "saf_mesh_workspace_bytes": (ctypes.c_int, [P(GridDesc), P(c_uint64)]),
+    "saf_mesh_count": (ctypes.c_int, [P(GridDesc), c_void_p, c_void_p, c_void_p, c_uint64, P(c_uint64), P(c_uint64),
+                                      c_void_p]),
+    "saf_mesh_emit": (ctypes.c_int, [P(GridDesc), c_void_p, c_void_p, c_void_p, c_uint64, c_void_p, c_void_p, c_void_p,
+                                     c_void_p]),
+    "saf_mesh_sample": (ctypes.c_int, [P(GridDesc), c_void_p, c_int64, c_void_p, c_int32, c_int32, c_int32, c_void_p,
+                                       c_void_p]),
 }
 
 _lib = None

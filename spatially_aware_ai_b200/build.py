@@ -19,7 +19,7 @@ ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"),
                 "-I", CSRC]
 # saf_fusion.cu reproduces the reference's fp32 roundings: never contract mul+add there.
-PER_FILE_FLAGS = {"saf_fusion.cu": ["-fmad=false"]}
+PER_FILE_FLAGS = {"saf_fusion.cu": ["-fmad=false"], "saf_mesh.cu": ["-fmad=false"]}
 
 
 def _nvcc():

@@ -2,6 +2,8 @@
 ``extract_mesh_by_id`` (/root/reference/extract_obj_mesh.py:12-36) and the volumes' ``extract_mesh``
 (/root/reference/clip_seem_fusion.py:824-888, clipfusion.py:723-763).
 """
+import ctypes
+
 import numpy as np
 
 
@@ -45,11 +47,73 @@ def _to_open3d(vertices, faces, colors):
     return mesh
 
 
-def extract_mesh_seem(volume):
-    raise NotImplementedError("extract_mesh (clip_seem_fusion.py:824-888) is listed under 'next' in DESIGN.md; "
-                              "GPU marching cubes has not landed yet")
+def _aligned_scratch(nbytes, device):
+    import torch
+    buf = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
+    return buf, (buf.data_ptr() + 255) // 256 * 256
+
+
+def marching_cubes_device(volume):
+    """Marching cubes (level 0) over the volume's TSDF with unobserved voxels (weight == 0) treated as NaN, faces
+    with a NaN vertex and unused vertices already removed (clip_seem_fusion.py:825-842).
+    Returns device tensors (verts [V,3] f32 in voxel-index coordinates, verts_world [V,3] f32, faces [F,3] i64)."""
+    import torch
+    from . import _lib
+    if not volume.tsdf.is_cuda:
+        raise RuntimeError("extract_mesh runs on a CUDA (sm_100) device only; there is no CPU path")
+    lib, dev = _lib.load(), volume.tsdf.device
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    grid = volume._grid_desc()
+    nbytes = ctypes.c_uint64()
+    _lib.check(lib.saf_mesh_workspace_bytes(ctypes.byref(grid), ctypes.byref(nbytes)), "saf_mesh_workspace_bytes")
+    scratch, base = _aligned_scratch(nbytes.value, dev)
+    nv, nf = ctypes.c_uint64(), ctypes.c_uint64()
+    _lib.check(lib.saf_mesh_count(ctypes.byref(grid), volume.tsdf.data_ptr(), volume.weight.data_ptr(), base,
+                                  nbytes.value, ctypes.byref(nv), ctypes.byref(nf), stream), "saf_mesh_count")
+    verts = torch.empty((nv.value, 3), dtype=torch.float32, device=dev)
+    verts_world = torch.empty((nv.value, 3), dtype=torch.float32, device=dev)
+    faces = torch.empty((nf.value, 3), dtype=torch.int64, device=dev)
+    if nv.value or nf.value:
+        _lib.check(lib.saf_mesh_emit(ctypes.byref(grid), volume.tsdf.data_ptr(), volume.weight.data_ptr(), base,
+                                     nbytes.value, verts.data_ptr(), verts_world.data_ptr(), faces.data_ptr(), stream),
+                   "saf_mesh_emit")
+    del scratch
+    return verts, verts_world, faces
+
+
+def sample_vertices(volume, verts, field, mode="bilinear", clamp01=False):
+    """torch.nn.functional.grid_sample of a per-voxel field at mesh vertices, as extract_mesh calls it
+    (clip_seem_fusion.py:843-877): field [N] or [N,C] (rows of the volume's slab) -> [V,C] on the device."""
+    import torch
+    from . import _lib
+    dev = volume.tsdf.device
+    n = volume.tsdf.shape[0]
+    field = field.to(device=dev, dtype=torch.float32).reshape(n, -1).contiguous()
+    out = torch.empty((verts.shape[0], field.shape[1]), dtype=torch.float32, device=dev)
+    m = {"bilinear": _lib.SAF_SAMPLE_TRILINEAR, "nearest": _lib.SAF_SAMPLE_NEAREST}[mode]
+    _lib.check(_lib.load().saf_mesh_sample(ctypes.byref(volume._grid_desc()), verts.data_ptr(), verts.shape[0],
+                                           field.data_ptr(), field.shape[1], m, int(bool(clamp01)), out.data_ptr(),
+                                           torch.cuda.current_stream(dev).cuda_stream), "saf_mesh_sample")
+    return out
 
 
 def extract_mesh_fusion(volume):
-    raise NotImplementedError("extract_mesh (clipfusion.py:723-763) is listed under 'next' in DESIGN.md; "
-                              "GPU marching cubes has not landed yet")
+    """ClipFusion.extract_mesh (clipfusion.py:723-763): (verts_world, faces, vertex_colors, vertex_clip_feats);
+    the first two as numpy arrays, the sampled attributes as device tensors, like the reference."""
+    verts, verts_world, faces = marching_cubes_device(volume)
+    vertex_colors = sample_vertices(volume, verts, volume.rgb, "bilinear", clamp01=True)
+    vertex_clip_feats = sample_vertices(volume, verts, volume.clip_feat, "bilinear")
+    return verts_world.cpu().numpy(), faces.cpu().numpy(), vertex_colors, vertex_clip_feats
+
+
+def extract_mesh_seem(volume):
+    """ClipSeemFusion.extract_mesh (clip_seem_fusion.py:824-888): adds vertex_obj_idx [V,1] and
+    vertex_segment_color [V,3], nearest samples of the caller-set `voxel_obj_idx` and
+    `objects_segmentation_color` attributes (clip_seem_fusion.py:349-372)."""
+    verts, verts_world, faces = marching_cubes_device(volume)
+    vertex_colors = sample_vertices(volume, verts, volume.rgb, "bilinear", clamp01=True)
+    vertex_clip_feats = sample_vertices(volume, verts, volume.clip_feat, "bilinear")
+    vertex_obj_idx = sample_vertices(volume, verts, volume.voxel_obj_idx, "nearest")
+    vertex_segment_color = sample_vertices(volume, verts, volume.objects_segmentation_color, "nearest", clamp01=True)
+    return (verts_world.cpu().numpy(), faces.cpu().numpy(), vertex_colors, vertex_clip_feats, vertex_obj_idx,
+            vertex_segment_color)

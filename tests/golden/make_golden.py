@@ -221,6 +221,63 @@ def run_query_golden():
     print("query ->", os.path.getsize(path) // 1024, "KiB")
 
 
+def run_mesh_golden():
+    """extract_mesh of both reference classes on the final state of the seem_a / fusion_a goldens.
+    skimage is not installed here, so the one library call inside extract_mesh
+    (skimage.measure.marching_cubes, clip_seem_fusion.py:829) is served by oracle/mc.py's
+    marching_cubes_raw; every other line is the unmodified reference running on torch-CPU."""
+    from oracle import mc
+
+    def fake_marching_cubes(volume, level=0):
+        assert level == 0
+        verts, faces = mc.marching_cubes_raw(volume)
+        return verts, faces, None, None
+
+    out = {}
+    rng = np.random.default_rng(91)
+    for name, mod in (("seem_a", clip_seem_fusion), ("fusion_a", clipfusion)):
+        with np.load(os.path.join(HERE, name + ".npz")) as z:
+            g = {k: z[k] for k in z.files}
+        cfgC = int(g["feature_dim"])
+        fake_clip = FakeClip(cfgC)
+        t_origin, t_nvox = torch.from_numpy(g["origin"]), torch.from_numpy(g["nvox"])
+        if name == "seem_a":
+            vol = mod.ClipSeemFusion(t_origin, float(g["voxel_size"]), t_nvox, float(g["trunc"]), False, 0, 0,
+                                     fake_clip, FakeSeg())
+        else:
+            real_clip = clipfusion.Clip
+            clipfusion.Clip = lambda model, pretraining: fake_clip
+            try:
+                vol = mod.ClipFusion(t_origin, float(g["voxel_size"]), t_nvox, float(g["trunc"]), False, "fake",
+                                     "fake", 0, 0)
+            finally:
+                clipfusion.Clip = real_clip
+        vol.tsdf.copy_(torch.from_numpy(g["tsdf"]))
+        vol.weight.copy_(torch.from_numpy(g["weight"]))
+        vol.rgb.copy_(torch.from_numpy(g["rgb_state"]))
+        vol.clip_feat.copy_(torch.from_numpy(g["clip_feat"]))
+        mod.skimage.measure.marching_cubes = fake_marching_cubes
+        if name == "seem_a":
+            n = int(np.prod(g["nvox"]))
+            obj = rng.integers(-1, 9, size=tuple(int(v) for v in g["nvox"])).astype(np.int64)
+            seg_color = rng.random((n, 3)).astype(np.float32) * 1.2 - 0.1     # exercises the clamp
+            vol.voxel_obj_idx = torch.from_numpy(obj)
+            vol.objects_segmentation_color = torch.from_numpy(seg_color)
+            verts, faces, colors, feats, vobj, vseg = vol.extract_mesh()
+            out.update(seem_obj=obj, seem_seg_color=seg_color, seem_vertex_obj=vobj.numpy(),
+                       seem_vertex_seg=vseg.numpy())
+        else:
+            verts, faces, colors, feats = vol.extract_mesh()
+        key = name.split("_")[0]
+        out.update({key + "_verts": np.asarray(verts), key + "_faces": np.asarray(faces),
+                    key + "_colors": colors.numpy(), key + "_feats": feats.numpy()})
+        print(name, "mesh:", np.asarray(verts).shape, np.asarray(faces).shape, np.asarray(verts).dtype,
+              np.asarray(faces).dtype, colors.dtype, feats.dtype)
+    path = os.path.join(HERE, "mesh.npz")
+    np.savez_compressed(path, **out)
+    print("mesh ->", os.path.getsize(path) // 1024, "KiB")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     only = sys.argv[1:]
@@ -229,3 +286,5 @@ if __name__ == "__main__":
             run_scene(name, spec)
     if not only or "query" in only:
         run_query_golden()
+    if not only or "mesh" in only:
+        run_mesh_golden()

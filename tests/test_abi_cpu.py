@@ -108,3 +108,31 @@ def test_extract_mesh_by_object_matches_reference_golden():
     assert np.array_equal(v, g["obj1_verts"]) and np.array_equal(f, g["obj1_faces"]) and np.array_equal(c, g["obj1_colors"])
     v, f, c, _ = saf.extract_mesh_by_object(g["mesh_verts"], g["mesh_faces"], g["mesh_colors"], g["mesh_vidx"], 99)
     assert len(v) == 0 and len(f) == 0 and len(c) == 0
+
+
+def test_mesh_workspace_bytes_host_logic(lib):
+    g = _lib.GridDesc()
+    g.voxel_size = 0.02
+    g.nvox[:] = [304, 304, 154]
+    g.x_begin, g.x_end = 0, 304
+    n = ctypes.c_uint64()
+    assert lib.saf_mesh_workspace_bytes(ctypes.byref(g), ctypes.byref(n)) == 0
+    voxels = 304 * 304 * 154
+    assert 12 * voxels <= n.value < 12 * voxels + 8 * (voxels // 256 + 2) + 4096
+    g.x_begin, g.x_end = 10, 5
+    assert lib.saf_mesh_workspace_bytes(ctypes.byref(g), ctypes.byref(n)) == -3
+    assert lib.saf_mesh_workspace_bytes(None, ctypes.byref(n)) == -1
+
+
+def test_mc_table_header_is_current():
+    """csrc/saf_mc_tables.h is generated by tools/gen_mc_tables.py; the committed copy must match the generator
+    (the CPU oracle derives its table from the same generator at import time)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_mc_tables", os.path.join(ROOT, "tools", "gen_mc_tables.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "t.h")
+        gen.write_header(path)
+        assert open(path).read() == open(os.path.join(ROOT, "spatially_aware_ai_b200", "csrc", "saf_mc_tables.h")).read()

@@ -89,3 +89,70 @@ def test_label_argmax_oracle():
     lab = Hh.golden_labels(g)
     ref = np.where(lab.any(axis=1), lab.argmax(axis=1), -1)   # clip_seem_fusion.py:315-325
     assert np.array_equal(vol.label_argmax(), ref)
+
+
+# ---- extract_mesh (oracle/mc.py) -------------------------------------------------------------------
+
+def test_mesh_oracle_matches_reference():
+    """The reference's extract_mesh (run with oracle marching cubes in place of the absent skimage call)
+    against the numpy restatement of everything around that call: bit-exact."""
+    from oracle import mc
+    m = Hh.load_golden("mesh")
+    g = Hh.load_golden("seem_a")
+    out = mc.extract_mesh(g["tsdf"], g["weight"], g["rgb_state"], g["clip_feat"], g["nvox"], g["voxel_size"],
+                          g["origin"], m["seem_obj"], m["seem_seg_color"])
+    for got, key in zip(out, ("seem_verts", "seem_faces", "seem_colors", "seem_feats", "seem_vertex_obj",
+                              "seem_vertex_seg")):
+        assert np.array_equal(got, m[key]), key
+    g = Hh.load_golden("fusion_a")
+    out = mc.extract_mesh(g["tsdf"], g["weight"], g["rgb_state"], g["clip_feat"], g["nvox"], g["voxel_size"],
+                          g["origin"])
+    for got, key in zip(out[:4], ("fusion_verts", "fusion_faces", "fusion_colors", "fusion_feats")):
+        assert np.array_equal(got, m[key]), key
+
+
+def _edge_census(faces):
+    from collections import Counter
+    c = Counter()
+    for a, b, d in faces:
+        for e in ((a, b), (b, d), (d, a)):
+            c[e] += 1
+    return c
+
+
+def test_marching_cubes_oracle_is_watertight_and_oriented():
+    """Properties of the from-scratch case table: closed surface of a sphere is a 2-manifold with outward
+    normals and vertices on the iso-surface; random noise (every ambiguous case) has no interior cracks."""
+    from oracle import mc
+    n = 20
+    grid = np.mgrid[0:n, 0:n, 0:n].astype(np.float32)
+    centre, radius = 9.3, 6.2
+    vol = (np.sqrt(((grid - centre) ** 2).sum(0)) - radius).astype(np.float32)
+    verts, faces = mc.marching_cubes_raw(vol)
+    c = _edge_census(faces)
+    assert max(c.values()) == 1 and all(c[(b, a)] == 1 for (a, b) in c)
+    p = verts[faces]
+    normals = np.cross(p[:, 1] - p[:, 0], p[:, 2] - p[:, 0])
+    assert ((normals * (p.mean(1) - centre)).sum(1) > 0).all()          # towards positive values
+    assert np.abs(np.linalg.norm(verts - centre, axis=1) - radius).max() < 0.03
+    assert len(verts) - len(c) // 2 + len(faces) == 2                    # Euler characteristic of a sphere
+    rng = np.random.default_rng(3)
+    vol = rng.standard_normal((10, 10, 10)).astype(np.float32)
+    verts, faces = mc.marching_cubes_raw(vol)
+    c = _edge_census(faces)
+    assert max(c.values()) == 1
+    open_edges = [(a, b) for (a, b) in c if c[(b, a)] != 1]
+    on_boundary = lambda i: bool(((verts[i] <= 0) | (verts[i] >= 9)).any())
+    assert all(on_boundary(a) and on_boundary(b) for a, b in open_edges)
+    assert set(np.unique(mc.N_TRIS)) <= set(range(6)) and mc.N_TRIS[0] == mc.N_TRIS[255] == 0
+
+
+def test_marching_cubes_oracle_nan_handling():
+    """Unobserved voxels are NaN: faces touching an edge with a NaN end are dropped by the reference's filter."""
+    from oracle import mc
+    vol = np.full((6, 6, 6), np.nan, np.float32)
+    vol[1:5, 1:5, 2] = -0.5
+    vol[1:5, 1:5, 3] = 0.5
+    verts, faces = mc.filter_mesh(*mc.marching_cubes_raw(vol))
+    assert len(faces) == 3 * 3 * 2 and len(verts) == 16 and not np.isnan(verts).any()
+    assert np.allclose(verts[:, 2], 2.5)
