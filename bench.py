@@ -56,6 +56,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--ref-frames-per-step", type=int, default=4)
     ap.add_argument("--rooms", type=int, default=0, help="debug: emulate the N-room multi-GPU workload on this rank only")
+    ap.add_argument("--window", type=int, default=8, choices=[1, 2, 4, 6, 8],
+                    help="frames fused per launch trio by saf_integrate_sequence (1 = frame by frame)")
     return ap.parse_args()
 
 
@@ -285,7 +287,9 @@ def run_native_arm(args):
             ctypes.memmove(ctypes.byref(arr[j]), ctypes.byref(pool_structs[(s * F + j) % P]), ctypes.sizeof(_lib.Frame))
         return arr
 
-    ws = vol._workspace(1, npy * npx * C)
+    window = args.window
+    ws = vol._workspace(1 if window == 1 else 1 + window // 2, npy * npx * C)
+    calls_per_step = (F + window - 1) // window
     grid_d, vol_d = vol._grid_desc(), vol._volume_desc()
     stream = torch.cuda.current_stream(dev).cuda_stream
     trunc = float(cfg.trunc)
@@ -439,13 +443,14 @@ def run_native_arm(args):
             "ms_per_step": ms / K_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(cfg, n_rooms), "frames_per_step": F, "frame_pool": P,
+                       "window": "%d consecutive frames per K1/K2/K3 launch trio (saf_integrate_sequence)" % window,
                        "l2": "no flush needed: each frame's feature rows (%.0f MB) exceed the 126 MB L2" %
                              (upd / max(1, n_frames) * (8 * C) / 1e6),
                        "parallelism": "x-slab per rank, no data-path collective" if world > 1 else "single GPU"},
             "frames_per_s": frames_per_s,
             "updates_per_frame": total_upd / n_frames, "tsdf_updates_per_frame": sum_over_ranks(tv) / n_frames if world == 1 else None,
             "visible_blocks_per_frame": blocks / n_frames,
-            "gpu_launches": 3 * n_frames,
+            "gpu_launches": 3 * calls_per_step * K_steps,
             "clocks": clocks, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
         }
         print(json.dumps(out))

@@ -41,10 +41,11 @@ def masked_tsdf(tsdf, weight, nvox):
     return out.reshape([int(v) for v in nvox])
 
 
-def marching_cubes_raw(vol):
+def marching_cubes_raw(vol, x_offset=0):
     """All iso-crossings of `vol` [nx,ny,nz] at level 0, NaN-unaware like the library call the reference makes:
     returns (verts [V,3] f32 in index coordinates - NaN when an endpoint of the edge is NaN -, faces [F,3] i64).
-    Order: vertices by (voxel flat index, axis) of their grid edge; faces by cell flat index, then table order."""
+    Order: vertices by (voxel flat index, axis) of their grid edge; faces by cell flat index, then table order.
+    x_offset: global x index of the sub-volume's first plane (x-slabs keep global coordinates)."""
     vol = np.asarray(vol, np.float32)
     nx, ny, nz = vol.shape
     with np.errstate(invalid="ignore"):
@@ -61,7 +62,9 @@ def marching_cubes_raw(vol):
         a, b = vol[lo][cross], vol[hi][cross]
         with np.errstate(invalid="ignore", divide="ignore"):
             t = (a / (a - b)).astype(np.float32)
-        idx = np.argwhere(cross).astype(np.float32)
+        idx = np.argwhere(cross)
+        idx[:, 0] += x_offset
+        idx = idx.astype(np.float32)
         idx[:, axis] = idx[:, axis] + t          # fp32 add, as the kernel does
         edge_ids.append(flat[lo][cross] * 3 + axis)
         positions.append(idx)

@@ -72,6 +72,10 @@ SIGNATURES = {
                                        P(Workspace), c_void_p, c_void_p, c_void_p]),
     "saf_feature_accumulate": (ctypes.c_int, [P(GridDesc), P(Volume), P(Frame), c_int32, c_int32, c_int32, c_int32,
                                               c_int32, P(Workspace), c_void_p]),
+    "saf_tsdf_update_window": (ctypes.c_int, [P(GridDesc), P(Volume), P(Frame), c_int32, c_int32, c_int32, c_float,
+                                              P(Workspace), c_void_p]),
+    "saf_feature_accumulate_window": (ctypes.c_int, [P(GridDesc), P(Volume), P(Frame), c_int32, c_int32, c_int32,
+                                                     c_int32, P(Workspace), c_void_p]),
     "saf_integrate": (ctypes.c_int, [P(GridDesc), P(Volume), P(Frame), c_int32, c_int32, c_int32, c_float, c_int32,
                                      P(Workspace), c_void_p]),
     "saf_integrate_sequence": (ctypes.c_int, [P(GridDesc), P(Volume), P(Frame), c_int32, c_int32, c_int32, c_float,

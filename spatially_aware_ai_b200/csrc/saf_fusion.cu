@@ -20,6 +20,7 @@
 #include <limits.h>
 #include <math.h>
 #include <algorithm>
+#include <stdlib.h>
 #include <string.h>
 
 #include "saf_internal.cuh"
@@ -34,6 +35,7 @@ struct FusionParams {
     float trunc;
     int32_t rgb_mode;
     int32_t frame_index;       // K3: which frame's list
+    int32_t sequential;        // window mode: the batch is a run of consecutive single-frame calls
     uint32_t pack_mask;        // frames whose feature image is repacked into the workspace
     uint32_t nb[3];
     uint32_t nblocks_total;
@@ -51,6 +53,8 @@ struct FusionParams {
     uint32_t* blk_count;       // [batch][nblocks_total]   valid voxels per visible block (by rank)
     uint32_t* blk_offset;      // [batch][nblocks_total+1] exclusive prefix of blk_count
     ValidEntry* lists;         // [batch][nblocks_total*512] rank r's entries start at r*512
+    WinEntry* ulist;           // window mode: [nblocks_total*512] voxels valid in any frame, rank r's start at r*512
+    float2* wcoords;           // window mode: [nblocks_total][batch][512] (gx, gy) per (block rank, frame, local voxel)
     float* tables;
     uint8_t* valid_out;
     uint8_t* tsdf_valid_out;
@@ -396,10 +400,15 @@ __global__ void __launch_bounds__(kK1Threads) frame_setup_kernel(const FusionPar
 constexpr int kK2Threads = 128;
 constexpr int kK2Iter = kBlockVoxels / kK2Threads;  // voxels per thread per block
 
-template <bool BATCH1>
+// SEQ = window mode: the batch is a run of consecutive single-frame integrate() calls.  Each voxel's TSDF running
+// average is advanced frame by frame in registers (read once, written once per window) and the kernel emits ONE
+// list of the voxels valid in at least one frame (WinEntry + per-frame coordinates) for the window feature kernel.
+template <bool BATCH1, bool SEQ>
 __global__ void __launch_bounds__(kK2Threads) tsdf_update_kernel(const FusionParams p)
 {
+    static_assert(!(BATCH1 && SEQ), "a one-frame window is the plain single-frame path");
     __shared__ uint32_t s_cnt[kK2Iter][kK2Threads / 32];
+    __shared__ uint32_t s_fcnt[2][SAF_MAX_BATCH];   // SEQ: per-frame tsdf_valid / valid counts of this CTA
     __shared__ uint32_t s_scan[33];
     extern __shared__ uint32_t s_off[];  // [n_k1]
     __shared__ bool is_last;
@@ -423,6 +432,10 @@ __global__ void __launch_bounds__(kK2Threads) tsdf_update_kernel(const FusionPar
     for (int b = 0; b < (BATCH1 ? 1 : SAF_MAX_BATCH); ++b) tv_count[b] = 0;
     Geom g;
     if (BATCH1) load_geom(p.frames[0], g);
+    if (SEQ) {
+        if (threadIdx.x < 2 * SAF_MAX_BATCH) s_fcnt[threadIdx.x / SAF_MAX_BATCH][threadIdx.x % SAF_MAX_BATCH] = 0;
+        __syncthreads();
+    }
     if (depth_cull) {
         const int ntiles = p.ntx * p.nty;
         for (int b = 0; b < B; ++b) {
@@ -492,7 +505,90 @@ __global__ void __launch_bounds__(kK2Threads) tsdf_update_kernel(const FusionPar
             bw[j] = 0;
             bt[j] = 0.0f;
         }
-        for (int b = 0; b < B; ++b) {
+        if (SEQ) {
+            __syncthreads();  // s_rank
+            const uint32_t rank = s_rank;
+            uint32_t m[kK2Iter];
+            bool dirty[kK2Iter];
+#pragma unroll
+            for (int j = 0; j < kK2Iter; ++j) {
+                m[j] = 0;
+                dirty[j] = false;
+            }
+            for (int b = 0; b < B; ++b) {
+                const saf_frame& f = p.frames[b];
+                load_geom(f, g);
+                float2* cdst = p.wcoords + ((uint64_t)rank * B + b) * kBlockVoxels;
+                uint32_t n_tv = 0, n_v = 0;
+#pragma unroll
+                for (int j = 0; j < kK2Iter; ++j) {
+                    float gx, gy, z;
+                    project(g.P, g.K, xw[j], yw[j], zw[j], fW, fH, gx, gy, z);
+                    const int px = nearest_index(gx, p.W), py = nearest_index(gy, p.H);
+                    const float d = (inside[j] && px >= 0 && py >= 0) ? __ldg(f.depth + (size_t)py * p.W + px) : 0.0f;
+                    const float sdf = __fdiv_rn(__fsub_rn(d, z), p.trunc);
+                    const bool in_view = inside[j] && (fabsf(gx) <= 1.0f) && (fabsf(gy) <= 1.0f) && (z > 0.0f);
+                    const bool valid = in_view && (fabsf(sdf) <= 1.0f);
+                    const bool tv = in_view && (sdf > -1.0f);
+                    if (tv) {
+                        // one single-frame call of clip_seem_fusion.py:730-744: bw = 1, bt = clamp(sdf)
+                        const int nw = tw[j] + 1;
+                        const float fnw = __int2float_rn(nw);
+                        t_old[j] = __fadd_rn(__fdiv_rn(fminf(fmaxf(sdf, -1.0f), 1.0f), fnw),
+                                             __fmul_rn(t_old[j], __fdiv_rn(__int2float_rn(tw[j]), fnw)));
+                        tw[j] = nw;
+                        dirty[j] = true;
+                    }
+                    if (valid) {
+                        m[j] |= 1u << b;
+                        cdst[threadIdx.x + j * kK2Threads] = make_float2(gx, gy);
+                    }
+                    if (p.valid_out && inside[j]) {
+                        if (valid) p.valid_out[(uint64_t)b * p.nslab + v[j]] = 1;
+                        if (tv) p.tsdf_valid_out[(uint64_t)b * p.nslab + v[j]] = 1;
+                    }
+                    n_tv += (uint32_t)__popc(__ballot_sync(0xffffffffu, tv));
+                    n_v += (uint32_t)__popc(__ballot_sync(0xffffffffu, valid));
+                }
+                if (lane == 0) {
+                    if (n_tv) atomicAdd(&s_fcnt[0][b], n_tv);
+                    if (n_v) atomicAdd(&s_fcnt[1][b], n_v);
+                }
+            }
+            // the block's union list, in voxel order
+            unsigned um[kK2Iter];
+#pragma unroll
+            for (int j = 0; j < kK2Iter; ++j) {
+                um[j] = __ballot_sync(0xffffffffu, m[j] != 0u);
+                if (lane == 0) s_cnt[j][warp] = (uint32_t)__popc(um[j]);
+            }
+            __syncthreads();
+            uint32_t run = 0;
+            WinEntry* seg = p.ulist + (uint64_t)rank * kBlockVoxels;
+#pragma unroll
+            for (int j = 0; j < kK2Iter; ++j) {
+#pragma unroll
+                for (int w = 0; w < kK2Threads / 32; ++w) {
+                    if (w == warp && m[j] != 0u) {
+                        WinEntry e;
+                        e.voxel = v[j];
+                        e.mask_local = m[j] | ((uint32_t)(threadIdx.x + j * kK2Threads) << 8);
+                        seg[run + __popc(um[j] & ((1u << lane) - 1u))] = e;
+                    }
+                    run += s_cnt[j][w];
+                }
+            }
+            if (threadIdx.x == 0) p.blk_count[rank] = run;
+#pragma unroll
+            for (int j = 0; j < kK2Iter; ++j) {
+                if (dirty[j]) {
+                    p.vol.tsdf[v[j]] = t_old[j];
+                    p.vol.tsdf_weight[v[j]] = tw[j];
+                }
+            }
+            __syncthreads();  // s_cnt / s_rank are reused by the next block
+        }
+        for (int b = 0; b < (SEQ ? 0 : B); ++b) {
             const saf_frame& f = p.frames[b];
             if (!BATCH1) load_geom(f, g);
             float gx[kK2Iter], gy[kK2Iter], z[kK2Iter], d[kK2Iter];
@@ -547,7 +643,7 @@ __global__ void __launch_bounds__(kK2Threads) tsdf_update_kernel(const FusionPar
         }
 #pragma unroll
         for (int j = 0; j < kK2Iter; ++j) {
-            if (bw[j] > 0) {
+            if (!SEQ && bw[j] > 0) {
                 // clip_seem_fusion.py:736-744: three separately rounded fp32 ops
                 const int nw = tw[j] + bw[j];
                 const float fnw = __int2float_rn(nw);
@@ -557,10 +653,17 @@ __global__ void __launch_bounds__(kK2Threads) tsdf_update_kernel(const FusionPar
             }
         }
     }
+    if (SEQ) {
+        __syncthreads();
+        if ((int)threadIdx.x < B) {
+            if (s_fcnt[0][threadIdx.x]) atomicAdd(&sc->n_tsdf_valid[threadIdx.x], s_fcnt[0][threadIdx.x]);
+            if (s_fcnt[1][threadIdx.x]) atomicAdd(&sc->acc_valid[threadIdx.x], s_fcnt[1][threadIdx.x]);
+        }
+    }
     // per-frame tsdf_valid totals: one atomic per warp
 #pragma unroll
     for (int b = 0; b < (BATCH1 ? 1 : SAF_MAX_BATCH); ++b) {
-        if (b >= B) break;
+        if (SEQ || b >= B) break;
         uint32_t c = tv_count[b];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
@@ -578,7 +681,23 @@ __global__ void __launch_bounds__(kK2Threads) tsdf_update_kernel(const FusionPar
     __threadfence();
     unsigned long long sv = 0, stv = 0;
     const uint32_t n_proc = atomicAdd(&sc->n_processed, 0u);
-    for (int b = 0; b < B; ++b) {
+    if (SEQ) {
+        // one union list for the window; the per-frame counts come from the atomics
+        const uint32_t total = cta_exclusive_scan(p.blk_count, p.blk_offset, n_proc, s_scan);
+        if (threadIdx.x == 0) {
+            p.blk_offset[n_proc] = total;
+            sc->n_union = total;
+            for (int b = 0; b < B; ++b) {
+                const uint32_t nv = atomicExch(&sc->acc_valid[b], 0u);
+                const uint32_t t = atomicExch(&sc->n_tsdf_valid[b], 0u);
+                sc->n_valid[b] = nv;
+                sc->last_tsdf_valid[b] = t;
+                sv += nv;
+                stv += t;
+            }
+        }
+    }
+    for (int b = 0; b < (SEQ ? 0 : B); ++b) {
         uint32_t* off = p.blk_offset + (uint64_t)b * (p.nblocks_total + 1);
         const uint32_t total = cta_exclusive_scan(p.blk_count + (uint64_t)b * p.nblocks_total, off, n_proc, s_scan);
         if (threadIdx.x == 0) {
@@ -881,6 +1000,264 @@ __global__ void __launch_bounds__(kK3Threads) feature_accumulate_generic_kernel(
 }
 
 // ---------------------------------------------------------------------------------------------
+// K3W: window mode of K3 (saf_integrate_sequence).  One warp per voxel that is valid in at least one of
+// the window's frames: the feature row is pulled in once (TMA ring), every valid frame's update is applied
+// to it in registers in frame order - the exact arithmetic of that many single-frame calls - and it is
+// written back once.  DRAM traffic per voxel update drops by the number of window frames that see the
+// voxel (consecutive frames of a scan overlap almost completely); the per-frame table rows are read through
+// L1 (the 16 warps of a CTA walk neighbouring voxels, so they share the same few rows of each frame).
+// ---------------------------------------------------------------------------------------------
+
+struct WindowTables {
+    const float* ptr[SAF_MAX_BATCH];     // [R,C]-row view of each frame's feature image
+    int64_t stride_r[SAF_MAX_BATCH];
+};
+
+__device__ __forceinline__ void sample_rgb(const FusionParams& p, const saf_frame& f, float gx, float gy, int px, int py,
+                                           float (&smp)[3])
+{
+    if (p.rgb_mode == SAF_RGB_NEAREST) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) smp[c] = (px >= 0 && py >= 0) ? __ldg(f.rgb + ((size_t)py * p.W + px) * 3 + c) : 0.0f;
+    } else {
+        Taps t;
+        bilinear_setup(gx, gy, p.W, p.H, t);
+        float val[4][3];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) val[k][c] = t.idx[k] >= 0 ? __ldg(f.rgb + (size_t)t.idx[k] * 3 + c) : 0.0f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) smp[c] = bilinear_mix(val[0][c], val[1][c], val[2][c], val[3][c], t.w);
+    }
+}
+
+template <int CHUNKS, int NST>
+__global__ void __launch_bounds__(kK3Threads) feature_accumulate_window_kernel(const __grid_constant__ FusionParams p,
+                                                                          const __grid_constant__ WindowTables wt)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int C = CHUNKS * 128;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const SlotCounters* sc = &p.hdr->slot[p.slot];
+    const uint32_t n = sc->n_union;
+    if (n == 0) return;
+    const uint32_t n_blocks = sc->n_blocks;
+    const int B = p.batch;
+
+    float* ring = reinterpret_cast<float*>(smem_raw);
+    float2* coords = reinterpret_cast<float2*>(ring + (size_t)kK3Warps * NST * C);   // [warp][32][SAF_MAX_BATCH]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(coords + (size_t)kK3Warps * 32 * SAF_MAX_BATCH);
+    float* my_ring = ring + (size_t)warp * NST * C;
+    float2* my_coords = coords + (size_t)warp * 32 * SAF_MAX_BATCH;
+    uint64_t* my_bars = bars + warp * NST;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kK3Warps * NST; ++i) mbar_init(&bars[i], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const uint32_t nwarps = gridDim.x * kK3Warps;
+    const uint32_t gwarp = blockIdx.x * kK3Warps + warp;
+    const uint32_t per_warp = (n + nwarps - 1) / nwarps;
+    const uint32_t first = min(n, gwarp * per_warp);
+    const uint32_t k_total = min(n, first + per_warp) - first;
+    const uint32_t* __restrict__ off = p.blk_offset;
+    uint32_t t_use = 0;
+
+    for (uint32_t kb = 0; kb < k_total; kb += 32) {
+        const uint32_t cnt = min(32u, k_total - kb);
+        uint32_t my_voxel = 0, my_mask = 0;
+        int my_w = 0;
+        if (lane < cnt) {
+            const uint32_t i = first + kb + lane;
+            uint32_t lo = 0, hi = n_blocks;  // off[lo] <= i < off[hi]
+            while (hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (__ldg(off + mid) <= i)
+                    lo = mid;
+                else
+                    hi = mid;
+            }
+            const WinEntry e = p.ulist[(uint64_t)lo * kBlockVoxels + (i - __ldg(off + lo))];
+            my_voxel = e.voxel;
+            my_mask = e.mask_local & 0xffu;
+            my_w = p.vol.weight[my_voxel];
+            const float2* src = p.wcoords + (uint64_t)lo * B * kBlockVoxels + (e.mask_local >> 8);
+            for (uint32_t mm = my_mask; mm; mm &= mm - 1u) {
+                const int b = __ffs(mm) - 1;
+                my_coords[lane * SAF_MAX_BATCH + b] = src[(size_t)b * kBlockVoxels];
+            }
+        }
+        const uint32_t pre = min((uint32_t)NST, cnt);
+        for (uint32_t q = 0; q < pre; ++q) {
+            const uint32_t vq = __shfl_sync(0xffffffffu, my_voxel, q);
+            if (lane == 0) {
+                const uint32_t s = (t_use + q) % NST;
+                mbar_arrive_expect_tx(&my_bars[s], (uint32_t)C * 4u);
+                tma_bulk_g2s(my_ring + (size_t)s * C, p.vol.clip_feat + (size_t)vq * C, (uint32_t)C * 4u, &my_bars[s]);
+            }
+        }
+        // rgb running average, label counters and weight of this lane's voxel, frame by frame
+        // (clip_seem_fusion.py:786-798, 808-822)
+        if (lane < cnt) {
+            float* dst = p.vol.rgb + (size_t)my_voxel * 3;
+            float acc[3] = {dst[0], dst[1], dst[2]};
+            int w = my_w;
+            for (uint32_t mm = my_mask; mm; mm &= mm - 1u) {
+                const int b = __ffs(mm) - 1;
+                const saf_frame& f = p.frames[b];
+                const float2 g = my_coords[lane * SAF_MAX_BATCH + b];
+                const float a = __frcp_rn(__int2float_rn(w + 1));
+                const float bb = __fmul_rn(__int2float_rn(w), a);
+                const int px = nearest_index(g.x, p.W), py = nearest_index(g.y, p.H);
+                float smp[3];
+                sample_rgb(p, f, g.x, g.y, px, py, smp);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) acc[c] = __fadd_rn(__fmul_rn(smp[c], a), __fmul_rn(acc[c], bb));
+                if (p.vol.labels_one_hot && f.seg) {
+                    const float lf = (px >= 0 && py >= 0) ? load_class_id(f.seg, f.seg_dtype, py * p.W + px) : 0.0f;
+                    const long long id = (long long)lf;
+                    if (id >= 0 && id < p.vol.n_classes)
+                        p.vol.labels_one_hot[(size_t)my_voxel * p.vol.n_classes + id] += 1;
+                    else
+                        atomicOr(&p.hdr->error_flags, SAF_FLAG_BAD_CLASS_ID);
+                }
+                ++w;
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) dst[c] = acc[c];
+            p.vol.weight[my_voxel] = w;
+        }
+        __syncwarp();  // my_coords written by the lanes, read by the whole warp below
+        for (uint32_t q = 0; q < cnt; ++q) {
+            const uint32_t s = t_use % NST;
+            const uint32_t parity = (t_use / NST) & 1u;
+            const uint32_t vq = __shfl_sync(0xffffffffu, my_voxel, q);
+            const uint32_t mq = __shfl_sync(0xffffffffu, my_mask, q);
+            int w = __shfl_sync(0xffffffffu, my_w, q);
+            float4* row = reinterpret_cast<float4*>(p.vol.clip_feat + (size_t)vq * C);
+            const float4* old4 = reinterpret_cast<const float4*>(my_ring + (size_t)s * C);
+            const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+            mbar_wait(&my_bars[s], parity);
+            float4 acc[CHUNKS];
+#pragma unroll
+            for (int j = 0; j < CHUNKS; ++j) acc[j] = old4[j * 32 + lane];
+            for (uint32_t mm = mq; mm; mm &= mm - 1u) {
+                const int b = __ffs(mm) - 1;
+                const float2 g = my_coords[q * SAF_MAX_BATCH + b];
+                // clip_seem_fusion.py:808-810
+                const float a = __frcp_rn(__int2float_rn(w + 1));
+                const float bb = __fmul_rn(__int2float_rn(w), a);
+                Taps t;
+                bilinear_setup(g.x, g.y, p.frames[b].npx, p.frames[b].npy, t);
+                const float4* tab4 = reinterpret_cast<const float4*>(wt.ptr[b]);
+                const int64_t tab_row4 = wt.stride_r[b] / 4;
+#pragma unroll
+                for (int j = 0; j < CHUNKS; ++j) {
+                    const int col = j * 32 + lane;
+                    const float4 t0 = t.idx[0] >= 0 ? __ldg(tab4 + t.idx[0] * tab_row4 + col) : zero;
+                    const float4 t1 = t.idx[1] >= 0 ? __ldg(tab4 + t.idx[1] * tab_row4 + col) : zero;
+                    const float4 t2 = t.idx[2] >= 0 ? __ldg(tab4 + t.idx[2] * tab_row4 + col) : zero;
+                    const float4 t3 = t.idx[3] >= 0 ? __ldg(tab4 + t.idx[3] * tab_row4 + col) : zero;
+                    acc[j] = blend4(mix4(t0, t1, t2, t3, t.w), acc[j], a, bb);
+                }
+                ++w;
+            }
+#pragma unroll
+            for (int j = 0; j < CHUNKS; ++j) st_stream_f4(row + j * 32 + lane, acc[j]);
+            __syncwarp();  // every lane has consumed stage s
+            if (q + NST < cnt) {
+                const uint32_t vn = __shfl_sync(0xffffffffu, my_voxel, q + NST);
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(&my_bars[s], (uint32_t)C * 4u);
+                    tma_bulk_g2s(my_ring + (size_t)s * C, p.vol.clip_feat + (size_t)vn * C, (uint32_t)C * 4u, &my_bars[s]);
+                }
+            }
+            ++t_use;
+        }
+        __syncwarp();  // the next batch overwrites my_coords
+    }
+}
+
+// Any feature_dim (window mode): rows straight from global memory, VEC = 4 or 1.
+template <int VEC>
+__global__ void __launch_bounds__(kK3Threads) feature_accumulate_window_generic_kernel(
+    const __grid_constant__ FusionParams p, const __grid_constant__ WindowTables wt)
+{
+    const int C = p.vol.feature_dim;
+    const int lane = threadIdx.x & 31;
+    const SlotCounters* sc = &p.hdr->slot[p.slot];
+    const uint32_t n = sc->n_union;
+    const uint32_t n_blocks = sc->n_blocks;
+    const int B = p.batch;
+    const uint32_t nwarps = gridDim.x * kK3Warps;
+    const uint32_t gwarp = blockIdx.x * kK3Warps + (threadIdx.x >> 5);
+    const uint32_t* __restrict__ off = p.blk_offset;
+    for (uint64_t i = gwarp; i < n; i += nwarps) {
+        uint32_t lo = 0, hi = n_blocks;
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(off + mid) <= (uint32_t)i)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        const WinEntry e = p.ulist[(uint64_t)lo * kBlockVoxels + ((uint32_t)i - __ldg(off + lo))];
+        const float2* src = p.wcoords + (uint64_t)lo * B * kBlockVoxels + (e.mask_local >> 8);
+        const int w0 = p.vol.weight[e.voxel];
+        float* row = p.vol.clip_feat + (size_t)e.voxel * C;
+        int w = w0;
+        for (uint32_t mm = e.mask_local & 0xffu; mm; mm &= mm - 1u) {
+            const int b = __ffs(mm) - 1;
+            const float2 g = src[(size_t)b * kBlockVoxels];
+            const float a = __frcp_rn(__int2float_rn(w + 1));
+            const float bb = __fmul_rn(__int2float_rn(w), a);
+            Taps t;
+            bilinear_setup(g.x, g.y, p.frames[b].npx, p.frames[b].npy, t);
+            const float* table = wt.ptr[b];
+            const int64_t sr = wt.stride_r[b];
+            if (VEC == 4) {
+                const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int col = lane; col < C / 4; col += 32) {
+                    const float4 o = reinterpret_cast<const float4*>(row)[col];
+                    float4 tv[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        tv[k] = t.idx[k] >= 0 ? __ldg(reinterpret_cast<const float4*>(table + t.idx[k] * sr) + col) : zero;
+                    reinterpret_cast<float4*>(row)[col] = blend4(mix4(tv[0], tv[1], tv[2], tv[3], t.w), o, a, bb);
+                }
+            } else {
+                for (int c = lane; c < C; c += 32) {
+                    float tv[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) tv[k] = t.idx[k] >= 0 ? __ldg(table + t.idx[k] * sr + c) : 0.0f;
+                    const float smp = bilinear_mix(tv[0], tv[1], tv[2], tv[3], t.w);
+                    row[c] = __fadd_rn(__fmul_rn(smp, a), __fmul_rn(row[c], bb));
+                }
+            }
+            ++w;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            // small state, frame by frame (weights advance exactly as above)
+            w = w0;
+            for (uint32_t mm = e.mask_local & 0xffu; mm; mm &= mm - 1u) {
+                const int b = __ffs(mm) - 1;
+                const float2 g = src[(size_t)b * kBlockVoxels];
+                ValidEntry ve;
+                ve.voxel = e.voxel;
+                ve.gx = g.x;
+                ve.gy = g.y;
+                ve.pad = 0;
+                update_small_state(p, p.frames[b], ve, w);
+                ++w;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // label argmax (clip_seem_fusion.py:315-325)
 // ---------------------------------------------------------------------------------------------
 
@@ -982,6 +1359,9 @@ static int build_params(const saf_grid_desc* grid, const saf_volume* vol, const 
     p->blk_count = (uint32_t*)(sb + L.off_blk_count);
     p->blk_offset = (uint32_t*)(sb + L.off_blk_offset);
     p->lists = (ValidEntry*)(sb + L.off_lists);
+    // window mode reuses the per-frame list regions: region 0 holds the union list, regions 1.. the coordinates
+    p->ulist = (WinEntry*)p->lists;
+    p->wcoords = (float2*)(p->lists + L.list_cap);
     p->tables = (float*)(sb + L.off_tables);
     return 0;
 }
@@ -1020,9 +1400,11 @@ static int launch_k2(const FusionParams& p, int sms, cudaStream_t st)
 {
     const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)p.nblocks_total, (uint64_t)sms * 8u);
     if (p.batch == 1)
-        tsdf_update_kernel<true><<<grid, kK2Threads, (size_t)p.n_k1 * 4, st>>>(p);
+        tsdf_update_kernel<true, false><<<grid, kK2Threads, (size_t)p.n_k1 * 4, st>>>(p);
+    else if (p.sequential)
+        tsdf_update_kernel<false, true><<<grid, kK2Threads, (size_t)p.n_k1 * 4, st>>>(p);
     else
-        tsdf_update_kernel<false><<<grid, kK2Threads, (size_t)p.n_k1 * 4, st>>>(p);
+        tsdf_update_kernel<false, false><<<grid, kK2Threads, (size_t)p.n_k1 * 4, st>>>(p);
     SAF_CHECK_LAUNCH("tsdf_update_kernel (K2)", st);
     return 0;
 }
@@ -1078,6 +1460,61 @@ static int launch_k3(FusionParams& p, int frame_index, int sms, int smem_optin, 
         feature_accumulate_generic_kernel<1><<<sms * 2, kK3Threads, 0, st>>>(p, table, stride_r);
     }
     SAF_CHECK_LAUNCH("feature_accumulate_generic_kernel (K3)", st);
+    return 0;
+}
+
+template <int CHUNKS, int NST>
+static int launch_k3w_fixed(const FusionParams& p, const WindowTables& wt, int sms, cudaStream_t st)
+{
+    constexpr size_t row = (size_t)CHUNKS * 128 * 4;
+    const size_t smem = (size_t)kK3Warps * NST * row + (size_t)kK3Warps * 32 * SAF_MAX_BATCH * sizeof(float2) +
+                        8 * (size_t)kK3Warps * NST;
+    auto kern = feature_accumulate_window_kernel<CHUNKS, NST>;
+    SAF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<sms, kK3Threads, smem, st>>>(p, wt);
+    SAF_CHECK_LAUNCH("feature_accumulate_window_kernel (K3W)", st);
+    return 0;
+}
+
+// ring stages per warp of K3W (2 or 3): fewer stages leave more of the SM's 256 KB to L1, which serves the
+// per-frame table rows.  SAF_K3W_NST overrides for A/B timing.
+static int k3w_stages()
+{
+    static int nst = 0;
+    if (!nst) {
+        const char* v = getenv("SAF_K3W_NST");
+        nst = (v && v[0] == '3') ? 3 : 2;
+    }
+    return nst;
+}
+
+static int launch_k3w(const FusionParams& p, int sms, cudaStream_t st)
+{
+    const int C = p.vol.feature_dim;
+    WindowTables wt;
+    bool rows16 = (C % 4 == 0) && (((uintptr_t)p.vol.clip_feat & 15u) == 0);
+    for (int b = 0; b < SAF_MAX_BATCH; ++b) {
+        wt.ptr[b] = nullptr;
+        wt.stride_r[b] = 0;
+        if (b >= p.batch) continue;
+        const bool packed = (p.pack_mask >> b) & 1u;
+        wt.ptr[b] = packed ? p.tables + (uint64_t)b * p.max_table_elems : p.frames[b].table;
+        wt.stride_r[b] = packed ? C : p.frames[b].table_stride_r;
+        rows16 = rows16 && (wt.stride_r[b] % 4 == 0) && (((uintptr_t)wt.ptr[b] & 15u) == 0);
+    }
+    if (rows16) {
+        const bool three = k3w_stages() == 3;
+        switch (C) {
+            case 512: return three ? launch_k3w_fixed<4, 3>(p, wt, sms, st) : launch_k3w_fixed<4, 2>(p, wt, sms, st);
+            case 768: return three ? launch_k3w_fixed<6, 3>(p, wt, sms, st) : launch_k3w_fixed<6, 2>(p, wt, sms, st);
+            case 1024: return launch_k3w_fixed<8, 2>(p, wt, sms, st);
+            default: break;
+        }
+        feature_accumulate_window_generic_kernel<4><<<sms * 2, kK3Threads, 0, st>>>(p, wt);
+    } else {
+        feature_accumulate_window_generic_kernel<1><<<sms * 2, kK3Threads, 0, st>>>(p, wt);
+    }
+    SAF_CHECK_LAUNCH("feature_accumulate_window_generic_kernel (K3W)", st);
     return 0;
 }
 
@@ -1195,25 +1632,69 @@ int saf_feature_accumulate(const saf_grid_desc* grid, const saf_volume* vol, con
     return launch_k3(p, frame_index, sms, smem_optin, (cudaStream_t)stream);
 }
 
+// Window-mode counterparts of saf_tsdf_update / saf_feature_accumulate: the batch is a run of consecutive
+// single-frame calls (what saf_integrate_sequence issues per window), after saf_frustum_cull on the same batch.
+int saf_tsdf_update_window(const saf_grid_desc* grid, const saf_volume* vol, const saf_frame* frames, int32_t batch,
+                           int32_t H, int32_t W, float trunc, const saf_workspace* ws, void* stream)
+{
+    int sms = 0;
+    int rc = device_sm_count(&sms, nullptr);
+    if (rc) return rc;
+    if (!vol || !vol->tsdf || !vol->tsdf_weight) return SAF_ERR_NULL;
+    if (!(trunc > 0.f)) return SAF_ERR_SHAPE;
+    if (batch < 2) return SAF_ERR_BATCH;
+    FusionParams p;
+    rc = build_params(grid, vol, frames, batch, H, W, trunc, SAF_RGB_BILINEAR, ws, &p);
+    if (rc) return rc;
+    if (ws->max_batch < 1 + (batch + 1) / 2) return SAF_ERR_WORKSPACE;
+    p.sequential = 1;
+    return launch_k2(p, sms, (cudaStream_t)stream);
+}
+
+int saf_feature_accumulate_window(const saf_grid_desc* grid, const saf_volume* vol, const saf_frame* frames,
+                                  int32_t batch, int32_t H, int32_t W, int32_t rgb_mode, const saf_workspace* ws,
+                                  void* stream)
+{
+    int sms = 0;
+    int rc = device_sm_count(&sms, nullptr);
+    if (rc) return rc;
+    if (batch < 2) return SAF_ERR_BATCH;
+    FusionParams p;
+    rc = build_params(grid, vol, frames, batch, H, W, 1.0f, rgb_mode, ws, &p);
+    if (rc) return rc;
+    rc = check_feature_args(vol, frames, batch, rgb_mode, ws, &p.pack_mask);
+    if (rc) return rc;
+    if (ws->max_batch < 1 + (batch + 1) / 2) return SAF_ERR_WORKSPACE;
+    p.sequential = 1;
+    return launch_k3w(p, sms, (cudaStream_t)stream);
+}
+
 // K1 + K2 of one integrate() call on `st_geo`, then its K3 launches on `st_feat`.
 static int integrate_call(const saf_grid_desc* grid, const saf_volume* vol, const saf_frame* frames, int32_t batch,
                           int32_t H, int32_t W, float trunc, int32_t rgb_mode, const saf_workspace* ws, uint32_t slot,
                           int sms, int smem_optin, cudaStream_t st_geo, cudaStream_t st_feat, cudaEvent_t geo_done,
-                          cudaEvent_t feat_done)
+                          cudaEvent_t feat_done, bool sequential = false)
 {
     FusionParams p;
     int rc = build_params(grid, vol, frames, batch, H, W, trunc, rgb_mode, ws, &p, slot);
     if (rc) return rc;
     rc = check_feature_args(vol, frames, batch, rgb_mode, ws, &p.pack_mask);
     if (rc) return rc;
+    p.sequential = (sequential && batch > 1) ? 1 : 0;
+    // the window's union list and coordinates live in list regions 0 and 1 .. ceil(batch / 2)
+    if (p.sequential && ws->max_batch < 1 + (batch + 1) / 2) return SAF_ERR_WORKSPACE;
     if ((rc = launch_k1(p, st_geo))) return rc;
     if ((rc = launch_k2(p, sms, st_geo))) return rc;
     if (geo_done) {
         SAF_CUDA_TRY(cudaEventRecord(geo_done, st_geo));
         SAF_CUDA_TRY(cudaStreamWaitEvent(st_feat, geo_done, 0));
     }
-    for (int b = 0; b < batch; ++b)
-        if ((rc = launch_k3(p, b, sms, smem_optin, st_feat))) return rc;
+    if (p.sequential) {
+        if ((rc = launch_k3w(p, sms, st_feat))) return rc;
+    } else {
+        for (int b = 0; b < batch; ++b)
+            if ((rc = launch_k3(p, b, sms, smem_optin, st_feat))) return rc;
+    }
     if (feat_done) SAF_CUDA_TRY(cudaEventRecord(feat_done, st_feat));
     return 0;
 }
@@ -1241,10 +1722,16 @@ int saf_integrate_sequence(const saf_grid_desc* grid, const saf_volume* vol, con
     if (rc) return rc;
     if (!(trunc > 0.f)) return SAF_ERR_SHAPE;
     cudaStream_t st = (cudaStream_t)stream;
-    if (n_frames < 4) {
-        for (int32_t i = 0; i < n_frames; ++i) {
-            rc = integrate_call(grid, vol, frames + i, 1, H, W, trunc, rgb_mode, ws, 0, sms, smem_optin, st, st, nullptr,
-                                nullptr);
+    // Window mode: up to 8 consecutive frames share one K1 / K2 / K3W launch trio (per-voxel updates are applied
+    // frame by frame inside the kernels, so the result is that of the single-frame calls).  It needs list regions
+    // for the window (saf_workspace.max_batch >= 1 + window / 2); a max_batch = 1 workspace runs frame by frame.
+    const int32_t window = ws && ws->max_batch >= 2 ? std::min<int32_t>(SAF_MAX_BATCH, 2 * (ws->max_batch - 1)) : 1;
+    const int32_t n_calls = (n_frames + window - 1) / window;
+    if (n_calls < 4) {
+        for (int32_t c = 0; c < n_calls; ++c) {
+            const int32_t i0 = c * window, nb = std::min(window, n_frames - i0);
+            rc = integrate_call(grid, vol, frames + i0, nb, H, W, trunc, rgb_mode, ws, 0, sms, smem_optin, st, st, nullptr,
+                                nullptr, true);
             if (rc) return rc;
         }
         return 0;
@@ -1276,12 +1763,13 @@ int saf_integrate_sequence(const saf_grid_desc* grid, const saf_volume* vol, con
     // the side stream starts after everything already queued on the caller's stream
     SAF_SEQ_TRY(cudaEventRecord(fork, st));
     SAF_SEQ_TRY(cudaStreamWaitEvent(side, fork, 0));
-    for (int32_t i = 0; i < n_frames; ++i) {
-        const uint32_t slot = (uint32_t)(i & 1);
-        // slot reuse: K3 of frame i-2 must have finished reading this slot's lists
-        if (i >= 2) SAF_SEQ_TRY(cudaStreamWaitEvent(side, feat_done[slot], 0));
-        rc = integrate_call(grid, vol, frames + i, 1, H, W, trunc, rgb_mode, ws, slot, sms, smem_optin, side, st,
-                            geo_done[slot], feat_done[slot]);
+    for (int32_t c = 0; c < n_calls; ++c) {
+        const uint32_t slot = (uint32_t)(c & 1);
+        const int32_t i0 = c * window, nb = std::min(window, n_frames - i0);
+        // slot reuse: the feature kernel of call c-2 must have finished reading this slot's lists
+        if (c >= 2) SAF_SEQ_TRY(cudaStreamWaitEvent(side, feat_done[slot], 0));
+        rc = integrate_call(grid, vol, frames + i0, nb, H, W, trunc, rgb_mode, ws, slot, sms, smem_optin, side, st,
+                            geo_done[slot], feat_done[slot], true);
         if (rc) {
             cleanup();
             return rc;

@@ -33,7 +33,8 @@ struct SlotCounters {
     uint32_t n_processed;                   // blocks K2 did not skip by the depth test (atomic, zeroed like above)
     uint32_t last_processed;
     uint32_t n_frustum_blocks;              // blocks K1 listed for the call
-    uint32_t pad2_[1];
+    uint32_t n_union;                       // window mode: voxels valid in at least one frame of the window
+    uint32_t acc_valid[SAF_MAX_BATCH];      // window mode: per-frame valid counts (atomics, folded like n_tsdf_valid)
 };
 
 // Device-resident workspace header (512 bytes).
@@ -60,6 +61,13 @@ struct WsHeader {
     uint32_t pad1_[1];
 };
 static_assert(sizeof(WsHeader) <= 512, "workspace header grew past its slot");
+
+// Window mode (saf_integrate_sequence): one voxel that is `valid` in at least one frame of the window.
+// The (gx, gy) of frame b live in a separate array at [(rank * B + b) * 512 + local].
+struct __align__(8) WinEntry {
+    uint32_t voxel;        // slab-local flat index
+    uint32_t mask_local;   // bits 0..7: frames of the window in which the voxel is valid; bits 8..16: index in its block
+};
 
 // One `valid` voxel of one frame: slab-local flat index and the normalised image coordinates
 // the reference reuses for all three samplers (clip_seem_fusion.py:752).

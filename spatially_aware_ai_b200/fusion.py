@@ -180,20 +180,35 @@ class _FusionVolume(torch.nn.Module):
                 f.K[:] = K_host[b].tolist()
         return frames, keep, (B, H, W, npy * npx * self.n_clip_feats)
 
-    def _integrate_frames(self, depth_imgs, rgb_imgs, poses, K, clip_feat_img, seg_maps):
+    def _integrate_frames(self, depth_imgs, rgb_imgs, poses, K, clip_feat_img, seg_maps, sequence=False):
         if not self.tsdf.is_cuda:
             raise RuntimeError("spatially_aware_ai_b200 volumes run on a CUDA (sm_100) device only; "
                                "call .to('cuda') - there is no CPU path")
         frames, keep, (B, H, W, table_elems) = self._make_frames(depth_imgs, rgb_imgs, poses, K, clip_feat_img, seg_maps)
-        if B > _lib.SAF_MAX_BATCH:
-            raise RuntimeError("batch of %d frames exceeds SAF_MAX_BATCH=%d" % (B, _lib.SAF_MAX_BATCH))
-        ws = self._workspace(B, table_elems)
         vol = self._volume_desc()
         stream = torch.cuda.current_stream(self.tsdf.device).cuda_stream
-        rc = _lib.load().saf_integrate(ctypes.byref(self._grid_desc()), ctypes.byref(vol), frames, B, H, W,
-                                       float(self.trunc), self._rgb_mode, ctypes.byref(ws), stream)
-        _lib.check(rc, "saf_integrate")
+        if sequence:
+            # B successive single-frame calls; a max_batch = 8 workspace lets the library fuse them 8 at a time
+            ws = self._workspace(_lib.SAF_MAX_BATCH, table_elems)
+            rc = _lib.load().saf_integrate_sequence(ctypes.byref(self._grid_desc()), ctypes.byref(vol), frames, B, H, W,
+                                                    float(self.trunc), self._rgb_mode, ctypes.byref(ws), stream)
+            _lib.check(rc, "saf_integrate_sequence")
+        else:
+            if B > _lib.SAF_MAX_BATCH:
+                raise RuntimeError("batch of %d frames exceeds SAF_MAX_BATCH=%d" % (B, _lib.SAF_MAX_BATCH))
+            ws = self._workspace(B, table_elems)
+            rc = _lib.load().saf_integrate(ctypes.byref(self._grid_desc()), ctypes.byref(vol), frames, B, H, W,
+                                           float(self.trunc), self._rgb_mode, ctypes.byref(ws), stream)
+            _lib.check(rc, "saf_integrate")
         del keep
+
+    def integrate_sequence(self, depth_imgs, rgb_imgs, poses, K):
+        """The reference's frame loop (clip_seem_fusion.py:305-313) as one call: same result as
+        ``for i in range(F): self.integrate(depth_imgs[i:i+1], rgb_imgs[i:i+1], poses[i:i+1], K[i:i+1])``,
+        but consecutive frames are fused 8 at a time on the device (each voxel's state is read and written
+        once per window instead of once per frame).  The producers are called once with all F frames."""
+        clip_feat_img, seg_maps = self._run_producers(depth_imgs, rgb_imgs, K)
+        self._integrate_frames(depth_imgs, rgb_imgs, poses, K, clip_feat_img, seg_maps, sequence=True)
 
     # -- bookkeeping ---------------------------------------------------------------------------
 
@@ -247,8 +262,8 @@ class ClipSeemFusion(_FusionVolume):
         self._init_volume(origin, voxel_size, nvox, trunc, self.clip.feature_dim, x_begin, x_end)
         self.debug_counter = 0
 
-    def integrate(self, depth_imgs, rgb_imgs, poses, K):
-        """clip_seem_fusion.py:676-822.  depth [B,H,W], rgb [B,H,W,3] in [0,1], poses [B,4,4], K [B,3,3]."""
+    def _run_producers(self, depth_imgs, rgb_imgs, K):
+        """clip_seem_fusion.py:683-695, 753-757: tiled-patch CLIP feature image and one class map per frame."""
         batch_size = rgb_imgs.shape[0]
         rgb_chw = rgb_imgs.permute(0, 3, 1, 2)
         if self.scale_patches_by_depth:
@@ -258,6 +273,11 @@ class ClipSeemFusion(_FusionVolume):
             clip_feat_img = self.clip.img_inference_tiled(rgb_chw, patch_size=self.clip_patch_size,
                                                           patch_stride=self.clip_patch_stride)
         seg_maps = [self.segmentation_model.run_on_image(rgb_chw[i]) for i in range(batch_size)]
+        return clip_feat_img, seg_maps
+
+    def integrate(self, depth_imgs, rgb_imgs, poses, K):
+        """clip_seem_fusion.py:676-822.  depth [B,H,W], rgb [B,H,W,3] in [0,1], poses [B,4,4], K [B,3,3]."""
+        clip_feat_img, seg_maps = self._run_producers(depth_imgs, rgb_imgs, K)
         self._integrate_frames(depth_imgs, rgb_imgs, poses, K, clip_feat_img, seg_maps)
 
     def extract_mesh(self):
@@ -287,8 +307,8 @@ class ClipFusion(_FusionVolume):
         self.scale_patches_by_depth = scale_patches_by_depth
         self._init_volume(origin, voxel_size, nvox, trunc, self.clip.feature_dim, x_begin, x_end)
 
-    def integrate(self, depth_imgs, rgb_imgs, poses, K):
-        """clipfusion.py:627-721."""
+    def _run_producers(self, depth_imgs, rgb_imgs, K):
+        """clipfusion.py:634-646."""
         rgb_chw = rgb_imgs.permute(0, 3, 1, 2)
         if self.scale_patches_by_depth:
             clip_feat_img = self.clip.img_inference_tiled_depthscaled(rgb_chw, depth_imgs, K,
@@ -296,6 +316,11 @@ class ClipFusion(_FusionVolume):
         else:
             clip_feat_img = self.clip.img_inference_tiled(rgb_chw, patch_size=self.clip_patch_size,
                                                           patch_stride=self.clip_patch_stride)
+        return clip_feat_img, None
+
+    def integrate(self, depth_imgs, rgb_imgs, poses, K):
+        """clipfusion.py:627-721."""
+        clip_feat_img, _ = self._run_producers(depth_imgs, rgb_imgs, K)
         self._integrate_frames(depth_imgs, rgb_imgs, poses, K, clip_feat_img, None)
 
     def extract_mesh(self):

@@ -128,3 +128,16 @@ def replay_gpu(g, device="cuda", x_begin=0, x_end=None, upto=None, seg_dtype=Non
         B = len(tables)
         counts.append([sum(st["last_valid"][:B]), sum(st["last_tsdf_valid"][:B])])
     return vol, np.array(counts)
+
+
+def replay_gpu_sequence(g, device="cuda", x_begin=0, x_end=None):
+    """All frames of a batch-1 golden through ONE integrate_sequence call (window mode)."""
+    import torch
+    assert g["batch"] == 1
+    vol, clip, seg = make_gpu_volume(g, device, x_begin, x_end)
+    n = len(g["counts"])
+    clip.next_table = torch.stack([torch.from_numpy(np.ascontiguousarray(golden_table(g, i))) for i in range(n)]).to(device)
+    seg.queue = [torch.from_numpy(g["seg"][i].astype(np.int64)).to(device) for i in range(n)]
+    vol.integrate_sequence(torch.from_numpy(g["depth"][:n]).to(device), torch.from_numpy(g["rgb"][:n]).to(device),
+                           torch.from_numpy(g["pose"][:n]).to(device), torch.from_numpy(g["K"][:n]).to(device))
+    return vol

@@ -370,3 +370,67 @@ def test_depth_aware_block_culling_keeps_results():
         blocks.append(st["last_blocks"])
         assert st["last_valid"][0] == orc.last_counts[0, 0] and st["last_tsdf_valid"][0] == orc.last_counts[0, 1]
     _check_against(vol, orc.tsdf, orc.weight, orc.tsdf_weight, orc.rgb, orc.clip_feat, orc.labels_one_hot, exact=True)
+
+
+# ---- window mode: saf_integrate_sequence fuses up to 8 consecutive frames per launch trio -----------------
+
+@pytest.mark.parametrize("name", ["seem_a", "fusion_a", "seem_edge"])
+def test_sequence_window_matches_reference_golden(name):
+    """One integrate_sequence call == the reference's frame loop of single-frame integrate() calls: bit-exact
+    against the golden state the unmodified reference produced frame by frame."""
+    g = Hh.load_golden(name)
+    vol = Hh.replay_gpu_sequence(g)
+    labels = Hh.golden_labels(g) if g["cls"] == "ClipSeemFusion" else None
+    _check_against(vol, g["tsdf"], g["weight"], g["tsdf_weight"], g["rgb_state"], g["clip_feat"], labels, exact=True)
+    st = vol.stats()
+    assert st["total_frames"] == len(g["counts"])
+    assert st["total_valid"] == int(g["counts"][:, 0].sum()) and st["total_tsdf_valid"] == int(g["counts"][:, 1].sum())
+
+
+@pytest.mark.parametrize("n_frames,C,step", [(19, 768, 1), (43, 512, 3), (9, 20, 7)])
+def test_sequence_window_matches_oracle(n_frames, C, step):
+    """Longer sequences (several windows, the overlapped two-slot path for >= 4 windows, a ragged last window),
+    the TMA-ring kernel (C = 768 / 512) and the generic one (C = 20), against the oracle run frame by frame."""
+    cfg = synth.SceneConfig(extent=(2.2, 2.0, 1.6), voxel_size=0.05, height=96, width=128, patch_size=64,
+                            patch_stride=32, feature_dim=C, frames=60, seed=21)
+    origin, nvox = cfg.grid()
+    g = dict(cls="ClipSeemFusion", feature_dim=C, origin=origin, nvox=nvox, voxel_size=cfg.voxel_size, trunc=cfg.trunc)
+    vol, clip, seg = Hh.make_gpu_volume(g)
+    orc = O.OracleVolume(origin, cfg.voxel_size, nvox, cfg.trunc, C, num_threads=0)
+    frames = [synth.make_frame(cfg, (i * step) % cfg.frames) for i in range(n_frames)]
+    total_valid = 0
+    for fr in frames:
+        cnt = orc.integrate(fr["depth"][None], fr["rgb"][None], fr["pose"][None], fr["K"][None], fr["table"][None],
+                            fr["seg"][None], want_masks=False)
+        total_valid += int(cnt[0, 0])
+    clip.next_table = torch.stack([torch.from_numpy(f["table"]) for f in frames]).cuda()
+    seg.queue = [torch.from_numpy(f["seg"]).cuda() for f in frames]
+    vol.integrate_sequence(torch.stack([torch.from_numpy(f["depth"]) for f in frames]).cuda(),
+                           torch.stack([torch.from_numpy(f["rgb"]) for f in frames]).cuda(),
+                           torch.stack([torch.from_numpy(f["pose"]) for f in frames]).cuda(),
+                           torch.stack([torch.from_numpy(f["K"]) for f in frames]).cuda())
+    _check_against(vol, orc.tsdf, orc.weight, orc.tsdf_weight, orc.rgb, orc.clip_feat, orc.labels_one_hot, exact=True)
+    st = vol.stats()
+    assert st["total_frames"] == n_frames and st["total_valid"] == total_valid
+
+
+def test_sequence_then_single_frames_interleave():
+    """Window calls and plain integrate() calls share the workspace and the counters."""
+    g = Hh.load_golden("seem_a")
+    vol, clip, seg = Hh.make_gpu_volume(g)
+    n = len(g["counts"])
+
+    def feed(lo, hi, sequence):
+        clip.next_table = torch.stack([torch.from_numpy(np.ascontiguousarray(Hh.golden_table(g, i)))
+                                       for i in range(lo, hi)]).cuda()
+        seg.queue = [torch.from_numpy(g["seg"][i].astype(np.int64)).cuda() for i in range(lo, hi)]
+        args = [torch.from_numpy(g[k][lo:hi]).cuda() for k in ("depth", "rgb", "pose", "K")]
+        (vol.integrate_sequence if sequence else vol.integrate)(*args)
+
+    feed(0, 1, False)
+    feed(1, 6, True)
+    for i in range(6, n):
+        feed(i, i + 1, False)
+    _check_against(vol, g["tsdf"], g["weight"], g["tsdf_weight"], g["rgb_state"], g["clip_feat"], Hh.golden_labels(g),
+                   exact=True)
+    assert vol.stats()["total_valid"] == int(g["counts"][:, 0].sum())
