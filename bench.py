@@ -56,7 +56,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--ref-frames-per-step", type=int, default=4)
     ap.add_argument("--rooms", type=int, default=0, help="debug: emulate the N-room multi-GPU workload on this rank only")
-    ap.add_argument("--window", type=int, default=8, choices=[1, 2, 4, 6, 8],
+    ap.add_argument("--window", type=int, default=8, choices=list(range(1, 9)),
                     help="frames fused per launch trio by saf_integrate_sequence (1 = frame by frame)")
     return ap.parse_args()
 
@@ -288,7 +288,7 @@ def run_native_arm(args):
         return arr
 
     window = args.window
-    ws = vol._workspace(1 if window == 1 else 1 + window // 2, npy * npx * C)
+    ws = vol._workspace(window, npy * npx * C)
     calls_per_step = (F + window - 1) // window
     grid_d, vol_d = vol._grid_desc(), vol._volume_desc()
     stream = torch.cuda.current_stream(dev).cuda_stream

@@ -174,8 +174,8 @@ int saf_feature_accumulate(const saf_grid_desc *grid, const saf_volume *vol, con
  * the `batch` frames are successive single-frame integrate() calls.  K2 advances each voxel's TSDF frame by
  * frame in registers and emits ONE list of the voxels valid in any frame; K3 reads each listed feature row
  * once, applies the valid frames' updates in order and writes it back once.  Results are those of the
- * single-frame calls.  Call saf_frustum_cull on the same batch first.  Needs a workspace with
- * max_batch >= 1 + ceil(batch / 2); 2 <= batch <= SAF_MAX_BATCH. */
+ * single-frame calls.  Call saf_frustum_cull on the same batch first.  2 <= batch <= the workspace's
+ * max_batch <= SAF_MAX_BATCH. */
 int saf_tsdf_update_window(const saf_grid_desc *grid, const saf_volume *vol, const saf_frame *frames,
                            int32_t batch, int32_t height, int32_t width, float trunc,
                            const saf_workspace *ws, void *stream);
@@ -190,7 +190,7 @@ int saf_integrate(const saf_grid_desc *grid, const saf_volume *vol, const saf_fr
 
 /* n_frames successive single-frame integrate() calls (the reference's frame loop,
  * clip_seem_fusion.py:305-313) issued from one host call.  With a workspace sized for max_batch >= 2 the
- * frames are fused in windows of min(SAF_MAX_BATCH, 2 * (max_batch - 1)) (see the window-mode calls above) and
+ * frames are fused in windows of max_batch frames (see the window-mode calls above) and
  * K1 + K2 of the next window overlap the feature kernel of the current one; a max_batch = 1 workspace runs
  * frame by frame.  Either way the result equals the frame loop's. */
 int saf_integrate_sequence(const saf_grid_desc *grid, const saf_volume *vol, const saf_frame *frames,

@@ -43,6 +43,7 @@ struct FusionParams {
     uint64_t nslab;
     uint64_t list_cap;
     uint64_t max_table_elems;
+    uint64_t table_slot_elems; // floats between consecutive frames' repacked tables
     uint32_t n_k1;             // number of K1 cull CTAs (segments of block_seg)
     uint32_t slot;             // which of the two per-call scratch slots this call uses
     WsHeader* hdr;
@@ -145,6 +146,29 @@ __device__ __forceinline__ void bilinear_setup(float gx, float gy, int W, int H,
     t.idx[1] = (nm && em) ? iyn * W + ixe : -1;
     t.idx[2] = (sm && wm) ? iys * W + ixw : -1;
     t.idx[3] = (sm && em) ? iys * W + ixe : -1;
+}
+
+// Same taps and weights for a table stored with a one-cell zero border ([(H+2)*(W+2)] rows): dropped taps are
+// redirected to the border, so all four indices are valid rows.
+__device__ __forceinline__ void bilinear_setup_padded(float gx, float gy, int W, int H, Taps& t)
+{
+    const float x = unnormalize(gx, W), y = unnormalize(gy, H);
+    const float xw = floorf(x), yn = floorf(y);
+    const float w = __fsub_rn(x, xw), e = __fsub_rn(1.0f, w);
+    const float n = __fsub_rn(y, yn), s = __fsub_rn(1.0f, n);
+    t.w[0] = __fmul_rn(s, e);
+    t.w[1] = __fmul_rn(s, w);
+    t.w[2] = __fmul_rn(n, e);
+    t.w[3] = __fmul_rn(n, w);
+    const bool ok = (xw >= -2.0f) && (xw <= __int2float_rn(W) + 1.0f) && (yn >= -2.0f) && (yn <= __int2float_rn(H) + 1.0f);
+    const int ixw = ok ? __float2int_rz(xw) : -2, iyn = ok ? __float2int_rz(yn) : -2;
+    const int cw = (ixw > -1 && ixw < W) ? ixw + 1 : 0, ce = (ixw + 1 > -1 && ixw + 1 < W) ? ixw + 2 : 0;
+    const int rn = (iyn > -1 && iyn < H) ? iyn + 1 : 0, rs = (iyn + 1 > -1 && iyn + 1 < H) ? iyn + 2 : 0;
+    const int pw = W + 2;
+    t.idx[0] = rn * pw + cw;
+    t.idx[1] = rn * pw + ce;
+    t.idx[2] = rs * pw + cw;
+    t.idx[3] = rs * pw + ce;
 }
 
 __device__ __forceinline__ float bilinear_mix(float v0, float v1, float v2, float v3, const float (&w)[4])
@@ -331,10 +355,24 @@ __global__ void __launch_bounds__(kK1Threads) frame_setup_kernel(const FusionPar
         const uint32_t pack_ctas = gridDim.x - cull_ctas;
         const int C = p.vol.feature_dim;
         for (int b = 0; b < p.batch; ++b) {
-            if (!((p.pack_mask >> b) & 1u)) continue;
             const saf_frame& f = p.frames[b];
+            float* dst = p.tables + (uint64_t)b * p.table_slot_elems;
+            if (p.sequential) {
+                // window mode: [(npy+2)*(npx+2), C] rows with a zero border, so that the feature kernel's four
+                // taps are always in range (dropped taps land on a zero row: grid_sample's zeros padding)
+                const int pw = f.npx + 2;
+                const int64_t Rp = (int64_t)(f.npy + 2) * pw;
+                for (int64_t e = (int64_t)(blockIdx.x - cull_ctas) * kK1Threads + threadIdx.x; e < Rp * C;
+                     e += (int64_t)pack_ctas * kK1Threads) {
+                    const int64_t r = e / C, c = e - r * C;
+                    const int py = (int)(r / pw) - 1, px = (int)(r % pw) - 1;
+                    const bool in = py >= 0 && py < f.npy && px >= 0 && px < f.npx;
+                    dst[e] = in ? f.table[c * f.table_stride_c + ((int64_t)py * f.npx + px) * f.table_stride_r] : 0.0f;
+                }
+                continue;
+            }
+            if (!((p.pack_mask >> b) & 1u)) continue;
             const int64_t R = (int64_t)f.npy * f.npx;
-            float* dst = p.tables + (uint64_t)b * p.max_table_elems;
             for (int64_t e = (int64_t)(blockIdx.x - cull_ctas) * kK1Threads + threadIdx.x; e < R * C;
                  e += (int64_t)pack_ctas * kK1Threads) {
                 const int64_t r = e / C, c = e - r * C;
@@ -346,7 +384,7 @@ __global__ void __launch_bounds__(kK1Threads) frame_setup_kernel(const FusionPar
     __shared__ uint32_t s_warp[kK1Threads / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t blk = blockIdx.x * kK1Threads + threadIdx.x;
-    bool vis = false;
+    uint32_t vis = 0;  // bit b: the block may be visible in frame b
     if (blk < p.nblocks_total) {
         const uint32_t bz = blk % p.nb[2];
         const uint32_t by = (blk / p.nb[2]) % p.nb[1];
@@ -357,7 +395,7 @@ __global__ void __launch_bounds__(kK1Threads) frame_setup_kernel(const FusionPar
         for (int b = 0; b < p.batch; ++b) {
             Geom g;
             load_geom(p.frames[b], g);
-            vis |= block_maybe_visible(g, cx, cy, cz, r, fW, fH);
+            vis |= (uint32_t)block_maybe_visible(g, cx, cy, cz, r, fW, fH) << b;
         }
     }
     // depth-tile maxima for K2's depth cull (only while the cull is switched on): one warp per tile, each
@@ -380,7 +418,7 @@ __global__ void __launch_bounds__(kK1Threads) frame_setup_kernel(const FusionPar
         }
     }
     // ordered compaction inside the CTA: this CTA's visible blocks, ascending, into its own segment
-    const unsigned m = __ballot_sync(0xffffffffu, vis);
+    const unsigned m = __ballot_sync(0xffffffffu, vis != 0u);
     if (lane == 0) s_warp[warp] = (uint32_t)__popc(m);
     __syncthreads();
     uint32_t base = 0, total = 0;
@@ -389,7 +427,7 @@ __global__ void __launch_bounds__(kK1Threads) frame_setup_kernel(const FusionPar
         if (w < warp) base += s_warp[w];
         total += s_warp[w];
     }
-    if (vis) p.block_seg[(size_t)blockIdx.x * kK1Threads + base + __popc(m & ((1u << lane) - 1u))] = blk;
+    if (vis) p.block_seg[(size_t)blockIdx.x * kK1Threads + base + __popc(m & ((1u << lane) - 1u))] = blk | (vis << 24);
     if (threadIdx.x == 0) p.cta_count[blockIdx.x] = total;
 }
 
@@ -465,22 +503,24 @@ __global__ void __launch_bounds__(kK2Threads) tsdf_update_kernel(const FusionPar
             else
                 hi = mid;
         }
-        const uint32_t blk = p.block_seg[(size_t)lo * kK1Threads + (bi - s_off[lo])];
+        const uint32_t packed = p.block_seg[(size_t)lo * kK1Threads + (bi - s_off[lo])];
+        const uint32_t blk = packed & 0xffffffu;
+        uint32_t fmask = packed >> 24;  // frames whose frustum the block may touch (K1)
         const uint32_t bz = blk % p.nb[2];
         const uint32_t by = (blk / p.nb[2]) % p.nb[1];
         const uint32_t bx = blk / (p.nb[2] * p.nb[1]);
         if (depth_cull) {
             float cx, cy, cz, r, half[3];
             block_sphere(p, bx, by, bz, cx, cy, cz, r, half);
-            bool reachable = false;
             for (int b = 0; b < B; ++b) {
+                if (!((fmask >> b) & 1u)) continue;
                 if (!BATCH1) load_geom(p.frames[b], g);
                 const float* tiles = (b == 0) ? s_tile : nullptr;
                 const float dfar = block_depth_bound(p, g, cx, cy, cz, r, tiles, p.tile_dmax + (size_t)b * kMaxDepthTiles,
                                                      s_zfar[b]);
-                reachable |= !(block_z_min(g, cx, cy, cz, half) > (dfar + p.trunc) * 1.001f + 1e-5f);  // NaN -> keep
+                if (block_z_min(g, cx, cy, cz, half) > (dfar + p.trunc) * 1.001f + 1e-5f) fmask &= ~(1u << b);  // NaN -> keep
             }
-            if (!reachable) continue;  // CTA-uniform: the whole block lies behind the surfaces it could see
+            if (!fmask) continue;  // CTA-uniform: the whole block lies behind the surfaces it could see
         }
         // claim the next list segment (arrival order; the list order does not affect any result)
         if (threadIdx.x == 0) s_rank = atomicAdd(&sc->n_processed, 1u);
@@ -516,6 +556,7 @@ __global__ void __launch_bounds__(kK2Threads) tsdf_update_kernel(const FusionPar
                 dirty[j] = false;
             }
             for (int b = 0; b < B; ++b) {
+                if (!((fmask >> b) & 1u)) continue;  // CTA-uniform
                 const saf_frame& f = p.frames[b];
                 load_geom(f, g);
                 float2* cdst = p.wcoords + ((uint64_t)rank * B + b) * kBlockVoxels;
@@ -589,6 +630,11 @@ __global__ void __launch_bounds__(kK2Threads) tsdf_update_kernel(const FusionPar
             __syncthreads();  // s_cnt / s_rank are reused by the next block
         }
         for (int b = 0; b < (SEQ ? 0 : B); ++b) {
+            if (!BATCH1 && !((fmask >> b) & 1u)) {  // CTA-uniform: no voxel of the block can be in view of frame b
+                __syncthreads();  // s_rank
+                if (threadIdx.x == 0) p.blk_count[(uint64_t)b * p.nblocks_total + s_rank] = 0;
+                continue;
+            }
             const saf_frame& f = p.frames[b];
             if (!BATCH1) load_geom(f, g);
             float gx[kK2Iter], gy[kK2Iter], z[kK2Iter], d[kK2Iter];
@@ -737,6 +783,7 @@ __global__ void __launch_bounds__(kK2Threads) tsdf_update_kernel(const FusionPar
         hdr->total_blocks += n_blocks;
         hdr->total_frames += (unsigned long long)B;
         hdr->last_slot = p.slot;
+        sc->k3_next = 0;            // K3W's chunk dispenser
         sc->n_blocks = n_proc;      // list segments K3 searches
         sc->n_frustum_blocks = n_blocks;
         sc->k2_done = 0;
@@ -1032,45 +1079,73 @@ __device__ __forceinline__ void sample_rgb(const FusionParams& p, const saf_fram
     }
 }
 
-template <int CHUNKS, int NST>
-__global__ void __launch_bounds__(kK3Threads) feature_accumulate_window_kernel(const __grid_constant__ FusionParams p,
-                                                                          const __grid_constant__ WindowTables wt)
+constexpr int kW3Warps = 24;                 // one CTA of 24 warps per SM: the kernel is latency-, not HBM-bound
+constexpr int kW3Threads = kW3Warps * 32;
+constexpr int kW3Chunk = 8;                  // union-list entries a warp claims at a time (dynamic balancing: the
+                                             // number of updates per entry varies from 1 to the window length)
+
+template <int CHUNKS>
+__global__ void __launch_bounds__(kW3Threads, 1)
+feature_accumulate_window_kernel(const __grid_constant__ FusionParams p, const __grid_constant__ WindowTables wt)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int C = CHUNKS * 128;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const SlotCounters* sc = &p.hdr->slot[p.slot];
+    SlotCounters* sc = &p.hdr->slot[p.slot];
     const uint32_t n = sc->n_union;
     if (n == 0) return;
     const uint32_t n_blocks = sc->n_blocks;
     const int B = p.batch;
 
+    // [ one feature row per warp (TMA landing zone) ][ coords: warp x chunk x frame ][ one mbarrier per warp ]
     float* ring = reinterpret_cast<float*>(smem_raw);
-    float2* coords = reinterpret_cast<float2*>(ring + (size_t)kK3Warps * NST * C);   // [warp][32][SAF_MAX_BATCH]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(coords + (size_t)kK3Warps * 32 * SAF_MAX_BATCH);
-    float* my_ring = ring + (size_t)warp * NST * C;
-    float2* my_coords = coords + (size_t)warp * 32 * SAF_MAX_BATCH;
-    uint64_t* my_bars = bars + warp * NST;
+    float2* coords = reinterpret_cast<float2*>(ring + (size_t)kW3Warps * C);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(coords + (size_t)kW3Warps * kW3Chunk * SAF_MAX_BATCH);
+    float* my_row = ring + (size_t)warp * C;
+    float2* my_coords = coords + (size_t)warp * kW3Chunk * SAF_MAX_BATCH;
+    uint64_t* my_bar = bars + warp;
+    __shared__ uint32_t s_ticket;
+    __shared__ volatile uint32_t s_sbase[8], s_sgen[8];
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kK3Warps * NST; ++i) mbar_init(&bars[i], 1);
+        for (int i = 0; i < kW3Warps; ++i) mbar_init(&bars[i], 1);
         fence_mbar_init();
+        s_ticket = 0;
     }
+    if (threadIdx.x < 8) s_sgen[threadIdx.x] = 0xffffffffu;
     __syncthreads();
 
-    const uint32_t nwarps = gridDim.x * kK3Warps;
-    const uint32_t gwarp = blockIdx.x * kK3Warps + warp;
-    const uint32_t per_warp = (n + nwarps - 1) / nwarps;
-    const uint32_t first = min(n, gwarp * per_warp);
-    const uint32_t k_total = min(n, first + per_warp) - first;
     const uint32_t* __restrict__ off = p.blk_offset;
-    uint32_t t_use = 0;
+    uint32_t t_use = 0;  // rows this warp has received (mbarrier parity = t_use & 1)
 
-    for (uint32_t kb = 0; kb < k_total; kb += 32) {
-        const uint32_t cnt = min(32u, k_total - kb);
+    // Work dispenser.  Warps take tickets from a CTA counter; every kW3Warps tickets form one "super chunk" of
+    // kW3Warps * kW3Chunk consecutive list entries that the warp holding its first ticket claims from the global
+    // counter.  The CTA's warps therefore walk neighbouring voxels (same few table rows per frame -> L1 hits),
+    // while the units stay small enough to balance the very uneven number of updates per entry.
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) {
+            const uint32_t t = atomicAdd(&s_ticket, 1u);
+            const uint32_t k = t / kW3Warps, c = t % kW3Warps, slot = k & 7u;
+            if (c == 0) {
+                base = atomicAdd(&sc->k3_next, (uint32_t)(kW3Warps * kW3Chunk));
+                s_sbase[slot] = base;
+                __threadfence_block();
+                s_sgen[slot] = k;
+            } else {
+                while (s_sgen[slot] != k) {
+                }
+                __threadfence_block();
+                base = s_sbase[slot];
+            }
+            base = min(base, n) + c * kW3Chunk;
+        }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint32_t cnt = min((uint32_t)kW3Chunk, n - base);
         uint32_t my_voxel = 0, my_mask = 0;
         int my_w = 0;
         if (lane < cnt) {
-            const uint32_t i = first + kb + lane;
+            const uint32_t i = base + lane;
             uint32_t lo = 0, hi = n_blocks;  // off[lo] <= i < off[hi]
             while (hi - lo > 1) {
                 const uint32_t mid = (lo + hi) >> 1;
@@ -1089,13 +1164,12 @@ __global__ void __launch_bounds__(kK3Threads) feature_accumulate_window_kernel(c
                 my_coords[lane * SAF_MAX_BATCH + b] = src[(size_t)b * kBlockVoxels];
             }
         }
-        const uint32_t pre = min((uint32_t)NST, cnt);
-        for (uint32_t q = 0; q < pre; ++q) {
-            const uint32_t vq = __shfl_sync(0xffffffffu, my_voxel, q);
+        {   // the landing zone is free (its last row went to registers): start the chunk's first row
+            const uint32_t v0 = __shfl_sync(0xffffffffu, my_voxel, 0);
             if (lane == 0) {
-                const uint32_t s = (t_use + q) % NST;
-                mbar_arrive_expect_tx(&my_bars[s], (uint32_t)C * 4u);
-                tma_bulk_g2s(my_ring + (size_t)s * C, p.vol.clip_feat + (size_t)vq * C, (uint32_t)C * 4u, &my_bars[s]);
+                fence_proxy_async();
+                mbar_arrive_expect_tx(my_bar, (uint32_t)C * 4u);
+                tma_bulk_g2s(my_row, p.vol.clip_feat + (size_t)v0 * C, (uint32_t)C * 4u, my_bar);
             }
         }
         // rgb running average, label counters and weight of this lane's voxel, frame by frame
@@ -1131,18 +1205,25 @@ __global__ void __launch_bounds__(kK3Threads) feature_accumulate_window_kernel(c
         }
         __syncwarp();  // my_coords written by the lanes, read by the whole warp below
         for (uint32_t q = 0; q < cnt; ++q) {
-            const uint32_t s = t_use % NST;
-            const uint32_t parity = (t_use / NST) & 1u;
             const uint32_t vq = __shfl_sync(0xffffffffu, my_voxel, q);
             const uint32_t mq = __shfl_sync(0xffffffffu, my_mask, q);
             int w = __shfl_sync(0xffffffffu, my_w, q);
             float4* row = reinterpret_cast<float4*>(p.vol.clip_feat + (size_t)vq * C);
-            const float4* old4 = reinterpret_cast<const float4*>(my_ring + (size_t)s * C);
-            const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-            mbar_wait(&my_bars[s], parity);
+            const float4* old4 = reinterpret_cast<const float4*>(my_row);
+            mbar_wait(my_bar, t_use & 1u);
+            ++t_use;
             float4 acc[CHUNKS];
 #pragma unroll
             for (int j = 0; j < CHUNKS; ++j) acc[j] = old4[j * 32 + lane];
+            __syncwarp();  // the row is in registers: the landing zone can take the next voxel's row already
+            if (q + 1 < cnt) {
+                const uint32_t vn = __shfl_sync(0xffffffffu, my_voxel, q + 1);
+                if (lane == 0) {
+                    fence_proxy_async();
+                    mbar_arrive_expect_tx(my_bar, (uint32_t)C * 4u);
+                    tma_bulk_g2s(my_row, p.vol.clip_feat + (size_t)vn * C, (uint32_t)C * 4u, my_bar);
+                }
+            }
             for (uint32_t mm = mq; mm; mm &= mm - 1u) {
                 const int b = __ffs(mm) - 1;
                 const float2 g = my_coords[q * SAF_MAX_BATCH + b];
@@ -1150,33 +1231,24 @@ __global__ void __launch_bounds__(kK3Threads) feature_accumulate_window_kernel(c
                 const float a = __frcp_rn(__int2float_rn(w + 1));
                 const float bb = __fmul_rn(__int2float_rn(w), a);
                 Taps t;
-                bilinear_setup(g.x, g.y, p.frames[b].npx, p.frames[b].npy, t);
-                const float4* tab4 = reinterpret_cast<const float4*>(wt.ptr[b]);
-                const int64_t tab_row4 = wt.stride_r[b] / 4;
+                bilinear_setup_padded(g.x, g.y, p.frames[b].npx, p.frames[b].npy, t);
+                const float4* tab4 = reinterpret_cast<const float4*>(wt.ptr[b]) + lane;   // zero-bordered [R',C] rows
+                const float4* r0 = tab4 + t.idx[0] * (C / 4);
+                const float4* r1 = tab4 + t.idx[1] * (C / 4);
+                const float4* r2 = tab4 + t.idx[2] * (C / 4);
+                const float4* r3 = tab4 + t.idx[3] * (C / 4);
 #pragma unroll
                 for (int j = 0; j < CHUNKS; ++j) {
-                    const int col = j * 32 + lane;
-                    const float4 t0 = t.idx[0] >= 0 ? __ldg(tab4 + t.idx[0] * tab_row4 + col) : zero;
-                    const float4 t1 = t.idx[1] >= 0 ? __ldg(tab4 + t.idx[1] * tab_row4 + col) : zero;
-                    const float4 t2 = t.idx[2] >= 0 ? __ldg(tab4 + t.idx[2] * tab_row4 + col) : zero;
-                    const float4 t3 = t.idx[3] >= 0 ? __ldg(tab4 + t.idx[3] * tab_row4 + col) : zero;
+                    const float4 t0 = __ldg(r0 + j * 32), t1 = __ldg(r1 + j * 32);
+                    const float4 t2 = __ldg(r2 + j * 32), t3 = __ldg(r3 + j * 32);
                     acc[j] = blend4(mix4(t0, t1, t2, t3, t.w), acc[j], a, bb);
                 }
                 ++w;
             }
 #pragma unroll
             for (int j = 0; j < CHUNKS; ++j) st_stream_f4(row + j * 32 + lane, acc[j]);
-            __syncwarp();  // every lane has consumed stage s
-            if (q + NST < cnt) {
-                const uint32_t vn = __shfl_sync(0xffffffffu, my_voxel, q + NST);
-                if (lane == 0) {
-                    mbar_arrive_expect_tx(&my_bars[s], (uint32_t)C * 4u);
-                    tma_bulk_g2s(my_ring + (size_t)s * C, p.vol.clip_feat + (size_t)vn * C, (uint32_t)C * 4u, &my_bars[s]);
-                }
-            }
-            ++t_use;
         }
-        __syncwarp();  // the next batch overwrites my_coords
+        __syncwarp();  // the next chunk overwrites my_coords
     }
 }
 
@@ -1214,24 +1286,22 @@ __global__ void __launch_bounds__(kK3Threads) feature_accumulate_window_generic_
             const float a = __frcp_rn(__int2float_rn(w + 1));
             const float bb = __fmul_rn(__int2float_rn(w), a);
             Taps t;
-            bilinear_setup(g.x, g.y, p.frames[b].npx, p.frames[b].npy, t);
-            const float* table = wt.ptr[b];
+            bilinear_setup_padded(g.x, g.y, p.frames[b].npx, p.frames[b].npy, t);
+            const float* table = wt.ptr[b];   // zero-bordered [R',C] rows
             const int64_t sr = wt.stride_r[b];
             if (VEC == 4) {
-                const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
                 for (int col = lane; col < C / 4; col += 32) {
                     const float4 o = reinterpret_cast<const float4*>(row)[col];
                     float4 tv[4];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        tv[k] = t.idx[k] >= 0 ? __ldg(reinterpret_cast<const float4*>(table + t.idx[k] * sr) + col) : zero;
+                    for (int k = 0; k < 4; ++k) tv[k] = __ldg(reinterpret_cast<const float4*>(table + t.idx[k] * sr) + col);
                     reinterpret_cast<float4*>(row)[col] = blend4(mix4(tv[0], tv[1], tv[2], tv[3], t.w), o, a, bb);
                 }
             } else {
                 for (int c = lane; c < C; c += 32) {
                     float tv[4];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) tv[k] = t.idx[k] >= 0 ? __ldg(table + t.idx[k] * sr + c) : 0.0f;
+                    for (int k = 0; k < 4; ++k) tv[k] = __ldg(table + t.idx[k] * sr + c);
                     const float smp = bilinear_mix(tv[0], tv[1], tv[2], tv[3], t.w);
                     row[c] = __fadd_rn(__fmul_rn(smp, a), __fmul_rn(row[c], bb));
                 }
@@ -1342,6 +1412,7 @@ static int build_params(const saf_grid_desc* grid, const saf_volume* vol, const 
     p->nslab = (uint64_t)p->nxs * (uint64_t)grid->nvox[1] * (uint64_t)grid->nvox[2];
     p->list_cap = L.list_cap;
     p->max_table_elems = (uint64_t)ws->max_table_elems;
+    p->table_slot_elems = L.table_slot_elems;
     unsigned char* base = (unsigned char*)ws->base;
     p->hdr = (WsHeader*)base;
     p->slot = slot;
@@ -1388,9 +1459,17 @@ static int check_feature_args(const saf_volume* vol, const saf_frame* frames, in
     return 0;
 }
 
+// window mode repacks every frame's feature image into its table slot of the workspace
+static int check_window_tables(const saf_volume* vol, const saf_frame* frames, int32_t batch, const saf_workspace* ws)
+{
+    for (int b = 0; b < batch; ++b)
+        if ((int64_t)frames[b].npy * frames[b].npx * vol->feature_dim > ws->max_table_elems) return SAF_ERR_WORKSPACE;
+    return 0;
+}
+
 static int launch_k1(const FusionParams& p, cudaStream_t st)
 {
-    const uint32_t pack_ctas = p.pack_mask ? 64u : 0u;
+    const uint32_t pack_ctas = (p.pack_mask || p.sequential) ? 64u : 0u;
     frame_setup_kernel<<<p.n_k1 + pack_ctas, kK1Threads, 0, st>>>(p, p.n_k1);
     SAF_CHECK_LAUNCH("frame_setup_kernel (K1)", st);
     return 0;
@@ -1444,7 +1523,7 @@ static int launch_k3(FusionParams& p, int frame_index, int sms, int smem_optin, 
     const int C = p.vol.feature_dim;
     const int R = f.npy * f.npx;
     const bool packed = (p.pack_mask >> frame_index) & 1u;
-    const float* table = packed ? p.tables + (uint64_t)frame_index * p.max_table_elems : f.table;
+    const float* table = packed ? p.tables + (uint64_t)frame_index * p.table_slot_elems : f.table;
     const int64_t stride_r = packed ? C : f.table_stride_r;
     const bool rows16 = (C % 4 == 0) && (stride_r % 4 == 0) && (((uintptr_t)table & 15u) == 0) &&
                         (((uintptr_t)p.vol.clip_feat & 15u) == 0);
@@ -1463,51 +1542,34 @@ static int launch_k3(FusionParams& p, int frame_index, int sms, int smem_optin, 
     return 0;
 }
 
-template <int CHUNKS, int NST>
+template <int CHUNKS>
 static int launch_k3w_fixed(const FusionParams& p, const WindowTables& wt, int sms, cudaStream_t st)
 {
     constexpr size_t row = (size_t)CHUNKS * 128 * 4;
-    const size_t smem = (size_t)kK3Warps * NST * row + (size_t)kK3Warps * 32 * SAF_MAX_BATCH * sizeof(float2) +
-                        8 * (size_t)kK3Warps * NST;
-    auto kern = feature_accumulate_window_kernel<CHUNKS, NST>;
+    const size_t smem = (size_t)kW3Warps * row + (size_t)kW3Warps * kW3Chunk * SAF_MAX_BATCH * sizeof(float2) +
+                        8 * (size_t)kW3Warps;
+    auto kern = feature_accumulate_window_kernel<CHUNKS>;
     SAF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<sms, kK3Threads, smem, st>>>(p, wt);
+    kern<<<sms, kW3Threads, smem, st>>>(p, wt);
     SAF_CHECK_LAUNCH("feature_accumulate_window_kernel (K3W)", st);
     return 0;
-}
-
-// ring stages per warp of K3W (2 or 3): fewer stages leave more of the SM's 256 KB to L1, which serves the
-// per-frame table rows.  SAF_K3W_NST overrides for A/B timing.
-static int k3w_stages()
-{
-    static int nst = 0;
-    if (!nst) {
-        const char* v = getenv("SAF_K3W_NST");
-        nst = (v && v[0] == '3') ? 3 : 2;
-    }
-    return nst;
 }
 
 static int launch_k3w(const FusionParams& p, int sms, cudaStream_t st)
 {
     const int C = p.vol.feature_dim;
     WindowTables wt;
-    bool rows16 = (C % 4 == 0) && (((uintptr_t)p.vol.clip_feat & 15u) == 0);
+    // K1 repacked every frame's feature image into the workspace (zero-bordered [R',C] rows)
+    const bool rows16 = (C % 4 == 0) && (((uintptr_t)p.vol.clip_feat & 15u) == 0) && (p.table_slot_elems % 4 == 0);
     for (int b = 0; b < SAF_MAX_BATCH; ++b) {
-        wt.ptr[b] = nullptr;
-        wt.stride_r[b] = 0;
-        if (b >= p.batch) continue;
-        const bool packed = (p.pack_mask >> b) & 1u;
-        wt.ptr[b] = packed ? p.tables + (uint64_t)b * p.max_table_elems : p.frames[b].table;
-        wt.stride_r[b] = packed ? C : p.frames[b].table_stride_r;
-        rows16 = rows16 && (wt.stride_r[b] % 4 == 0) && (((uintptr_t)wt.ptr[b] & 15u) == 0);
+        wt.ptr[b] = b < p.batch ? p.tables + (uint64_t)b * p.table_slot_elems : nullptr;
+        wt.stride_r[b] = C;
     }
     if (rows16) {
-        const bool three = k3w_stages() == 3;
         switch (C) {
-            case 512: return three ? launch_k3w_fixed<4, 3>(p, wt, sms, st) : launch_k3w_fixed<4, 2>(p, wt, sms, st);
-            case 768: return three ? launch_k3w_fixed<6, 3>(p, wt, sms, st) : launch_k3w_fixed<6, 2>(p, wt, sms, st);
-            case 1024: return launch_k3w_fixed<8, 2>(p, wt, sms, st);
+            case 512: return launch_k3w_fixed<4>(p, wt, sms, st);
+            case 768: return launch_k3w_fixed<6>(p, wt, sms, st);
+            case 1024: return launch_k3w_fixed<8>(p, wt, sms, st);
             default: break;
         }
         feature_accumulate_window_generic_kernel<4><<<sms * 2, kK3Threads, 0, st>>>(p, wt);
@@ -1646,7 +1708,6 @@ int saf_tsdf_update_window(const saf_grid_desc* grid, const saf_volume* vol, con
     FusionParams p;
     rc = build_params(grid, vol, frames, batch, H, W, trunc, SAF_RGB_BILINEAR, ws, &p);
     if (rc) return rc;
-    if (ws->max_batch < 1 + (batch + 1) / 2) return SAF_ERR_WORKSPACE;
     p.sequential = 1;
     return launch_k2(p, sms, (cudaStream_t)stream);
 }
@@ -1664,8 +1725,11 @@ int saf_feature_accumulate_window(const saf_grid_desc* grid, const saf_volume* v
     if (rc) return rc;
     rc = check_feature_args(vol, frames, batch, rgb_mode, ws, &p.pack_mask);
     if (rc) return rc;
-    if (ws->max_batch < 1 + (batch + 1) / 2) return SAF_ERR_WORKSPACE;
+    if ((rc = check_window_tables(vol, frames, batch, ws))) return rc;
     p.sequential = 1;
+    // saf_frustum_cull does not know the call is a window: repack the feature images here (K1's pack CTAs only)
+    frame_setup_kernel<<<64, kK1Threads, 0, (cudaStream_t)stream>>>(p, 0u);
+    SAF_CHECK_LAUNCH("frame_setup_kernel (table repack)", (cudaStream_t)stream);
     return launch_k3w(p, sms, (cudaStream_t)stream);
 }
 
@@ -1681,8 +1745,8 @@ static int integrate_call(const saf_grid_desc* grid, const saf_volume* vol, cons
     rc = check_feature_args(vol, frames, batch, rgb_mode, ws, &p.pack_mask);
     if (rc) return rc;
     p.sequential = (sequential && batch > 1) ? 1 : 0;
-    // the window's union list and coordinates live in list regions 0 and 1 .. ceil(batch / 2)
-    if (p.sequential && ws->max_batch < 1 + (batch + 1) / 2) return SAF_ERR_WORKSPACE;
+    if (p.sequential && (rc = check_window_tables(vol, frames, batch, ws))) return rc;
+    // (the window's union list and coordinates live in list regions 0 and 1 .. ceil(batch / 2) <= batch - 1)
     if ((rc = launch_k1(p, st_geo))) return rc;
     if ((rc = launch_k2(p, sms, st_geo))) return rc;
     if (geo_done) {
@@ -1723,9 +1787,9 @@ int saf_integrate_sequence(const saf_grid_desc* grid, const saf_volume* vol, con
     if (!(trunc > 0.f)) return SAF_ERR_SHAPE;
     cudaStream_t st = (cudaStream_t)stream;
     // Window mode: up to 8 consecutive frames share one K1 / K2 / K3W launch trio (per-voxel updates are applied
-    // frame by frame inside the kernels, so the result is that of the single-frame calls).  It needs list regions
-    // for the window (saf_workspace.max_batch >= 1 + window / 2); a max_batch = 1 workspace runs frame by frame.
-    const int32_t window = ws && ws->max_batch >= 2 ? std::min<int32_t>(SAF_MAX_BATCH, 2 * (ws->max_batch - 1)) : 1;
+    // frame by frame inside the kernels, so the result is that of the single-frame calls).  The window is the
+    // workspace's max_batch; a max_batch = 1 workspace runs frame by frame.
+    const int32_t window = ws ? std::max<int32_t>(1, std::min<int32_t>(SAF_MAX_BATCH, ws->max_batch)) : 1;
     const int32_t n_calls = (n_frames + window - 1) / window;
     if (n_calls < 4) {
         for (int32_t c = 0; c < n_calls; ++c) {

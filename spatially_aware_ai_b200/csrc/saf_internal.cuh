@@ -26,7 +26,7 @@ struct SlotCounters {
     uint32_t n_blocks;                      // list segments (blocks K2 processed) of the call, written by K2's last CTA
     uint32_t k2_done;                       // CTA completion ticket of K2
     uint32_t frame_base_parity;             // total_frames before this call, & 1
-    uint32_t pad_;
+    uint32_t k3_next;                       // window mode: next unclaimed entry of the union list (K3W's dispenser)
     uint32_t n_valid[SAF_MAX_BATCH];        // length of each frame's valid list
     uint32_t n_tsdf_valid[SAF_MAX_BATCH];   // accumulators (atomics), folded and zeroed by K2's last CTA
     uint32_t last_tsdf_valid[SAF_MAX_BATCH];
@@ -84,11 +84,12 @@ constexpr uint32_t kMaxK1Ctas = 2048;       // K1's last CTA scans this many per
 // Workspace layout (all offsets 256-byte aligned):
 //   header | slot 0 | slot 1        with, per slot,
 //   cta_count[n_k1] | tile_dmax[max_batch][kMaxDepthTiles] | block_seg[n_k1*256] | blk_count[max_batch][nblocks_total]
-//   | blk_offset[max_batch][nblocks_total+1] | lists[max_batch][nblocks_total*512] | tables[max_batch][max_table_elems]
+//   | blk_offset[max_batch][nblocks_total+1] | lists[max_batch][nblocks_total*512] | tables[max_batch][table_slot_elems]
 struct WsLayout {
     uint64_t bytes;
     uint64_t list_cap;
     uint64_t slot0, slot_stride;            // byte offset of slot 0 and distance to slot 1
+    uint64_t table_slot_elems;  // floats reserved per frame in tables[]
     uint64_t off_cta_count, off_cta_dmax, off_block_seg, off_blk_count, off_blk_offset, off_lists, off_tables;  // within a slot
     uint32_t nblocks_total;
     uint32_t n_k1;
@@ -123,7 +124,9 @@ inline int compute_layout(const saf_grid_desc* g, int32_t max_batch, int64_t max
     L->off_blk_offset = align_up(L->off_blk_count + 4ull * max_batch * nblocks, 256);
     L->off_lists = align_up(L->off_blk_offset + 4ull * max_batch * (nblocks + 1), 256);
     L->off_tables = align_up(L->off_lists + (uint64_t)max_batch * L->list_cap * sizeof(ValidEntry), 256);
-    L->slot_stride = align_up(L->off_tables + (uint64_t)max_batch * (uint64_t)max_table_elems * 4ull, 256);
+    // window mode repacks every frame's feature image with a zero border: (npy+2)(npx+2) <= 9 npy npx rows
+    L->table_slot_elems = (uint64_t)max_table_elems * (max_batch > 1 ? 9ull : 1ull);
+    L->slot_stride = align_up(L->off_tables + (uint64_t)max_batch * L->table_slot_elems * 4ull, 256);
     L->slot0 = 512;
     L->bytes = L->slot0 + 2 * L->slot_stride;
     return 0;
