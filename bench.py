@@ -249,13 +249,15 @@ def run_native_arm(args):
                              cfg.patch_size, cfg.patch_stride, clip, seg, x_begin=x_begin, x_end=x_end).to(dev)
 
     # ---- frame pool: identical on every rank; frame i is taken in room (i % n_rooms) ----------------------
-    F, K_steps, W_steps = args.frames_per_step, args.steps, args.warmup
-    P = min(args.pool, F * (K_steps + W_steps))
+    # weak scaling: every step visits every room `--frames-per-step` times, so the scan (and the frame count
+    # every rank is handed) grows with the number of rooms while the work inside each room stays fixed
+    F, K_steps, W_steps = args.frames_per_step * n_rooms, args.steps, args.warmup
+    P = min(args.pool * n_rooms, F * (K_steps + W_steps))
     P = max(n_rooms, P - P % n_rooms)
-    stride = max(1, cfg.frames // P)
+    stride = max(1, cfg.frames // (P // n_rooms))
     host = []
     for i in range(P):
-        fr = synth.make_frame(cfg, (i * stride) % cfg.frames, table_layout="hwc")
+        fr = synth.make_frame(cfg, ((i // n_rooms) * stride) % cfg.frames, table_layout="hwc")
         fr["pose"] = fr["pose"].copy()
         fr["pose"][0, 3] += (i % n_rooms) * room_dx
         host.append(fr)
@@ -319,13 +321,26 @@ def run_native_arm(args):
 
     # ---- value: inputs resident, K steps through the C ABI -------------------------------------------------
     steps_arr = [step_structs(s) for s in range(W_steps + K_steps)]
-    for s in range(W_steps):
-        run_step(steps_arr[s])
-    barrier()
-    st0 = vol.stats()
+    # The clock sampler (nvidia-smi -lms) is started BEFORE the warm-up and given time to deliver its first
+    # sample: the first NVML initialisation on a fresh box stalls the GPU for tens of milliseconds, which must
+    # not land in the timed region.  A short burn-in (same steps, untimed) follows so that clocks have ramped.
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        t_wait = time.time()
+        while not sampler.lines and time.time() - t_wait < 8.0:
+            time.sleep(0.05)
+    barrier()
+    t_burn = time.time()
+    while time.time() - t_burn < 0.5:
+        run_step(steps_arr[0])
+        torch.cuda.synchronize(dev)
+    for s in range(W_steps):
+        run_step(steps_arr[s])
+    barrier()
+    if rank == 0:
+        sampler.lines.clear()            # keep only samples taken during the timed region
+    st0 = vol.stats()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
@@ -336,6 +351,8 @@ def run_native_arm(args):
     ms = max_over_ranks(ev0.elapsed_time(ev1))
     clocks = sampler.stop() if rank == 0 else None
     st1 = vol.stats()
+    sys.stderr.write("[bench] rank %d: %.3f ms/step; depth_cull_on=%d last_blocks=%d last_processed=%d\n" %
+                     (rank, ms / K_steps, st1["depth_cull_on"], st1["last_blocks"], st1["last_processed"]))
     upd = st1["total_valid"] - st0["total_valid"]
     tv = st1["total_tsdf_valid"] - st0["total_tsdf_valid"]
     blocks = st1["total_blocks"] - st0["total_blocks"]
@@ -351,17 +368,42 @@ def run_native_arm(args):
         Pe = min(P, 64 - 64 % n_rooms if n_rooms > 1 else 64)
         h_depth = torch.stack([torch.from_numpy(f["depth"]) for f in host[:Pe]]).pin_memory()
         h_rgb = torch.stack([torch.from_numpy(f["rgb"]) for f in host[:Pe]]).pin_memory()
-        h_pose = torch.stack([torch.from_numpy(f["pose"]) for f in host[:Pe]]).pin_memory()
-        h_K = torch.stack([torch.from_numpy(f["K"]) for f in host[:Pe]]).pin_memory()
-        tables = [d_table[i].permute(2, 0, 1)[None] for i in range(Pe)]   # producer outputs stay on the device
+        h_pose = torch.stack([torch.from_numpy(f["pose"]) for f in host[:Pe]])
+        h_K = torch.stack([torch.from_numpy(f["K"]) for f in host[:Pe]])
+        tables_chw = d_table.permute(0, 3, 1, 2)            # producer outputs stay on the device
+        chunk = 8 if window > 1 else 1
+        copy_stream = torch.cuda.Stream(dev)
+
+        def stage(idx):
+            """H2D of one chunk's depth + rgb from pinned memory, on the copy stream (prefetch)."""
+            with torch.cuda.stream(copy_stream):
+                sel = torch.as_tensor(idx)
+                dd = torch.empty((len(idx), H, Wd), device=dev)
+                rr = torch.empty((len(idx), H, Wd, 3), device=dev)
+                for k, i in enumerate(idx):
+                    dd[k].copy_(h_depth[i], non_blocking=True)
+                    rr[k].copy_(h_rgb[i], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return dd, rr, sel, ev
 
         def e2e_step(s):
-            for j in range(F):
-                i = (s * F + j) % Pe
-                clip.next_table = tables[i]
-                seg.queue = [d_seg[i]]
-                vol.integrate(h_depth[i:i + 1].to(dev, non_blocking=True), h_rgb[i:i + 1].to(dev, non_blocking=True),
-                              h_pose[i:i + 1], h_K[i:i + 1])
+            ids = [(s * F + j) % Pe for j in range(F)]
+            chunks = [ids[k:k + chunk] for k in range(0, F, chunk)]
+            nxt = stage(chunks[0])
+            for ci, idx in enumerate(chunks):
+                dd, rr, sel, ev = nxt
+                if ci + 1 < len(chunks):
+                    nxt = stage(chunks[ci + 1])          # overlaps the fusion of this chunk
+                torch.cuda.current_stream(dev).wait_event(ev)
+                clip.next_table = tables_chw[sel.to(dev)] if len(idx) > 1 else tables_chw[idx[0]][None]
+                seg.queue = [d_seg[i] for i in idx]
+                if chunk > 1:
+                    vol.integrate_sequence(dd, rr, h_pose[sel], h_K[sel])
+                else:
+                    vol.integrate(dd, rr, h_pose[sel], h_K[sel])
+                dd.record_stream(torch.cuda.current_stream(dev))
+                rr.record_stream(torch.cuda.current_stream(dev))
             return vol.stats()   # device -> host read of the step's counters (synchronises)
 
         e2e_steps = max(1, min(K_steps, 5))
@@ -377,11 +419,14 @@ def run_native_arm(args):
         h2d = F * (H * Wd * 4 + H * Wd * 12)
         e2e = {"value": e_upd / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": ctypes.sizeof(_lib.Stats),
                "frames_per_s": e2e_steps * F / dt, "steps": e2e_steps,
-               "note": "ClipSeemFusion.integrate per frame; depth+rgb H2D from pinned memory each frame, pose/K passed "
-                       "as host tensors; feature image and class map come from device-resident stand-ins for the "
-                       "CLIP / kMaX producers (DNN inference is outside the path)"}
+               "note": "%s; depth+rgb of every frame copied H2D from pinned memory inside the timed region (prefetched "
+                       "one chunk ahead on a copy stream), pose/K passed as host tensors; feature image and class map "
+                       "come from device-resident stand-ins for the CLIP / kMaX producers (DNN inference is outside "
+                       "the path); the step's counters are read back to the host" %
+                       ("ClipSeemFusion.integrate_sequence on chunks of 8 frames" if chunk > 1 else
+                        "ClipSeemFusion.integrate per frame")}
 
-    # ---- roofline of the dominant kernel (K3), timed per launch with CUDA events -------------------------
+    # ---- roofline of the dominant kernel (feature accumulate), timed per launch with CUDA events -----------
     roof = None
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -389,41 +434,58 @@ def run_native_arm(args):
             peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        n_probe = min(P, 40)
-        k3_ms, k3_b, k3_updates, k1_ms, k2_ms = 0.0, 0, 0, 0.0, 0.0
+        bw = window if window > 1 else 1
+        n_probe = max(1, min(P // bw, 6 if bw > 1 else 40))     # windows (or frames) timed one launch at a time
+        k3_ms, k3_b, k3_updates, k1_ms, k2_ms, timed = 0.0, 0, 0, 0.0, 0.0, 0
         ea, eb, e0, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
         for i in range(n_probe):
-            fr = ctypes.pointer(pool_structs[i])
+            fr = ctypes.cast(ctypes.byref(pool_structs, i * bw * ctypes.sizeof(_lib.Frame)), ctypes.POINTER(_lib.Frame))
+            before = vol.stats()["total_valid"]
             ea.record()
-            _lib.check(lib.saf_frustum_cull(ctypes.byref(grid_d), fr, 1, H, Wd, trunc, ctypes.byref(ws), stream), "K1")
+            _lib.check(lib.saf_frustum_cull(ctypes.byref(grid_d), fr, bw, H, Wd, trunc, ctypes.byref(ws), stream), "K1")
             eb.record()
-            _lib.check(lib.saf_tsdf_update(ctypes.byref(grid_d), ctypes.byref(vol_d), fr, 1, H, Wd, trunc,
-                                           ctypes.byref(ws), None, None, stream), "K2")
+            if bw > 1:
+                _lib.check(lib.saf_tsdf_update_window(ctypes.byref(grid_d), ctypes.byref(vol_d), fr, bw, H, Wd, trunc,
+                                                      ctypes.byref(ws), stream), "K2W")
+            else:
+                _lib.check(lib.saf_tsdf_update(ctypes.byref(grid_d), ctypes.byref(vol_d), fr, 1, H, Wd, trunc,
+                                               ctypes.byref(ws), None, None, stream), "K2")
             e0.record()
-            _lib.check(lib.saf_feature_accumulate(ctypes.byref(grid_d), ctypes.byref(vol_d), fr, 1, 0, H, Wd,
-                                                  _lib.SAF_RGB_BILINEAR, ctypes.byref(ws), stream), "K3")
+            if bw > 1:
+                _lib.check(lib.saf_feature_accumulate_window(ctypes.byref(grid_d), ctypes.byref(vol_d), fr, bw, H, Wd,
+                                                             _lib.SAF_RGB_BILINEAR, ctypes.byref(ws), stream), "K3W")
+            else:
+                _lib.check(lib.saf_feature_accumulate(ctypes.byref(grid_d), ctypes.byref(vol_d), fr, 1, 0, H, Wd,
+                                                      _lib.SAF_RGB_BILINEAR, ctypes.byref(ws), stream), "K3")
             e1.record()
             torch.cuda.synchronize(dev)
-            nv = vol.stats()["last_valid"][0]
+            nv = vol.stats()["total_valid"] - before
             if nv == 0:
                 continue
+            timed += 1
             k1_ms += ea.elapsed_time(eb)
             k2_ms += eb.elapsed_time(e0)
             k3_ms += e0.elapsed_time(e1)
-            k3_b += k3_bytes(cfg, nv)
+            k3_b += nv * (8 * C + 40) + bw * (H * Wd * 13 + npy * npx * C * 4)
             k3_updates += nv
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "k3_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "k3w_traffic.json" if bw > 1 else "k3_traffic.json")
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         achieved = k3_b / (k3_ms * 1e-3) / 1e9 if k3_ms > 0 else 0.0
-        roof = {"bound": "hbm", "kernel": "feature_accumulate_kernel (K3)", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "launches_timed": n_probe, "avg_launch_us": k3_ms / max(1, n_probe) * 1e3,
-                "k1_avg_us": k1_ms / max(1, n_probe) * 1e3, "k2_avg_us": k2_ms / max(1, n_probe) * 1e3,
-                "avg_updates_per_launch": k3_updates / max(1, n_probe),
+        roof = {"bound": "hbm",
+                "kernel": "feature_accumulate_window_kernel (K3W, %d-frame window)" % bw if bw > 1 else
+                          "feature_accumulate_kernel (K3)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_src, "launches_timed": timed, "avg_launch_us": k3_ms / max(1, timed) * 1e3,
+                "k1_avg_us": k1_ms / max(1, timed) * 1e3, "k2_avg_us": k2_ms / max(1, timed) * 1e3,
+                "avg_updates_per_launch": k3_updates / max(1, timed),
                 "algorithmic_bytes_per_update": 8 * C + 40,
-                "whole_step_gbs": whole_bytes / (ms * 1e-3) / 1e9, "whole_step_frac": whole_bytes / (ms * 1e-3) / 1e9 / peak}
+                "whole_step_gbs": whole_bytes / (ms * 1e-3) / 1e9, "whole_step_frac": whole_bytes / (ms * 1e-3) / 1e9 / peak,
+                "note": ("`achieved` counts SURVEY 8(d)'s algorithmic bytes (8C+40 per voxel update: what frame-by-frame "
+                         "fusion must move); the window kernel reads and writes each feature row once per window "
+                         "instead of once per frame, so its DRAM traffic (`traffic`, ncu) is a fraction of that and "
+                         "`frac` can exceed 1 - the kernel is bound by L1/issue, not HBM (profiles/)") if bw > 1 else None}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) -------------------------------------------------------
     cpu = None

@@ -20,6 +20,7 @@
 #include <limits.h>
 #include <math.h>
 #include <algorithm>
+#include <vector>
 #include <stdlib.h>
 #include <string.h>
 
@@ -791,6 +792,66 @@ __global__ void __launch_bounds__(kK2Threads) tsdf_update_kernel(const FusionPar
 }
 
 // ---------------------------------------------------------------------------------------------
+// K0: which frames of a sequence can touch this slab at all?  (multi-GPU x-slabs: every rank is handed every
+// frame, clip_seem_fusion.py:305-313 has no notion of slabs.)  One CTA per frame: depth-tile maxima into shared
+// memory, then K1's frustum test and K2's depth-reach test for the slab's blocks until one passes.  A frame
+// that fails for every block cannot produce a tsdf_valid voxel here, so the host drops it from the windows.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) frame_reach_kernel(const FusionParams p, const saf_frame* __restrict__ frames,
+                                                          int32_t n_frames, uint32_t* __restrict__ reach)
+{
+    __shared__ float s_tile[kMaxDepthTiles];
+    __shared__ float s_max[8];
+    const int fi = blockIdx.x;
+    if (fi >= n_frames) return;
+    const saf_frame& f = frames[fi];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ts = 1 << p.tile_shift, ntiles = p.ntx * p.nty;
+    float wmax = 0.0f;
+    for (int t = warp; t < ntiles; t += 8) {
+        const int x0 = (t % p.ntx) * ts, y0 = (t / p.ntx) * ts;
+        const int x1 = min(p.W, x0 + ts);
+        float dm = 0.0f;
+        for (int y = y0 + lane; y < min(p.H, y0 + ts); y += 32)
+            for (int x = x0; x < x1; ++x) dm = fmaxf(dm, __ldg(f.depth + (size_t)y * p.W + x));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dm = fmaxf(dm, __shfl_xor_sync(0xffffffffu, dm, o));
+        if (lane == 0) s_tile[t] = dm;
+        wmax = fmaxf(wmax, dm);
+    }
+    if (lane == 0) s_max[warp] = wmax;
+    __syncthreads();
+    float image_max = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) image_max = fmaxf(image_max, s_max[w]);
+    Geom g;
+    load_geom(f, g);
+    const float fW = (float)p.W, fH = (float)p.H;
+    for (uint32_t b0 = 0; b0 < p.nblocks_total; b0 += 256) {
+        const uint32_t blk = b0 + threadIdx.x;
+        bool hit = false;
+        if (blk < p.nblocks_total) {
+            const uint32_t bz = blk % p.nb[2];
+            const uint32_t by = (blk / p.nb[2]) % p.nb[1];
+            const uint32_t bx = blk / (p.nb[2] * p.nb[1]);
+            float cx, cy, cz, r, half[3];
+            block_sphere(p, bx, by, bz, cx, cy, cz, r, half);
+            if (block_maybe_visible(g, cx, cy, cz, r, fW, fH)) {
+                const float dfar = block_depth_bound(p, g, cx, cy, cz, r, s_tile, nullptr, image_max);
+                hit = !(block_z_min(g, cx, cy, cz, half) > (dfar + p.trunc) * 1.001f + 1e-5f);  // NaN -> keep
+            }
+        }
+        if (__syncthreads_or(hit)) {
+            if (threadIdx.x == 0) reach[fi] = 1u;
+            return;
+        }
+    }
+    if (threadIdx.x == 0) reach[fi] = 0u;
+}
+
+__global__ void add_skipped_frames_kernel(WsHeader* hdr, unsigned long long n) { hdr->total_frames += n; }
+
+// ---------------------------------------------------------------------------------------------
 // K3: per-voxel feature / rgb / label accumulation (clip_seem_fusion.py:751-822)
 // ---------------------------------------------------------------------------------------------
 
@@ -1079,13 +1140,14 @@ __device__ __forceinline__ void sample_rgb(const FusionParams& p, const saf_fram
     }
 }
 
-constexpr int kW3Warps = 24;                 // one CTA of 24 warps per SM: the kernel is latency-, not HBM-bound
-constexpr int kW3Threads = kW3Warps * 32;
+// One CTA of kW3Warps warps per SM (16 or 24): the kernel is latency-, not HBM-bound.  16 warps leave registers for
+// two K2 CTAs of the NEXT window on the same SM (saf_integrate_sequence runs them on a side stream), whose
+// ALU-bound work fills the issue slots K3W leaves idle while it waits on L1.
 constexpr int kW3Chunk = 8;                  // union-list entries a warp claims at a time (dynamic balancing: the
                                              // number of updates per entry varies from 1 to the window length)
 
-template <int CHUNKS>
-__global__ void __launch_bounds__(kW3Threads, 1)
+template <int CHUNKS, int kW3Warps>
+__global__ void __maxnreg__(80)
 feature_accumulate_window_kernel(const __grid_constant__ FusionParams p, const __grid_constant__ WindowTables wt)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1542,17 +1604,29 @@ static int launch_k3(FusionParams& p, int frame_index, int sms, int smem_optin, 
     return 0;
 }
 
-template <int CHUNKS>
+template <int CHUNKS, int kW3Warps>
 static int launch_k3w_fixed(const FusionParams& p, const WindowTables& wt, int sms, cudaStream_t st)
 {
+    constexpr int kW3Threads = kW3Warps * 32;
     constexpr size_t row = (size_t)CHUNKS * 128 * 4;
     const size_t smem = (size_t)kW3Warps * row + (size_t)kW3Warps * kW3Chunk * SAF_MAX_BATCH * sizeof(float2) +
                         8 * (size_t)kW3Warps;
-    auto kern = feature_accumulate_window_kernel<CHUNKS>;
+    auto kern = feature_accumulate_window_kernel<CHUNKS, kW3Warps>;
     SAF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<sms, kW3Threads, smem, st>>>(p, wt);
     SAF_CHECK_LAUNCH("feature_accumulate_window_kernel (K3W)", st);
     return 0;
+}
+
+// warps per K3W CTA; SAF_K3W_WARPS=16|24 overrides for A/B timing
+static int k3w_warps()
+{
+    static int w = 0;
+    if (!w) {
+        const char* v = getenv("SAF_K3W_WARPS");
+        w = (v && v[0] == '2') ? 24 : ((v && v[0] == '1') ? 16 : 24);
+    }
+    return w;
 }
 
 static int launch_k3w(const FusionParams& p, int sms, cudaStream_t st)
@@ -1566,10 +1640,11 @@ static int launch_k3w(const FusionParams& p, int sms, cudaStream_t st)
         wt.stride_r[b] = C;
     }
     if (rows16) {
+        const bool w16 = k3w_warps() == 16;
         switch (C) {
-            case 512: return launch_k3w_fixed<4>(p, wt, sms, st);
-            case 768: return launch_k3w_fixed<6>(p, wt, sms, st);
-            case 1024: return launch_k3w_fixed<8>(p, wt, sms, st);
+            case 512: return w16 ? launch_k3w_fixed<4, 16>(p, wt, sms, st) : launch_k3w_fixed<4, 24>(p, wt, sms, st);
+            case 768: return w16 ? launch_k3w_fixed<6, 16>(p, wt, sms, st) : launch_k3w_fixed<6, 24>(p, wt, sms, st);
+            case 1024: return w16 ? launch_k3w_fixed<8, 16>(p, wt, sms, st) : launch_k3w_fixed<8, 24>(p, wt, sms, st);
             default: break;
         }
         feature_accumulate_window_generic_kernel<4><<<sms * 2, kK3Threads, 0, st>>>(p, wt);
@@ -1790,6 +1865,41 @@ int saf_integrate_sequence(const saf_grid_desc* grid, const saf_volume* vol, con
     // frame by frame inside the kernels, so the result is that of the single-frame calls).  The window is the
     // workspace's max_batch; a max_batch = 1 workspace runs frame by frame.
     const int32_t window = ws ? std::max<int32_t>(1, std::min<int32_t>(SAF_MAX_BATCH, ws->max_batch)) : 1;
+    // Sub-slab volumes (multi-GPU): drop the frames that cannot touch this slab before forming windows.  Costs
+    // one small kernel, a copy of the frames and one stream synchronisation per call, so it is only done when
+    // the slab is a strict part of the grid and the sequence is long enough to amortise it.
+    std::vector<saf_frame> kept;
+    if (grid && frames && ws && ws->base && (grid->x_begin > 0 || grid->x_end < grid->nvox[0]) && n_frames >= 16) {
+        FusionParams p;
+        rc = build_params(grid, vol, frames, 1, H, W, trunc, rgb_mode, ws, &p, 0);
+        if (rc) return rc;
+        void* dbuf = nullptr;
+        const size_t fbytes = sizeof(saf_frame) * (size_t)n_frames, rbytes = sizeof(uint32_t) * (size_t)n_frames;
+        SAF_CUDA_TRY(cudaMallocAsync(&dbuf, fbytes + rbytes, st));
+        std::vector<uint32_t> reach((size_t)n_frames);
+        cudaError_t e = cudaMemcpyAsync(dbuf, frames, fbytes, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) {
+            frame_reach_kernel<<<n_frames, 256, 0, st>>>(p, (const saf_frame*)dbuf, n_frames,
+                                                         (uint32_t*)((unsigned char*)dbuf + fbytes));
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(reach.data(), (unsigned char*)dbuf + fbytes, rbytes, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        cudaFreeAsync(dbuf, st);
+        if (e != cudaSuccess) return (int)e;
+        kept.reserve((size_t)n_frames);
+        for (int32_t i = 0; i < n_frames; ++i)
+            if (reach[(size_t)i]) kept.push_back(frames[i]);
+        const unsigned long long skipped = (unsigned long long)n_frames - kept.size();
+        if (skipped) {
+            add_skipped_frames_kernel<<<1, 1, 0, st>>>(p.hdr, skipped);
+            SAF_CHECK_LAUNCH("add_skipped_frames_kernel", st);
+        }
+        frames = kept.data();
+        n_frames = (int32_t)kept.size();
+        if (n_frames == 0) return 0;
+    }
     const int32_t n_calls = (n_frames + window - 1) / window;
     if (n_calls < 4) {
         for (int32_t c = 0; c < n_calls; ++c) {

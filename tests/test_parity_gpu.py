@@ -434,3 +434,37 @@ def test_sequence_then_single_frames_interleave():
     _check_against(vol, g["tsdf"], g["weight"], g["tsdf_weight"], g["rgb_state"], g["clip_feat"], Hh.golden_labels(g),
                    exact=True)
     assert vol.stats()["total_valid"] == int(g["counts"][:, 0].sum())
+
+
+def test_sequence_on_slab_drops_unreachable_frames():
+    """Multi-GPU layout: two rooms side by side along x, this volume holds only room 0's slab and is handed every
+    frame (cameras alternate between the rooms).  Frames that cannot touch the slab are dropped by the reach
+    pre-pass; the result must equal the oracle fed every frame."""
+    cfg = synth.SceneConfig(extent=(2.0, 2.0, 1.6), voxel_size=0.05, height=48, width=64, patch_size=32,
+                            patch_stride=16, feature_dim=8, frames=40, seed=17)
+    origin, nvox_room = cfg.grid()
+    slab_nx = int(nvox_room[0]) + 4
+    nvox = nvox_room.copy()
+    nvox[0] = slab_nx * 2
+    g = dict(cls="ClipSeemFusion", feature_dim=8, origin=origin, nvox=nvox, voxel_size=cfg.voxel_size, trunc=cfg.trunc)
+    for own in (0, 1):
+        xb, xe = own * slab_nx, (own + 1) * slab_nx
+        vol, clip, seg = Hh.make_gpu_volume(g, x_begin=xb, x_end=xe)
+        orc = O.OracleVolume(origin, cfg.voxel_size, nvox, cfg.trunc, 8, x_begin=xb, x_end=xe, num_threads=0)
+        frames = []
+        for i in range(24):
+            fr = synth.make_frame(cfg, i)
+            fr["pose"] = fr["pose"].copy()
+            fr["pose"][0, 3] += (i % 2) * slab_nx * cfg.voxel_size
+            frames.append(fr)
+            orc.integrate(fr["depth"][None], fr["rgb"][None], fr["pose"][None], fr["K"][None], fr["table"][None],
+                          fr["seg"][None], want_masks=False)
+        clip.next_table = torch.stack([torch.from_numpy(f["table"]) for f in frames]).cuda()
+        seg.queue = [torch.from_numpy(f["seg"]).cuda() for f in frames]
+        vol.integrate_sequence(torch.stack([torch.from_numpy(f["depth"]) for f in frames]).cuda(),
+                               torch.stack([torch.from_numpy(f["rgb"]) for f in frames]).cuda(),
+                               torch.stack([torch.from_numpy(f["pose"]) for f in frames]),
+                               torch.stack([torch.from_numpy(f["K"]) for f in frames]))
+        _check_against(vol, orc.tsdf, orc.weight, orc.tsdf_weight, orc.rgb, orc.clip_feat, orc.labels_one_hot, exact=True)
+        st = vol.stats()
+        assert st["total_frames"] == 24 and st["total_valid"] == int(orc.weight.sum()) > 0

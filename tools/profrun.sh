@@ -1,5 +1,3 @@
-python -m pytest tests/test_parity_gpu.py -q -k "sequence or golden or depth_aware or slabs or cfg1" 2>&1 | tail -n 5
-python tools/prof_window.py 8 6 > gpurun_out/prof_w8.txt 2>&1
-python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e --window 8 > gpurun_out/bench_w8.json 2> gpurun_out/bench_w8.err
-ncu --set full --import-source on --clock-control none -k regex:feature_accumulate_window -s 3 -c 2 -o gpurun_out/r01_k3w -f python tools/prof_window.py 8 4 > gpurun_out/ncu_k3w.log 2>&1
-tail -n 2 gpurun_out/prof_w8.txt; cat gpurun_out/bench_w8.json | cut -c1-200
+python bench.py --steps 10 --warmup 3 > gpurun_out/b1.json 2> gpurun_out/b1.err
+python bench.py --steps 10 --warmup 3 --window 1 --no-cpu-baseline > gpurun_out/b2.json 2> gpurun_out/b2.err
+for f in b1 b2; do tail -n 2 gpurun_out/$f.err; cut -c1-150 gpurun_out/$f.json; done
