@@ -21,6 +21,7 @@
 #include <math.h>
 #include <algorithm>
 #include <vector>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -349,6 +350,28 @@ __device__ uint32_t cta_exclusive_scan(const uint32_t* src, uint32_t* dst, uint3
     return total;
 }
 
+// K0: largest depth of every (1 << tile_shift)^2 tile of the frames' depth images, for K1's depth cull.  One warp
+// per (frame, tile), each lane walks pixel rows.  Launched with every call but returns at once while the cull is
+// switched off.
+__global__ void __launch_bounds__(256) depth_tiles_kernel(const FusionParams p)
+{
+    if (!p.hdr->depth_cull) return;
+    const int lane = threadIdx.x & 31;
+    const int ts = 1 << p.tile_shift, ntiles = p.ntx * p.nty;
+    const int item = (int)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (item >= p.batch * ntiles) return;
+    const int b = item / ntiles, t = item - b * ntiles;
+    const float* __restrict__ dimg = p.frames[b].depth;
+    const int x0 = (t % p.ntx) * ts, y0 = (t / p.ntx) * ts;
+    const int x1 = min(p.W, x0 + ts), y1 = min(p.H, y0 + ts);
+    float dm = 0.0f;
+    for (int y = y0; y < y1; ++y)
+        for (int x = x0 + lane; x < x1; x += 32) dm = fmaxf(dm, __ldg(dimg + (size_t)y * p.W + x));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dm = fmaxf(dm, __shfl_xor_sync(0xffffffffu, dm, o));
+    if (lane == 0) p.tile_dmax[(size_t)b * kMaxDepthTiles + t] = dm;
+}
+
 __global__ void __launch_bounds__(kK1Threads) frame_setup_kernel(const FusionParams p, uint32_t cull_ctas)
 {
     if (blockIdx.x >= cull_ctas) {
@@ -383,40 +406,57 @@ __global__ void __launch_bounds__(kK1Threads) frame_setup_kernel(const FusionPar
         return;
     }
     __shared__ uint32_t s_warp[kK1Threads / 32];
+    __shared__ float s_zfar[SAF_MAX_BATCH];     // whole-image depth bound per frame
+    extern __shared__ float s_tiles[];          // [batch][ntiles] depth-tile maxima (K0), only while the cull is on
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t blk = blockIdx.x * kK1Threads + threadIdx.x;
-    uint32_t vis = 0;  // bit b: the block may be visible in frame b
+    // Depth cull (switched on by K2's policy only while it pays): a voxel is tsdf_valid only if z < depth + trunc
+    // (clip_seem_fusion.py:722-728), so a block whose nearest z lies behind (largest depth over the image tiles
+    // its projection can touch) + trunc cannot be touched by that frame.  NaN depths never win fmaxf; pixels
+    // outside the image sample depth 0.
+    const bool depth_cull = p.hdr->depth_cull != 0;
+    const int ntiles = p.ntx * p.nty;
+    if (depth_cull) {
+        if (threadIdx.x < SAF_MAX_BATCH) s_zfar[threadIdx.x] = 0.0f;
+        __syncthreads();
+        for (int b = 0; b < p.batch; ++b) {
+            float dm = 0.0f;
+            for (int t = threadIdx.x; t < ntiles; t += kK1Threads) {
+                const float v = __ldcg(p.tile_dmax + (size_t)b * kMaxDepthTiles + t);
+                s_tiles[b * ntiles + t] = v;
+                dm = fmaxf(dm, v);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) dm = fmaxf(dm, __shfl_xor_sync(0xffffffffu, dm, o));
+            // non-negative floats order like their bit patterns
+            if (lane == 0) atomicMax(reinterpret_cast<int*>(&s_zfar[b]), __float_as_int(dm));
+        }
+        __syncthreads();
+    }
+    uint32_t vis = 0;       // bit b: the block may be touched by frame b
+    uint32_t frustum = 0;   // ... before the depth test
     if (blk < p.nblocks_total) {
         const uint32_t bz = blk % p.nb[2];
         const uint32_t by = (blk / p.nb[2]) % p.nb[1];
         const uint32_t bx = blk / (p.nb[2] * p.nb[1]);
-        float cx, cy, cz, r;
-        block_sphere(p, bx, by, bz, cx, cy, cz, r);
+        float cx, cy, cz, r, half[3];
+        block_sphere(p, bx, by, bz, cx, cy, cz, r, half);
         const float fW = (float)p.W, fH = (float)p.H;
         for (int b = 0; b < p.batch; ++b) {
             Geom g;
             load_geom(p.frames[b], g);
-            vis |= (uint32_t)block_maybe_visible(g, cx, cy, cz, r, fW, fH) << b;
+            if (!block_maybe_visible(g, cx, cy, cz, r, fW, fH)) continue;
+            frustum |= 1u << b;
+            if (depth_cull) {
+                const float dfar = block_depth_bound(p, g, cx, cy, cz, r, s_tiles + b * ntiles, nullptr, s_zfar[b]);
+                if (block_z_min(g, cx, cy, cz, half) > (dfar + p.trunc) * 1.001f + 1e-5f) continue;  // NaN -> keep
+            }
+            vis |= 1u << b;
         }
     }
-    // depth-tile maxima for K2's depth cull (only while the cull is switched on): one warp per tile, each
-    // lane walks one pixel row of the tile
-    if (p.hdr->depth_cull) {
-        const int ts = 1 << p.tile_shift, ntiles = p.ntx * p.nty;
-        const int gw = (int)blockIdx.x * (kK1Threads / 32) + warp, nw = (int)cull_ctas * (kK1Threads / 32);
-        for (int b = 0; b < p.batch; ++b) {
-            const float* __restrict__ dimg = p.frames[b].depth;
-            for (int t = gw; t < ntiles; t += nw) {
-                const int x0 = (t % p.ntx) * ts, y0 = (t / p.ntx) * ts;
-                const int x1 = min(p.W, x0 + ts);
-                float dm = 0.0f;
-                for (int y = y0 + lane; y < min(p.H, y0 + ts); y += 32)
-                    for (int x = x0; x < x1; ++x) dm = fmaxf(dm, __ldg(dimg + (size_t)y * p.W + x));
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) dm = fmaxf(dm, __shfl_xor_sync(0xffffffffu, dm, o));
-                if (lane == 0) p.tile_dmax[(size_t)b * kMaxDepthTiles + t] = dm;
-            }
-        }
+    if (depth_cull) {
+        const uint32_t nf = (uint32_t)__popc(__ballot_sync(0xffffffffu, frustum != 0u));
+        if (lane == 0 && nf) atomicAdd(&p.hdr->slot[p.slot].n_frustum_acc, nf);
     }
     // ordered compaction inside the CTA: this CTA's visible blocks, ascending, into its own segment
     const unsigned m = __ballot_sync(0xffffffffu, vis != 0u);
@@ -456,12 +496,7 @@ __global__ void __launch_bounds__(kK2Threads) tsdf_update_kernel(const FusionPar
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // K1 left one ordered segment of visible blocks per cull CTA: rank -> (segment, position)
     const uint32_t n_blocks = cta_exclusive_scan(p.cta_count, s_off, p.n_k1, s_scan);
-    // Depth cull: a voxel is tsdf_valid only if z < depth + trunc (clip_seem_fusion.py:722-728), so a block whose
-    // nearest z lies behind (largest depth over the image tiles its projection can touch) + trunc is skipped.
-    // NaN depths never win fmaxf; pixels outside the image sample depth 0.
-    __shared__ float s_tile[kMaxDepthTiles];   // frame 0's tile maxima (batch-1 fast path)
-    __shared__ float s_zfar[SAF_MAX_BATCH];    // whole-image bound per frame (fallback)
-    const bool depth_cull = hdr->depth_cull != 0;
+    const bool depth_cull = hdr->depth_cull != 0;   // K1 applied the depth test to the block list (policy below)
     __shared__ uint32_t s_rank;                // list segment claimed for the block being processed
     const int B = BATCH1 ? 1 : p.batch;
     const float fW = (float)p.W, fH = (float)p.H;
@@ -475,26 +510,6 @@ __global__ void __launch_bounds__(kK2Threads) tsdf_update_kernel(const FusionPar
         if (threadIdx.x < 2 * SAF_MAX_BATCH) s_fcnt[threadIdx.x / SAF_MAX_BATCH][threadIdx.x % SAF_MAX_BATCH] = 0;
         __syncthreads();
     }
-    if (depth_cull) {
-        const int ntiles = p.ntx * p.nty;
-        for (int b = 0; b < B; ++b) {
-            float dm = 0.0f;
-            for (int t = threadIdx.x; t < ntiles; t += kK2Threads) {
-                const float v = __ldcg(p.tile_dmax + (size_t)b * kMaxDepthTiles + t);
-                if (b == 0) s_tile[t] = v;
-                dm = fmaxf(dm, v);
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) dm = fmaxf(dm, __shfl_xor_sync(0xffffffffu, dm, o));
-            if (lane == 0) s_scan[warp] = dm;
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                for (int w = 1; w < kK2Threads / 32; ++w) dm = fmaxf(dm, s_scan[w]);
-                s_zfar[b] = dm;
-            }
-            __syncthreads();
-        }
-    }
     for (uint32_t bi = blockIdx.x; bi < n_blocks; bi += gridDim.x) {
         uint32_t lo = 0, hi = p.n_k1;  // s_off[lo] <= bi < s_off[hi] (with s_off[n_k1] = n_blocks)
         while (hi - lo > 1) {
@@ -506,23 +521,10 @@ __global__ void __launch_bounds__(kK2Threads) tsdf_update_kernel(const FusionPar
         }
         const uint32_t packed = p.block_seg[(size_t)lo * kK1Threads + (bi - s_off[lo])];
         const uint32_t blk = packed & 0xffffffu;
-        uint32_t fmask = packed >> 24;  // frames whose frustum the block may touch (K1)
+        const uint32_t fmask = packed >> 24;  // frames that can touch the block (K1: frustum and depth reach)
         const uint32_t bz = blk % p.nb[2];
         const uint32_t by = (blk / p.nb[2]) % p.nb[1];
         const uint32_t bx = blk / (p.nb[2] * p.nb[1]);
-        if (depth_cull) {
-            float cx, cy, cz, r, half[3];
-            block_sphere(p, bx, by, bz, cx, cy, cz, r, half);
-            for (int b = 0; b < B; ++b) {
-                if (!((fmask >> b) & 1u)) continue;
-                if (!BATCH1) load_geom(p.frames[b], g);
-                const float* tiles = (b == 0) ? s_tile : nullptr;
-                const float dfar = block_depth_bound(p, g, cx, cy, cz, r, tiles, p.tile_dmax + (size_t)b * kMaxDepthTiles,
-                                                     s_zfar[b]);
-                if (block_z_min(g, cx, cy, cz, half) > (dfar + p.trunc) * 1.001f + 1e-5f) fmask &= ~(1u << b);  // NaN -> keep
-            }
-            if (!fmask) continue;  // CTA-uniform: the whole block lies behind the surfaces it could see
-        }
         // claim the next list segment (arrival order; the list order does not affect any result)
         if (threadIdx.x == 0) s_rank = atomicAdd(&sc->n_processed, 1u);
         float xw[kK2Iter], yw[kK2Iter], zw[kK2Iter], t_old[kK2Iter], bt[kK2Iter];
@@ -727,7 +729,7 @@ __global__ void __launch_bounds__(kK2Threads) tsdf_update_kernel(const FusionPar
     if (!is_last) return;
     __threadfence();
     unsigned long long sv = 0, stv = 0;
-    const uint32_t n_proc = atomicAdd(&sc->n_processed, 0u);
+    const uint32_t n_proc = atomicAdd(&sc->n_processed, 0u);  // == n_blocks: every listed block claimed a segment
     if (SEQ) {
         // one union list for the window; the per-frame counts come from the atomics
         const uint32_t total = cta_exclusive_scan(p.blk_count, p.blk_offset, n_proc, s_scan);
@@ -762,13 +764,14 @@ __global__ void __launch_bounds__(kK2Threads) tsdf_update_kernel(const FusionPar
         // (depth_cull_cooldown counts idle calls while on, remaining cool-down calls while off)
         sc->n_processed = 0;
         sc->last_processed = n_proc;
+        const uint32_t n_frustum = depth_cull ? atomicExch(&sc->n_frustum_acc, 0u) : n_blocks;
         if (!depth_cull) {
             if (hdr->depth_cull_cooldown) hdr->depth_cull_cooldown -= 1;
             else if (n_blocks >= 64 && stv * 4ull < (unsigned long long)n_proc * kBlockVoxels * (unsigned long long)B) {
                 hdr->depth_cull = 1;
                 hdr->depth_cull_cooldown = 0;
             }
-        } else if ((n_blocks - n_proc) * 8u < n_blocks) {
+        } else if ((n_frustum - n_blocks) * 8u < n_frustum) {
             // ineffective on this call; give up only after 16 such calls in a row (cameras may alternate
             // between views where it helps and views where it does not)
             if (++hdr->depth_cull_cooldown >= 16) {
@@ -786,7 +789,7 @@ __global__ void __launch_bounds__(kK2Threads) tsdf_update_kernel(const FusionPar
         hdr->last_slot = p.slot;
         sc->k3_next = 0;            // K3W's chunk dispenser
         sc->n_blocks = n_proc;      // list segments K3 searches
-        sc->n_frustum_blocks = n_blocks;
+        sc->n_frustum_blocks = n_frustum;
         sc->k2_done = 0;
     }
 }
@@ -1532,7 +1535,10 @@ static int check_window_tables(const saf_volume* vol, const saf_frame* frames, i
 static int launch_k1(const FusionParams& p, cudaStream_t st)
 {
     const uint32_t pack_ctas = (p.pack_mask || p.sequential) ? 64u : 0u;
-    frame_setup_kernel<<<p.n_k1 + pack_ctas, kK1Threads, 0, st>>>(p, p.n_k1);
+    const int ntiles = p.ntx * p.nty;
+    depth_tiles_kernel<<<(p.batch * ntiles + 7) / 8, 256, 0, st>>>(p);
+    SAF_CHECK_LAUNCH("depth_tiles_kernel (K0)", st);
+    frame_setup_kernel<<<p.n_k1 + pack_ctas, kK1Threads, (size_t)p.batch * ntiles * sizeof(float), st>>>(p, p.n_k1);
     SAF_CHECK_LAUNCH("frame_setup_kernel (K1)", st);
     return 0;
 }
@@ -1892,6 +1898,7 @@ int saf_integrate_sequence(const saf_grid_desc* grid, const saf_volume* vol, con
         for (int32_t i = 0; i < n_frames; ++i)
             if (reach[(size_t)i]) kept.push_back(frames[i]);
         const unsigned long long skipped = (unsigned long long)n_frames - kept.size();
+        if (getenv("SAF_DEBUG_REACH")) fprintf(stderr, "[saf] reach pre-pass: %d frames, %zu kept\n", n_frames, kept.size());
         if (skipped) {
             add_skipped_frames_kernel<<<1, 1, 0, st>>>(p.hdr, skipped);
             SAF_CHECK_LAUNCH("add_skipped_frames_kernel", st);

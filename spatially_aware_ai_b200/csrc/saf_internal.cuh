@@ -30,7 +30,8 @@ struct SlotCounters {
     uint32_t n_valid[SAF_MAX_BATCH];        // length of each frame's valid list
     uint32_t n_tsdf_valid[SAF_MAX_BATCH];   // accumulators (atomics), folded and zeroed by K2's last CTA
     uint32_t last_tsdf_valid[SAF_MAX_BATCH];
-    uint32_t n_processed;                   // blocks K2 did not skip by the depth test (atomic, zeroed like above)
+    uint32_t n_processed;                   // list segments claimed by K2's CTAs (atomic, zeroed like above)
+    uint32_t n_frustum_acc;                 // blocks inside a frustum before K1's depth test (atomic, zeroed like above)
     uint32_t last_processed;
     uint32_t n_frustum_blocks;              // blocks K1 listed for the call
     uint32_t n_union;                       // window mode: voxels valid in at least one frame of the window

@@ -1,3 +1,5 @@
-python bench.py --steps 10 --warmup 3 > gpurun_out/b1.json 2> gpurun_out/b1.err
-python bench.py --steps 10 --warmup 3 --window 1 --no-cpu-baseline > gpurun_out/b2.json 2> gpurun_out/b2.err
-for f in b1 b2; do tail -n 2 gpurun_out/$f.err; cut -c1-150 gpurun_out/$f.json; done
+python -m pytest tests -q -m gpu -k "slab or sequence" 2>&1 | tail -n 3
+export SAF_DEBUG_REACH=1
+python tools/prof_rooms.py 2 0 48 2>&1 | tail -n 2
+python tools/prof_rooms.py 4 1 48 2>&1 | tail -n 2
+python tools/prof_rooms.py 8 3 48 2>&1 | tail -n 2
