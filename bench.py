@@ -378,11 +378,15 @@ def run_native_arm(args):
             """H2D of one chunk's depth + rgb from pinned memory, on the copy stream (prefetch)."""
             with torch.cuda.stream(copy_stream):
                 sel = torch.as_tensor(idx)
-                dd = torch.empty((len(idx), H, Wd), device=dev)
-                rr = torch.empty((len(idx), H, Wd, 3), device=dev)
-                for k, i in enumerate(idx):
-                    dd[k].copy_(h_depth[i], non_blocking=True)
-                    rr[k].copy_(h_rgb[i], non_blocking=True)
+                if idx[-1] - idx[0] == len(idx) - 1:       # consecutive pinned frames: one copy per tensor
+                    dd = h_depth[idx[0]:idx[-1] + 1].to(dev, non_blocking=True)
+                    rr = h_rgb[idx[0]:idx[-1] + 1].to(dev, non_blocking=True)
+                else:
+                    dd = torch.empty((len(idx), H, Wd), device=dev)
+                    rr = torch.empty((len(idx), H, Wd, 3), device=dev)
+                    for k, i in enumerate(idx):
+                        dd[k].copy_(h_depth[i], non_blocking=True)
+                        rr[k].copy_(h_rgb[i], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
             return dd, rr, sel, ev
