@@ -260,6 +260,17 @@ int saf_mesh_emit(const saf_grid_desc *grid, const float *tsdf, const int32_t *w
 int saf_mesh_sample(const saf_grid_desc *grid, const float *verts, int64_t n_verts, const float *field,
                     int32_t channels, int32_t mode, int32_t clamp01, float *out, void *stream);
 
+/* ---- object labelling: flood_fill_3d (handy_utils.py:295-480) without its in-situ classifier -----
+ * 26-connected components of equal class id over the per-voxel class grid [nx,ny,nz] (int64, as
+ * saf_label_argmax writes it; -1 = unobserved and `null_class` = 133 are background); components with
+ * fewer than `min_voxels` (3) voxels are rejected; accepted objects are numbered -2, -3, ... in
+ * ascending order of their first voxel (the reference's scan order).  out_obj: device int32 [nx*ny*nz],
+ * the reference's voxel_obj_ids (-1 elsewhere).  Synchronises `stream`; *n_objects_out (host) = count. */
+int saf_label_components_workspace_bytes(int64_t n_voxels, uint64_t *bytes_out);
+int saf_label_components(const int64_t *labels, int32_t nx, int32_t ny, int32_t nz, int32_t null_class,
+                         int32_t min_voxels, int32_t *out_obj, void *ws, uint64_t ws_bytes,
+                         uint32_t *n_objects_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -278,6 +278,32 @@ def run_mesh_golden():
     print("mesh ->", os.path.getsize(path) // 1024, "KiB")
 
 
+def run_objects_golden():
+    """flood_fill_3d (handy_utils.py:295-480) on a random class grid with an untrained in-situ model."""
+    rng = np.random.default_rng(123)
+    shape = (18, 15, 13)
+    grid = rng.choice(np.array([-1, 133, 0, 5, 17, 60]), size=shape, p=[0.45, 0.15, 0.1, 0.1, 0.1, 0.1]).astype(np.int64)
+    grid[2:6, 3:7, 4:8] = 60           # one solid object
+    grid[10:12, :, 6] = 133            # a null-class sheet cutting through
+
+    class _Model:
+        model_trained = False
+        labels = ["null"]
+
+    know, ids = handy_utils.flood_fill_3d(grid, None, None, None, _Model(), None)
+    keys = list(know["unique_objects"].keys())
+    out = dict(class_grid=grid, voxel_obj_ids=ids.astype(np.int32), obj_ids=np.array(keys),
+               obj_class_id=np.array([know["unique_objects"][k]["class_id"] for k in keys], np.int64),
+               obj_index=np.array([know["unique_objects"][k]["object_index"] for k in keys], np.int64),
+               obj_size=np.array([len(know["unique_objects"][k]["voxels"]) for k in keys], np.int64),
+               count_keys=np.array(list(know["object_counts"].keys())),
+               count_vals=np.array(list(know["object_counts"].values()), np.int64),
+               class_names=np.array(handy_utils.predefined_classes))
+    path = os.path.join(HERE, "objects.npz")
+    np.savez_compressed(path, **out)
+    print("objects:", len(keys), "objects ->", os.path.getsize(path) // 1024, "KiB")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     only = sys.argv[1:]
@@ -288,3 +314,5 @@ if __name__ == "__main__":
         run_query_golden()
     if not only or "mesh" in only:
         run_mesh_golden()
+    if not only or "objects" in only:
+        run_objects_golden()

@@ -156,3 +156,14 @@ def test_marching_cubes_oracle_nan_handling():
     verts, faces = mc.filter_mesh(*mc.marching_cubes_raw(vol))
     assert len(faces) == 3 * 3 * 2 and len(verts) == 16 and not np.isnan(verts).any()
     assert np.allclose(verts[:, 2], 2.5)
+
+
+# ---- object labelling (oracle/components.py) --------------------------------------------------------
+
+def test_objects_oracle_matches_reference():
+    """The reference's flood_fill_3d (pure Python, run unmodified for the golden) against the scipy restatement."""
+    from oracle import components as CC
+    g = Hh.load_golden("objects")
+    ids, n = CC.label_objects(g["class_grid"])
+    assert n == len(g["obj_ids"]) == 99
+    assert np.array_equal(ids, g["voxel_obj_ids"])
