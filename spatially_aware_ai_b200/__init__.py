@@ -5,9 +5,11 @@ Public surface (same names as the reference's):
     Clip                                run_query / clip_feature_surgery / text_inference wrapper
     extract_mesh_by_object, extract_mesh_by_id
     label_objects, build_scene_knowledge  object labelling (the flood fill of handy_utils.flood_fill_3d)
+    save_state, load_state              grid files in the reference's .npy formats + full state for re-fusion
 plus the functional query API (query_scores, query_topk, surgery_weights, relevance_*).
 All compute goes through libsaf_b200.so (include/saf_b200.h); there is no CPU or PyTorch fallback.
 """
+from .checkpoint import load_state, save_state  # noqa: F401
 from .fusion import ClipFusion, ClipSeemFusion  # noqa: F401
 from .mesh import extract_mesh_by_id, extract_mesh_by_object  # noqa: F401
 from .objects import build_scene_knowledge, label_objects  # noqa: F401
@@ -15,5 +17,5 @@ from .query import (Clip, query_scores, query_topk, relevance_half, relevance_mi
                     relevance_outliers, surgery_weights)
 
 __all__ = ["ClipSeemFusion", "ClipFusion", "Clip", "extract_mesh_by_object", "extract_mesh_by_id", "label_objects",
-           "build_scene_knowledge", "query_scores",
+           "build_scene_knowledge", "save_state", "load_state", "query_scores",
            "query_topk", "surgery_weights", "relevance_minmax", "relevance_half", "relevance_outliers"]

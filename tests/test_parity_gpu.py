@@ -468,3 +468,26 @@ def test_sequence_on_slab_drops_unreachable_frames():
         _check_against(vol, orc.tsdf, orc.weight, orc.tsdf_weight, orc.rgb, orc.clip_feat, orc.labels_one_hot, exact=True)
         st = vol.stats()
         assert st["total_frames"] == 24 and st["total_valid"] == int(orc.weight.sum()) > 0
+
+
+def test_checkpoint_resume_equals_uninterrupted_fusion(tmp_path):
+    """Scene Manager v00 -> v01 (BASELINE config 5): integrate, save, load into a fresh volume, integrate more
+    frames == integrating everything into one volume, bit for bit."""
+    import spatially_aware_ai_b200 as saf
+    g = Hh.load_golden("seem_a")
+    n = len(g["counts"])
+
+    def feed(vol, clip, seg, lo, hi):
+        for i in range(lo, hi):
+            clip.next_table = torch.from_numpy(np.ascontiguousarray(Hh.golden_table(g, i))).cuda()[None]
+            seg.queue = [torch.from_numpy(g["seg"][i].astype(np.int64)).cuda()]
+            vol.integrate(*[torch.from_numpy(g[k][i:i + 1]).cuda() for k in ("depth", "rgb", "pose", "K")])
+
+    first, clip, seg = Hh.make_gpu_volume(g)
+    feed(first, clip, seg, 0, 5)
+    saf.save_state(first, str(tmp_path))
+    resumed, clip2, seg2 = Hh.make_gpu_volume(g)
+    saf.load_state(resumed, str(tmp_path))
+    feed(resumed, clip2, seg2, 5, n)
+    _check_against(resumed, g["tsdf"], g["weight"], g["tsdf_weight"], g["rgb_state"], g["clip_feat"],
+                   Hh.golden_labels(g), exact=True)
