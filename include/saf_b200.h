@@ -271,6 +271,15 @@ int saf_label_components(const int64_t *labels, int32_t nx, int32_t ny, int32_t 
                          int32_t min_voxels, int32_t *out_obj, void *ws, uint64_t ws_bytes,
                          uint32_t *n_objects_out, void *stream);
 
+/* ---- scene bounds: backproject_pcd (clipfusion.py:510-572) -------------------------------------------
+ * nu x nv pixel samples (columns us[nu], rows vs[nv]; the reference uses round(linspace) with 7 each) of every
+ * frame back-projected to world space: ray = K^-1 (u, v, 1), point = R (ray * depth) + t.
+ *   depth device [F,H,W] f32, poses device [F,4,4] camera->world, k_inverse device [F,3,3],
+ *   xyz_out device [F, nv*nu, 3] f32, valid_out device [F, nv*nu] u8 (depth not NaN, > 0, < max_depth). */
+int saf_backproject_samples(const float *depth, const float *poses, const float *k_inverse, const int32_t *us,
+                            const int32_t *vs, int32_t n_frames, int32_t height, int32_t width, int32_t nu,
+                            int32_t nv, float max_depth, float *xyz_out, uint8_t *valid_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

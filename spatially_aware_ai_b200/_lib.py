@@ -90,6 +90,8 @@ SIGNATURES = {
     "saf_label_components_workspace_bytes": (ctypes.c_int, [c_int64, P(c_uint64)]),
     "saf_label_components": (ctypes.c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
                                             c_uint64, P(ctypes.c_uint32), c_void_p]),
+    "saf_backproject_samples": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+                                               c_int32, c_int32, c_float, c_void_p, c_void_p, c_void_p]),
     "saf_mesh_workspace_bytes": (ctypes.c_int, [P(GridDesc), P(c_uint64)]),
     "saf_mesh_count": (ctypes.c_int, [P(GridDesc), c_void_p, c_void_p, c_void_p, c_uint64, P(c_uint64), P(c_uint64),
                                       c_void_p]),

@@ -483,7 +483,7 @@ constexpr int kK2Iter = kBlockVoxels / kK2Threads;  // voxels per thread per blo
 // average is advanced frame by frame in registers (read once, written once per window) and the kernel emits ONE
 // list of the voxels valid in at least one frame (WinEntry + per-frame coordinates) for the window feature kernel.
 template <bool BATCH1, bool SEQ>
-__global__ void __launch_bounds__(kK2Threads) tsdf_update_kernel(const FusionParams p)
+__global__ void __launch_bounds__(kK2Threads, SEQ ? 6 : 1) tsdf_update_kernel(const FusionParams p)
 {
     static_assert(!(BATCH1 && SEQ), "a one-frame window is the plain single-frame path");
     __shared__ uint32_t s_cnt[kK2Iter][kK2Threads / 32];

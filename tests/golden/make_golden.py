@@ -304,6 +304,39 @@ def run_objects_golden():
     print("objects:", len(keys), "objects ->", os.path.getsize(path) // 1024, "KiB")
 
 
+def run_bounds_golden():
+    """backproject_pcd (clipfusion.py:510-572) + the bounds rule of clip_seem_fusion.py:276-288."""
+    cfg = synth.SceneConfig(extent=(2.2, 2.0, 1.6), voxel_size=0.05, height=48, width=64, patch_size=32,
+                            patch_stride=16, feature_dim=8, frames=12, missing_fraction=0.1, seed=33, name="bounds")
+    frames = [synth.make_frame(cfg, i) for i in range(cfg.frames)]
+    frames[3]["depth"][:, :20] = np.nan
+    frames[5]["depth"][:] *= 3.0          # beyond max_depth
+
+    class _Dataset(torch.utils.data.Dataset):
+        imwidth, imheight = cfg.width, cfg.height
+
+        def __len__(self):
+            return len(frames)
+
+        def __getitem__(self, i):
+            f = frames[i]
+            return (torch.from_numpy(f["rgb"]), torch.from_numpy(f["depth"]), torch.from_numpy(f["pose"]),
+                    torch.from_numpy(f["K"]), i)
+
+    max_depth = 4
+    xyz, rgb = clipfusion.backproject_pcd(_Dataset(), batch_size=1, num_workers=0, device="cpu", max_depth=max_depth)
+    trunc_m = 3 * cfg.voxel_size
+    minbound = torch.tensor(np.percentile(xyz.cpu(), 1, axis=0)).float() - trunc_m
+    maxbound = torch.tensor(np.percentile(xyz.cpu(), 99, axis=0)).float() + trunc_m
+    nvox = ((maxbound - minbound) / cfg.voxel_size).round().int()
+    path = os.path.join(HERE, "bounds.npz")
+    np.savez_compressed(path, depth=np.stack([f["depth"] for f in frames]), pose=np.stack([f["pose"] for f in frames]),
+                        K=np.stack([f["K"] for f in frames]), max_depth=np.float64(max_depth), xyz=xyz.numpy(),
+                        origin=minbound.numpy(), nvox=nvox.numpy(), voxel_size=np.float64(cfg.voxel_size),
+                        trunc_vox=np.int64(3))
+    print("bounds:", tuple(xyz.shape), "origin", minbound.tolist(), "nvox", nvox.tolist())
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     only = sys.argv[1:]
@@ -316,3 +349,5 @@ if __name__ == "__main__":
         run_mesh_golden()
     if not only or "objects" in only:
         run_objects_golden()
+    if not only or "bounds" in only:
+        run_bounds_golden()

@@ -167,3 +167,16 @@ def test_objects_oracle_matches_reference():
     ids, n = CC.label_objects(g["class_grid"])
     assert n == len(g["obj_ids"]) == 99
     assert np.array_equal(ids, g["voxel_obj_ids"])
+
+
+# ---- scene bounds (oracle/bounds.py) -------------------------------------------------------------------
+
+def test_bounds_oracle_matches_reference():
+    """backproject_pcd + percentile bounds of the unmodified reference against the numpy restatement.
+    Floating point (K^-1 by LU in torch vs numpy): 1e-5 absolute on the points, identical grid size."""
+    from oracle import bounds as B
+    g = Hh.load_golden("bounds")
+    xyz, _ = B.backproject_samples(g["depth"], g["pose"], g["K"], float(g["max_depth"]))
+    assert xyz.shape == g["xyz"].shape and np.abs(xyz - g["xyz"]).max() <= 1e-5
+    origin, nvox = B.scene_bounds(xyz, float(g["voxel_size"]), int(g["trunc_vox"]))
+    assert np.abs(origin - g["origin"]).max() <= 1e-5 and np.array_equal(nvox, g["nvox"])
