@@ -255,25 +255,28 @@ def run_native_arm(args):
     P = min(args.pool * n_rooms, F * (K_steps + W_steps))
     P = max(n_rooms, P - P % n_rooms)
     stride = max(1, cfg.frames // (P // n_rooms))
+    # the n_rooms frames of one visit share their images (the rooms are identical): only the pose is shifted,
+    # so the resident pool is P / n_rooms images whatever the number of rooms
+    base = [synth.make_frame(cfg, (b * stride) % cfg.frames, table_layout="hwc") for b in range(P // n_rooms)]
     host = []
     for i in range(P):
-        fr = synth.make_frame(cfg, ((i // n_rooms) * stride) % cfg.frames, table_layout="hwc")
+        fr = dict(base[i // n_rooms])
         fr["pose"] = fr["pose"].copy()
         fr["pose"][0, 3] += (i % n_rooms) * room_dx
         host.append(fr)
-    d_depth = torch.stack([torch.from_numpy(f["depth"]) for f in host]).to(dev)
-    d_rgb = torch.stack([torch.from_numpy(f["rgb"]) for f in host]).to(dev)
-    d_seg = torch.stack([torch.from_numpy(f["seg"]) for f in host]).to(dev)
-    d_table = torch.stack([torch.from_numpy(np.ascontiguousarray(f["table"].transpose(1, 2, 0))) for f in host]).to(dev)
+    d_depth = torch.stack([torch.from_numpy(f["depth"]) for f in base]).to(dev)
+    d_rgb = torch.stack([torch.from_numpy(f["rgb"]) for f in base]).to(dev)
+    d_seg = torch.stack([torch.from_numpy(f["seg"]) for f in base]).to(dev)
+    d_table = torch.stack([torch.from_numpy(np.ascontiguousarray(f["table"].transpose(1, 2, 0))) for f in base]).to(dev)
     npy, npx = cfg.npatches
     H, Wd, C = cfg.height, cfg.width, cfg.feature_dim
 
     def frame_struct(dst, i):
-        dst.depth = d_depth[i].data_ptr()
-        dst.rgb = d_rgb[i].data_ptr()
-        dst.seg = d_seg[i].data_ptr()
+        dst.depth = d_depth[i // n_rooms].data_ptr()
+        dst.rgb = d_rgb[i // n_rooms].data_ptr()
+        dst.seg = d_seg[i // n_rooms].data_ptr()
         dst.seg_dtype = _lib.SAF_SEG_U8
-        dst.table = d_table[i].data_ptr()
+        dst.table = d_table[i // n_rooms].data_ptr()
         dst.table_stride_c, dst.table_stride_r = 1, C
         dst.npy, dst.npx = npy, npx
         dst.pose[:] = host[i]["pose"].reshape(-1).tolist()
@@ -400,8 +403,9 @@ def run_native_arm(args):
                 if ci + 1 < len(chunks):
                     nxt = stage(chunks[ci + 1])          # overlaps the fusion of this chunk
                 torch.cuda.current_stream(dev).wait_event(ev)
-                clip.next_table = tables_chw[sel.to(dev)] if len(idx) > 1 else tables_chw[idx[0]][None]
-                seg.queue = [d_seg[i] for i in idx]
+                clip.next_table = tables_chw[(sel // n_rooms).to(dev)] if len(idx) > 1 else \
+                    tables_chw[idx[0] // n_rooms][None]
+                seg.queue = [d_seg[i // n_rooms] for i in idx]
                 if chunk > 1:
                     vol.integrate_sequence(dd, rr, h_pose[sel], h_K[sel])
                 else:

@@ -1,5 +1,3 @@
-for w in 16 24; do
-SAF_K3W_WARPS=$w python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench_w8_$w.json 2> gpurun_out/bench_w8_$w.err
-grep "\[bench\]" gpurun_out/bench_w8_$w.err
-done
+python -m pytest tests/test_parity_gpu.py -q -k "sequence" 2>&1 | tail -n 3
 python tools/prof_window.py 8 6 2>&1 | tail -n 1
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench_p1.json 2> gpurun_out/bench_p1.err; grep "\[bench\]" gpurun_out/bench_p1.err
