@@ -1396,34 +1396,75 @@ __global__ void __launch_bounds__(kK3Threads) feature_accumulate_window_generic_
 // label argmax (clip_seem_fusion.py:315-325)
 // ---------------------------------------------------------------------------------------------
 
+// kArgmaxRows rows per warp iteration: all their loads are issued before the first reduction, which is what keeps
+// enough bytes in flight for HBM (one 572-byte row per iteration reached 2.5 TB/s)
+constexpr int kArgmaxRows = 6;
+
 __global__ void __launch_bounds__(256) label_argmax_kernel(const int32_t* __restrict__ labels, int64_t n, int n_classes,
                                                            long long* __restrict__ out)
 {
     const int lane = threadIdx.x & 31;
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x / 32);
-    for (int64_t v = (int64_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5); v < n; v += nwarps) {
-        const int32_t* row = labels + v * n_classes;
-        int best_val = INT_MIN, best_idx = INT_MAX;
-        bool any = false;
-        for (int c = lane; c < n_classes; c += 32) {
-            const int x = __ldg(row + c);
-            any |= (x != 0);
-            if (x > best_val) {  // strictly greater keeps the first maximum within a lane
-                best_val = x;
-                best_idx = c;
+    const int64_t gwarp = (int64_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    if (n_classes > 160) {  // generic path: one row at a time
+        for (int64_t v = gwarp; v < n; v += nwarps) {
+            const int32_t* row = labels + v * n_classes;
+            int best_val = INT_MIN, best_idx = INT_MAX;
+            bool any = false;
+            for (int c = lane; c < n_classes; c += 32) {
+                const int x = __ldg(row + c);
+                any |= (x != 0);
+                if (x > best_val) {  // strictly greater keeps the first maximum within a lane
+                    best_val = x;
+                    best_idx = c;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const int ov = __shfl_xor_sync(0xffffffffu, best_val, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, best_idx, o);
+                if (ov > best_val || (ov == best_val && oi < best_idx)) {
+                    best_val = ov;
+                    best_idx = oi;
+                }
+            }
+            any = __any_sync(0xffffffffu, any);
+            if (lane == 0) out[v] = any ? (long long)best_idx : -1ll;
+        }
+        return;
+    }
+    // n_classes <= 160 (the reference's 143): five elements per lane and row, kArgmaxRows rows in flight
+    for (int64_t v0 = gwarp * kArgmaxRows; v0 < n; v0 += nwarps * kArgmaxRows) {
+        int x[kArgmaxRows][5];
+#pragma unroll
+        for (int r = 0; r < kArgmaxRows; ++r) {
+            const int64_t v = v0 + r;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const int c = lane + 32 * k;
+                x[r][k] = (v < n && c < n_classes) ? __ldg(labels + v * n_classes + c) : INT_MIN;
             }
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const int ov = __shfl_xor_sync(0xffffffffu, best_val, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, best_idx, o);
-            if (ov > best_val || (ov == best_val && oi < best_idx)) {
-                best_val = ov;
-                best_idx = oi;
+        for (int r = 0; r < kArgmaxRows; ++r) {
+            const int64_t v = v0 + r;
+            int best_val = INT_MIN, best_idx = INT_MAX;
+            bool any = false;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const int c = lane + 32 * k;
+                any |= (c < n_classes) && (x[r][k] != 0);
+                if (x[r][k] > best_val) {
+                    best_val = x[r][k];
+                    best_idx = c;
+                }
             }
+            // warp argmax with the first maximum winning: redux.sync max of the values, then min of the indices at it
+            const int warp_max = __reduce_max_sync(0xffffffffu, best_val);
+            const int warp_idx = __reduce_min_sync(0xffffffffu, best_val == warp_max ? best_idx : INT_MAX);
+            any = __any_sync(0xffffffffu, any);
+            if (lane == 0 && v < n) out[v] = any ? (long long)warp_idx : -1ll;
         }
-        any = __any_sync(0xffffffffu, any);
-        if (lane == 0) out[v] = any ? (long long)best_idx : -1ll;
     }
 }
 
@@ -1970,8 +2011,8 @@ int saf_label_argmax(const int32_t* labels, int64_t n, int32_t n_classes, int64_
     if (!labels || !out) return SAF_ERR_NULL;
     if (n < 0 || n_classes <= 0) return SAF_ERR_SHAPE;
     if (n == 0) return 0;
-    const int64_t want = (n + 7) / 8;
-    const int grid = (int)std::min<int64_t>(want, (int64_t)sms * 8);
+    const int64_t want = (n + 8 * kArgmaxRows - 1) / (8 * kArgmaxRows);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sms * 8));
     label_argmax_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(labels, n, n_classes, (long long*)out);
     SAF_CHECK_LAUNCH("label_argmax_kernel", (cudaStream_t)stream);
     return 0;
