@@ -1146,6 +1146,12 @@ __device__ __forceinline__ void sample_rgb(const FusionParams& p, const saf_fram
 // One CTA of kW3Warps warps per SM (16 or 24): the kernel is latency-, not HBM-bound.  16 warps leave registers for
 // two K2 CTAs of the NEXT window on the same SM (saf_integrate_sequence runs them on a side stream), whose
 // ALU-bound work fills the issue slots K3W leaves idle while it waits on L1.
+#ifndef K3W2_MAXNREG
+#define K3W2_MAXNREG 128
+#endif
+#ifndef K3W2_WARPS
+#define K3W2_WARPS 16
+#endif
 constexpr int kW3Chunk = 8;                  // union-list entries a warp claims at a time (dynamic balancing: the
                                              // number of updates per entry varies from 1 to the window length)
 
@@ -1312,6 +1318,232 @@ feature_accumulate_window_kernel(const __grid_constant__ FusionParams p, const _
             }
 #pragma unroll
             for (int j = 0; j < CHUNKS; ++j) st_stream_f4(row + j * 32 + lane, acc[j]);
+        }
+        __syncwarp();  // the next chunk overwrites my_coords
+    }
+}
+
+template <int CHUNKS, int kW3Warps>
+__global__ void __maxnreg__(K3W2_MAXNREG)
+feature_accumulate_window_pair_kernel(const __grid_constant__ FusionParams p, const __grid_constant__ WindowTables wt)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int C = CHUNKS * 128;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    SlotCounters* sc = &p.hdr->slot[p.slot];
+    const uint32_t n = sc->n_union;
+    if (n == 0) return;
+    const uint32_t n_blocks = sc->n_blocks;
+    const int B = p.batch;
+
+    // [ one feature row per warp (TMA landing zone) ][ coords: warp x chunk x frame ][ one mbarrier per warp ]
+    float* ring = reinterpret_cast<float*>(smem_raw);
+    float2* coords = reinterpret_cast<float2*>(ring + (size_t)kW3Warps * 2 * C);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(coords + (size_t)kW3Warps * kW3Chunk * SAF_MAX_BATCH);
+    float* my_row = ring + (size_t)warp * 2 * C;   // two landing rows: the pair of voxels the warp updates together
+    float2* my_coords = coords + (size_t)warp * kW3Chunk * SAF_MAX_BATCH;
+    uint64_t* my_bar = bars + warp;
+    __shared__ uint32_t s_ticket;
+    __shared__ volatile uint32_t s_sbase[8], s_sgen[8];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kW3Warps; ++i) mbar_init(&bars[i], 1);
+        fence_mbar_init();
+        s_ticket = 0;
+    }
+    if (threadIdx.x < 8) s_sgen[threadIdx.x] = 0xffffffffu;
+    __syncthreads();
+
+    const uint32_t* __restrict__ off = p.blk_offset;
+    uint32_t t_use = 0;  // rows this warp has received (mbarrier parity = t_use & 1)
+
+    // Work dispenser.  Warps take tickets from a CTA counter; every kW3Warps tickets form one "super chunk" of
+    // kW3Warps * kW3Chunk consecutive list entries that the warp holding its first ticket claims from the global
+    // counter.  The CTA's warps therefore walk neighbouring voxels (same few table rows per frame -> L1 hits),
+    // while the units stay small enough to balance the very uneven number of updates per entry.
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) {
+            const uint32_t t = atomicAdd(&s_ticket, 1u);
+            const uint32_t k = t / kW3Warps, c = t % kW3Warps, slot = k & 7u;
+            if (c == 0) {
+                base = atomicAdd(&sc->k3_next, (uint32_t)(kW3Warps * kW3Chunk));
+                s_sbase[slot] = base;
+                __threadfence_block();
+                s_sgen[slot] = k;
+            } else {
+                while (s_sgen[slot] != k) {
+                }
+                __threadfence_block();
+                base = s_sbase[slot];
+            }
+            base = min(base, n) + c * kW3Chunk;
+        }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint32_t cnt = min((uint32_t)kW3Chunk, n - base);
+        uint32_t my_voxel = 0, my_mask = 0;
+        int my_w = 0;
+        if (lane < cnt) {
+            const uint32_t i = base + lane;
+            uint32_t lo = 0, hi = n_blocks;  // off[lo] <= i < off[hi]
+            while (hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (__ldg(off + mid) <= i)
+                    lo = mid;
+                else
+                    hi = mid;
+            }
+            const WinEntry e = p.ulist[(uint64_t)lo * kBlockVoxels + (i - __ldg(off + lo))];
+            my_voxel = e.voxel;
+            my_mask = e.mask_local & 0xffu;
+            my_w = p.vol.weight[my_voxel];
+            const float2* src = p.wcoords + (uint64_t)lo * B * kBlockVoxels + (e.mask_local >> 8);
+            for (uint32_t mm = my_mask; mm; mm &= mm - 1u) {
+                const int b = __ffs(mm) - 1;
+                my_coords[lane * SAF_MAX_BATCH + b] = src[(size_t)b * kBlockVoxels];
+            }
+        }
+        {   // the landing zone is free (its last rows went to registers): start the chunk's first pair of rows
+            const uint32_t v0 = __shfl_sync(0xffffffffu, my_voxel, 0);
+            const uint32_t v1 = __shfl_sync(0xffffffffu, my_voxel, 1);
+            if (lane == 0) {
+                fence_proxy_async();
+                mbar_arrive_expect_tx(my_bar, (cnt > 1 ? 2u : 1u) * (uint32_t)C * 4u);
+                tma_bulk_g2s(my_row, p.vol.clip_feat + (size_t)v0 * C, (uint32_t)C * 4u, my_bar);
+                if (cnt > 1) tma_bulk_g2s(my_row + C, p.vol.clip_feat + (size_t)v1 * C, (uint32_t)C * 4u, my_bar);
+            }
+        }
+        // rgb running average, label counters and weight of this lane's voxel, frame by frame
+        // (clip_seem_fusion.py:786-798, 808-822)
+        if (lane < cnt) {
+            float* dst = p.vol.rgb + (size_t)my_voxel * 3;
+            float acc[3] = {dst[0], dst[1], dst[2]};
+            int w = my_w;
+            for (uint32_t mm = my_mask; mm; mm &= mm - 1u) {
+                const int b = __ffs(mm) - 1;
+                const saf_frame& f = p.frames[b];
+                const float2 g = my_coords[lane * SAF_MAX_BATCH + b];
+                const float a = __frcp_rn(__int2float_rn(w + 1));
+                const float bb = __fmul_rn(__int2float_rn(w), a);
+                const int px = nearest_index(g.x, p.W), py = nearest_index(g.y, p.H);
+                float smp[3];
+                sample_rgb(p, f, g.x, g.y, px, py, smp);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) acc[c] = __fadd_rn(__fmul_rn(smp[c], a), __fmul_rn(acc[c], bb));
+                if (p.vol.labels_one_hot && f.seg) {
+                    const float lf = (px >= 0 && py >= 0) ? load_class_id(f.seg, f.seg_dtype, py * p.W + px) : 0.0f;
+                    const long long id = (long long)lf;
+                    if (id >= 0 && id < p.vol.n_classes)
+                        p.vol.labels_one_hot[(size_t)my_voxel * p.vol.n_classes + id] += 1;
+                    else
+                        atomicOr(&p.hdr->error_flags, SAF_FLAG_BAD_CLASS_ID);
+                }
+                ++w;
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) dst[c] = acc[c];
+            p.vol.weight[my_voxel] = w;
+        }
+        __syncwarp();  // my_coords written by the lanes, read by the whole warp below
+        for (uint32_t q = 0; q < cnt; q += 2) {
+            // two neighbouring voxels per pass: they nearly always use the same four table rows in a frame, so the
+            // rows are loaded once for both, and the two running averages are independent dependency chains
+            const bool two = q + 1 < cnt;
+            const uint32_t v0 = __shfl_sync(0xffffffffu, my_voxel, q);
+            const uint32_t v1 = __shfl_sync(0xffffffffu, my_voxel, two ? q + 1 : q);
+            const uint32_t m0 = __shfl_sync(0xffffffffu, my_mask, q);
+            const uint32_t m1 = two ? __shfl_sync(0xffffffffu, my_mask, q + 1) : 0u;
+            int w0 = __shfl_sync(0xffffffffu, my_w, q);
+            int w1 = __shfl_sync(0xffffffffu, my_w, two ? q + 1 : q);
+            const float4* old4 = reinterpret_cast<const float4*>(my_row);
+            mbar_wait(my_bar, t_use & 1u);
+            ++t_use;
+            float4 acc0[CHUNKS], acc1[CHUNKS];
+#pragma unroll
+            for (int j = 0; j < CHUNKS; ++j) {
+                acc0[j] = old4[j * 32 + lane];
+                acc1[j] = old4[(two ? C / 4 : 0) + j * 32 + lane];
+            }
+            __syncwarp();  // both rows are in registers: the landing zone can take the next pair already
+            if (q + 2 < cnt) {
+                const bool two_n = q + 3 < cnt;
+                const uint32_t n0 = __shfl_sync(0xffffffffu, my_voxel, q + 2);
+                const uint32_t n1 = __shfl_sync(0xffffffffu, my_voxel, two_n ? q + 3 : q + 2);
+                if (lane == 0) {
+                    fence_proxy_async();
+                    mbar_arrive_expect_tx(my_bar, (two_n ? 2u : 1u) * (uint32_t)C * 4u);
+                    tma_bulk_g2s(my_row, p.vol.clip_feat + (size_t)n0 * C, (uint32_t)C * 4u, my_bar);
+                    if (two_n) tma_bulk_g2s(my_row + C, p.vol.clip_feat + (size_t)n1 * C, (uint32_t)C * 4u, my_bar);
+                }
+            }
+            for (uint32_t mm = m0 | m1; mm; mm &= mm - 1u) {
+                const int b = __ffs(mm) - 1;
+                const bool in0 = (m0 >> b) & 1u, in1 = (m1 >> b) & 1u;
+                const float4* tab4 = reinterpret_cast<const float4*>(wt.ptr[b]) + lane;   // zero-bordered [R',C] rows
+                Taps t0, t1;
+                float a0 = 0.f, b0 = 0.f, a1 = 0.f, b1 = 0.f;
+                if (in0) {   // clip_seem_fusion.py:808-810
+                    const float2 g = my_coords[q * SAF_MAX_BATCH + b];
+                    bilinear_setup_padded(g.x, g.y, p.frames[b].npx, p.frames[b].npy, t0);
+                    a0 = __frcp_rn(__int2float_rn(w0 + 1));
+                    b0 = __fmul_rn(__int2float_rn(w0), a0);
+                    ++w0;
+                }
+                if (in1) {
+                    const float2 g = my_coords[(q + 1) * SAF_MAX_BATCH + b];
+                    bilinear_setup_padded(g.x, g.y, p.frames[b].npx, p.frames[b].npy, t1);
+                    a1 = __frcp_rn(__int2float_rn(w1 + 1));
+                    b1 = __fmul_rn(__int2float_rn(w1), a1);
+                    ++w1;
+                }
+                if (in0 && in1 && t0.idx[0] == t1.idx[0] && t0.idx[1] == t1.idx[1] && t0.idx[2] == t1.idx[2] &&
+                    t0.idx[3] == t1.idx[3]) {
+                    const float4* r0 = tab4 + t0.idx[0] * (C / 4);
+                    const float4* r1 = tab4 + t0.idx[1] * (C / 4);
+                    const float4* r2 = tab4 + t0.idx[2] * (C / 4);
+                    const float4* r3 = tab4 + t0.idx[3] * (C / 4);
+#pragma unroll
+                    for (int j = 0; j < CHUNKS; ++j) {
+                        const float4 x0 = __ldg(r0 + j * 32), x1 = __ldg(r1 + j * 32);
+                        const float4 x2 = __ldg(r2 + j * 32), x3 = __ldg(r3 + j * 32);
+                        acc0[j] = blend4(mix4(x0, x1, x2, x3, t0.w), acc0[j], a0, b0);
+                        acc1[j] = blend4(mix4(x0, x1, x2, x3, t1.w), acc1[j], a1, b1);
+                    }
+                } else {
+                    if (in0) {
+                        const float4* r0 = tab4 + t0.idx[0] * (C / 4);
+                        const float4* r1 = tab4 + t0.idx[1] * (C / 4);
+                        const float4* r2 = tab4 + t0.idx[2] * (C / 4);
+                        const float4* r3 = tab4 + t0.idx[3] * (C / 4);
+#pragma unroll
+                        for (int j = 0; j < CHUNKS; ++j) {
+                            const float4 x0 = __ldg(r0 + j * 32), x1 = __ldg(r1 + j * 32);
+                            const float4 x2 = __ldg(r2 + j * 32), x3 = __ldg(r3 + j * 32);
+                            acc0[j] = blend4(mix4(x0, x1, x2, x3, t0.w), acc0[j], a0, b0);
+                        }
+                    }
+                    if (in1) {
+                        const float4* r0 = tab4 + t1.idx[0] * (C / 4);
+                        const float4* r1 = tab4 + t1.idx[1] * (C / 4);
+                        const float4* r2 = tab4 + t1.idx[2] * (C / 4);
+                        const float4* r3 = tab4 + t1.idx[3] * (C / 4);
+#pragma unroll
+                        for (int j = 0; j < CHUNKS; ++j) {
+                            const float4 x0 = __ldg(r0 + j * 32), x1 = __ldg(r1 + j * 32);
+                            const float4 x2 = __ldg(r2 + j * 32), x3 = __ldg(r3 + j * 32);
+                            acc1[j] = blend4(mix4(x0, x1, x2, x3, t1.w), acc1[j], a1, b1);
+                        }
+                    }
+                }
+            }
+            float4* row0 = reinterpret_cast<float4*>(p.vol.clip_feat + (size_t)v0 * C);
+#pragma unroll
+            for (int j = 0; j < CHUNKS; ++j) st_stream_f4(row0 + j * 32 + lane, acc0[j]);
+            if (two) {
+                float4* row1 = reinterpret_cast<float4*>(p.vol.clip_feat + (size_t)v1 * C);
+#pragma unroll
+                for (int j = 0; j < CHUNKS; ++j) st_stream_f4(row1 + j * 32 + lane, acc1[j]);
+            }
         }
         __syncwarp();  // the next chunk overwrites my_coords
     }
@@ -1652,6 +1884,20 @@ static int launch_k3(FusionParams& p, int frame_index, int sms, int smem_optin, 
 }
 
 template <int CHUNKS, int kW3Warps>
+static int launch_k3w_pair(const FusionParams& p, const WindowTables& wt, int sms, cudaStream_t st)
+{
+    constexpr int kW3Threads = kW3Warps * 32;
+    constexpr size_t row = (size_t)CHUNKS * 128 * 4;
+    const size_t smem = (size_t)kW3Warps * 2 * row + (size_t)kW3Warps * kW3Chunk * SAF_MAX_BATCH * sizeof(float2) +
+                        8 * (size_t)kW3Warps;
+    auto kern = feature_accumulate_window_pair_kernel<CHUNKS, kW3Warps>;
+    SAF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<sms, kW3Threads, smem, st>>>(p, wt);
+    SAF_CHECK_LAUNCH("feature_accumulate_window_pair_kernel (K3W)", st);
+    return 0;
+}
+
+template <int CHUNKS, int kW3Warps>
 static int launch_k3w_fixed(const FusionParams& p, const WindowTables& wt, int sms, cudaStream_t st)
 {
     constexpr int kW3Threads = kW3Warps * 32;
@@ -1663,6 +1909,17 @@ static int launch_k3w_fixed(const FusionParams& p, const WindowTables& wt, int s
     kern<<<sms, kW3Threads, smem, st>>>(p, wt);
     SAF_CHECK_LAUNCH("feature_accumulate_window_kernel (K3W)", st);
     return 0;
+}
+
+// two voxels per warp pass in K3W (default); SAF_K3W_PAIR=0 selects the one-voxel kernel (A/B timing)
+static bool k3w_pair()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SAF_K3W_PAIR");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
 }
 
 // warps per K3W CTA; SAF_K3W_WARPS=16|24 overrides for A/B timing
@@ -1687,6 +1944,13 @@ static int launch_k3w(const FusionParams& p, int sms, cudaStream_t st)
         wt.stride_r[b] = C;
     }
     if (rows16) {
+        if (k3w_pair()) {
+            switch (C) {
+                case 512: return launch_k3w_pair<4, K3W2_WARPS>(p, wt, sms, st);
+                case 768: return launch_k3w_pair<6, K3W2_WARPS>(p, wt, sms, st);
+                default: break;   // C = 1024: two rows of accumulators do not fit the register budget
+            }
+        }
         const bool w16 = k3w_warps() == 16;
         switch (C) {
             case 512: return w16 ? launch_k3w_fixed<4, 16>(p, wt, sms, st) : launch_k3w_fixed<4, 24>(p, wt, sms, st);

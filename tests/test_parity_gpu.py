@@ -186,26 +186,38 @@ def test_cfg1_full_parity_run():
     _check_against(vol, orc.tsdf, orc.weight, orc.tsdf_weight, orc.rgb, orc.clip_feat, orc.labels_one_hot, exact=True)
 
 
-def test_size_independent_properties_at_cfg2_scale():
+@pytest.mark.parametrize("mode,n_frames,step", [("frame", 6, 37), ("window", 20, 3)])
+def test_size_independent_properties_at_cfg2_scale(mode, n_frames, step):
     """At a ScanNet-scale grid (2 cm, 640x480) the oracle is too slow for a full comparison; check
     invariants instead: counter sums equal the kernels' own valid counts, every histogram row sums
-    to the voxel's weight, untouched voxels stay zero, and a sampled x-slab matches the oracle."""
-    cfg = synth.baseline_config("cfg2", feature_dim=512, frames=6, extent=(6.0, 6.0, 3.0))
+    to the voxel's weight, untouched voxels stay zero, and a sampled x-slab matches the oracle.
+    "frame": one integrate() per frame; "window": one integrate_sequence() call (2.5 windows of 8)."""
+    cfg = synth.baseline_config("cfg2", feature_dim=512, frames=n_frames, extent=(6.0, 6.0, 3.0))
     origin, nvox = cfg.grid()
     g = dict(cls="ClipSeemFusion", feature_dim=cfg.feature_dim, origin=origin, nvox=nvox,
              voxel_size=cfg.voxel_size, trunc=cfg.trunc)
     vol, clip, seg = Hh.make_gpu_volume(g)
     xs0, xs1 = 150, 162
     orc = O.OracleVolume(origin, cfg.voxel_size, nvox, cfg.trunc, cfg.feature_dim, x_begin=xs0, x_end=xs1, num_threads=0)
-    for i in range(cfg.frames):
-        fr = synth.make_frame(cfg, i * 37, table_layout="hwc")
-        clip.next_table = torch.from_numpy(np.ascontiguousarray(fr["table"].transpose(1, 2, 0))).cuda() \
-            .permute(2, 0, 1)[None]
-        seg.queue = [torch.from_numpy(fr["seg"]).cuda()]
-        vol.integrate(torch.from_numpy(fr["depth"]).cuda()[None], torch.from_numpy(fr["rgb"]).cuda()[None],
-                      torch.from_numpy(fr["pose"]).cuda()[None], torch.from_numpy(fr["K"]).cuda()[None])
+    frames = [synth.make_frame(cfg, i * step, table_layout="hwc") for i in range(cfg.frames)]
+    for fr in frames:
         orc.integrate(fr["depth"][None], fr["rgb"][None], fr["pose"][None], fr["K"][None], fr["table"][None],
                       fr["seg"][None], want_masks=False)
+    if mode == "frame":
+        for fr in frames:
+            clip.next_table = torch.from_numpy(np.ascontiguousarray(fr["table"].transpose(1, 2, 0))).cuda() \
+                .permute(2, 0, 1)[None]
+            seg.queue = [torch.from_numpy(fr["seg"]).cuda()]
+            vol.integrate(torch.from_numpy(fr["depth"]).cuda()[None], torch.from_numpy(fr["rgb"]).cuda()[None],
+                          torch.from_numpy(fr["pose"]).cuda()[None], torch.from_numpy(fr["K"]).cuda()[None])
+    else:
+        clip.next_table = torch.stack([torch.from_numpy(np.ascontiguousarray(f["table"].transpose(1, 2, 0)))
+                                       for f in frames]).cuda().permute(0, 3, 1, 2)
+        seg.queue = [torch.from_numpy(f["seg"]).cuda() for f in frames]
+        vol.integrate_sequence(torch.stack([torch.from_numpy(f["depth"]) for f in frames]).cuda(),
+                               torch.stack([torch.from_numpy(f["rgb"]) for f in frames]).cuda(),
+                               torch.stack([torch.from_numpy(f["pose"]) for f in frames]),
+                               torch.stack([torch.from_numpy(f["K"]) for f in frames]))
     st = vol.stats()
     assert st["total_frames"] == cfg.frames
     assert int(vol.weight.sum(dtype=torch.int64)) == st["total_valid"] > 0
