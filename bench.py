@@ -258,7 +258,11 @@ def run_native_arm(args):
     stride = max(1, cfg.frames // (P // n_rooms))
     # the n_rooms frames of one visit share their images (the rooms are identical): only the pose is shifted,
     # so the resident pool is P / n_rooms images whatever the number of rooms
-    base = [synth.make_frame(cfg, (b * stride) % cfg.frames, table_layout="hwc") for b in range(P // n_rooms)]
+    from concurrent.futures import ThreadPoolExecutor
+    n_threads = max(1, min(8, (os.cpu_count() or 1) // max(1, world)))   # numpy's generators release the GIL
+    with ThreadPoolExecutor(n_threads) as pool_ex:
+        base = list(pool_ex.map(lambda b: synth.make_frame(cfg, (b * stride) % cfg.frames, table_layout="hwc"),
+                                range(P // n_rooms)))
     host = []
     for i in range(P):
         fr = dict(base[i // n_rooms])

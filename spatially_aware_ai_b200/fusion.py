@@ -3,6 +3,9 @@
 (/root/reference/clipfusion.py:575-763), with the per-frame work done by the sm_100a kernels in
 libsaf_b200.so.  PyTorch is only the owner of device memory and streams here.
 
+Additions to the reference surface: ``integrate_sequence`` (the frame loop as one call, fused 8 frames at a time
+on the device), ``label_argmax``, ``stats`` / ``check_errors``; ``extract_mesh`` runs on the device.
+
 Differences a caller can observe:
   * tensors must live on a CUDA device (sm_100); there is no CPU path - it raises instead.
   * ``xyz_world`` is not stored (12 B/voxel re-read every frame in the reference); voxel centres
