@@ -483,7 +483,7 @@ constexpr int kK2Iter = kBlockVoxels / kK2Threads;  // voxels per thread per blo
 // average is advanced frame by frame in registers (read once, written once per window) and the kernel emits ONE
 // list of the voxels valid in at least one frame (WinEntry + per-frame coordinates) for the window feature kernel.
 template <bool BATCH1, bool SEQ>
-__global__ void __launch_bounds__(kK2Threads, SEQ ? 6 : 1) tsdf_update_kernel(const FusionParams p)
+__global__ void __launch_bounds__(kK2Threads, SEQ ? 8 : 1) tsdf_update_kernel(const FusionParams p)
 {
     static_assert(!(BATCH1 && SEQ), "a one-frame window is the plain single-frame path");
     __shared__ uint32_t s_cnt[kK2Iter][kK2Threads / 32];
@@ -1818,7 +1818,7 @@ static int launch_k1(const FusionParams& p, cudaStream_t st)
 
 static int launch_k2(const FusionParams& p, int sms, cudaStream_t st)
 {
-    const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)p.nblocks_total, (uint64_t)sms * 8u);
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)p.nblocks_total, (uint64_t)sms * (p.sequential ? 32u : 8u));
     if (p.batch == 1)
         tsdf_update_kernel<true, false><<<grid, kK2Threads, (size_t)p.n_k1 * 4, st>>>(p);
     else if (p.sequential)
