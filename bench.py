@@ -57,7 +57,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--ref-frames-per-step", type=int, default=4)
     ap.add_argument("--rooms", type=int, default=0, help="debug: emulate the N-room multi-GPU workload on this rank only")
-    ap.add_argument("--window", type=int, default=8, choices=list(range(1, 9)),
+    ap.add_argument("--window", type=int, default=16, choices=list(range(1, 17)),
                     help="frames fused per launch trio by saf_integrate_sequence (1 = frame by frame)")
     return ap.parse_args()
 
@@ -403,7 +403,7 @@ def run_native_arm(args):
         h_pose = torch.stack([torch.from_numpy(f["pose"]) for f in host[:Pe]])
         h_K = torch.stack([torch.from_numpy(f["K"]) for f in host[:Pe]])
         tables_chw = d_table.permute(0, 3, 1, 2)            # producer outputs stay on the device
-        chunk = 8 if window > 1 else 1
+        chunk = window
         copy_stream = torch.cuda.Stream(dev)
 
         def stage(idx):
@@ -460,7 +460,7 @@ def run_native_arm(args):
                        "one chunk ahead on a copy stream), pose/K passed as host tensors; feature image and class map "
                        "come from device-resident stand-ins for the CLIP / kMaX producers (DNN inference is outside "
                        "the path); the step's counters are read back to the host" %
-                       ("ClipSeemFusion.integrate_sequence on chunks of 8 frames" if chunk > 1 else
+                       ("ClipSeemFusion.integrate_sequence on chunks of %d frames" % chunk if chunk > 1 else
                         "ClipSeemFusion.integrate per frame")}
 
     # ---- roofline of the dominant kernel (feature accumulate), timed per launch with CUDA events -----------

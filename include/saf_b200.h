@@ -30,8 +30,8 @@
 extern "C" {
 #endif
 
-#define SAF_ABI_VERSION 1
-#define SAF_MAX_BATCH 8          /* frames per integrate() call; every reference caller uses 1 */
+#define SAF_ABI_VERSION 2
+#define SAF_MAX_BATCH 16         /* frames per integrate() call / per window; every reference caller uses 1 */
 #define SAF_BLOCK_EDGE 8         /* voxel blocks are 8x8x8 */
 
 /* argument errors */

@@ -11,8 +11,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # SAF_LIB_PATH: load another build of the same ABI (A/B timing of kernel variants)
 LIB_PATH = os.environ.get("SAF_LIB_PATH") or os.path.join(HERE, "libsaf_b200.so")
 
-SAF_ABI_VERSION = 1
-SAF_MAX_BATCH = 8
+SAF_ABI_VERSION = 2
+SAF_MAX_BATCH = 16
 
 SAF_SEG_NONE, SAF_SEG_U8, SAF_SEG_I16, SAF_SEG_I32, SAF_SEG_I64, SAF_SEG_F32 = range(6)
 SAF_RGB_NEAREST, SAF_RGB_BILINEAR = 0, 1

@@ -52,7 +52,7 @@ struct FusionParams {
     uint32_t* cta_count;       // [n_k1]              visible blocks found by each K1 CTA
     float* tile_dmax;          // [batch][kMaxDepthTiles] largest depth in each (1 << tile_shift)^2 tile of the depth image
     int32_t tile_shift, ntx, nty;
-    uint32_t* block_seg;       // [n_k1*256]          per-CTA ordered segments
+    uint2* block_seg;          // [n_k1*256]          per-CTA ordered segments of {block id, per-frame mask}
     uint32_t* blk_count;       // [batch][nblocks_total]   valid voxels per visible block (by rank)
     uint32_t* blk_offset;      // [batch][nblocks_total+1] exclusive prefix of blk_count
     ValidEntry* lists;         // [batch][nblocks_total*512] rank r's entries start at r*512
@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(kK1Threads) frame_setup_kernel(const FusionPar
         if (w < warp) base += s_warp[w];
         total += s_warp[w];
     }
-    if (vis) p.block_seg[(size_t)blockIdx.x * kK1Threads + base + __popc(m & ((1u << lane) - 1u))] = blk | (vis << 24);
+    if (vis) p.block_seg[(size_t)blockIdx.x * kK1Threads + base + __popc(m & ((1u << lane) - 1u))] = make_uint2(blk, vis);
     if (threadIdx.x == 0) p.cta_count[blockIdx.x] = total;
 }
 
@@ -519,9 +519,9 @@ __global__ void __launch_bounds__(kK2Threads, SEQ ? 8 : 1) tsdf_update_kernel(co
             else
                 hi = mid;
         }
-        const uint32_t packed = p.block_seg[(size_t)lo * kK1Threads + (bi - s_off[lo])];
-        const uint32_t blk = packed & 0xffffffu;
-        const uint32_t fmask = packed >> 24;  // frames that can touch the block (K1: frustum and depth reach)
+        const uint2 packed = p.block_seg[(size_t)lo * kK1Threads + (bi - s_off[lo])];
+        const uint32_t blk = packed.x;
+        const uint32_t fmask = packed.y;  // frames that can touch the block (K1: frustum and depth reach)
         const uint32_t bz = blk % p.nb[2];
         const uint32_t by = (blk / p.nb[2]) % p.nb[1];
         const uint32_t bx = blk / (p.nb[2] * p.nb[1]);
@@ -616,7 +616,7 @@ __global__ void __launch_bounds__(kK2Threads, SEQ ? 8 : 1) tsdf_update_kernel(co
                     if (w == warp && m[j] != 0u) {
                         WinEntry e;
                         e.voxel = v[j];
-                        e.mask_local = m[j] | ((uint32_t)(threadIdx.x + j * kK2Threads) << 8);
+                        e.mask_local = m[j] | ((uint32_t)(threadIdx.x + j * kK2Threads) << 16);
                         seg[run + __popc(um[j] & ((1u << lane) - 1u))] = e;
                     }
                     run += s_cnt[j][w];
@@ -1227,9 +1227,9 @@ feature_accumulate_window_kernel(const __grid_constant__ FusionParams p, const _
             }
             const WinEntry e = p.ulist[(uint64_t)lo * kBlockVoxels + (i - __ldg(off + lo))];
             my_voxel = e.voxel;
-            my_mask = e.mask_local & 0xffu;
+            my_mask = e.mask_local & 0xffffu;
             my_w = p.vol.weight[my_voxel];
-            const float2* src = p.wcoords + (uint64_t)lo * B * kBlockVoxels + (e.mask_local >> 8);
+            const float2* src = p.wcoords + (uint64_t)lo * B * kBlockVoxels + (e.mask_local >> 16);
             for (uint32_t mm = my_mask; mm; mm &= mm - 1u) {
                 const int b = __ffs(mm) - 1;
                 my_coords[lane * SAF_MAX_BATCH + b] = src[(size_t)b * kBlockVoxels];
@@ -1395,9 +1395,9 @@ feature_accumulate_window_pair_kernel(const __grid_constant__ FusionParams p, co
             }
             const WinEntry e = p.ulist[(uint64_t)lo * kBlockVoxels + (i - __ldg(off + lo))];
             my_voxel = e.voxel;
-            my_mask = e.mask_local & 0xffu;
+            my_mask = e.mask_local & 0xffffu;
             my_w = p.vol.weight[my_voxel];
-            const float2* src = p.wcoords + (uint64_t)lo * B * kBlockVoxels + (e.mask_local >> 8);
+            const float2* src = p.wcoords + (uint64_t)lo * B * kBlockVoxels + (e.mask_local >> 16);
             for (uint32_t mm = my_mask; mm; mm &= mm - 1u) {
                 const int b = __ffs(mm) - 1;
                 my_coords[lane * SAF_MAX_BATCH + b] = src[(size_t)b * kBlockVoxels];
@@ -1573,11 +1573,11 @@ __global__ void __launch_bounds__(kK3Threads) feature_accumulate_window_generic_
                 hi = mid;
         }
         const WinEntry e = p.ulist[(uint64_t)lo * kBlockVoxels + ((uint32_t)i - __ldg(off + lo))];
-        const float2* src = p.wcoords + (uint64_t)lo * B * kBlockVoxels + (e.mask_local >> 8);
+        const float2* src = p.wcoords + (uint64_t)lo * B * kBlockVoxels + (e.mask_local >> 16);
         const int w0 = p.vol.weight[e.voxel];
         float* row = p.vol.clip_feat + (size_t)e.voxel * C;
         int w = w0;
-        for (uint32_t mm = e.mask_local & 0xffu; mm; mm &= mm - 1u) {
+        for (uint32_t mm = e.mask_local & 0xffffu; mm; mm &= mm - 1u) {
             const int b = __ffs(mm) - 1;
             const float2 g = src[(size_t)b * kBlockVoxels];
             const float a = __frcp_rn(__int2float_rn(w + 1));
@@ -1609,7 +1609,7 @@ __global__ void __launch_bounds__(kK3Threads) feature_accumulate_window_generic_
         if (lane == 0) {
             // small state, frame by frame (weights advance exactly as above)
             w = w0;
-            for (uint32_t mm = e.mask_local & 0xffu; mm; mm &= mm - 1u) {
+            for (uint32_t mm = e.mask_local & 0xffffu; mm; mm &= mm - 1u) {
                 const int b = __ffs(mm) - 1;
                 const float2 g = src[(size_t)b * kBlockVoxels];
                 ValidEntry ve;
@@ -1764,7 +1764,7 @@ static int build_params(const saf_grid_desc* grid, const saf_volume* vol, const 
         if ((uint32_t)p->ntx * (uint32_t)p->nty <= kMaxDepthTiles) break;
         p->tile_shift += 1;
     }
-    p->block_seg = (uint32_t*)(sb + L.off_block_seg);
+    p->block_seg = (uint2*)(sb + L.off_block_seg);
     p->blk_count = (uint32_t*)(sb + L.off_blk_count);
     p->blk_offset = (uint32_t*)(sb + L.off_blk_offset);
     p->lists = (ValidEntry*)(sb + L.off_lists);
@@ -1811,7 +1811,10 @@ static int launch_k1(const FusionParams& p, cudaStream_t st)
     const int ntiles = p.ntx * p.nty;
     depth_tiles_kernel<<<(p.batch * ntiles + 7) / 8, 256, 0, st>>>(p);
     SAF_CHECK_LAUNCH("depth_tiles_kernel (K0)", st);
-    frame_setup_kernel<<<p.n_k1 + pack_ctas, kK1Threads, (size_t)p.batch * ntiles * sizeof(float), st>>>(p, p.n_k1);
+    const size_t k1_smem = (size_t)p.batch * ntiles * sizeof(float);
+    if (k1_smem > 48u * 1024u)
+        SAF_CUDA_TRY(cudaFuncSetAttribute(frame_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem));
+    frame_setup_kernel<<<p.n_k1 + pack_ctas, kK1Threads, k1_smem, st>>>(p, p.n_k1);
     SAF_CHECK_LAUNCH("frame_setup_kernel (K1)", st);
     return 0;
 }
@@ -2002,7 +2005,7 @@ int saf_workspace_init(const saf_workspace* ws, const saf_grid_desc* grid, void*
     h.nb[1] = L.nb[1];
     h.nb[2] = L.nb[2];
     cudaStream_t st = (cudaStream_t)stream;
-    SAF_CUDA_TRY(cudaMemsetAsync(ws->base, 0, 512, st));
+    SAF_CUDA_TRY(cudaMemsetAsync(ws->base, 0, kWsHeaderBytes, st));
     // header is tiny: a synchronous-with-stream copy from pageable memory is fine here
     SAF_CUDA_TRY(cudaMemcpyAsync(ws->base, &h, sizeof(h), cudaMemcpyHostToDevice, st));
     SAF_CUDA_TRY(cudaStreamSynchronize(st));

@@ -38,7 +38,7 @@ struct SlotCounters {
     uint32_t acc_valid[SAF_MAX_BATCH];      // window mode: per-frame valid counts (atomics, folded like n_tsdf_valid)
 };
 
-// Device-resident workspace header (512 bytes).
+// Device-resident workspace header (kWsHeaderBytes).
 struct WsHeader {
     SlotCounters slot[2];
     uint32_t error_flags;
@@ -61,13 +61,14 @@ struct WsHeader {
     uint32_t nb[3];                         // blocks per axis of the slab
     uint32_t pad1_[1];
 };
-static_assert(sizeof(WsHeader) <= 512, "workspace header grew past its slot");
+constexpr uint64_t kWsHeaderBytes = 1024;
+static_assert(sizeof(WsHeader) <= kWsHeaderBytes, "workspace header grew past its slot");
 
 // Window mode (saf_integrate_sequence): one voxel that is `valid` in at least one frame of the window.
 // The (gx, gy) of frame b live in a separate array at [(rank * B + b) * 512 + local].
 struct __align__(8) WinEntry {
     uint32_t voxel;        // slab-local flat index
-    uint32_t mask_local;   // bits 0..7: frames of the window in which the voxel is valid; bits 8..16: index in its block
+    uint32_t mask_local;   // bits 0..15: frames of the window in which the voxel is valid; bits 16..24: index in its block
 };
 
 // One `valid` voxel of one frame: slab-local flat index and the normalised image coordinates
@@ -84,7 +85,7 @@ constexpr uint32_t kMaxK1Ctas = 2048;       // K1's last CTA scans this many per
 
 // Workspace layout (all offsets 256-byte aligned):
 //   header | slot 0 | slot 1        with, per slot,
-//   cta_count[n_k1] | tile_dmax[max_batch][kMaxDepthTiles] | block_seg[n_k1*256] | blk_count[max_batch][nblocks_total]
+//   cta_count[n_k1] | tile_dmax[max_batch][kMaxDepthTiles] | block_seg[n_k1*256] (uint2) | blk_count[max_batch][nblocks_total]
 //   | blk_offset[max_batch][nblocks_total+1] | lists[max_batch][nblocks_total*512] | tables[max_batch][table_slot_elems]
 struct WsLayout {
     uint64_t bytes;
@@ -121,14 +122,14 @@ inline int compute_layout(const saf_grid_desc* g, int32_t max_batch, int64_t max
     L->off_cta_count = 0;
     L->off_cta_dmax = align_up(L->off_cta_count + 4ull * L->n_k1, 256);
     L->off_block_seg = align_up(L->off_cta_dmax + 4ull * max_batch * kMaxDepthTiles, 256);
-    L->off_blk_count = align_up(L->off_block_seg + 4ull * L->n_k1 * kK1Threads, 256);
+    L->off_blk_count = align_up(L->off_block_seg + 8ull * L->n_k1 * kK1Threads, 256);   // uint2 {block, frame mask}
     L->off_blk_offset = align_up(L->off_blk_count + 4ull * max_batch * nblocks, 256);
     L->off_lists = align_up(L->off_blk_offset + 4ull * max_batch * (nblocks + 1), 256);
     L->off_tables = align_up(L->off_lists + (uint64_t)max_batch * L->list_cap * sizeof(ValidEntry), 256);
     // window mode repacks every frame's feature image with a zero border: (npy+2)(npx+2) <= 9 npy npx rows
     L->table_slot_elems = (uint64_t)max_table_elems * (max_batch > 1 ? 9ull : 1ull);
     L->slot_stride = align_up(L->off_tables + (uint64_t)max_batch * L->table_slot_elems * 4ull, 256);
-    L->slot0 = 512;
+    L->slot0 = kWsHeaderBytes;
     L->bytes = L->slot0 + 2 * L->slot_stride;
     return 0;
 }

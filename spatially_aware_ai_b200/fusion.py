@@ -3,7 +3,7 @@
 (/root/reference/clipfusion.py:575-763), with the per-frame work done by the sm_100a kernels in
 libsaf_b200.so.  PyTorch is only the owner of device memory and streams here.
 
-Additions to the reference surface: ``integrate_sequence`` (the frame loop as one call, fused 8 frames at a time
+Additions to the reference surface: ``integrate_sequence`` (the frame loop as one call, fused 16 frames at a time
 on the device), ``label_argmax``, ``stats`` / ``check_errors``; ``extract_mesh`` runs on the device.
 
 Differences a caller can observe:
@@ -191,7 +191,7 @@ class _FusionVolume(torch.nn.Module):
         vol = self._volume_desc()
         stream = torch.cuda.current_stream(self.tsdf.device).cuda_stream
         if sequence:
-            # B successive single-frame calls; a max_batch = 8 workspace lets the library fuse them 8 at a time
+            # B successive single-frame calls; a max_batch = SAF_MAX_BATCH workspace lets the library fuse them 16 at a time
             ws = self._workspace(_lib.SAF_MAX_BATCH, table_elems)
             rc = _lib.load().saf_integrate_sequence(ctypes.byref(self._grid_desc()), ctypes.byref(vol), frames, B, H, W,
                                                     float(self.trunc), self._rgb_mode, ctypes.byref(ws), stream)
@@ -208,7 +208,7 @@ class _FusionVolume(torch.nn.Module):
     def integrate_sequence(self, depth_imgs, rgb_imgs, poses, K):
         """The reference's frame loop (clip_seem_fusion.py:305-313) as one call: same result as
         ``for i in range(F): self.integrate(depth_imgs[i:i+1], rgb_imgs[i:i+1], poses[i:i+1], K[i:i+1])``,
-        but consecutive frames are fused 8 at a time on the device (each voxel's state is read and written
+        but consecutive frames are fused 16 at a time on the device (each voxel's state is read and written
         once per window instead of once per frame).  The producers are called once with all F frames."""
         clip_feat_img, seg_maps = self._run_producers(depth_imgs, rgb_imgs, K)
         self._integrate_frames(depth_imgs, rgb_imgs, poses, K, clip_feat_img, seg_maps, sequence=True)

@@ -71,7 +71,7 @@ def test_workspace_bytes_host_logic(lib):
     assert n2.value < n.value / 3.7
     # argument errors
     assert lib.saf_workspace_bytes(ctypes.byref(g), 0, 0, ctypes.byref(n)) == -2
-    assert lib.saf_workspace_bytes(ctypes.byref(g), 9, 0, ctypes.byref(n)) == -2
+    assert lib.saf_workspace_bytes(ctypes.byref(g), 17, 0, ctypes.byref(n)) == -2
     g.x_end = 400
     assert lib.saf_workspace_bytes(ctypes.byref(g), 1, 0, ctypes.byref(n)) == -3
     assert lib.saf_workspace_bytes(None, 1, 0, ctypes.byref(n)) == -1
