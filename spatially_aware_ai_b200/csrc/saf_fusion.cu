@@ -1152,7 +1152,10 @@ __device__ __forceinline__ void sample_rgb(const FusionParams& p, const saf_fram
 #ifndef K3W2_WARPS
 #define K3W2_WARPS 16
 #endif
-constexpr int kW3Chunk = 8;                  // union-list entries a warp claims at a time (dynamic balancing: the
+#ifndef K3W_CHUNK
+#define K3W_CHUNK 8
+#endif
+constexpr int kW3Chunk = K3W_CHUNK;                  // union-list entries a warp claims at a time (dynamic balancing: the
                                              // number of updates per entry varies from 1 to the window length)
 
 template <int CHUNKS, int kW3Warps>
