@@ -1,20 +1,27 @@
-// saf_fusion.cu -- per-frame RGB-D integration on sm_100a.
+// saf_fusion.cu -- RGB-D integration on sm_100a.
 //
 // Replaces ClipSeemFusion.integrate (/root/reference/clip_seem_fusion.py:676-822) and
-// ClipFusion.integrate (/root/reference/clipfusion.py:627-721).  Three kernels per call:
-//   K1 frame_setup_kernel      conservative frustum test of 8^3 voxel blocks -> ascending list of
-//                              visible blocks (+ repack of channel-major feature images to [R,C])
-//   K2 tsdf_update_kernel      exact per-voxel projection / depth sample / masks / TSDF running
-//                              average for the listed blocks; emits each block's `valid` voxels in
-//                              voxel order plus per-block counts and their prefix sums
-//   K3 feature_accumulate_*    one warp per listed voxel: the voxel's C-float feature row is pulled
-//                              into a per-warp shared-memory ring by TMA bulk copies, blended with
-//                              the bilinear sample of the frame's [R,C] table (also TMA-staged in
-//                              shared memory) and streamed back with 128-bit stores; rgb, label
-//                              counter and weight are handled one lane per voxel.
-// The lists are deterministic and spatially ordered (ascending block, then voxel): each K3 warp takes a
-// contiguous run of them, i.e. neighbouring voxels, which keeps its feature rows close together in DRAM
-// and lets the per-voxel 4-byte accesses (weight, rgb, label counter) of its lanes share sectors.
+// ClipFusion.integrate (/root/reference/clipfusion.py:627-721), and the frame loop around them
+// (clip_seem_fusion.py:305-313).  Kernels of one call (a frame, a reference batch, or a window of up to
+// SAF_MAX_BATCH consecutive frames):
+//   K0 depth_tiles_kernel      32x32-pixel depth maxima per frame (only while the adaptive depth cull is on)
+//   K1 frame_setup_kernel      per 8^3 voxel block and frame: conservative frustum test (+ depth-reach test)
+//                              -> ascending list of {block, per-frame mask}; repacks feature images to [R,C]
+//   K2 tsdf_update_kernel      exact per-voxel projection / depth sample / masks / TSDF running average for
+//                              the listed blocks and frames; emits each block's `valid` voxels in voxel
+//                              order plus per-block counts and their prefix sums.  Window mode: the average
+//                              is advanced frame by frame in registers and ONE union list is emitted
+//   K3 feature_accumulate_*    single frame: one warp per listed voxel, the voxel's C-float feature row is
+//                              pulled into a per-warp shared-memory ring by TMA bulk copies, blended with the
+//                              bilinear sample of the frame's [R,C] table (TMA-staged in shared memory) and
+//                              streamed back with 128-bit stores; rgb, label counter and weight one lane per
+//                              voxel
+//   K3W feature_accumulate_window_*  window mode: each listed row is read once, every valid frame's update is
+//                              applied in frame order in registers, and it is written once (two neighbouring
+//                              voxels per warp pass share their table-row loads)
+// The lists are deterministic and spatially ordered (ascending block, then voxel): warps work on runs of
+// neighbouring voxels, which keeps their feature rows close together in DRAM, lets the per-voxel 4-byte
+// accesses (weight, rgb, label counter) of the lanes share sectors and keeps the table rows in L1.
 // All decisions that feed masks use explicitly rounded intrinsics in the reference's op order;
 // this file is compiled with -fmad=false so nothing is contracted behind our back.
 #include <limits.h>
@@ -781,7 +788,6 @@ __global__ void __launch_bounds__(kK2Threads, SEQ ? 8 : 1) tsdf_update_kernel(co
         } else {
             hdr->depth_cull_cooldown = 0;
         }
-        sc->frame_base_parity = (uint32_t)(hdr->total_frames & 1ull);
         hdr->total_valid += sv;
         hdr->total_tsdf_valid += stv;
         hdr->total_blocks += n_blocks;
@@ -1143,9 +1149,8 @@ __device__ __forceinline__ void sample_rgb(const FusionParams& p, const saf_fram
     }
 }
 
-// One CTA of kW3Warps warps per SM (16 or 24): the kernel is latency-, not HBM-bound.  16 warps leave registers for
-// two K2 CTAs of the NEXT window on the same SM (saf_integrate_sequence runs them on a side stream), whose
-// ALU-bound work fills the issue slots K3W leaves idle while it waits on L1.
+// One CTA of kW3Warps warps per SM: the kernel is latency-, not HBM-bound (24 warps x 80 registers for the
+// one-voxel-per-pass kernel, 16 x 128 for the pair kernel).
 #ifndef K3W2_MAXNREG
 #define K3W2_MAXNREG 128
 #endif
@@ -1928,17 +1933,6 @@ static bool k3w_pair()
     return v == 1;
 }
 
-// warps per K3W CTA; SAF_K3W_WARPS=16|24 overrides for A/B timing
-static int k3w_warps()
-{
-    static int w = 0;
-    if (!w) {
-        const char* v = getenv("SAF_K3W_WARPS");
-        w = (v && v[0] == '2') ? 24 : ((v && v[0] == '1') ? 16 : 24);
-    }
-    return w;
-}
-
 static int launch_k3w(const FusionParams& p, int sms, cudaStream_t st)
 {
     const int C = p.vol.feature_dim;
@@ -1957,11 +1951,10 @@ static int launch_k3w(const FusionParams& p, int sms, cudaStream_t st)
                 default: break;   // C = 1024: two rows of accumulators do not fit the register budget
             }
         }
-        const bool w16 = k3w_warps() == 16;
         switch (C) {
-            case 512: return w16 ? launch_k3w_fixed<4, 16>(p, wt, sms, st) : launch_k3w_fixed<4, 24>(p, wt, sms, st);
-            case 768: return w16 ? launch_k3w_fixed<6, 16>(p, wt, sms, st) : launch_k3w_fixed<6, 24>(p, wt, sms, st);
-            case 1024: return w16 ? launch_k3w_fixed<8, 16>(p, wt, sms, st) : launch_k3w_fixed<8, 24>(p, wt, sms, st);
+            case 512: return launch_k3w_fixed<4, 24>(p, wt, sms, st);
+            case 768: return launch_k3w_fixed<6, 24>(p, wt, sms, st);
+            case 1024: return launch_k3w_fixed<8, 24>(p, wt, sms, st);
             default: break;
         }
         feature_accumulate_window_generic_kernel<4><<<sms * 2, kK3Threads, 0, st>>>(p, wt);

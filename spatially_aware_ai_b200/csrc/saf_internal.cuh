@@ -21,11 +21,11 @@ constexpr int kBlockVoxels = kBlockEdge * kBlockEdge * kBlockEdge;
 // Per-call counters.  There are two slots so that K1/K2 of frame i+1 (side stream) can run while K3 of
 // frame i (main stream) is still consuming frame i's lists (saf_integrate_sequence).  They are produced
 // by the kernels themselves (no host memsets): K2's last CTA publishes the per-block list offsets,
-// n_valid, the frame parity K3 uses for its zig-zag walk, and folds the call into the running totals.
+// n_valid, and folds the call into the running totals.
 struct SlotCounters {
     uint32_t n_blocks;                      // list segments (blocks K2 processed) of the call, written by K2's last CTA
     uint32_t k2_done;                       // CTA completion ticket of K2
-    uint32_t frame_base_parity;             // total_frames before this call, & 1
+    uint32_t reserved_;
     uint32_t k3_next;                       // window mode: next unclaimed entry of the union list (K3W's dispenser)
     uint32_t n_valid[SAF_MAX_BATCH];        // length of each frame's valid list
     uint32_t n_tsdf_valid[SAF_MAX_BATCH];   // accumulators (atomics), folded and zeroed by K2's last CTA
