@@ -392,13 +392,13 @@ __global__ void __launch_bounds__(kK1Threads) frame_setup_kernel(const FusionPar
                 // window mode: [(npy+2)*(npx+2), C] rows with a zero border, so that the feature kernel's four
                 // taps are always in range (dropped taps land on a zero row: grid_sample's zeros padding)
                 const int pw = f.npx + 2;
-                const int64_t Rp = (int64_t)(f.npy + 2) * pw;
-                for (int64_t e = (int64_t)(blockIdx.x - cull_ctas) * kK1Threads + threadIdx.x; e < Rp * C;
-                     e += (int64_t)pack_ctas * kK1Threads) {
-                    const int64_t r = e / C, c = e - r * C;
-                    const int py = (int)(r / pw) - 1, px = (int)(r % pw) - 1;
+                const int Rp = (f.npy + 2) * pw;
+                for (int r = (int)(blockIdx.x - cull_ctas); r < Rp; r += (int)pack_ctas) {   // one padded row per CTA pass
+                    const int py = r / pw - 1, px = r % pw - 1;
                     const bool in = py >= 0 && py < f.npy && px >= 0 && px < f.npx;
-                    dst[e] = in ? f.table[c * f.table_stride_c + ((int64_t)py * f.npx + px) * f.table_stride_r] : 0.0f;
+                    const float* src = f.table + ((int64_t)py * f.npx + px) * f.table_stride_r;
+                    for (int c = threadIdx.x; c < C; c += kK1Threads)
+                        dst[(int64_t)r * C + c] = in ? src[(int64_t)c * f.table_stride_c] : 0.0f;
                 }
                 continue;
             }
