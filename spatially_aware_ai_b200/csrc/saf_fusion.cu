@@ -1184,7 +1184,7 @@ feature_accumulate_window_kernel(const __grid_constant__ FusionParams p, const _
     float2* my_coords = coords + (size_t)warp * kW3Chunk * SAF_MAX_BATCH;
     uint64_t* my_bar = bars + warp;
     __shared__ uint32_t s_ticket;
-    __shared__ volatile uint32_t s_sbase[8], s_sgen[8];
+    __shared__ volatile uint32_t s_sbase[8], s_ssize[8], s_sgen[8];
     if (threadIdx.x == 0) {
         for (int i = 0; i < kW3Warps; ++i) mbar_init(&bars[i], 1);
         fence_mbar_init();
@@ -1201,26 +1201,34 @@ feature_accumulate_window_kernel(const __grid_constant__ FusionParams p, const _
     // counter.  The CTA's warps therefore walk neighbouring voxels (same few table rows per frame -> L1 hits),
     // while the units stay small enough to balance the very uneven number of updates per entry.
     for (;;) {
-        uint32_t base = 0;
+        uint32_t base = 0, chunk = kW3Chunk;
         if (lane == 0) {
             const uint32_t t = atomicAdd(&s_ticket, 1u);
             const uint32_t k = t / kW3Warps, c = t % kW3Warps, slot = k & 7u;
             if (c == 0) {
-                base = atomicAdd(&sc->k3_next, (uint32_t)(kW3Warps * kW3Chunk));
+                // towards the end of the list the units are halved, so that the CTAs finish closer together
+                const uint32_t seen = *reinterpret_cast<volatile uint32_t*>(&sc->k3_next);
+                const uint32_t csz = (seen < n && n - seen < gridDim.x * (uint32_t)(kW3Warps * kW3Chunk) * 2u)
+                                         ? (uint32_t)kW3Chunk / 2u : (uint32_t)kW3Chunk;
+                base = atomicAdd(&sc->k3_next, (uint32_t)kW3Warps * csz);
                 s_sbase[slot] = base;
+                s_ssize[slot] = csz;
                 __threadfence_block();
                 s_sgen[slot] = k;
+                chunk = csz;
             } else {
                 while (s_sgen[slot] != k) {
                 }
                 __threadfence_block();
                 base = s_sbase[slot];
+                chunk = s_ssize[slot];
             }
-            base = min(base, n) + c * kW3Chunk;
+            base = min(base, n) + c * chunk;
         }
         base = __shfl_sync(0xffffffffu, base, 0);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
         if (base >= n) break;
-        const uint32_t cnt = min((uint32_t)kW3Chunk, n - base);
+        const uint32_t cnt = min(chunk, n - base);
         uint32_t my_voxel = 0, my_mask = 0;
         int my_w = 0;
         if (lane < cnt) {
@@ -1352,7 +1360,7 @@ feature_accumulate_window_pair_kernel(const __grid_constant__ FusionParams p, co
     float2* my_coords = coords + (size_t)warp * kW3Chunk * SAF_MAX_BATCH;
     uint64_t* my_bar = bars + warp;
     __shared__ uint32_t s_ticket;
-    __shared__ volatile uint32_t s_sbase[8], s_sgen[8];
+    __shared__ volatile uint32_t s_sbase[8], s_ssize[8], s_sgen[8];
     if (threadIdx.x == 0) {
         for (int i = 0; i < kW3Warps; ++i) mbar_init(&bars[i], 1);
         fence_mbar_init();
@@ -1369,26 +1377,34 @@ feature_accumulate_window_pair_kernel(const __grid_constant__ FusionParams p, co
     // counter.  The CTA's warps therefore walk neighbouring voxels (same few table rows per frame -> L1 hits),
     // while the units stay small enough to balance the very uneven number of updates per entry.
     for (;;) {
-        uint32_t base = 0;
+        uint32_t base = 0, chunk = kW3Chunk;
         if (lane == 0) {
             const uint32_t t = atomicAdd(&s_ticket, 1u);
             const uint32_t k = t / kW3Warps, c = t % kW3Warps, slot = k & 7u;
             if (c == 0) {
-                base = atomicAdd(&sc->k3_next, (uint32_t)(kW3Warps * kW3Chunk));
+                // towards the end of the list the units are halved, so that the CTAs finish closer together
+                const uint32_t seen = *reinterpret_cast<volatile uint32_t*>(&sc->k3_next);
+                const uint32_t csz = (seen < n && n - seen < gridDim.x * (uint32_t)(kW3Warps * kW3Chunk) * 2u)
+                                         ? (uint32_t)kW3Chunk / 2u : (uint32_t)kW3Chunk;
+                base = atomicAdd(&sc->k3_next, (uint32_t)kW3Warps * csz);
                 s_sbase[slot] = base;
+                s_ssize[slot] = csz;
                 __threadfence_block();
                 s_sgen[slot] = k;
+                chunk = csz;
             } else {
                 while (s_sgen[slot] != k) {
                 }
                 __threadfence_block();
                 base = s_sbase[slot];
+                chunk = s_ssize[slot];
             }
-            base = min(base, n) + c * kW3Chunk;
+            base = min(base, n) + c * chunk;
         }
         base = __shfl_sync(0xffffffffu, base, 0);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
         if (base >= n) break;
-        const uint32_t cnt = min((uint32_t)kW3Chunk, n - base);
+        const uint32_t cnt = min(chunk, n - base);
         uint32_t my_voxel = 0, my_mask = 0;
         int my_w = 0;
         if (lane < cnt) {
