@@ -192,7 +192,9 @@ int saf_integrate(const saf_grid_desc *grid, const saf_volume *vol, const saf_fr
  * clip_seem_fusion.py:305-313) issued from one host call.  With a workspace sized for max_batch >= 2 the
  * frames are fused in windows of max_batch frames (see the window-mode calls above) and
  * K1 + K2 of the next window overlap the feature kernel of the current one; a max_batch = 1 workspace runs
- * frame by frame.  Either way the result equals the frame loop's. */
+ * frame by frame.  Either way the result equals the frame loop's.  For a sub-slab volume (x_begin > 0 or
+ * x_end < nvox[0]) and n_frames >= 16 the call first drops the frames that cannot touch the slab (a small
+ * pre-pass kernel; this variant synchronises `stream` once before it launches the windows). */
 int saf_integrate_sequence(const saf_grid_desc *grid, const saf_volume *vol, const saf_frame *frames,
                            int32_t n_frames, int32_t height, int32_t width, float trunc,
                            int32_t rgb_mode, const saf_workspace *ws, void *stream);

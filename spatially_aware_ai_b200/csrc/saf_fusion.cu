@@ -2192,28 +2192,26 @@ int saf_integrate_sequence(const saf_grid_desc* grid, const saf_volume* vol, con
     // workspace's max_batch; a max_batch = 1 workspace runs frame by frame.
     const int32_t window = ws ? std::max<int32_t>(1, std::min<int32_t>(SAF_MAX_BATCH, ws->max_batch)) : 1;
     // Sub-slab volumes (multi-GPU): drop the frames that cannot touch this slab before forming windows.  Costs
-    // one small kernel, a copy of the frames and one stream synchronisation per call, so it is only done when
-    // the slab is a strict part of the grid and the sequence is long enough to amortise it.
+    // one small kernel, a copy of the frame descriptors into the workspace and one stream synchronisation per
+    // call, so it is only done when the slab is a strict part of the grid and the sequence is long enough to
+    // amortise it.
     std::vector<saf_frame> kept;
     if (grid && frames && ws && ws->base && (grid->x_begin > 0 || grid->x_end < grid->nvox[0]) && n_frames >= 16) {
         FusionParams p;
         rc = build_params(grid, vol, frames, 1, H, W, trunc, rgb_mode, ws, &p, 0);
         if (rc) return rc;
-        void* dbuf = nullptr;
+        // scratch: the (idle) list region of slot 0 holds the frame descriptors and the flags - no allocation
         const size_t fbytes = sizeof(saf_frame) * (size_t)n_frames, rbytes = sizeof(uint32_t) * (size_t)n_frames;
-        SAF_CUDA_TRY(cudaMallocAsync(&dbuf, fbytes + rbytes, st));
-        std::vector<uint32_t> reach((size_t)n_frames);
-        cudaError_t e = cudaMemcpyAsync(dbuf, frames, fbytes, cudaMemcpyHostToDevice, st);
-        if (e == cudaSuccess) {
-            frame_reach_kernel<<<n_frames, 256, 0, st>>>(p, (const saf_frame*)dbuf, n_frames,
-                                                         (uint32_t*)((unsigned char*)dbuf + fbytes));
-            e = cudaGetLastError();
+        const bool fits = fbytes + rbytes <= (size_t)p.list_cap * sizeof(ValidEntry);   // else: keep every frame
+        unsigned char* dbuf = reinterpret_cast<unsigned char*>(p.lists);
+        std::vector<uint32_t> reach((size_t)n_frames, 1u);
+        if (fits) {
+            SAF_CUDA_TRY(cudaMemcpyAsync(dbuf, frames, fbytes, cudaMemcpyHostToDevice, st));
+            frame_reach_kernel<<<n_frames, 256, 0, st>>>(p, (const saf_frame*)dbuf, n_frames, (uint32_t*)(dbuf + fbytes));
+            SAF_CHECK_LAUNCH("frame_reach_kernel", st);
+            SAF_CUDA_TRY(cudaMemcpyAsync(reach.data(), dbuf + fbytes, rbytes, cudaMemcpyDeviceToHost, st));
+            SAF_CUDA_TRY(cudaStreamSynchronize(st));
         }
-        if (e == cudaSuccess)
-            e = cudaMemcpyAsync(reach.data(), (unsigned char*)dbuf + fbytes, rbytes, cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        cudaFreeAsync(dbuf, st);
-        if (e != cudaSuccess) return (int)e;
         kept.reserve((size_t)n_frames);
         for (int32_t i = 0; i < n_frames; ++i)
             if (reach[(size_t)i]) kept.push_back(frames[i]);
