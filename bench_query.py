@@ -3,9 +3,12 @@
 T CLIP text embeddings scored by cosine against an [M, C] fused feature matrix.
 
     python bench_query.py [--rows M] [--texts T] [--dim C] [--k K] [--precision tf32|fp32]
+    torchrun --nproc-per-node N bench_query.py --rows M ...     # M rows split into N x-slabs, one per rank
 
 Prints one JSON line: scores kernel GB/s and TFLOP/s (CUDA events, median of --iters), top-k time,
-and the numpy oracle's time on a bounded row sample for scale.
+and the numpy oracle's time on a bounded row sample for scale.  Under torchrun every rank scores its own slab of
+the rows and the per-rank top-k lists are combined with an NCCL all_gather (slab.gather_topk): the only
+collective of the query path; the line then reports the global top-k time (max over ranks) as well.
 """
 import argparse
 import json
@@ -32,15 +35,25 @@ def main():
     args = ap.parse_args()
 
     import torch
+    import torch.distributed as dist
     import spatially_aware_ai_b200 as saf
-    dev = torch.device("cuda:0")
-    M, T, C = args.rows, args.texts, args.dim
-    g = torch.Generator(device=dev).manual_seed(0)
+    from spatially_aware_ai_b200 import slab
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=dev)
+    M_total, T, C = args.rows, args.texts, args.dim
+    r_begin, r_end = slab.slab_bounds(M_total, world, rank)      # rows stand for voxels: a contiguous slab per rank
+    M = r_end - r_begin
+    g = torch.Generator(device=dev).manual_seed(rank)
     F = torch.empty((M, C), dtype=torch.float32, device=dev)
     step = 1 << 20
     for r0 in range(0, M, step):
         F[r0:r0 + step].normal_(generator=g)
-    X = torch.randn((T, C), generator=g, device=dev)
+    X = torch.randn((T, C), generator=torch.Generator(device=dev).manual_seed(12345), device=dev)
     X = X / X.norm(dim=1, keepdim=True)
     out = torch.empty((M, T), dtype=torch.float32, device=dev)
     peaks = {}
@@ -65,7 +78,8 @@ def main():
     read_b = M * C * 4 + T * C * 4
     write_b = M * T * 4
     flops = 2.0 * M * C * T
-    res = {"metric": "query_scores", "rows": M, "texts": T, "dim": C, "precision": args.precision,
+    res = {"metric": "query_scores", "rows": M, "rows_total": M_total, "n_gpus": world, "texts": T, "dim": C,
+           "precision": args.precision,
            "scores_ms": ms, "read_GBps": read_b / ms / 1e6, "read_plus_write_GBps": (read_b + write_b) / ms / 1e6,
            "tflops": flops / ms / 1e9, "hbm_peak_GBps": peaks.get("hbm_gbs"),
            "frac_hbm_rw": (read_b + write_b) / ms / 1e6 / peaks["hbm_gbs"] if peaks else None,
@@ -75,6 +89,22 @@ def main():
         res["topk_ms"] = tk
         res["topk_k"] = args.k
         res["topk_read_GBps"] = read_b / tk / 1e6
+        if world > 1:
+            def global_topk():
+                ts, ti = saf.query_topk(F, X, args.k, norm="nan_to_num", mode="dot", precision=args.precision,
+                                        index_base=r_begin)
+                return slab.gather_topk(ts, ti, args.k)
+
+            gs, gi = global_topk()
+            dist.barrier()
+            tg = torch.tensor([timed(global_topk, 2)], dtype=torch.float64, device=dev)
+            dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+            res["global_topk_ms"] = float(tg.item())
+            res["global_topk_rows_per_s"] = M_total / (float(tg.item()) * 1e-3)
+            # every rank holds the same merged list; its winners come from all slabs
+            owners = torch.bucketize(gi[:, 0].contiguous(), torch.tensor(
+                [slab.slab_bounds(M_total, world, r)[1] for r in range(world)], device=dev), right=True)
+            res["top1_owner_ranks"] = sorted(set(owners.cpu().tolist()))
     # CPU: numpy (MKL/OpenBLAS sgemm, all cores) on a row sample
     from oracle import oracle as O
     Fs = F[: args.cpu_rows].cpu().numpy()
@@ -87,7 +117,10 @@ def main():
     res["gpu_rows_per_s"] = M / (ms * 1e-3)
     res["max_abs_err_vs_oracle"] = float(np.abs(got - ref).max())
     res["cpu_cores"] = os.cpu_count()
-    print(json.dumps(res))
+    if rank == 0:
+        print(json.dumps(res))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
