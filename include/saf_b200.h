@@ -239,7 +239,11 @@ int saf_query_topk(const float *feats, int64_t M, int32_t C, int64_t ldf, const 
  * (level 0) on the host, drops faces with a NaN vertex and the vertices no face uses, then samples
  * rgb / clip_feat (trilinear) and voxel_obj_idx / objects_segmentation_color (nearest) at the
  * vertices with torch grid_sample.  The three calls below do the same on the device, without the
- * host round trip; vertices are ordered by (voxel, axis) of their grid edge and faces by cell. */
+ * host round trip; vertices are ordered by (voxel, axis) of their grid edge and faces by cell.
+ * x-slabs: halo_tsdf / halo_weight (device [ny*nz], both or neither) and halo_field (device [ny*nz,
+ * channels]) are the NEXT slab's first plane (x = x_end); with them the slab also meshes the cells across
+ * the cut and emits the vertices lying in that plane, so that the slabs' meshes join without a gap
+ * (spatially_aware_ai_b200/slab.py exchanges the planes and welds the duplicated vertices).  NULL = none. */
 
 #define SAF_SAMPLE_TRILINEAR 0   /* grid_sample mode="bilinear" on the 5-D view */
 #define SAF_SAMPLE_NEAREST   1
@@ -248,19 +252,23 @@ int saf_query_topk(const float *feats, int64_t M, int32_t C, int64_t ldf, const 
 int saf_mesh_workspace_bytes(const saf_grid_desc *grid, uint64_t *bytes_out);
 /* Pass 1: classify cells, count surviving faces and used vertices.  Synchronises `stream` and
  * returns the counts so that the caller can allocate the outputs.  ws: device, 256-byte aligned. */
-int saf_mesh_count(const saf_grid_desc *grid, const float *tsdf, const int32_t *weight, void *ws,
-                   uint64_t ws_bytes, uint64_t *n_verts_out, uint64_t *n_faces_out, void *stream);
+int saf_mesh_count(const saf_grid_desc *grid, const float *tsdf, const int32_t *weight,
+                   const float *halo_tsdf, const int32_t *halo_weight, void *ws, uint64_t ws_bytes,
+                   uint64_t *n_verts_out, uint64_t *n_faces_out, void *stream);
 /* Pass 2 (same inputs and workspace as the saf_mesh_count call before it): vertices in voxel-index
- * coordinates [V,3] (global x), optionally also verts * voxel_size + origin (clip_seem_fusion.py:880),
- * and faces [F,3] int64. */
-int saf_mesh_emit(const saf_grid_desc *grid, const float *tsdf, const int32_t *weight, void *ws,
-                  uint64_t ws_bytes, float *verts_out, float *verts_world_out, int64_t *faces_out,
+ * coordinates [V,3] (global x), optionally also verts * voxel_size + origin (clip_seem_fusion.py:880) and
+ * each vertex's grid edge id ((x*ny + y)*nz + z)*3 + axis in global numbering [V] int64 (the identity slabs
+ * weld by), and faces [F,3] int64. */
+int saf_mesh_emit(const saf_grid_desc *grid, const float *tsdf, const int32_t *weight,
+                  const float *halo_tsdf, const int32_t *halo_weight, void *ws, uint64_t ws_bytes,
+                  float *verts_out, float *verts_world_out, int64_t *edge_ids_out, int64_t *faces_out,
                   void *stream);
 /* grid_sample of a per-voxel field [N,channels] (slab-local rows) at `verts` (index coordinates):
  * grid = (verts + 0.5) / nvox * 2 - 1, align_corners=False, zeros padding, mode SAF_SAMPLE_*;
  * clamp01 != 0 applies .clamp(0, 1) (the colour outputs).  out: device [V,channels]. */
 int saf_mesh_sample(const saf_grid_desc *grid, const float *verts, int64_t n_verts, const float *field,
-                    int32_t channels, int32_t mode, int32_t clamp01, float *out, void *stream);
+                    const float *halo_field, int32_t channels, int32_t mode, int32_t clamp01, float *out,
+                    void *stream);
 
 /* ---- object labelling: flood_fill_3d (handy_utils.py:295-480) without its in-situ classifier -----
  * 26-connected components of equal class id over the per-voxel class grid [nx,ny,nz] (int64, as

@@ -41,11 +41,12 @@ def masked_tsdf(tsdf, weight, nvox):
     return out.reshape([int(v) for v in nvox])
 
 
-def marching_cubes_raw(vol, x_offset=0):
+def marching_cubes_raw(vol, x_offset=0, return_ids=False):
     """All iso-crossings of `vol` [nx,ny,nz] at level 0, NaN-unaware like the library call the reference makes:
     returns (verts [V,3] f32 in index coordinates - NaN when an endpoint of the edge is NaN -, faces [F,3] i64).
     Order: vertices by (voxel flat index, axis) of their grid edge; faces by cell flat index, then table order.
-    x_offset: global x index of the sub-volume's first plane (x-slabs keep global coordinates)."""
+    x_offset: global x index of the sub-volume's first plane (x-slabs keep global coordinates).
+    return_ids: also return each vertex's grid-edge id ((x*ny + y)*nz + z)*3 + axis with the global x."""
     vol = np.asarray(vol, np.float32)
     nx, ny, nz = vol.shape
     with np.errstate(invalid="ignore"):
@@ -73,8 +74,9 @@ def marching_cubes_raw(vol, x_offset=0):
     order = np.argsort(edge_ids, kind="stable")
     edge_ids, verts = edge_ids[order], positions[order]
     # faces
+    global_ids = edge_ids + np.int64(x_offset) * ny * nz * 3
     if min(nx, ny, nz) < 2:
-        return verts, np.zeros((0, 3), np.int64)
+        return (verts, np.zeros((0, 3), np.int64), global_ids) if return_ids else (verts, np.zeros((0, 3), np.int64))
     case = np.zeros((nx - 1, ny - 1, nz - 1), np.int32)
     for c in range(8):
         dx, dy, dz = c & 1, (c >> 1) & 1, (c >> 2) & 1
@@ -99,20 +101,23 @@ def marching_cubes_raw(vol, x_offset=0):
         face_rows.append(np.searchsorted(edge_ids, ids))
         face_keys.append(((cc[:, 0] * ny + cc[:, 1]) * nz + cc[:, 2]) * 8 + s)
     if not face_rows:
-        return verts, np.zeros((0, 3), np.int64)
+        return (verts, np.zeros((0, 3), np.int64), global_ids) if return_ids else (verts, np.zeros((0, 3), np.int64))
     faces = np.concatenate(face_rows)
     keys = np.concatenate(face_keys)
     faces = faces[np.argsort(keys, kind="stable")]
-    return verts, faces.astype(np.int64)
+    return (verts, faces.astype(np.int64), global_ids) if return_ids else (verts, faces.astype(np.int64))
 
 
-def filter_mesh(verts, faces):
-    """clip_seem_fusion.py:832-842: drop faces touching a NaN vertex, then vertices no face uses."""
+def filter_mesh(verts, faces, ids=None):
+    """clip_seem_fusion.py:832-842: drop faces touching a NaN vertex, then vertices no face uses
+    (`ids`, when given, are filtered along with the vertices)."""
     good = ~np.any(np.isnan(verts[faces]), axis=(1, 2))
     faces = faces[good]
     used = np.zeros(len(verts), bool)
     used[np.unique(faces.flatten())] = True
     reindex = np.cumsum(used) - 1
+    if ids is not None:
+        return verts[used], reindex[faces], ids[used]
     return verts[used], reindex[faces]
 
 

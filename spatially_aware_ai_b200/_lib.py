@@ -93,12 +93,12 @@ SIGNATURES = {
     "saf_backproject_samples": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                                c_int32, c_int32, c_float, c_void_p, c_void_p, c_void_p]),
     "saf_mesh_workspace_bytes": (ctypes.c_int, [P(GridDesc), P(c_uint64)]),
-    "saf_mesh_count": (ctypes.c_int, [P(GridDesc), c_void_p, c_void_p, c_void_p, c_uint64, P(c_uint64), P(c_uint64),
-                                      c_void_p]),
-    "saf_mesh_emit": (ctypes.c_int, [P(GridDesc), c_void_p, c_void_p, c_void_p, c_uint64, c_void_p, c_void_p, c_void_p,
-                                     c_void_p]),
-    "saf_mesh_sample": (ctypes.c_int, [P(GridDesc), c_void_p, c_int64, c_void_p, c_int32, c_int32, c_int32, c_void_p,
-                                       c_void_p]),
+    "saf_mesh_count": (ctypes.c_int, [P(GridDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_uint64,
+                                      P(c_uint64), P(c_uint64), c_void_p]),
+    "saf_mesh_emit": (ctypes.c_int, [P(GridDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_uint64, c_void_p,
+                                     c_void_p, c_void_p, c_void_p, c_void_p]),
+    "saf_mesh_sample": (ctypes.c_int, [P(GridDesc), c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+                                       c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -32,7 +32,10 @@ constexpr int kMcThreads = 256;
 struct McParams {
     const float* tsdf;
     const int32_t* weight;
-    int nxs, ny, nz;       // slab extents
+    const float* halo_tsdf;       // optional plane x_end of the grid (the next slab's first plane), [ny*nz]
+    const int32_t* halo_weight;
+    int64_t n_own;                // voxels of the slab itself; voxels n_own.. are the halo plane
+    int nxs, ny, nz;       // planes meshed (slab + halo plane when present), grid extents
     int x_begin;
     int64_t n;             // voxels of the slab
     uint32_t nblk;         // CTAs of the per-voxel kernels
@@ -55,6 +58,7 @@ __device__ __forceinline__ int edge_base_corner(int e)
 __device__ __forceinline__ float masked_tsdf(const McParams& p, int64_t v)
 {
     // clip_seem_fusion.py:826: tsdf.masked_fill(weight == 0, nan)
+    if (v >= p.n_own) return __ldg(p.halo_weight + (v - p.n_own)) == 0 ? __int_as_float(0x7fc00000) : __ldg(p.halo_tsdf + (v - p.n_own));
     return __ldg(p.weight + v) == 0 ? __int_as_float(0x7fc00000) : __ldg(p.tsdf + v);
 }
 
@@ -190,7 +194,8 @@ __global__ void __launch_bounds__(1024) mc_scan_kernel(const McParams p)
 }
 
 __global__ void __launch_bounds__(kMcThreads) mc_emit_verts_kernel(const McParams p, float* __restrict__ verts,
-                                                                   float* __restrict__ verts_world)
+                                                                   float* __restrict__ verts_world,
+                                                                   long long* __restrict__ edge_ids)
 {
     __shared__ uint32_t s_warp[kMcThreads / 32];
     const int64_t v = (int64_t)blockIdx.x * kMcThreads + threadIdx.x;
@@ -219,6 +224,8 @@ __global__ void __launch_bounds__(kMcThreads) mc_emit_verts_kernel(const McParam
             // clip_seem_fusion.py:880: verts * voxel_size + origin
             if (verts_world) verts_world[(size_t)idx * 3 + k] = __fadd_rn(__fmul_rn(pos[k], p.voxel_size), p.origin[k]);
         }
+        // identity of the vertex: its grid edge in GLOBAL numbering (slabs weld their cut-plane copies by it)
+        if (edge_ids) edge_ids[idx] = ((((long long)(x + p.x_begin) * p.ny + y) * p.nz + z) * 3) + a;
         p.edge_idx[v * 3 + a] = idx + 1u;
         ++idx;
     }
@@ -257,10 +264,12 @@ struct SampleParams {
     const float* verts;    // [V,3] index coordinates (global x)
     int64_t n_verts;
     const float* field;    // [n, C] rows of the slab
+    const float* halo_field;   // optional [ny*nz, C] rows of plane x_end (the next slab's first plane)
+    int64_t n_own;
     float* out;            // [V, C]
     int C;
     int nvox[3];           // global grid
-    int x_begin, x_end;
+    int x_begin, x_end;    // x_end includes the halo plane when halo_field is set
     int nearest;
     int clamp01;
 };
@@ -321,7 +330,8 @@ __global__ void __launch_bounds__(256) mesh_sample_kernel(const SampleParams p)
                 float4 val[8];
 #pragma unroll
                 for (int t = 0; t < 8; ++t)
-                    if (t < ntap && row[t] >= 0) val[t] = __ldg(reinterpret_cast<const float4*>(p.field + row[t] * p.C) + col);
+                    if (t < ntap && row[t] >= 0) val[t] = __ldg(reinterpret_cast<const float4*>(row[t] >= p.n_own ? p.halo_field + (row[t] - p.n_own) * p.C
+                                                                                        : p.field + row[t] * p.C) + col);
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {
@@ -345,7 +355,8 @@ __global__ void __launch_bounds__(256) mesh_sample_kernel(const SampleParams p)
                 float acc = 0.0f;
 #pragma unroll
                 for (int t = 0; t < 8; ++t)
-                    if (t < ntap && row[t] >= 0) acc = __fadd_rn(acc, __fmul_rn(__ldg(p.field + row[t] * p.C + c), w[t]));
+                    if (t < ntap && row[t] >= 0) acc = __fadd_rn(acc, __fmul_rn(__ldg((row[t] >= p.n_own ? p.halo_field + (row[t] - p.n_own) * p.C
+                                                                                  : p.field + row[t] * p.C) + c), w[t]));
                 if (p.clamp01) acc = fminf(fmaxf(acc, 0.f), 1.f);
                 out[c] = acc;
             }
@@ -365,7 +376,7 @@ int mc_layout(const saf_grid_desc* g, McLayout* L)
     if (g->nvox[0] <= 0 || g->nvox[1] <= 0 || g->nvox[2] <= 0 || g->x_begin < 0 || g->x_end > g->nvox[0] ||
         g->x_begin >= g->x_end)
         return SAF_ERR_GRID;
-    L->n = (int64_t)(g->x_end - g->x_begin) * g->nvox[1] * g->nvox[2];
+    L->n = (int64_t)(g->x_end - g->x_begin + 1) * g->nvox[1] * g->nvox[2];   // the slab plus one halo plane
     if (L->n * 3 >= (1ll << 32)) return SAF_ERR_GRID;   // edge -> vertex map is 32-bit
     L->nblk = (uint32_t)((L->n + kMcThreads - 1) / kMcThreads);
     auto up = [](uint64_t v) { return (v + 255ull) & ~255ull; };
@@ -377,23 +388,29 @@ int mc_layout(const saf_grid_desc* g, McLayout* L)
     return 0;
 }
 
-int mc_params(const saf_grid_desc* g, const float* tsdf, const int32_t* weight, void* ws, uint64_t ws_bytes, McParams* p)
+int mc_params(const saf_grid_desc* g, const float* tsdf, const int32_t* weight, const float* halo_tsdf,
+              const int32_t* halo_weight, void* ws, uint64_t ws_bytes, McParams* p)
 {
     McLayout L;
     int rc = mc_layout(g, &L);
     if (rc) return rc;
     if (!tsdf || !weight || !ws) return SAF_ERR_NULL;
+    if ((halo_tsdf == nullptr) != (halo_weight == nullptr)) return SAF_ERR_NULL;
+    if (halo_tsdf && g->x_end >= g->nvox[0]) return SAF_ERR_GRID;   // the last slab has no plane beyond it
     if (ws_bytes < L.bytes) return SAF_ERR_WORKSPACE;
     if (((uintptr_t)ws & 255u) != 0) return SAF_ERR_ALIGNMENT;
     unsigned char* base = (unsigned char*)ws;
     p->tsdf = tsdf;
     p->weight = weight;
-    p->nxs = g->x_end - g->x_begin;
+    p->halo_tsdf = halo_tsdf;
+    p->halo_weight = halo_weight;
+    p->nxs = g->x_end - g->x_begin + (halo_tsdf ? 1 : 0);
     p->ny = g->nvox[1];
     p->nz = g->nvox[2];
     p->x_begin = g->x_begin;
-    p->n = L.n;
-    p->nblk = L.nblk;
+    p->n_own = (int64_t)(g->x_end - g->x_begin) * g->nvox[1] * g->nvox[2];
+    p->n = (int64_t)p->nxs * g->nvox[1] * g->nvox[2];
+    p->nblk = (uint32_t)((p->n + kMcThreads - 1) / kMcThreads);
     p->totals = (uint64_t*)(base + L.off_totals);
     p->blk_tri = (uint32_t*)(base + L.off_blk_tri);
     p->blk_vert = (uint32_t*)(base + L.off_blk_vert);
@@ -420,15 +437,16 @@ int saf_mesh_workspace_bytes(const saf_grid_desc* grid, uint64_t* bytes_out)
     return 0;
 }
 
-int saf_mesh_count(const saf_grid_desc* grid, const float* tsdf, const int32_t* weight, void* ws, uint64_t ws_bytes,
-                   uint64_t* n_verts_out, uint64_t* n_faces_out, void* stream)
+int saf_mesh_count(const saf_grid_desc* grid, const float* tsdf, const int32_t* weight, const float* halo_tsdf,
+                   const int32_t* halo_weight, void* ws, uint64_t ws_bytes, uint64_t* n_verts_out,
+                   uint64_t* n_faces_out, void* stream)
 {
     int sms = 0;
     int rc = device_sm_count(&sms, nullptr);
     if (rc) return rc;
     if (!n_verts_out || !n_faces_out) return SAF_ERR_NULL;
     McParams p;
-    rc = mc_params(grid, tsdf, weight, ws, ws_bytes, &p);
+    rc = mc_params(grid, tsdf, weight, halo_tsdf, halo_weight, ws, ws_bytes, &p);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     SAF_CUDA_TRY(cudaMemsetAsync(p.edge_idx, 0, 12ull * (uint64_t)p.n, st));
@@ -446,26 +464,27 @@ int saf_mesh_count(const saf_grid_desc* grid, const float* tsdf, const int32_t* 
     return 0;
 }
 
-int saf_mesh_emit(const saf_grid_desc* grid, const float* tsdf, const int32_t* weight, void* ws, uint64_t ws_bytes,
-                  float* verts_out, float* verts_world_out, int64_t* faces_out, void* stream)
+int saf_mesh_emit(const saf_grid_desc* grid, const float* tsdf, const int32_t* weight, const float* halo_tsdf,
+                  const int32_t* halo_weight, void* ws, uint64_t ws_bytes, float* verts_out, float* verts_world_out,
+                  int64_t* edge_ids_out, int64_t* faces_out, void* stream)
 {
     int sms = 0;
     int rc = device_sm_count(&sms, nullptr);
     if (rc) return rc;
     if (!verts_out || !faces_out) return SAF_ERR_NULL;
     McParams p;
-    rc = mc_params(grid, tsdf, weight, ws, ws_bytes, &p);
+    rc = mc_params(grid, tsdf, weight, halo_tsdf, halo_weight, ws, ws_bytes, &p);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    mc_emit_verts_kernel<<<p.nblk, kMcThreads, 0, st>>>(p, verts_out, verts_world_out);
+    mc_emit_verts_kernel<<<p.nblk, kMcThreads, 0, st>>>(p, verts_out, verts_world_out, (long long*)edge_ids_out);
     SAF_CHECK_LAUNCH("mc_emit_verts_kernel", st);
     mc_emit_faces_kernel<<<p.nblk, kMcThreads, 0, st>>>(p, (long long*)faces_out);
     SAF_CHECK_LAUNCH("mc_emit_faces_kernel", st);
     return 0;
 }
 
-int saf_mesh_sample(const saf_grid_desc* grid, const float* verts, int64_t n_verts, const float* field, int32_t channels,
-                    int32_t mode, int32_t clamp01, float* out, void* stream)
+int saf_mesh_sample(const saf_grid_desc* grid, const float* verts, int64_t n_verts, const float* field,
+                    const float* halo_field, int32_t channels, int32_t mode, int32_t clamp01, float* out, void* stream)
 {
     int sms = 0;
     int rc = device_sm_count(&sms, nullptr);
@@ -481,16 +500,19 @@ int saf_mesh_sample(const saf_grid_desc* grid, const float* verts, int64_t n_ver
     p.verts = verts;
     p.n_verts = n_verts;
     p.field = field;
+    p.halo_field = halo_field;
+    p.n_own = (int64_t)(grid->x_end - grid->x_begin) * grid->nvox[1] * grid->nvox[2];
     p.out = out;
     p.C = channels;
     for (int k = 0; k < 3; ++k) p.nvox[k] = grid->nvox[k];
     p.x_begin = grid->x_begin;
-    p.x_end = grid->x_end;
+    p.x_end = grid->x_end + (halo_field ? 1 : 0);
     p.nearest = mode == SAF_SAMPLE_NEAREST;
     p.clamp01 = clamp01;
     const int64_t want = (n_verts + 7) / 8;
     const int blocks = (int)std::min<int64_t>(want, (int64_t)sms * 8);
-    const bool vec4 = (channels % 4 == 0) && (((uintptr_t)field & 15u) == 0) && (((uintptr_t)out & 15u) == 0);
+    const bool vec4 = (channels % 4 == 0) && (((uintptr_t)field & 15u) == 0) && (((uintptr_t)out & 15u) == 0) &&
+                      (((uintptr_t)halo_field & 15u) == 0);
     cudaStream_t st = (cudaStream_t)stream;
     if (vec4)
         mesh_sample_kernel<4><<<blocks, 256, 0, st>>>(p);

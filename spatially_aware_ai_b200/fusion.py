@@ -283,9 +283,11 @@ class ClipSeemFusion(_FusionVolume):
         clip_feat_img, seg_maps = self._run_producers(depth_imgs, rgb_imgs, K)
         self._integrate_frames(depth_imgs, rgb_imgs, poses, K, clip_feat_img, seg_maps)
 
-    def extract_mesh(self):
+    def extract_mesh(self, halo=None, return_edge_ids=False):
+        """clip_seem_fusion.py:824-888 on the device.  halo / return_edge_ids: x-slabs only, see
+        mesh.extract_mesh_seem."""
         from .mesh import extract_mesh_seem
-        return extract_mesh_seem(self)
+        return extract_mesh_seem(self, halo, return_edge_ids)
 
 
 class ClipFusion(_FusionVolume):
@@ -326,6 +328,8 @@ class ClipFusion(_FusionVolume):
         clip_feat_img, _ = self._run_producers(depth_imgs, rgb_imgs, K)
         self._integrate_frames(depth_imgs, rgb_imgs, poses, K, clip_feat_img, None)
 
-    def extract_mesh(self):
+    def extract_mesh(self, halo=None, return_edge_ids=False):
+        """clipfusion.py:723-763 on the device.  halo / return_edge_ids: x-slabs only, see
+        mesh.extract_mesh_fusion."""
         from .mesh import extract_mesh_fusion
-        return extract_mesh_fusion(self)
+        return extract_mesh_fusion(self, halo, return_edge_ids)

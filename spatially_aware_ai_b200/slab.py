@@ -9,7 +9,9 @@ is used only to combine small results:
 
   * query: each rank's top-k [T,k] (score, global voxel index) is all-gathered and merged;
   * surgery weights depend on global row 0: its owner broadcasts the T scores of that row;
-  * meshes: per-slab vertex/face arrays are gathered to rank 0 (sizes first, then payloads).
+  * meshes: every rank but the last receives its successor's first plane (tsdf, weight and the sampled fields)
+    so that it can mesh the cells across the cut; per-slab vertex/face arrays are then gathered to rank 0
+    (sizes first, then payloads) and the vertices duplicated on the cut planes are welded.
 """
 import numpy as np
 import torch
@@ -65,6 +67,101 @@ def broadcast_row0_scores(local_row0_scores, owner_rank, group=None):
     buf = local_row0_scores.clone()
     dist.broadcast(buf, src=owner_rank, group=group)
     return buf
+
+
+def first_plane(volume, extra=()):
+    """The arrays of the volume's first x-plane that its predecessor needs for seam cells and vertex sampling."""
+    n_plane = volume._dims[1] * volume._dims[2]
+    out = {"tsdf": volume.tsdf[:n_plane], "weight": volume.weight[:n_plane], "rgb": volume.rgb[:n_plane],
+           "clip_feat": volume.clip_feat[:n_plane]}
+    for name in extra:   # e.g. "voxel_obj_idx", "objects_segmentation_color" (clip_seem_fusion.py:349-372)
+        t = getattr(volume, name)
+        out[name] = t.reshape(-1, *t.shape[3:])[:n_plane] if t.dim() >= 3 else t.reshape(t.shape[0], -1)[:n_plane]
+    return out
+
+
+def exchange_halo(volume, extra=(), group=None):
+    """Every rank sends its first plane to rank - 1 and receives rank + 1's: returns the `halo` dict for
+    extract_mesh(halo=...), or None on the last rank.  Slabs must be in rank order."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    mine = {k: v.contiguous() for k, v in first_plane(volume, extra).items()}
+    halo = {k: torch.empty_like(v) for k, v in mine.items()} if rank + 1 < world else None
+    ops = []
+    for k in sorted(mine):
+        if rank > 0:
+            ops.append(dist.P2POp(dist.isend, mine[k], rank - 1, group))
+        if halo is not None:
+            ops.append(dist.P2POp(dist.irecv, halo[k], rank + 1, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return halo
+
+
+def weld_slab_meshes(parts):
+    """Join per-slab meshes (in slab order) into one: parts[r] = (verts [V,3], faces [F,3] i64, edge_ids [V] i64,
+    attrs) with attrs a tuple of [V,c] arrays and edge_ids the vertices' global grid-edge ids
+    (mesh.marching_cubes_device(..., return_edge_ids=True)).  A vertex that a slab emitted on its successor's first
+    plane is a copy of the successor's vertex with the same edge id when the successor has it: faces are re-pointed
+    to the successor's vertex (whose attributes were sampled with its own rows) and the copy is dropped."""
+    n = len(parts)
+    verts = [np.asarray(p[0], np.float32).reshape(-1, 3) for p in parts]
+    faces = [np.asarray(p[1], np.int64).reshape(-1, 3) for p in parts]
+    ids = [np.asarray(p[2], np.int64).reshape(-1) for p in parts]
+    attrs = [tuple(np.asarray(a) for a in p[3]) for p in parts]
+    keep = [np.ones(len(v), bool) for v in verts]
+    target = [np.full(len(v), -1, np.int64) for v in verts]   # for dropped copies: the successor's local vertex
+    for r in range(n - 1):
+        if not len(ids[r]) or not len(ids[r + 1]):
+            continue
+        order = np.argsort(ids[r + 1], kind="stable")
+        pos = np.searchsorted(ids[r + 1], ids[r], sorter=order)
+        pos = np.minimum(pos, len(order) - 1)
+        hit = ids[r + 1][order[pos]] == ids[r]
+        keep[r][hit] = False
+        target[r][hit] = order[pos[hit]]
+    base, new_index = 0, []
+    for r in range(n):
+        new_index.append(np.cumsum(keep[r]) - 1 + base)
+        base += int(keep[r].sum())
+    out_faces = []
+    for r in range(n):
+        remap = new_index[r].copy()
+        dropped = ~keep[r]
+        if dropped.any():
+            remap[dropped] = new_index[r + 1][target[r][dropped]]
+        out_faces.append(remap[faces[r]])
+    if not n:
+        return np.zeros((0, 3), np.float32), np.zeros((0, 3), np.int64), ()
+    out_verts = np.concatenate([verts[r][keep[r]] for r in range(n)])
+    out_faces = np.concatenate(out_faces)
+    out_attrs = tuple(np.concatenate([attrs[r][k][keep[r]] for r in range(n)]) for k in range(len(attrs[0])))
+    # canonical order of the single-grid mesh: vertices by ascending edge id (a copy kept because its successor
+    # does not use that vertex sits at the end of its slab's list, but belongs among the successor's first plane)
+    all_ids = np.concatenate([ids[r][keep[r]] for r in range(n)])
+    order = np.argsort(all_ids, kind="stable")
+    inverse = np.empty_like(order)
+    inverse[order] = np.arange(len(order))
+    return out_verts[order], inverse[out_faces], tuple(a[order] for a in out_attrs)
+
+
+def extract_mesh_distributed(volume, extra=(), dst=0, group=None):
+    """extract_mesh of a grid sharded into x-slabs (one volume per rank, slabs in rank order): exchanges the first
+    planes, lets every rank mesh its slab plus the cells across its cut, gathers the pieces on `dst` and welds
+    them.  Returns on `dst` the tuple extract_mesh() returns for the whole grid (numpy arrays; vertices in the
+    single-grid order), None elsewhere.  `extra`: per-voxel attributes set by the caller that the volume's
+    extract_mesh samples too ("voxel_obj_idx", "objects_segmentation_color" for ClipSeemFusion)."""
+    rank = dist.get_rank(group)
+    halo = exchange_halo(volume, extra, group)
+    out = volume.extract_mesh(halo=halo, return_edge_ids=True)
+    verts, faces, ids = out[0], out[1], out[-1]
+    attrs = tuple(a.detach().cpu().numpy() for a in out[2:-1])
+    pieces = [None] * dist.get_world_size(group) if rank == dst else None
+    dist.gather_object((verts, faces, ids, attrs), pieces, dst=dst, group=group)
+    if rank != dst:
+        return None
+    wv, wf, wattrs = weld_slab_meshes(pieces)
+    return (wv, wf) + tuple(wattrs)
 
 
 def gather_mesh(verts, faces, dst=0, group=None):

@@ -131,3 +131,48 @@ def test_mesh_of_fused_scene_is_closed_band():
     idx = np.rint((verts - origin) / cfg.voxel_size).astype(int)
     w = _np(vol.weight).reshape([int(v) for v in nvox])
     assert (w[idx[:, 0], idx[:, 1], idx[:, 2]] > 0).mean() > 0.99
+
+
+def test_slab_meshes_with_halo_weld_to_the_full_grid_mesh():
+    """Multi-GPU mesh extraction, emulated in one process: three slab volumes, each given its successor's first
+    plane (what slab.exchange_halo delivers over NCCL), mesh their own cells plus the cells across the cut;
+    welded, the result is the mesh of the whole grid: identical vertex positions and faces, attributes of the
+    vertices identical except on the cut planes (there a tap of weight ~1e-7 lies in the predecessor's slab:
+    1e-5 tolerance)."""
+    from spatially_aware_ai_b200 import slab
+    nvox, C = (22, 13, 11), 8
+    g, state = _random_volume(nvox, C, seed=77)
+    full, _, _ = Hh.make_gpu_volume(g)
+    _load_state(full, state)
+    fv, ff, fc, ffeat = full.extract_mesh()
+    ny_nz = nvox[1] * nvox[2]
+    cuts = [0, 7, 15, nvox[0]]
+    vols = []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        v, _, _ = Hh.make_gpu_volume(g, x_begin=a, x_end=b)
+        _load_state(v, {k: s[a * ny_nz:b * ny_nz] for k, s in state.items()})
+        vols.append(v)
+    parts, planes = [], []
+    for r, v in enumerate(vols):
+        halo = slab.first_plane(vols[r + 1]) if r + 1 < len(vols) else None
+        verts, faces, cols, feats, ids = v.extract_mesh(halo=halo, return_edge_ids=True)
+        # against the oracle on the slab plus its halo plane (global coordinates)
+        a, b = cuts[r], cuts[r + 1]
+        hi = min(b + 1, nvox[0])
+        ov, of, oids = mc.filter_mesh(*mc.marching_cubes_raw(
+            mc.masked_tsdf(state["tsdf"][a * ny_nz:hi * ny_nz], state["weight"][a * ny_nz:hi * ny_nz], (hi - a, nvox[1], nvox[2])),
+            x_offset=a, return_ids=True))
+        world = (ov * np.float32(g["voxel_size"]) + g["origin"]).astype(np.float32)
+        assert np.array_equal(faces, of) and np.array_equal(verts, world) and np.array_equal(ids, oids)
+        parts.append((verts, faces, ids, (_np(cols), _np(feats))))
+        if b < nvox[0]:
+            planes.append(np.float32(np.float32(b) * np.float32(g["voxel_size"])) + g["origin"][0])
+    wv, wf, (wc, wfeat) = slab.weld_slab_meshes(parts)
+    assert len(wv) == len(fv) and len(wf) == len(ff)
+    # both meshes list their vertices in ascending edge-id order, slab by slab: after welding the orders coincide
+    assert np.array_equal(wv, fv) and np.array_equal(wf, ff)
+    dc = np.abs(wc - _np(fc)).max(axis=1)
+    df = np.abs(wfeat - _np(ffeat)).max(axis=1)
+    on_cut = np.isin(wv[:, 0], np.array(planes, np.float32))
+    assert on_cut.any() and not dc[~on_cut].any() and not df[~on_cut].any()
+    assert dc.max() <= 1e-5 and df.max() <= 1e-5

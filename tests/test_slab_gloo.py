@@ -84,3 +84,80 @@ def test_gather_topk_row0_and_mesh_world2(tmp_path):
     z0 = np.load(tmp_path / "r0.npz")
     assert z0["mv"].shape == (2 + 3, 3) and z0["mf"].shape == (1 + 2, 3)
     assert z0["mf"][1:].min() >= 2      # rank 1's faces re-based past rank 0's vertices
+
+
+# ---- seam cells for slab meshes: halo exchange (gloo) and welding (numpy) --------------------------------------
+
+def _mesh_sets(verts, faces):
+    """Order-independent description of a mesh: the set of vertex positions and of faces as position triples
+    (rotation-normalised so that the winding still counts)."""
+    vset = {tuple(v) for v in verts.tolist()}
+    fset = set()
+    for f in faces:
+        tri = [tuple(verts[i].tolist()) for i in f]
+        k = tri.index(min(tri))
+        fset.add(tuple(tri[k:] + tri[:k]))
+    return vset, fset
+
+
+def test_weld_slab_meshes_equals_full_grid_mesh():
+    """Three slabs meshed on their own cells plus the cells across each cut (halo plane), welded: the same
+    vertices and faces as the mesh of the whole grid (oracle marching cubes on both sides)."""
+    from oracle import mc
+    rng = np.random.default_rng(21)
+    nx, ny, nz = 17, 9, 8
+    vol = rng.uniform(-1, 1, (nx, ny, nz)).astype(np.float32)
+    vol[rng.random(vol.shape) < 0.25] = np.nan
+    full_v, full_f = mc.filter_mesh(*mc.marching_cubes_raw(vol))
+    cuts = [0, 5, 11, nx]
+    vol[6, 3, 2] = vol[11, 4, 4] = 0.0                        # exact zeros: coincident vertices of different edges
+    full_v, full_f = mc.filter_mesh(*mc.marching_cubes_raw(vol))
+    parts = []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        hi = min(b + 1, nx)                                   # the successor's first plane, when there is one
+        v, f, ids = mc.filter_mesh(*mc.marching_cubes_raw(vol[a:hi], x_offset=a, return_ids=True))
+        parts.append((v, f, ids, (v[:, :1].copy(),)))         # one attribute: the vertex's own x
+    assert sum(len(p[0]) for p in parts) > len(full_v)        # the cut planes' vertices exist twice before welding
+    v, f, (attr,) = slab.weld_slab_meshes(parts)
+    assert len(v) == len(full_v) and len(f) == len(full_f)
+    assert _mesh_sets(v, f) == _mesh_sets(full_v, full_f)
+    assert np.array_equal(v, full_v) and np.array_equal(f, full_f)      # even the order is the single-grid one
+    assert np.array_equal(attr[:, 0], v[:, 0])
+
+
+def _halo_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import spatially_aware_ai_b200 as saf
+        from tests.helpers import FakeClip, FakeSeg
+        nvox = (6, 4, 3)
+        a, b = slab.slab_bounds(nvox[0], world, rank)
+        vol = saf.ClipSeemFusion(torch.zeros(3), 0.5, torch.tensor(nvox), 1.0, False, 0, 0, FakeClip(5), FakeSeg(),
+                                 x_begin=a, x_end=b)
+        n = (b - a) * 12
+        base = a * 12
+        vol.tsdf.copy_(torch.arange(base, base + n, dtype=torch.float32))
+        vol.weight.copy_(torch.arange(base, base + n, dtype=torch.int32))
+        vol.rgb.copy_(torch.arange(base * 3, (base + n) * 3, dtype=torch.float32).view(n, 3))
+        vol.clip_feat.copy_(torch.arange(base * 5, (base + n) * 5, dtype=torch.float32).view(n, 5))
+        vol.voxel_obj_idx = torch.arange(base, base + n, dtype=torch.int32).view(b - a, 4, 3)
+        halo = slab.exchange_halo(vol, extra=("voxel_obj_idx",))
+        out = {"rank": np.array([rank])}
+        if halo is not None:
+            out.update({k: v.numpy() for k, v in halo.items()})
+        np.savez(os.path.join(out_dir, "h%d.npz" % rank), **out)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_exchange_halo_world2(tmp_path):
+    mp.spawn(_halo_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    h0, h1 = np.load(tmp_path / "h0.npz"), np.load(tmp_path / "h1.npz")
+    first = 3 * 12                                            # rank 1's first voxel
+    assert np.array_equal(h0["tsdf"], np.arange(first, first + 12, dtype=np.float32))
+    assert np.array_equal(h0["weight"], np.arange(first, first + 12, dtype=np.int32))
+    assert np.array_equal(h0["rgb"], np.arange(first * 3, (first + 12) * 3, dtype=np.float32).reshape(12, 3))
+    assert np.array_equal(h0["clip_feat"], np.arange(first * 5, (first + 12) * 5, dtype=np.float32).reshape(12, 5))
+    assert np.array_equal(h0["voxel_obj_idx"].reshape(-1), np.arange(first, first + 12, dtype=np.int32))
+    assert set(h1.files) == {"rank"}                                    # the last rank has no successor
