@@ -549,8 +549,9 @@ def run_native_arm(args):
             "frames_per_s": frames_per_s,
             "updates_per_frame": total_upd / n_frames, "tsdf_updates_per_frame": sum_over_ranks(tv) / n_frames if world == 1 else None,
             "visible_blocks_per_frame": blocks / n_frames,
-            # K0 + K1 + K2 + K3W per window; sub-slab ranks add the frame-reach kernel and a counter kernel per call
-            "gpu_launches": (4 * calls_per_step + (2 if n_rooms > 1 else 0)) * K_steps,
+            # rank 0's count: K0 + K1 + K2 + K3W per window the library launched (its own counter); sub-slab ranks
+            # add the frame-reach kernel and a counter kernel per sequence call
+            "gpu_launches": 4 * (st1["total_calls"] - st0["total_calls"]) + (2 * K_steps if n_rooms > 1 else 0),
             "timed_region_attempts_ms": attempts,
             "clocks": clocks, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
         }

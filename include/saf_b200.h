@@ -118,6 +118,7 @@ typedef struct saf_stats {
     uint32_t error_flags;        /* SAF_FLAG_* (sticky)                                               */
     uint32_t last_processed;     /* visible blocks of the last call that survived K2's depth test     */
     uint32_t depth_cull_on;      /* 1 while the adaptive depth-aware block cull is switched on        */
+    uint64_t total_calls;        /* integrate() calls / windows launched (one K0+K1+K2 trio each)      */
 } saf_stats;
 
 /* Caller-owned device scratch.  `base` is a device allocation of `bytes` (>= saf_workspace_bytes

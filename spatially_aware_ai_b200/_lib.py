@@ -49,7 +49,7 @@ class Stats(ctypes.Structure):
                 ("total_blocks", c_uint64), ("last_blocks", ctypes.c_uint32),
                 ("last_valid", ctypes.c_uint32 * SAF_MAX_BATCH), ("last_tsdf_valid", ctypes.c_uint32 * SAF_MAX_BATCH),
                 ("error_flags", ctypes.c_uint32), ("last_processed", ctypes.c_uint32),
-                ("depth_cull_on", ctypes.c_uint32)]
+                ("depth_cull_on", ctypes.c_uint32), ("total_calls", c_uint64)]
 
 
 class Workspace(ctypes.Structure):

@@ -791,6 +791,7 @@ __global__ void __launch_bounds__(kK2Threads, SEQ ? 8 : 1) tsdf_update_kernel(co
         hdr->total_valid += sv;
         hdr->total_tsdf_valid += stv;
         hdr->total_blocks += n_blocks;
+        hdr->total_calls += 1ull;
         hdr->total_frames += (unsigned long long)B;
         hdr->last_slot = p.slot;
         sc->k3_next = 0;            // K3W's chunk dispenser
@@ -2037,6 +2038,7 @@ int saf_read_stats(const saf_workspace* ws, saf_stats* out, void* stream)
     out->total_valid = h.total_valid;
     out->total_tsdf_valid = h.total_tsdf_valid;
     out->total_blocks = h.total_blocks;
+    out->total_calls = h.total_calls;
     const SlotCounters& sc = h.slot[h.last_slot & 1u];
     out->last_blocks = sc.n_frustum_blocks;
     for (int b = 0; b < SAF_MAX_BATCH; ++b) {

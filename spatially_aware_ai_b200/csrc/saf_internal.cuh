@@ -51,6 +51,7 @@ struct WsHeader {
     unsigned long long total_valid;
     unsigned long long total_tsdf_valid;
     unsigned long long total_blocks;
+    unsigned long long total_calls;         // integrate() calls / windows (one K0+K1+K2 launch trio each)
     // immutable after saf_workspace_init
     uint64_t magic;
     uint64_t bytes;

@@ -218,7 +218,7 @@ class _FusionVolume(torch.nn.Module):
     def stats(self, check=True):
         """Counters kept by the kernels: frames, sum of valid / tsdf_valid voxels, visible blocks."""
         if self._ws is None:
-            return dict(total_frames=0, total_valid=0, total_tsdf_valid=0, total_blocks=0, last_blocks=0,
+            return dict(total_frames=0, total_valid=0, total_tsdf_valid=0, total_blocks=0, total_calls=0, last_blocks=0,
                         last_valid=[], last_tsdf_valid=[], error_flags=0)
         st = _lib.Stats()
         stream = torch.cuda.current_stream(self.tsdf.device).cuda_stream
@@ -226,10 +226,10 @@ class _FusionVolume(torch.nn.Module):
         out = dict(total_frames=st.total_frames, total_valid=st.total_valid, total_tsdf_valid=st.total_tsdf_valid,
                    total_blocks=st.total_blocks, last_blocks=st.last_blocks, last_valid=list(st.last_valid),
                    last_tsdf_valid=list(st.last_tsdf_valid), error_flags=st.error_flags,
-                   last_processed=st.last_processed, depth_cull_on=st.depth_cull_on)
+                   last_processed=st.last_processed, depth_cull_on=st.depth_cull_on, total_calls=st.total_calls)
         carry = getattr(self, "_stats_carry", None)
         if carry:
-            for k in ("total_frames", "total_valid", "total_tsdf_valid", "total_blocks"):
+            for k in ("total_frames", "total_valid", "total_tsdf_valid", "total_blocks", "total_calls"):
                 out[k] += carry[k]
             out["error_flags"] |= carry["error_flags"]
         if check and out["error_flags"] & _lib.SAF_FLAG_BAD_CLASS_ID:
