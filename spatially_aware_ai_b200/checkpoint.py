@@ -107,3 +107,83 @@ def load_state(volume, directory):
             continue   # e.g. a ClipFusion volume loading a ClipSeemFusion checkpoint: no label histogram to fill
         _stream_in(os.path.join(directory, name), t)
     return meta
+
+
+# ---- mesh and scene files (clip_seem_fusion.py:576-604) -------------------------------------------------------
+
+def save_mesh_ply(path, verts, faces, vertex_colors=None):
+    """Binary little-endian PLY with per-vertex RGBA, the layout ``trimesh.Trimesh(...).export("x.ply")`` writes for
+    mesh_rgb / mesh_segmentation (clip_seem_fusion.py:576-595): float32 x y z, uint8 red green blue alpha, faces
+    as (uint8 3, int32 x 3).  Colours are floats in [0,1] ([V,3] or [V,4]) or uint8."""
+    verts = np.asarray(verts, np.float32).reshape(-1, 3)
+    faces = np.asarray(faces, np.int64).reshape(-1, 3)
+    header = ["ply", "format binary_little_endian 1.0", "comment spatially_aware_ai_b200",
+              "element vertex %d" % len(verts), "property float x", "property float y", "property float z"]
+    vdtype = [("x", "<f4"), ("y", "<f4"), ("z", "<f4")]
+    rgba = None
+    if vertex_colors is not None:
+        c = vertex_colors.detach().cpu().numpy() if hasattr(vertex_colors, "detach") else np.asarray(vertex_colors)
+        c = c.reshape(len(verts), -1) if len(verts) else c.reshape(0, 3)
+        if c.dtype != np.uint8:
+            c = np.rint(np.clip(c.astype(np.float64), 0, 1) * 255).astype(np.uint8)
+        rgba = np.full((len(verts), 4), 255, np.uint8)
+        rgba[:, : c.shape[1]] = c[:, :4]
+        header += ["property uchar red", "property uchar green", "property uchar blue", "property uchar alpha"]
+        vdtype += [("red", "u1"), ("green", "u1"), ("blue", "u1"), ("alpha", "u1")]
+    header += ["element face %d" % len(faces), "property list uchar int vertex_indices", "end_header"]
+    vrec = np.empty(len(verts), dtype=vdtype)
+    vrec["x"], vrec["y"], vrec["z"] = verts[:, 0], verts[:, 1], verts[:, 2]
+    if rgba is not None:
+        vrec["red"], vrec["green"], vrec["blue"], vrec["alpha"] = rgba.T
+    frec = np.empty(len(faces), dtype=[("n", "u1"), ("v", "<i4", (3,))])
+    frec["n"] = 3
+    frec["v"] = faces.astype(np.int32)
+    with open(path, "wb") as f:
+        f.write(("\n".join(header) + "\n").encode("ascii"))
+        f.write(vrec.tobytes())
+        f.write(frec.tobytes())
+
+
+def load_mesh_ply(path):
+    """Reads the files save_mesh_ply writes (and trimesh's binary PLY export of a coloured triangle mesh):
+    returns (verts [V,3] f32, faces [F,3] i64, colors [V,4] u8 or None)."""
+    with open(path, "rb") as f:
+        data = f.read()
+    end = data.index(b"end_header\n") + len(b"end_header\n")
+    lines = data[:end].decode("ascii").splitlines()
+    if "format binary_little_endian 1.0" not in lines:
+        raise ValueError("only binary little-endian PLY is supported")
+    nv = nf = 0
+    props, element = {"vertex": [], "face": []}, None
+    for ln in lines:
+        tok = ln.split()
+        if tok[:1] == ["element"]:
+            element = tok[1]
+            if element == "vertex":
+                nv = int(tok[2])
+            elif element == "face":
+                nf = int(tok[2])
+        elif tok[:1] == ["property"] and element in props:
+            props[element].append(tok[1:])
+    types = {"float": "<f4", "uchar": "u1", "int": "<i4", "uint": "<u4", "double": "<f8"}
+    vdtype = np.dtype([(p[-1], types[p[0]]) for p in props["vertex"]])
+    vrec = np.frombuffer(data, dtype=vdtype, count=nv, offset=end)
+    lst = props["face"][0]
+    if lst[0] != "list":
+        raise ValueError("unsupported face element")
+    fdtype = np.dtype([("n", types[lst[1]]), ("v", types[lst[2]], (3,))])
+    frec = np.frombuffer(data, dtype=fdtype, count=nf, offset=end + nv * vdtype.itemsize)
+    if nf and not (frec["n"] == 3).all():
+        raise ValueError("only triangle meshes are supported")
+    verts = np.stack([vrec["x"], vrec["y"], vrec["z"]], axis=1).astype(np.float32)
+    colors = None
+    if "red" in vrec.dtype.names:
+        alpha = vrec["alpha"] if "alpha" in vrec.dtype.names else np.full(nv, 255, np.uint8)
+        colors = np.stack([vrec["red"], vrec["green"], vrec["blue"], alpha], axis=1).astype(np.uint8)
+    return verts, frec["v"].astype(np.int64), colors
+
+
+def save_scene_knowledge(path, scene_knowledge):
+    """clip_seem_fusion.py:597-598: ``json.dump(scene_knowledge, f, default=str)``."""
+    with open(path, "w") as f:
+        json.dump(scene_knowledge, f, default=str)

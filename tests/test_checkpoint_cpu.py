@@ -58,3 +58,32 @@ def test_slab_and_class_mismatch(tmp_path):
     plain = _volume(cls="fusion", x_begin=2, x_end=5)        # no label histogram: the file is skipped
     saf.load_state(plain, str(tmp_path))
     assert torch.equal(plain.clip_feat, vol.clip_feat) and torch.equal(plain.tsdf_weight, vol.tsdf_weight)
+
+
+def test_mesh_ply_and_scene_knowledge_round_trip(tmp_path):
+    from spatially_aware_ai_b200 import checkpoint
+    rng = np.random.default_rng(4)
+    verts = rng.standard_normal((50, 3)).astype(np.float32)
+    faces = rng.integers(0, 50, (80, 3)).astype(np.int64)
+    colors = rng.random((50, 3)).astype(np.float32)
+    path = str(tmp_path / "mesh_rgb.ply")
+    checkpoint.save_mesh_ply(path, verts, faces, torch.from_numpy(colors))
+    head = open(path, "rb").read(400).decode("ascii", "ignore")
+    assert head.startswith("ply\nformat binary_little_endian 1.0") and "element vertex 50" in head and "element face 80" in head
+    v, f, c = checkpoint.load_mesh_ply(path)
+    assert np.array_equal(v, verts) and np.array_equal(f, faces)
+    assert c.shape == (50, 4) and (c[:, 3] == 255).all()
+    assert np.array_equal(c[:, :3], np.rint(colors * 255).astype(np.uint8))
+    # how the reference reloads the colours (clip_seem_fusion.py:228-231): uint8 / 255
+    assert np.abs(c[:, :3] / 255.0 - colors).max() <= 0.5 / 255 + 1e-7
+    checkpoint.save_mesh_ply(path, verts, faces)                       # no colours
+    v, f, c = checkpoint.load_mesh_ply(path)
+    assert np.array_equal(v, verts) and np.array_equal(f, faces) and c is None
+    checkpoint.save_mesh_ply(path, verts[:0], faces[:0], colors[:0])   # empty mesh
+    v, f, c = checkpoint.load_mesh_ply(path)
+    assert v.shape == (0, 3) and f.shape == (0, 3)
+    import json
+    sk = {"unique_objects": {"chair:1": {"class_id": 56, "voxels": [(1, 2, 3)], "color": np.int64(7)}}, "scan_version": "v01"}
+    checkpoint.save_scene_knowledge(str(tmp_path / "scene_knowledge.json"), sk)
+    back = json.load(open(tmp_path / "scene_knowledge.json"))
+    assert back["unique_objects"]["chair:1"]["voxels"] == [[1, 2, 3]] and back["scan_version"] == "v01"
