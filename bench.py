@@ -229,8 +229,14 @@ def run_native_arm(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU path)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    json_fd = None
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
+        # stdout must carry exactly one line (the JSON): NCCL prints its version banner to fd 1 whatever
+        # NCCL_DEBUG_FILE says, so fd 1 is pointed at stderr for the whole run and the line goes to a saved copy
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        sys.stdout.flush()
+        json_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     n_rooms = args.rooms if (args.rooms and world == 1) else world
     cfg = scene_config(args, n_rooms)
@@ -555,7 +561,12 @@ def run_native_arm(args):
             "timed_region_attempts_ms": attempts,
             "clocks": clocks, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
         }
-        print(json.dumps(out))
+        line = json.dumps(out) + "\n"
+        if json_fd is not None:
+            os.write(json_fd, line.encode())
+        else:
+            sys.stdout.write(line)
+            sys.stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 

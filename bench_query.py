@@ -42,8 +42,12 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    json_fd = None
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        sys.stdout.flush()
+        json_fd = os.dup(1)       # NCCL prints its version banner to fd 1: keep stdout to the one JSON line
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     M_total, T, C = args.rows, args.texts, args.dim
     r_begin, r_end = slab.slab_bounds(M_total, world, rank)      # rows stand for voxels: a contiguous slab per rank
@@ -118,7 +122,10 @@ def main():
     res["max_abs_err_vs_oracle"] = float(np.abs(got - ref).max())
     res["cpu_cores"] = os.cpu_count()
     if rank == 0:
-        print(json.dumps(res))
+        if json_fd is not None:
+            os.write(json_fd, (json.dumps(res) + "\n").encode())
+        else:
+            print(json.dumps(res))
     if world > 1:
         dist.destroy_process_group()
 
