@@ -137,3 +137,24 @@ def test_mc_table_header_is_current():
         path = os.path.join(d, "t.h")
         gen.write_header(path)
         assert open(path).read() == open(os.path.join(ROOT, "spatially_aware_ai_b200", "csrc", "saf_mc_tables.h")).read()
+
+
+def test_build_scene_knowledge_matches_reference_golden():
+    """Host-side bookkeeping of flood_fill_3d / add_object (handy_utils.py:244-292, 351-480) from the labelled grid
+    the reference itself produced: same object ids, classes, indices, sizes and counts, in the same order."""
+    import spatially_aware_ai_b200 as saf
+    from tests import helpers as Hh
+    g = Hh.load_golden("objects")
+    names = [str(s) for s in g["class_names"]]
+    know = saf.build_scene_knowledge(g["voxel_obj_ids"], g["class_grid"], names, [[i, i, i] for i in range(len(names))])
+    uo = know["unique_objects"]
+    assert list(uo.keys()) == [str(s) for s in g["obj_ids"]]
+    assert [uo[k]["class_id"] for k in uo] == g["obj_class_id"].tolist()
+    assert [uo[k]["object_index"] for k in uo] == g["obj_index"].tolist()
+    assert [len(uo[k]["voxels"]) for k in uo] == g["obj_size"].tolist()
+    assert all(uo[k]["color"] == [uo[k]["class_id"]] * 3 and uo[k]["gt_label"] == k and not uo[k]["merged"] for k in uo)
+    assert know["object_counts"] == dict(zip([str(s) for s in g["count_keys"]], g["count_vals"].tolist()))
+    # every listed voxel carries the object's index in the grid
+    first = next(iter(uo.values()))
+    assert all(g["voxel_obj_ids"][v] == first["object_index"] for v in first["voxels"])
+    assert set(know) >= {"unique_objects", "object_counts", "unchanged_objects", "new_objects", "missing_objects"}
