@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SAF_ABI_VERSION 2
+#define SAF_ABI_VERSION 3
 #define SAF_MAX_BATCH 16         /* frames per integrate() call / per window; every reference caller uses 1 */
 #define SAF_BLOCK_EDGE 8         /* voxel blocks are 8x8x8 */
 
@@ -54,6 +54,15 @@ extern "C" {
 #define SAF_SEG_I64  4
 #define SAF_SEG_F32  5
 
+/* Element types of saf_frame.depth / saf_frame.rgb.  The reference's integrate() takes fp32 tensors; its
+ * dataset classes produce them from sensor formats with depth = float(u16 millimetres) / 1000 and
+ * rgb = float(u8) / 255 (clipfusion.py:185-188, 245-254, 355-362).  The sensor-format types move 3.25x fewer
+ * bytes host -> device and are converted in-kernel with exactly those roundings. */
+#define SAF_DEPTH_F32    0   /* metres                                  */
+#define SAF_DEPTH_U16_MM 1   /* uint16 millimetres, depth = v / 1000    */
+#define SAF_RGB_F32      0   /* [0,1]                                   */
+#define SAF_RGB_U8       1   /* uint8, rgb = v / 255                    */
+
 /* rgb sampling: clipfusion.py:701-706 (nearest) / clip_seem_fusion.py:793-798 (bilinear) */
 #define SAF_RGB_NEAREST  0
 #define SAF_RGB_BILINEAR 1
@@ -64,13 +73,20 @@ extern "C" {
 /* Voxel grid geometry.  ClipSeemFusion.__init__ arguments origin / voxel_size / nvox
  * (clip_seem_fusion.py:612-672); x_begin/x_end select the x-slab the buffers hold
  * (0 / nvox[0] for the whole grid).  Voxel centres are fl(fl(i)*voxel_size)+origin with the
- * GLOBAL index i, exactly as clip_seem_fusion.py:664-669 computes xyz_world. */
+ * GLOBAL index i, exactly as clip_seem_fusion.py:664-669 computes xyz_world.
+ * Block-cyclic slabs (multi-GPU load balance): with x_span > 0 the buffers hold the stripes
+ * [x_begin + k*x_stride, x_begin + k*x_stride + x_span) for k = 0, 1, ... clipped to x_end, concatenated in
+ * order (rank r of n: x_begin = r*x_span, x_stride = n*x_span, x_end = nvox[0]).  x_span and x_stride are
+ * multiples of SAF_BLOCK_EDGE.  Fusion, label argmax and the query accept such slabs; the mesh and object
+ * entry points need contiguous slabs (x_span = 0) and return SAF_ERR_UNSUPPORTED otherwise. */
 typedef struct saf_grid_desc {
     float   origin[3];
     float   voxel_size;
     int32_t nvox[3];
     int32_t x_begin;
     int32_t x_end;
+    int32_t x_span;    /* 0 = one contiguous slab [x_begin, x_end) */
+    int32_t x_stride;
 } saf_grid_desc;
 
 /* Device buffers of one slab; names, dtypes and shapes are the reference's registered buffers
@@ -89,18 +105,18 @@ typedef struct saf_volume {
 /* One RGB-D frame plus the two producer outputs integrate() pulls in
  * (clip_seem_fusion.py:691-695 feature image, :755 class map). */
 typedef struct saf_frame {
-    const float *depth;       /* device [H,W] metres, 0 = missing                                  */
-    const float *rgb;         /* device [H,W,3] in [0,1] (the reference's rgb_imgs[b], HWC)          */
+    const void  *depth;       /* device [H,W] of depth_dtype (f32 metres), 0 = missing             */
+    const void  *rgb;         /* device [H,W,3] of rgb_dtype (f32 in [0,1]; the reference's rgb_imgs[b], HWC) */
     const void  *seg;         /* device [H,W] class ids of type seg_dtype, or NULL                   */
     const float *table;       /* device feature image: element (c, py, px) at                        */
     int64_t      table_stride_c;  /*   table[c*stride_c + (py*npx+px)*stride_r]  (elements)          */
     int64_t      table_stride_r;
     int32_t      npy, npx;    /* patch grid (clipfusion.py:795-796)                                  */
     int32_t      seg_dtype;   /* SAF_SEG_*                                                           */
-    int32_t      reserved;
+    int32_t      depth_dtype; /* SAF_DEPTH_*                                                         */
     float        pose[16];    /* camera->world, row-major 4x4 (clipfusion.py:308-312 axes)           */
     float        K[9];        /* intrinsics, row-major 3x3                                           */
-    int32_t      reserved2;
+    int32_t      rgb_dtype;   /* SAF_RGB_F32 / SAF_RGB_U8                                            */
     const float *pose_device; /* optional device copies of pose[16] / K[9]: when non-NULL the kernels  */
     const float *K_device;    /* read these instead (the reference's callers hand integrate() CUDA     */
                               /* tensors, clip_seem_fusion.py:308-311; no host sync needed this way)   */
@@ -119,6 +135,10 @@ typedef struct saf_stats {
     uint32_t last_processed;     /* visible blocks of the last call that survived K2's depth test     */
     uint32_t depth_cull_on;      /* 1 while the adaptive depth-aware block cull is switched on        */
     uint64_t total_calls;        /* integrate() calls / windows launched (one K0+K1+K2 trio each)      */
+    uint64_t total_union;        /* window mode: sum over windows of the voxels valid in >= 1 frame of the window
+                                    (= feature rows read and written once per window)                  */
+    uint32_t last_union;         /* ... of the most recent window                                      */
+    uint32_t reserved;
 } saf_stats;
 
 /* Caller-owned device scratch.  `base` is a device allocation of `bytes` (>= saf_workspace_bytes

@@ -50,6 +50,22 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 
 
+def depth_from_mm(depth_u16):
+    """clipfusion.py:187-188 / 253-254 / 357-362: depth = float32(uint16 millimetres) / 1000 (true fp32 division)."""
+    return np.asarray(depth_u16, np.uint16).astype(np.float32) / np.float32(1000)
+
+
+def rgb_from_u8(rgb_u8):
+    """clipfusion.py:185 / 245 / 355: rgb = float32(uint8) / 255 (true fp32 division)."""
+    return np.asarray(rgb_u8, np.uint8).astype(np.float32) / np.float32(255)
+
+
+def check_sensor_conversions():
+    """Mismatches of the kernels' division-free conversion against the true divisions, over all inputs."""
+    lib().saf_oracle_check_sensor_conversions.restype = ctypes.c_int
+    return int(lib().saf_oracle_check_sensor_conversions())
+
+
 class OracleVolume:
     """State + integrate() of ClipSeemFusion (with_labels=True, bilinear rgb) or ClipFusion
     (with_labels=False, nearest rgb) on an x-slab of the grid.  clip_seem_fusion.py:612-674."""

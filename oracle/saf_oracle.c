@@ -274,3 +274,25 @@ void saf_oracle_label_argmax(const int32_t *labels, int64_t n, int n_classes, in
 }
 
 int saf_oracle_max_batch(void) { return SAF_ORACLE_MAX_BATCH; }
+
+/* Sensor-format inputs.  The reference's dataset classes (clipfusion.py:185-188, 245-254, 355-362) turn what is on
+ * disk into integrate()'s fp32 arguments with   rgb = float(u8) / 255   and   depth = float(u16 mm) / 1000
+ * (torch: true fp32 divisions).  The CUDA kernels take the sensor formats directly and evaluate the quotients
+ * without a division: q0 = x * fl(1/d); r = fma(-d, q0, x); q = fma(r, fl(1/d), q0).  This function checks that
+ * sequence against the true division for EVERY possible input and returns the number of mismatches (0). */
+int saf_oracle_check_sensor_conversions(void)
+{
+    volatile float y1000 = 1.0f / 1000.0f, y255 = 1.0f / 255.0f;
+    int bad = 0;
+    for (int i = 0; i < 65536; ++i) {
+        const float x = (float)i, q0 = x * y1000;
+        if (fmaf(fmaf(-1000.0f, q0, x), y1000, q0) != x / 1000.0f)
+            ++bad;
+    }
+    for (int i = 0; i < 256; ++i) {
+        const float x = (float)i, q0 = x * y255;
+        if (fmaf(fmaf(-255.0f, q0, x), y255, q0) != x / 255.0f)
+            ++bad;
+    }
+    return bad;
+}

@@ -11,11 +11,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # SAF_LIB_PATH: load another build of the same ABI (A/B timing of kernel variants)
 LIB_PATH = os.environ.get("SAF_LIB_PATH") or os.path.join(HERE, "libsaf_b200.so")
 
-SAF_ABI_VERSION = 2
+SAF_ABI_VERSION = 3
 SAF_MAX_BATCH = 16
 
 SAF_SEG_NONE, SAF_SEG_U8, SAF_SEG_I16, SAF_SEG_I32, SAF_SEG_I64, SAF_SEG_F32 = range(6)
 SAF_RGB_NEAREST, SAF_RGB_BILINEAR = 0, 1
+SAF_DEPTH_F32, SAF_DEPTH_U16_MM = 0, 1
+SAF_RGB_F32, SAF_RGB_U8 = 0, 1
+SAF_BLOCK_EDGE = 8
 SAF_FLAG_BAD_CLASS_ID = 1
 SAF_NORM_NONE, SAF_NORM_NAN_TO_NUM, SAF_NORM_CLAMP_MIN = 0, 1, 2
 SAF_SCORE_DOT, SAF_SCORE_SOFTMAX100, SAF_SCORE_SURGERY = 0, 1, 2
@@ -28,7 +31,7 @@ c_void_p, c_int32, c_int64, c_uint64, c_float = (ctypes.c_void_p, ctypes.c_int32
 
 class GridDesc(ctypes.Structure):
     _fields_ = [("origin", c_float * 3), ("voxel_size", c_float), ("nvox", c_int32 * 3),
-                ("x_begin", c_int32), ("x_end", c_int32)]
+                ("x_begin", c_int32), ("x_end", c_int32), ("x_span", c_int32), ("x_stride", c_int32)]
 
 
 class Volume(ctypes.Structure):
@@ -40,8 +43,8 @@ class Volume(ctypes.Structure):
 class Frame(ctypes.Structure):
     _fields_ = [("depth", c_void_p), ("rgb", c_void_p), ("seg", c_void_p), ("table", c_void_p),
                 ("table_stride_c", c_int64), ("table_stride_r", c_int64), ("npy", c_int32), ("npx", c_int32),
-                ("seg_dtype", c_int32), ("reserved", c_int32), ("pose", c_float * 16), ("K", c_float * 9),
-                ("reserved2", c_int32), ("pose_device", c_void_p), ("K_device", c_void_p)]
+                ("seg_dtype", c_int32), ("depth_dtype", c_int32), ("pose", c_float * 16), ("K", c_float * 9),
+                ("rgb_dtype", c_int32), ("pose_device", c_void_p), ("K_device", c_void_p)]
 
 
 class Stats(ctypes.Structure):
@@ -49,7 +52,8 @@ class Stats(ctypes.Structure):
                 ("total_blocks", c_uint64), ("last_blocks", ctypes.c_uint32),
                 ("last_valid", ctypes.c_uint32 * SAF_MAX_BATCH), ("last_tsdf_valid", ctypes.c_uint32 * SAF_MAX_BATCH),
                 ("error_flags", ctypes.c_uint32), ("last_processed", ctypes.c_uint32),
-                ("depth_cull_on", ctypes.c_uint32), ("total_calls", c_uint64)]
+                ("depth_cull_on", ctypes.c_uint32), ("total_calls", c_uint64), ("total_union", c_uint64),
+                ("last_union", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
 
 
 class Workspace(ctypes.Structure):

@@ -29,7 +29,7 @@ _STATE_FILES = {
 
 
 def _grid_shape(volume, tensor):
-    nxs = volume.x_end - volume.x_begin
+    nxs = len(volume.global_x_planes())
     return (nxs, volume._dims[1], volume._dims[2]) + tuple(tensor.shape[1:])
 
 
@@ -80,8 +80,8 @@ def save_state(volume, directory):
     origin = volume.origin.detach().cpu().tolist() if isinstance(volume.origin, torch.Tensor) else list(volume.origin)
     meta = dict(format_version=FORMAT_VERSION, cls=type(volume).__name__, origin=[float(v) for v in origin],
                 voxel_size=float(volume.voxel_size), nvox=[int(v) for v in volume._dims], trunc=float(volume.trunc),
-                x_begin=int(volume.x_begin), x_end=int(volume.x_end), feature_dim=int(volume.n_clip_feats),
-                files=written, stats=volume.stats(check=False) if volume.tsdf.is_cuda else None)
+                x_begin=int(volume.x_begin), x_end=int(volume.x_end), x_span=int(volume.x_span),
+                x_stride=int(volume.x_stride), feature_dim=int(volume.n_clip_feats), files=written, stats=volume.stats(check=False) if volume.tsdf.is_cuda else None)
     with open(os.path.join(directory, "volume_state.json"), "w") as f:
         json.dump(meta, f, indent=1, default=str)
     return meta
@@ -94,9 +94,9 @@ def load_state(volume, directory):
     if meta.get("format_version") != FORMAT_VERSION:
         raise ValueError("unsupported checkpoint format %r" % meta.get("format_version"))
     mine = dict(nvox=[int(v) for v in volume._dims], x_begin=int(volume.x_begin), x_end=int(volume.x_end),
-                feature_dim=int(volume.n_clip_feats))
+                x_span=int(volume.x_span), x_stride=int(volume.x_stride), feature_dim=int(volume.n_clip_feats))
     for key, val in mine.items():
-        if meta[key] != val:
+        if meta.get(key, 0) != val:
             raise ValueError("checkpoint %s = %r does not match the volume's %r" % (key, meta[key], val))
     if abs(meta["voxel_size"] - float(volume.voxel_size)) > 1e-9 * max(1.0, abs(meta["voxel_size"])):
         raise ValueError("checkpoint voxel_size %r does not match the volume's %r" % (meta["voxel_size"], volume.voxel_size))

@@ -196,6 +196,34 @@ __device__ __forceinline__ float load_class_id(const void* seg, int dtype, int p
     }
 }
 
+// Sensor-format inputs: what the reference's dataset classes hold before they convert
+// (clipfusion.py:185-188, 245, 254, 355, 362): rgb = float(u8) / 255, depth = float(u16 millimetres) / 1000.
+// Both quotients are produced without a division: q0 = x * fl(1/d), r = fma(-d, q0, x), q = fma(r, fl(1/d), q0)
+// is the correctly rounded x / d for every u8 / u16 input (checked exhaustively: oracle/saf_oracle.c
+// saf_oracle_check_sensor_conversions, tests/test_oracle_golden.py).
+__device__ __forceinline__ float depth_from_mm(uint16_t v)
+{
+    const float x = __uint2float_rn((uint32_t)v), y = 1.0f / 1000.0f;
+    const float q0 = __fmul_rn(x, y);
+    return __fmaf_rn(__fmaf_rn(-1000.0f, q0, x), y, q0);
+}
+__device__ __forceinline__ float unorm_from_u8(uint8_t v)
+{
+    const float x = __uint2float_rn((uint32_t)v), y = 1.0f / 255.0f;
+    const float q0 = __fmul_rn(x, y);
+    return __fmaf_rn(__fmaf_rn(-255.0f, q0, x), y, q0);
+}
+__device__ __forceinline__ float load_depth(const saf_frame& f, size_t pix)
+{
+    if (f.depth_dtype == SAF_DEPTH_U16_MM) return depth_from_mm(__ldg(reinterpret_cast<const uint16_t*>(f.depth) + pix));
+    return __ldg(reinterpret_cast<const float*>(f.depth) + pix);
+}
+__device__ __forceinline__ float load_rgb(const saf_frame& f, size_t elem)
+{
+    if (f.rgb_dtype == SAF_RGB_U8) return unorm_from_u8(__ldg(reinterpret_cast<const uint8_t*>(f.rgb) + elem));
+    return __ldg(reinterpret_cast<const float*>(f.rgb) + elem);
+}
+
 // ---------------------------------------------------------------------------------------------
 // K1: frame set-up (frustum cull of voxel blocks + feature-image repack)
 // ---------------------------------------------------------------------------------------------
@@ -242,7 +270,7 @@ __device__ __forceinline__ void block_sphere(const FusionParams& p, uint32_t bx,
               ez = min(kBlockEdge, p.grid.nvox[2] - z0);
     const float vs = p.grid.voxel_size;
     const float hx = 0.5f * vs * (float)(ex - 1), hy = 0.5f * vs * (float)(ey - 1), hz = 0.5f * vs * (float)(ez - 1);
-    cx = p.grid.origin[0] + vs * (float)(p.grid.x_begin + x0) + hx;
+    cx = p.grid.origin[0] + vs * (float)slab_global_x(p.grid, x0) + hx;   // a block never straddles two stripes
     cy = p.grid.origin[1] + vs * (float)y0 + hy;
     cz = p.grid.origin[2] + vs * (float)z0 + hz;
     r = sqrtf(hx * hx + hy * hy + hz * hz) + 0.01f * vs;
@@ -368,12 +396,12 @@ __global__ void __launch_bounds__(256) depth_tiles_kernel(const FusionParams p)
     const int item = (int)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (item >= p.batch * ntiles) return;
     const int b = item / ntiles, t = item - b * ntiles;
-    const float* __restrict__ dimg = p.frames[b].depth;
+    const saf_frame& f = p.frames[b];
     const int x0 = (t % p.ntx) * ts, y0 = (t / p.ntx) * ts;
     const int x1 = min(p.W, x0 + ts), y1 = min(p.H, y0 + ts);
     float dm = 0.0f;
     for (int y = y0; y < y1; ++y)
-        for (int x = x0 + lane; x < x1; x += 32) dm = fmaxf(dm, __ldg(dimg + (size_t)y * p.W + x));
+        for (int x = x0 + lane; x < x1; x += 32) dm = fmaxf(dm, load_depth(f, (size_t)y * p.W + x));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) dm = fmaxf(dm, __shfl_xor_sync(0xffffffffu, dm, o));
     if (lane == 0) p.tile_dmax[(size_t)b * kMaxDepthTiles + t] = dm;
@@ -547,7 +575,7 @@ __global__ void __launch_bounds__(kK2Threads, SEQ ? 8 : 1) tsdf_update_kernel(co
             const int iz = (int)bz * kBlockEdge + (local & 7);
             inside[j] = lx < (int)p.nxs && iy < ny && iz < nz;
             v[j] = inside[j] ? (uint32_t)(((uint64_t)lx * ny + iy) * nz + iz) : 0u;
-            xw[j] = voxel_centre(lx + p.grid.x_begin, p.grid.voxel_size, p.grid.origin[0]);
+            xw[j] = voxel_centre(slab_global_x(p.grid, lx), p.grid.voxel_size, p.grid.origin[0]);
             yw[j] = voxel_centre(iy, p.grid.voxel_size, p.grid.origin[1]);
             zw[j] = voxel_centre(iz, p.grid.voxel_size, p.grid.origin[2]);
             t_old[j] = inside[j] ? p.vol.tsdf[v[j]] : 0.0f;
@@ -576,7 +604,7 @@ __global__ void __launch_bounds__(kK2Threads, SEQ ? 8 : 1) tsdf_update_kernel(co
                     float gx, gy, z;
                     project(g.P, g.K, xw[j], yw[j], zw[j], fW, fH, gx, gy, z);
                     const int px = nearest_index(gx, p.W), py = nearest_index(gy, p.H);
-                    const float d = (inside[j] && px >= 0 && py >= 0) ? __ldg(f.depth + (size_t)py * p.W + px) : 0.0f;
+                    const float d = (inside[j] && px >= 0 && py >= 0) ? load_depth(f, (size_t)py * p.W + px) : 0.0f;
                     const float sdf = __fdiv_rn(__fsub_rn(d, z), p.trunc);
                     const bool in_view = inside[j] && (fabsf(gx) <= 1.0f) && (fabsf(gy) <= 1.0f) && (z > 0.0f);
                     const bool valid = in_view && (fabsf(sdf) <= 1.0f);
@@ -652,7 +680,7 @@ __global__ void __launch_bounds__(kK2Threads, SEQ ? 8 : 1) tsdf_update_kernel(co
             for (int j = 0; j < kK2Iter; ++j) {
                 project(g.P, g.K, xw[j], yw[j], zw[j], fW, fH, gx[j], gy[j], z[j]);
                 const int px = nearest_index(gx[j], p.W), py = nearest_index(gy[j], p.H);
-                d[j] = (inside[j] && px >= 0 && py >= 0) ? __ldg(f.depth + (size_t)py * p.W + px) : 0.0f;
+                d[j] = (inside[j] && px >= 0 && py >= 0) ? load_depth(f, (size_t)py * p.W + px) : 0.0f;
             }
             bool valid[kK2Iter];
             unsigned vmask[kK2Iter];
@@ -743,6 +771,7 @@ __global__ void __launch_bounds__(kK2Threads, SEQ ? 8 : 1) tsdf_update_kernel(co
         if (threadIdx.x == 0) {
             p.blk_offset[n_proc] = total;
             sc->n_union = total;
+            hdr->total_union += total;
             for (int b = 0; b < B; ++b) {
                 const uint32_t nv = atomicExch(&sc->acc_valid[b], 0u);
                 const uint32_t t = atomicExch(&sc->n_tsdf_valid[b], 0u);
@@ -823,7 +852,7 @@ __global__ void __launch_bounds__(256) frame_reach_kernel(const FusionParams p, 
         const int x1 = min(p.W, x0 + ts);
         float dm = 0.0f;
         for (int y = y0 + lane; y < min(p.H, y0 + ts); y += 32)
-            for (int x = x0; x < x1; ++x) dm = fmaxf(dm, __ldg(f.depth + (size_t)y * p.W + x));
+            for (int x = x0; x < x1; ++x) dm = fmaxf(dm, load_depth(f, (size_t)y * p.W + x));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) dm = fmaxf(dm, __shfl_xor_sync(0xffffffffu, dm, o));
         if (lane == 0) s_tile[t] = dm;
@@ -896,7 +925,7 @@ __device__ __forceinline__ void update_small_state(const FusionParams& p, const 
     const int px = nearest_index(e.gx, p.W), py = nearest_index(e.gy, p.H);
     if (p.rgb_mode == SAF_RGB_NEAREST) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) smp[c] = (px >= 0 && py >= 0) ? __ldg(f.rgb + ((size_t)py * p.W + px) * 3 + c) : 0.0f;
+        for (int c = 0; c < 3; ++c) smp[c] = (px >= 0 && py >= 0) ? load_rgb(f, ((size_t)py * p.W + px) * 3 + c) : 0.0f;
     } else {
         Taps t;
         bilinear_setup(e.gx, e.gy, p.W, p.H, t);
@@ -904,7 +933,7 @@ __device__ __forceinline__ void update_small_state(const FusionParams& p, const 
 #pragma unroll
         for (int k = 0; k < 4; ++k)
 #pragma unroll
-            for (int c = 0; c < 3; ++c) val[k][c] = t.idx[k] >= 0 ? __ldg(f.rgb + (size_t)t.idx[k] * 3 + c) : 0.0f;
+            for (int c = 0; c < 3; ++c) val[k][c] = t.idx[k] >= 0 ? load_rgb(f, (size_t)t.idx[k] * 3 + c) : 0.0f;
 #pragma unroll
         for (int c = 0; c < 3; ++c) smp[c] = bilinear_mix(val[0][c], val[1][c], val[2][c], val[3][c], t.w);
     }
@@ -1136,7 +1165,7 @@ __device__ __forceinline__ void sample_rgb(const FusionParams& p, const saf_fram
 {
     if (p.rgb_mode == SAF_RGB_NEAREST) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) smp[c] = (px >= 0 && py >= 0) ? __ldg(f.rgb + ((size_t)py * p.W + px) * 3 + c) : 0.0f;
+        for (int c = 0; c < 3; ++c) smp[c] = (px >= 0 && py >= 0) ? load_rgb(f, ((size_t)py * p.W + px) * 3 + c) : 0.0f;
     } else {
         Taps t;
         bilinear_setup(gx, gy, p.W, p.H, t);
@@ -1144,7 +1173,7 @@ __device__ __forceinline__ void sample_rgb(const FusionParams& p, const saf_fram
 #pragma unroll
         for (int k = 0; k < 4; ++k)
 #pragma unroll
-            for (int c = 0; c < 3; ++c) val[k][c] = t.idx[k] >= 0 ? __ldg(f.rgb + (size_t)t.idx[k] * 3 + c) : 0.0f;
+            for (int c = 0; c < 3; ++c) val[k][c] = t.idx[k] >= 0 ? load_rgb(f, (size_t)t.idx[k] * 3 + c) : 0.0f;
 #pragma unroll
         for (int c = 0; c < 3; ++c) smp[c] = bilinear_mix(val[0][c], val[1][c], val[2][c], val[3][c], t.w);
     }
@@ -1574,6 +1603,312 @@ feature_accumulate_window_pair_kernel(const __grid_constant__ FusionParams p, co
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K3W, tile kernel (default for C = 512 / 768 / 1024).  The pair kernel above pulls four table rows through L1 for
+// every (voxel, frame) update - 12 KB of on-chip traffic per 6 KB row read-modify-write, with a table working set
+// (16 frames x 4-6 rows x C floats) that does not fit next to the landing zones, so a fifth of those loads miss.
+// Here the roles are swapped: a tile of G = NSET * 8 neighbouring voxels keeps its accumulators in REGISTERS for
+// the whole window and the frames are walked in order, so the four table rows of a frame are loaded once per
+// (frame, set of 8 voxels) and reused by every voxel of the set that the frame sees.
+//
+//   warps [0, NBUF)              producers: claim G consecutive union-list entries, start the TMA bulk copies of
+//                                their feature rows into a landing buffer, do the voxels' small state (rgb average,
+//                                label counters, weight) one lane per voxel, and write the tile's update metadata
+//                                (per valid (frame, voxel): bilinear weights, a = 1/(w+1), b = w*a, table rows) into
+//                                shared memory - computed ONCE per update instead of redundantly by 32 lanes
+//   warps [NBUF, NBUF+NSET*CHUNKS)  compute: warp (set, chunk) owns the 128-channel slice `chunk` of the set's 8
+//                                voxels: accumulators from the landing buffer to registers (the buffer is handed back
+//                                to the producer at once), then for every frame of the window in order the exact
+//                                mul/fma chains as packed f32x2 operations, the frame's table rows software-pipelined
+//                                one frame ahead in registers; rows are written back with 128-bit streaming stores
+//
+// mbarriers: full[2*NBUF] (producer arrival + TMA bytes), rows_free[NBUF], meta_free[2*NBUF] (one arrival per compute
+// warp).  Producer p fills ring positions p, p+NBUF, ...; its landing buffer is p, its metadata alternates between
+// slots p and p+NBUF, so metadata is never waited for.  A producer that finds the list exhausted publishes a tile
+// with n_rows = 0.  Arithmetic per voxel = the single-frame calls in frame order (clip_seem_fusion.py:800-814).
+// ---------------------------------------------------------------------------------------------
+
+constexpr int kTileSlots = 8;    // voxels per set (accumulator registers: 8 x float4 per thread)
+
+struct __align__(16) TileUpdate {   // one (frame, voxel) feature update
+    float w[4];                     // bilinear weights nw, ne, sw, se
+    float a, b;                     // clip_seem_fusion.py:808-810
+    uint32_t rows;                  // the four rows of the frame's zero-bordered table, one byte each
+    uint32_t pad;
+};
+
+template <int NSET>
+struct __align__(128) TileMeta {
+    uint32_t n_rows;                                // 0: the producer found the list exhausted
+    uint32_t fmask[NSET];                           // frames in which any voxel of the set is valid
+    uint32_t voxel[NSET * kTileSlots];
+    uint32_t prim_rows[NSET][SAF_MAX_BATCH];        // rows of the set's first valid voxel in the frame
+    uint8_t vmask[NSET][SAF_MAX_BATCH];             // voxels of the set valid in the frame
+    TileUpdate upd[NSET][SAF_MAX_BATCH][kTileSlots];
+};
+
+struct RowRegs {   // this thread's 4-float column of the four table rows of one frame
+    f32x2_t lo[4], hi[4];
+};
+
+__device__ __forceinline__ void load_rows(RowRegs& T, const float* __restrict__ table, uint32_t rows, int C, int col4)
+{
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(table + (size_t)((rows >> (8 * k)) & 0xffu) * C) + col4);
+        T.lo[k] = v.x;
+        T.hi[k] = v.y;
+    }
+}
+
+// bilinear_mix + blend4 on one packed pair: ((t0 w0 + t1 w1) + t2 w2) + t3 w3 as mul / fma / fma / fma, then
+// smp a + old b as mul, mul, add - each lane of the pair rounded like the scalar code
+__device__ __forceinline__ f32x2_t mix_blend2(const f32x2_t (&t)[4], const f32x2_t (&w)[4], f32x2_t a, f32x2_t b, f32x2_t old)
+{
+    const f32x2_t smp = fma2_rn(t[3], w[3], fma2_rn(t[2], w[2], fma2_rn(t[1], w[1], mul2_rn(t[0], w[0]))));
+    // ptxas (12.9) contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with --fmad false and explicit .rn, which
+    // would drop one of the reference's three roundings: the final add is therefore two scalar add.rn
+    float xl, xh, yl, yh;
+    unpack2(mul2_rn(smp, a), xl, xh);
+    unpack2(mul2_rn(old, b), yl, yh);
+    return pack2(__fadd_rn(xl, yl), __fadd_rn(xh, yh));
+}
+
+template <int CHUNKS, int NSET, int NBUF>
+__global__ void __launch_bounds__((CHUNKS * NSET + NBUF) * 32, 1)
+feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, const __grid_constant__ WindowTables wt)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int C = CHUNKS * 128;
+    constexpr int G = NSET * kTileSlots;
+    constexpr int NCW = CHUNKS * NSET;
+    static_assert(G <= 32, "one producer lane per voxel of the tile");
+    using Meta = TileMeta<NSET>;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    SlotCounters* sc = &p.hdr->slot[p.slot];
+    const uint32_t n = sc->n_union;
+    if (n == 0) return;
+
+    float* rows_buf = reinterpret_cast<float*>(smem_raw);                                   // [NBUF][G][C]
+    Meta* metas = reinterpret_cast<Meta*>(smem_raw + (size_t)NBUF * G * C * sizeof(float));  // [2*NBUF]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(metas + 2 * NBUF);
+    uint64_t* full = bars;                    // [2*NBUF]
+    uint64_t* meta_free = bars + 2 * NBUF;    // [2*NBUF]
+    uint64_t* rows_free = bars + 4 * NBUF;    // [NBUF]
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2 * NBUF; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&meta_free[i], NCW);
+        }
+        for (int i = 0; i < NBUF; ++i) mbar_init(&rows_free[i], NCW);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp < NBUF) {
+        // ------------------------------- producer -------------------------------
+        const uint32_t n_blocks = sc->n_blocks;
+        const uint32_t* __restrict__ off = p.blk_offset;
+        const int B = p.batch;
+        float* my_rows = rows_buf + (size_t)warp * G * C;
+        const int set = lane / kTileSlots, slot = lane % kTileSlots;
+        for (uint32_t j = 0;; ++j) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&sc->k3_next, (uint32_t)G);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const uint32_t cnt = base < n ? min((uint32_t)G, n - base) : 0u;
+            const uint32_t ms = (uint32_t)warp + (uint32_t)NBUF * (j & 1u);
+            Meta* M = metas + ms;
+            if (cnt == 0) {
+                mbar_wait(&meta_free[ms], ((j >> 1) & 1u) ^ 1u);
+                if (lane == 0) {
+                    M->n_rows = 0;
+                    mbar_arrive(&full[ms]);
+                }
+                break;
+            }
+            uint32_t my_voxel = 0, my_mask = 0, my_local = 0, my_rank = 0;
+            if (lane < cnt) {
+                const uint32_t i = base + lane;
+                uint32_t lo = 0, hi = n_blocks;  // off[lo] <= i < off[hi]
+                while (hi - lo > 1) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (__ldg(off + mid) <= i)
+                        lo = mid;
+                    else
+                        hi = mid;
+                }
+                const WinEntry e = p.ulist[(uint64_t)lo * kBlockVoxels + (i - __ldg(off + lo))];
+                my_voxel = e.voxel;
+                my_mask = e.mask_local & 0xffffu;
+                my_local = e.mask_local >> 16;
+                my_rank = lo;
+            }
+            // the landing buffer was handed back when the compute warps took its rows to registers
+            mbar_wait(&rows_free[warp], (j & 1u) ^ 1u);
+            if (lane == 0) mbar_expect_tx(&full[ms], cnt * (uint32_t)C * 4u);
+            __syncwarp();
+            if (lane < cnt)
+                tma_bulk_g2s(my_rows + (size_t)lane * C, p.vol.clip_feat + (size_t)my_voxel * C, (uint32_t)C * 4u, &full[ms]);
+            // which voxel of each set comes first in every frame (its rows are the ones prefetched for the set)
+            uint32_t first_bits = 0, my_ballot = 0;
+#pragma unroll
+            for (int b = 0; b < SAF_MAX_BATCH; ++b) {
+                const uint32_t bal = __ballot_sync(0xffffffffu, (my_mask >> b) & 1u);
+                if (((bal >> (set * kTileSlots)) & ((1u << slot) - 1u)) == 0u) first_bits |= 1u << b;
+                if (lane == b) my_ballot = bal;
+            }
+            // the metadata slot was last read two of this producer's tiles ago
+            mbar_wait(&meta_free[ms], ((j >> 1) & 1u) ^ 1u);
+            if (lane < SAF_MAX_BATCH) {
+#pragma unroll
+                for (int s = 0; s < NSET; ++s) M->vmask[s][lane] = (uint8_t)((my_ballot >> (s * kTileSlots)) & 0xffu);
+            }
+#pragma unroll
+            for (int s = 0; s < NSET; ++s) {
+                const uint32_t fm = __ballot_sync(0xffffffffu, lane < SAF_MAX_BATCH &&
+                                                                   ((my_ballot >> (s * kTileSlots)) & 0xffu) != 0u);
+                if (lane == 0) M->fmask[s] = fm;
+            }
+            if (lane == 0) M->n_rows = cnt;
+            if (lane < cnt) {
+                M->voxel[lane] = my_voxel;
+                // per valid frame: update metadata for the compute warps, and this voxel's small state
+                // (clip_seem_fusion.py:786-798, 808-822)
+                const float2* src = p.wcoords + (uint64_t)my_rank * B * kBlockVoxels + my_local;
+                float* dst = p.vol.rgb + (size_t)my_voxel * 3;
+                float acc[3] = {dst[0], dst[1], dst[2]};
+                int w = p.vol.weight[my_voxel];
+                for (uint32_t mm = my_mask; mm; mm &= mm - 1u) {
+                    const int b = __ffs(mm) - 1;
+                    const saf_frame& f = p.frames[b];
+                    const float2 g = src[(size_t)b * kBlockVoxels];
+                    const float a = __frcp_rn(__int2float_rn(w + 1));
+                    const float bb = __fmul_rn(__int2float_rn(w), a);
+                    Taps t;
+                    bilinear_setup_padded(g.x, g.y, f.npx, f.npy, t);
+                    const uint32_t rows = (uint32_t)t.idx[0] | ((uint32_t)t.idx[1] << 8) | ((uint32_t)t.idx[2] << 16) |
+                                          ((uint32_t)t.idx[3] << 24);
+                    TileUpdate u;
+                    u.w[0] = t.w[0];
+                    u.w[1] = t.w[1];
+                    u.w[2] = t.w[2];
+                    u.w[3] = t.w[3];
+                    u.a = a;
+                    u.b = bb;
+                    u.rows = rows;
+                    u.pad = 0;
+                    M->upd[set][b][slot] = u;
+                    if ((first_bits >> b) & 1u) M->prim_rows[set][b] = rows;
+                    const int px = nearest_index(g.x, p.W), py = nearest_index(g.y, p.H);
+                    float smp[3];
+                    sample_rgb(p, f, g.x, g.y, px, py, smp);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) acc[c] = __fadd_rn(__fmul_rn(smp[c], a), __fmul_rn(acc[c], bb));
+                    if (p.vol.labels_one_hot && f.seg) {
+                        const float lf = (px >= 0 && py >= 0) ? load_class_id(f.seg, f.seg_dtype, py * p.W + px) : 0.0f;
+                        const long long id = (long long)lf;
+                        if (id >= 0 && id < p.vol.n_classes)
+                            p.vol.labels_one_hot[(size_t)my_voxel * p.vol.n_classes + id] += 1;
+                        else
+                            atomicOr(&p.hdr->error_flags, SAF_FLAG_BAD_CLASS_ID);
+                    }
+                    ++w;
+                }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) dst[c] = acc[c];
+                p.vol.weight[my_voxel] = w;
+            }
+            __syncwarp();   // every lane's metadata is written before the arrival publishes it
+            if (lane == 0) mbar_arrive(&full[ms]);
+        }
+        return;
+    }
+
+    // ------------------------------- compute -------------------------------
+    const int cw = warp - NBUF;
+    const int set = cw / CHUNKS, chunk = cw % CHUNKS;
+    const int col4 = chunk * 32 + lane;   // this thread's float4 column of every row
+    uint32_t done = 0;                    // producers that have published their last tile
+    for (uint32_t t = 0; done != (1u << NBUF) - 1u; ++t) {
+        const uint32_t pi = t % NBUF, j = t / NBUF;
+        if ((done >> pi) & 1u) continue;
+        const uint32_t ms = pi + (uint32_t)NBUF * (j & 1u);
+        mbar_wait(&full[ms], (j >> 1) & 1u);
+        const Meta* M = metas + ms;
+        const uint32_t n_rows = M->n_rows;
+        if (n_rows == 0) {
+            done |= 1u << pi;
+            continue;
+        }
+        // accumulators of the set's voxels: landing buffer -> registers, then the buffer goes back to the producer
+        f32x2_t acc_lo[kTileSlots], acc_hi[kTileSlots];
+        const ulonglong2* land = reinterpret_cast<const ulonglong2*>(rows_buf + (size_t)pi * G * C) + col4;
+#pragma unroll
+        for (int s = 0; s < kTileSlots; ++s) {
+            if ((uint32_t)(set * kTileSlots + s) < n_rows) {
+                const ulonglong2 v = land[(size_t)(set * kTileSlots + s) * (C / 4)];
+                acc_lo[s] = v.x;
+                acc_hi[s] = v.y;
+            } else {
+                acc_lo[s] = 0ull;
+                acc_hi[s] = 0ull;
+            }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&rows_free[pi]);
+
+        const uint32_t fm = M->fmask[set];
+        if (fm) {
+            RowRegs T, Tn;
+            int b = __ffs(fm) - 1;
+            uint32_t cur_rows = M->prim_rows[set][b];
+            load_rows(T, wt.ptr[b], cur_rows, C, col4);
+            for (uint32_t rest = fm & (fm - 1u);; rest &= rest - 1u) {
+                // the next frame's rows are requested before this frame's arithmetic starts
+                const int bn = rest ? __ffs(rest) - 1 : -1;
+                uint32_t nxt_rows = 0;
+                if (bn >= 0) {
+                    nxt_rows = M->prim_rows[set][bn];
+                    load_rows(Tn, wt.ptr[bn], nxt_rows, C, col4);
+                }
+                const uint32_t vm = M->vmask[set][b];
+#pragma unroll
+                for (int s = 0; s < kTileSlots; ++s) {
+                    if ((vm >> s) & 1u) {
+                        const uint4 m0 = *reinterpret_cast<const uint4*>(&M->upd[set][b][s]);
+                        const uint4 m1 = *(reinterpret_cast<const uint4*>(&M->upd[set][b][s]) + 1);
+                        if (m1.z != cur_rows) {   // a voxel of the set straddles a table cell boundary: rare
+                            cur_rows = m1.z;
+                            load_rows(T, wt.ptr[b], cur_rows, C, col4);
+                        }
+                        const float w0 = __uint_as_float(m0.x), w1 = __uint_as_float(m0.y), w2 = __uint_as_float(m0.z),
+                                    w3 = __uint_as_float(m0.w), a = __uint_as_float(m1.x), bb = __uint_as_float(m1.y);
+                        const f32x2_t wp[4] = {pack2(w0, w0), pack2(w1, w1), pack2(w2, w2), pack2(w3, w3)};
+                        const f32x2_t ap = pack2(a, a), bp = pack2(bb, bb);
+                        acc_lo[s] = mix_blend2(T.lo, wp, ap, bp, acc_lo[s]);
+                        acc_hi[s] = mix_blend2(T.hi, wp, ap, bp, acc_hi[s]);
+                    }
+                }
+                if (bn < 0) break;
+                T = Tn;
+                cur_rows = nxt_rows;
+                b = bn;
+            }
+#pragma unroll
+            for (int s = 0; s < kTileSlots; ++s) {
+                if ((uint32_t)(set * kTileSlots + s) < n_rows) {
+                    const uint32_t v = M->voxel[set * kTileSlots + s];
+                    st_stream_b64x2(reinterpret_cast<ulonglong2*>(p.vol.clip_feat + (size_t)v * C) + col4, acc_lo[s], acc_hi[s]);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&meta_free[ms]);
+    }
+}
+
 // Any feature_dim (window mode): rows straight from global memory, VEC = 4 or 1.
 template <int VEC>
 __global__ void __launch_bounds__(kK3Threads) feature_accumulate_window_generic_kernel(
@@ -1759,6 +2094,7 @@ static int build_params(const saf_grid_desc* grid, const saf_volume* vol, const 
     for (int b = 0; b < batch; ++b) {
         p->frames[b] = frames[b];
         if (!frames[b].depth) return SAF_ERR_NULL;
+        if (frames[b].depth_dtype != SAF_DEPTH_F32 && frames[b].depth_dtype != SAF_DEPTH_U16_MM) return SAF_ERR_DTYPE;
         if ((frames[b].pose_device == nullptr) != (frames[b].K_device == nullptr)) return SAF_ERR_NULL;
     }
     p->batch = batch;
@@ -1771,7 +2107,7 @@ static int build_params(const saf_grid_desc* grid, const saf_volume* vol, const 
     p->nb[2] = L.nb[2];
     p->nblocks_total = L.nblocks_total;
     p->n_k1 = L.n_k1;
-    p->nxs = (uint32_t)(grid->x_end - grid->x_begin);
+    p->nxs = (uint32_t)slab_planes(*grid);
     p->nslab = (uint64_t)p->nxs * (uint64_t)grid->nvox[1] * (uint64_t)grid->nvox[2];
     p->list_cap = L.list_cap;
     p->max_table_elems = (uint64_t)ws->max_table_elems;
@@ -1813,6 +2149,7 @@ static int check_feature_args(const saf_volume* vol, const saf_frame* frames, in
         if (!f.rgb || !f.table) return SAF_ERR_NULL;
         if (f.npy <= 0 || f.npx <= 0) return SAF_ERR_SHAPE;
         if (f.seg && (f.seg_dtype < SAF_SEG_U8 || f.seg_dtype > SAF_SEG_F32)) return SAF_ERR_DTYPE;
+        if (f.rgb_dtype != SAF_RGB_F32 && f.rgb_dtype != SAF_RGB_U8) return SAF_ERR_DTYPE;
         const int64_t elems = (int64_t)f.npy * f.npx * vol->feature_dim;
         if (f.table_stride_c != 1) {
             if (elems > ws->max_table_elems) return SAF_ERR_WORKSPACE;
@@ -1939,15 +2276,29 @@ static int launch_k3w_fixed(const FusionParams& p, const WindowTables& wt, int s
     return 0;
 }
 
-// two voxels per warp pass in K3W (default); SAF_K3W_PAIR=0 selects the one-voxel kernel (A/B timing)
-static bool k3w_pair()
+template <int CHUNKS, int NSET, int NBUF>
+static int launch_k3w_tile(const FusionParams& p, const WindowTables& wt, int sms, cudaStream_t st)
+{
+    constexpr int kThreads = (CHUNKS * NSET + NBUF) * 32;
+    constexpr size_t smem = (size_t)NBUF * NSET * kTileSlots * CHUNKS * 128 * sizeof(float) +
+                            2 * (size_t)NBUF * sizeof(TileMeta<NSET>) + 5 * (size_t)NBUF * sizeof(uint64_t);
+    auto kern = feature_accumulate_window_tile_kernel<CHUNKS, NSET, NBUF>;
+    SAF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<sms, kThreads, smem, st>>>(p, wt);
+    SAF_CHECK_LAUNCH("feature_accumulate_window_tile_kernel (K3W)", st);
+    return 0;
+}
+
+// K3W variant: 2 = tile kernel (default), 1 = pair kernel, 0 = one voxel per warp pass.  SAF_K3W_VARIANT in the
+// environment selects one of the older kernels for A/B timing.
+static int k3w_variant()
 {
     static int v = -1;
     if (v < 0) {
-        const char* e = getenv("SAF_K3W_PAIR");
-        v = (e && e[0] == '0') ? 0 : 1;
+        const char* e = getenv("SAF_K3W_VARIANT");
+        v = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
     }
-    return v == 1;
+    return v;
 }
 
 static int launch_k3w(const FusionParams& p, int sms, cudaStream_t st)
@@ -1961,7 +2312,18 @@ static int launch_k3w(const FusionParams& p, int sms, cudaStream_t st)
         wt.stride_r[b] = C;
     }
     if (rows16) {
-        if (k3w_pair()) {
+        // the tile kernel addresses table rows with one byte each
+        bool small_tables = true;
+        for (int b = 0; b < p.batch; ++b) small_tables &= (p.frames[b].npy + 2) * (p.frames[b].npx + 2) <= 256;
+        if (k3w_variant() == 2 && small_tables) {
+            switch (C) {
+                case 512: return launch_k3w_tile<4, 3, 3>(p, wt, sms, st);
+                case 768: return launch_k3w_tile<6, 2, 3>(p, wt, sms, st);
+                case 1024: return launch_k3w_tile<8, 2, 2>(p, wt, sms, st);
+                default: break;
+            }
+        }
+        if (k3w_variant() >= 1) {
             switch (C) {
                 case 512: return launch_k3w_pair<4, K3W2_WARPS>(p, wt, sms, st);
                 case 768: return launch_k3w_pair<6, K3W2_WARPS>(p, wt, sms, st);
@@ -2039,6 +2401,8 @@ int saf_read_stats(const saf_workspace* ws, saf_stats* out, void* stream)
     out->total_tsdf_valid = h.total_tsdf_valid;
     out->total_blocks = h.total_blocks;
     out->total_calls = h.total_calls;
+    out->total_union = h.total_union;
+    out->last_union = h.slot[h.last_slot & 1u].n_union;
     const SlotCounters& sc = h.slot[h.last_slot & 1u];
     out->last_blocks = sc.n_frustum_blocks;
     for (int b = 0; b < SAF_MAX_BATCH; ++b) {

@@ -52,6 +52,7 @@ struct WsHeader {
     unsigned long long total_tsdf_valid;
     unsigned long long total_blocks;
     unsigned long long total_calls;         // integrate() calls / windows (one K0+K1+K2 launch trio each)
+    unsigned long long total_union;         // window mode: sum of the windows' union-list lengths
     // immutable after saf_workspace_init
     uint64_t magic;
     uint64_t bytes;
@@ -101,15 +102,35 @@ struct WsLayout {
 
 inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 
+// x-planes held by a slab (contiguous, or block-cyclic stripes: see saf_grid_desc)
+__host__ __device__ inline int slab_planes(const saf_grid_desc& g)
+{
+    const int len = g.x_end - g.x_begin;
+    if (g.x_span <= 0) return len;
+    const int full = len / g.x_stride, rem = len % g.x_stride;
+    return full * g.x_span + (rem < g.x_span ? rem : g.x_span);
+}
+// global x index of slab-local plane lx
+__host__ __device__ inline int slab_global_x(const saf_grid_desc& g, int lx)
+{
+    if (g.x_span <= 0) return g.x_begin + lx;
+    return g.x_begin + (lx / g.x_span) * g.x_stride + (lx % g.x_span);
+}
+inline bool slab_desc_ok(const saf_grid_desc& g)
+{
+    if (g.x_begin < 0 || g.x_end > g.nvox[0] || g.x_begin >= g.x_end) return false;
+    if (g.x_span == 0) return true;
+    return g.x_span > 0 && g.x_span % SAF_BLOCK_EDGE == 0 && g.x_stride >= g.x_span && g.x_stride % SAF_BLOCK_EDGE == 0;
+}
+
 inline int compute_layout(const saf_grid_desc* g, int32_t max_batch, int64_t max_table_elems, WsLayout* L)
 {
     if (!g || !L) return SAF_ERR_NULL;
     if (max_batch < 1 || max_batch > SAF_MAX_BATCH) return SAF_ERR_BATCH;
-    if (g->nvox[0] <= 0 || g->nvox[1] <= 0 || g->nvox[2] <= 0 || g->x_begin < 0 || g->x_end > g->nvox[0] ||
-        g->x_begin >= g->x_end || !(g->voxel_size > 0.f))
+    if (g->nvox[0] <= 0 || g->nvox[1] <= 0 || g->nvox[2] <= 0 || !slab_desc_ok(*g) || !(g->voxel_size > 0.f))
         return SAF_ERR_GRID;
     if (max_table_elems < 0) return SAF_ERR_SHAPE;
-    const uint64_t nxs = (uint64_t)(g->x_end - g->x_begin);
+    const uint64_t nxs = (uint64_t)slab_planes(*g);
     const uint64_t n = nxs * (uint64_t)g->nvox[1] * (uint64_t)g->nvox[2];
     if (n >= (1ull << 31)) return SAF_ERR_GRID;  // voxel indices are 32-bit
     L->nb[0] = (uint32_t)((nxs + kBlockEdge - 1) / kBlockEdge);
@@ -155,6 +176,14 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase)
 {
     asm volatile(
@@ -192,6 +221,37 @@ __device__ __forceinline__ void st_stream_f4(float4* p, const float4& v)
     asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
                  "f"(v.w)
                  : "memory");
+}
+
+// ---- packed fp32 pairs (sm_100 {mul,fma}.rn.f32x2: two IEEE-rounded fp32 operations per instruction, the same
+// roundings as the scalar intrinsics, half the issue slots; SASS FMUL2 / FFMA2).  No add2: ptxas fuses a packed
+// mul + add pair into FFMA2 regardless of --fmad false, see mix_blend2 in saf_fusion.cu ----------------
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pack2(float lo, float hi)
+{
+    f32x2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2_t v, float& lo, float& hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2_t mul2_rn(f32x2_t a, f32x2_t b)
+{
+    f32x2_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2_t fma2_rn(f32x2_t a, f32x2_t b, f32x2_t c)
+{
+    f32x2_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ void st_stream_b64x2(void* p, f32x2_t lo, f32x2_t hi)
+{
+    asm volatile("st.global.L1::no_allocate.v2.b64 [%0], {%1,%2};" ::"l"(p), "l"(lo), "l"(hi) : "memory");
 }
 
 // ---- exact fp32 scoring helpers shared by the fp32 query kernel and the top-k rescoring kernel, so that

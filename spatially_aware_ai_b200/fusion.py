@@ -12,7 +12,9 @@ Differences a caller can observe:
     are recomputed in-kernel with the reference's exact roundings.  The attribute still exists
     as a lazily computed property.
   * optional ``x_begin`` / ``x_end`` keyword arguments hold only an x-slab of the grid
-    (multi-GPU partitioning); buffers then cover that slab, coordinates stay global.
+    (multi-GPU partitioning); buffers then cover that slab, coordinates stay global.  ``x_span`` /
+    ``x_stride`` make the slab block-cyclic (stripes of x_span planes every x_stride planes), which
+    balances the ranks when a camera sees only part of the grid per frame.
   * class ids outside [0, n_classes) cannot raise inside a kernel; they set a sticky flag that
     ``check_errors()`` (and ``stats()``) turn into the RuntimeError torch's one_hot would raise.
 """
@@ -39,7 +41,7 @@ class _FusionVolume(torch.nn.Module):
     _with_labels = True
     _rgb_mode = _lib.SAF_RGB_BILINEAR
 
-    def _init_volume(self, origin, voxel_size, nvox, trunc, feature_dim, x_begin=0, x_end=None):
+    def _init_volume(self, origin, voxel_size, nvox, trunc, feature_dim, x_begin=0, x_end=None, x_span=0, x_stride=0):
         self.origin = origin
         self.voxel_size = voxel_size
         self.nvox = nvox
@@ -50,8 +52,13 @@ class _FusionVolume(torch.nn.Module):
         self.x_end = dims[0] if x_end is None else int(x_end)
         if not (0 <= self.x_begin < self.x_end <= dims[0]):
             raise ValueError("x-slab [%d,%d) outside the grid" % (self.x_begin, self.x_end))
+        # block-cyclic slabs: stripes of x_span planes every x_stride planes (saf_grid_desc)
+        self.x_span, self.x_stride = int(x_span), int(x_stride)
+        if self.x_span and (self.x_span % _lib.SAF_BLOCK_EDGE or self.x_stride % _lib.SAF_BLOCK_EDGE or
+                            self.x_stride < self.x_span or self.x_span < 0):
+            raise ValueError("x_span / x_stride must be multiples of %d with x_stride >= x_span" % _lib.SAF_BLOCK_EDGE)
         self._dims = dims
-        n = (self.x_end - self.x_begin) * dims[1] * dims[2]
+        n = len(self.global_x_planes()) * dims[1] * dims[2]
         self.register_buffer("tsdf", torch.zeros(n, dtype=torch.float32))
         self.register_buffer("rgb", torch.zeros((n, 3), dtype=torch.float32))
         self.register_buffer("clip_feat", torch.zeros((n, self.n_clip_feats), dtype=torch.float32))
@@ -77,14 +84,24 @@ class _FusionVolume(torch.nn.Module):
             g.voxel_size = float(self.voxel_size)
             g.nvox[:] = self._dims
             g.x_begin, g.x_end = self.x_begin, self.x_end
+            g.x_span, g.x_stride = self.x_span, self.x_stride
             self._grid = g
         return self._grid
+
+    def global_x_planes(self):
+        """Global x index of every slab-local plane (a contiguous range, or the rank's block-cyclic stripes)."""
+        if not self.x_span:
+            return list(range(self.x_begin, self.x_end))
+        out = []
+        for start in range(self.x_begin, self.x_end, self.x_stride):
+            out.extend(range(start, min(start + self.x_span, self.x_end)))
+        return out
 
     @property
     def xyz_world(self):
         """World coordinates of the slab's voxel centres, computed like clip_seem_fusion.py:664-669."""
         dev = self.tsdf.device
-        x = torch.arange(self.x_begin, self.x_end, device=dev)
+        x = torch.as_tensor(self.global_x_planes(), device=dev)
         y = torch.arange(self._dims[1], device=dev)
         z = torch.arange(self._dims[2], device=dev)
         xx, yy, zz = torch.meshgrid(x, y, z, indexing="ij")
@@ -134,8 +151,12 @@ class _FusionVolume(torch.nn.Module):
         for name, t in (("depth_imgs", depth_imgs), ("rgb_imgs", rgb_imgs), ("clip feature image", clip_feat_img)):
             if t.device != dev:
                 raise RuntimeError("%s is on %s but the volume is on %s" % (name, t.device, dev))
-        depth = depth_imgs.to(torch.float32).contiguous()
-        rgb = rgb_imgs.to(torch.float32).contiguous()
+        # sensor formats stay as they are (converted in-kernel with the dataset classes' roundings,
+        # clipfusion.py:185-188): uint16 millimetres / uint8; anything else is handed over as fp32
+        depth = depth_imgs.contiguous() if depth_imgs.dtype == torch.uint16 else depth_imgs.to(torch.float32).contiguous()
+        rgb = rgb_imgs.contiguous() if rgb_imgs.dtype == torch.uint8 else rgb_imgs.to(torch.float32).contiguous()
+        depth_dtype = _lib.SAF_DEPTH_U16_MM if depth.dtype == torch.uint16 else _lib.SAF_DEPTH_F32
+        rgb_dtype = _lib.SAF_RGB_U8 if rgb.dtype == torch.uint8 else _lib.SAF_RGB_F32
         table = clip_feat_img[:, : self.n_clip_feats]
         if table.dtype != torch.float32:
             table = table.to(torch.float32)
@@ -160,6 +181,7 @@ class _FusionVolume(torch.nn.Module):
             f = frames[b]
             f.depth = depth[b].data_ptr()
             f.rgb = rgb[b].data_ptr()
+            f.depth_dtype, f.rgb_dtype = depth_dtype, rgb_dtype
             f.table = table[b].data_ptr()
             f.table_stride_c, f.table_stride_r = sc, sr
             f.npy, f.npx = npy, npx
@@ -205,12 +227,31 @@ class _FusionVolume(torch.nn.Module):
             _lib.check(rc, "saf_integrate")
         del keep
 
-    def integrate_sequence(self, depth_imgs, rgb_imgs, poses, K):
+    @staticmethod
+    def _producer_inputs(depth_imgs, rgb_imgs):
+        """The CLIP / segmentation producers take what the reference hands them: fp32 metres and fp32 [0,1]."""
+        rgb_f = rgb_imgs.float() / 255 if rgb_imgs.dtype == torch.uint8 else rgb_imgs
+        depth_f = depth_imgs.float() / 1000 if depth_imgs.dtype == torch.uint16 else depth_imgs
+        return depth_f, rgb_f
+
+    def integrate_sequence(self, depth_imgs, rgb_imgs, poses, K, clip_feat_img=None, seg_maps=None):
         """The reference's frame loop (clip_seem_fusion.py:305-313) as one call: same result as
         ``for i in range(F): self.integrate(depth_imgs[i:i+1], rgb_imgs[i:i+1], poses[i:i+1], K[i:i+1])``,
         but consecutive frames are fused 16 at a time on the device (each voxel's state is read and written
-        once per window instead of once per frame).  The producers are called once with all F frames."""
-        clip_feat_img, seg_maps = self._run_producers(depth_imgs, rgb_imgs, K)
+        once per window instead of once per frame).  The producers are called once with all F frames, unless
+        their outputs are passed in: ``clip_feat_img`` [F,C,npy,npx] and (ClipSeemFusion) ``seg_maps``, a list
+        of F class maps [H,W].
+
+        ``depth_imgs`` may be uint16 millimetres and ``rgb_imgs`` uint8 - the formats the reference's dataset
+        classes read from disk before ``float() / 1000`` and ``float() / 255`` (clipfusion.py:185-188); the
+        kernels convert with those exact roundings, so the result equals feeding the converted fp32 tensors.
+        (The producers are then handed ``rgb_imgs.float() / 255``.)"""
+        if clip_feat_img is None:
+            clip_feat_img, seg_auto = self._run_producers(*self._producer_inputs(depth_imgs, rgb_imgs), K)
+            if seg_maps is None:
+                seg_maps = seg_auto
+        if not self._with_labels:
+            seg_maps = None
         self._integrate_frames(depth_imgs, rgb_imgs, poses, K, clip_feat_img, seg_maps, sequence=True)
 
     # -- bookkeeping ---------------------------------------------------------------------------
@@ -219,17 +260,18 @@ class _FusionVolume(torch.nn.Module):
         """Counters kept by the kernels: frames, sum of valid / tsdf_valid voxels, visible blocks."""
         if self._ws is None:
             return dict(total_frames=0, total_valid=0, total_tsdf_valid=0, total_blocks=0, total_calls=0, last_blocks=0,
-                        last_valid=[], last_tsdf_valid=[], error_flags=0)
+                        last_valid=[], last_tsdf_valid=[], error_flags=0, total_union=0, last_union=0)
         st = _lib.Stats()
         stream = torch.cuda.current_stream(self.tsdf.device).cuda_stream
         _lib.check(_lib.load().saf_read_stats(ctypes.byref(self._ws), ctypes.byref(st), stream), "saf_read_stats")
         out = dict(total_frames=st.total_frames, total_valid=st.total_valid, total_tsdf_valid=st.total_tsdf_valid,
                    total_blocks=st.total_blocks, last_blocks=st.last_blocks, last_valid=list(st.last_valid),
                    last_tsdf_valid=list(st.last_tsdf_valid), error_flags=st.error_flags,
-                   last_processed=st.last_processed, depth_cull_on=st.depth_cull_on, total_calls=st.total_calls)
+                   last_processed=st.last_processed, depth_cull_on=st.depth_cull_on, total_calls=st.total_calls,
+                   total_union=st.total_union, last_union=st.last_union)
         carry = getattr(self, "_stats_carry", None)
         if carry:
-            for k in ("total_frames", "total_valid", "total_tsdf_valid", "total_blocks", "total_calls"):
+            for k in ("total_frames", "total_valid", "total_tsdf_valid", "total_blocks", "total_calls", "total_union"):
                 out[k] += carry[k]
             out["error_flags"] |= carry["error_flags"]
         if check and out["error_flags"] & _lib.SAF_FLAG_BAD_CLASS_ID:
@@ -255,14 +297,14 @@ class ClipSeemFusion(_FusionVolume):
     _rgb_mode = _lib.SAF_RGB_BILINEAR
 
     def __init__(self, origin, voxel_size, nvox, trunc, scale_patches_by_depth, clip_patch_size, clip_patch_stride,
-                 clip_model, seg_model, x_begin=0, x_end=None):
+                 clip_model, seg_model, x_begin=0, x_end=None, x_span=0, x_stride=0):
         super().__init__()
         self.clip = clip_model
         self.clip_patch_size = clip_patch_size
         self.clip_patch_stride = clip_patch_stride
         self.scale_patches_by_depth = scale_patches_by_depth
         self.segmentation_model = seg_model
-        self._init_volume(origin, voxel_size, nvox, trunc, self.clip.feature_dim, x_begin, x_end)
+        self._init_volume(origin, voxel_size, nvox, trunc, self.clip.feature_dim, x_begin, x_end, x_span, x_stride)
         self.debug_counter = 0
 
     def _run_producers(self, depth_imgs, rgb_imgs, K):
@@ -280,7 +322,7 @@ class ClipSeemFusion(_FusionVolume):
 
     def integrate(self, depth_imgs, rgb_imgs, poses, K):
         """clip_seem_fusion.py:676-822.  depth [B,H,W], rgb [B,H,W,3] in [0,1], poses [B,4,4], K [B,3,3]."""
-        clip_feat_img, seg_maps = self._run_producers(depth_imgs, rgb_imgs, K)
+        clip_feat_img, seg_maps = self._run_producers(*self._producer_inputs(depth_imgs, rgb_imgs), K)
         self._integrate_frames(depth_imgs, rgb_imgs, poses, K, clip_feat_img, seg_maps)
 
     def extract_mesh(self, halo=None, return_edge_ids=False):
@@ -298,7 +340,7 @@ class ClipFusion(_FusionVolume):
     _rgb_mode = _lib.SAF_RGB_NEAREST
 
     def __init__(self, origin, voxel_size, nvox, trunc, scale_patches_by_depth, clip_model, clip_pretraining,
-                 clip_patch_size, clip_patch_stride, x_begin=0, x_end=None):
+                 clip_patch_size, clip_patch_stride, x_begin=0, x_end=None, x_span=0, x_stride=0):
         super().__init__()
         if isinstance(clip_model, str):
             from .query import Clip
@@ -310,7 +352,7 @@ class ClipFusion(_FusionVolume):
         self.clip_patch_size = clip_patch_size
         self.clip_patch_stride = clip_patch_stride
         self.scale_patches_by_depth = scale_patches_by_depth
-        self._init_volume(origin, voxel_size, nvox, trunc, self.clip.feature_dim, x_begin, x_end)
+        self._init_volume(origin, voxel_size, nvox, trunc, self.clip.feature_dim, x_begin, x_end, x_span, x_stride)
 
     def _run_producers(self, depth_imgs, rgb_imgs, K):
         """clipfusion.py:634-646."""
@@ -325,7 +367,7 @@ class ClipFusion(_FusionVolume):
 
     def integrate(self, depth_imgs, rgb_imgs, poses, K):
         """clipfusion.py:627-721."""
-        clip_feat_img, _ = self._run_producers(depth_imgs, rgb_imgs, K)
+        clip_feat_img, _ = self._run_producers(*self._producer_inputs(depth_imgs, rgb_imgs), K)
         self._integrate_frames(depth_imgs, rgb_imgs, poses, K, clip_feat_img, None)
 
     def extract_mesh(self, halo=None, return_edge_ids=False):

@@ -1,5 +1,8 @@
 """Seeded synthetic RGB-D scenes in the shape the reference's datasets deliver.
 
+Frames are quantised like sensor data: ``rgb = uint8 / 255`` and ``depth = uint16 millimetres / 1000``
+(clipfusion.py:185-188), and both representations are returned (``rgb`` / ``rgb_u8``, ``depth`` / ``depth_mm``).
+
 The fusion path consumes, per frame, exactly what the reference's dataset classes return
 (/root/reference/clipfusion.py:86-494): ``rgb[H,W,3]`` float32 in [0,1], ``depth[H,W]`` float32
 metres (0 = missing), ``pose[4,4]`` camera->world with right-down-forward axes
@@ -136,10 +139,13 @@ def make_frame(cfg, i, table_layout="chw"):
     rng = np.random.default_rng([cfg.seed, i])
     K = intrinsics(cfg)
     pose = camera_pose(cfg, i)
-    depth = render_depth(cfg, pose, K)
+    depth_mm, depth = quantize_depth(render_depth(cfg, pose, K))
     if cfg.missing_fraction > 0:
-        depth[rng.random(depth.shape) < cfg.missing_fraction] = 0.0
-    rgb = rng.random((cfg.height, cfg.width, 3), dtype=np.float32)
+        missing = rng.random(depth.shape, dtype=np.float32) < cfg.missing_fraction
+        depth[missing] = 0.0
+        depth_mm[missing] = 0
+    rgb_u8 = rng.integers(0, 256, size=(cfg.height, cfg.width, 3), dtype=np.uint8)
+    rgb = rgb_u8.astype(np.float32) / np.float32(255)
     sb = cfg.seg_block
     coarse = rng.integers(0, cfg.n_seg_classes, size=(-(-cfg.height // sb), -(-cfg.width // sb)), dtype=np.int64)
     seg = np.kron(coarse, np.ones((sb, sb), dtype=np.int64))[: cfg.height, : cfg.width].astype(np.uint8)
@@ -147,7 +153,16 @@ def make_frame(cfg, i, table_layout="chw"):
     table = rng.standard_normal((cfg.feature_dim, npy, npx), dtype=np.float32)
     if table_layout == "hwc":
         table = np.ascontiguousarray(table.transpose(1, 2, 0)).transpose(2, 0, 1)
-    return dict(depth=depth, rgb=rgb, seg=np.ascontiguousarray(seg), table=table, pose=pose, K=K, index=i)
+    return dict(depth=depth, rgb=rgb, seg=np.ascontiguousarray(seg), table=table, pose=pose, K=K, index=i,
+                depth_mm=depth_mm, rgb_u8=rgb_u8)
+
+
+def quantize_depth(depth_m):
+    """Metres -> (uint16 millimetres, float32 metres) the way a depth sensor file delivers them: the fp32 depth
+    is float32(mm) / 1000, exactly what the reference's dataset classes compute (clipfusion.py:187-188), so the
+    sensor-format and the fp32 inputs of a synthetic frame carry identical values."""
+    mm = np.clip(np.rint(np.asarray(depth_m, np.float64) * 1000.0), 0, 65535).astype(np.uint16)
+    return mm, mm.astype(np.float32) / np.float32(1000)
 
 
 def perturbed_pose(cfg, i, rng):
@@ -162,3 +177,26 @@ def perturbed_pose(cfg, i, rng):
     pose[:3, :3] = pose[:3, :3] @ (rz @ ry @ rx)
     pose[:3, 3] += rng.uniform(-0.2, 0.2, size=3)
     return pose.astype(np.float32)
+
+
+class FakeClip:
+    """Duck-typed stand-in for the reference's Clip image producer (clipfusion.py:808-839): returns a
+    pre-generated tiled-patch feature image.  DNN inference is upstream of the fusion path; tests and benches
+    inject this where the reference injects a real open_clip model."""
+
+    def __init__(self, feature_dim):
+        self.feature_dim = feature_dim
+        self.next_table = None
+
+    def img_inference_tiled(self, rgb_imgs, patch_size, patch_stride):
+        return self.next_table
+
+
+class FakeSeg:
+    """Duck-typed kMaX stand-in (handy_utils.py:103-161): returns pre-generated class maps."""
+
+    def __init__(self):
+        self.queue = []
+
+    def run_on_image(self, img):
+        return self.queue.pop(0)

@@ -70,26 +70,7 @@ def cosine_rows(a, b):
 
 # ---- GPU-side replay through the drop-in classes ------------------------------------------------
 
-class FakeClip:
-    """Duck-typed producer: returns the pre-generated tiled-patch feature image
-    (stands in for clipfusion.py:808-839)."""
-
-    def __init__(self, feature_dim):
-        self.feature_dim = feature_dim
-        self.next_table = None
-
-    def img_inference_tiled(self, rgb_imgs, patch_size, patch_stride):
-        return self.next_table
-
-
-class FakeSeg:
-    """Duck-typed kMaX stand-in (handy_utils.py:103-161): returns the pre-generated class map."""
-
-    def __init__(self):
-        self.queue = []
-
-    def run_on_image(self, img):
-        return self.queue.pop(0)
+from spatially_aware_ai_b200.synth import FakeClip, FakeSeg  # noqa: E402,F401
 
 
 def make_gpu_volume(g, device="cuda", x_begin=0, x_end=None):
