@@ -1,24 +1,29 @@
 #!/usr/bin/env python
-"""bench.py -- RGB-D fusion throughput (voxel-updates/s, frames/s) on B200, next to the CPU oracle.
+"""bench.py -- RGB-D fusion throughput (voxel-updates/s, frames/s) on B200, next to the reference's CPU path.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            # own arm (sm_100a kernels)
-    python bench.py --impl reference [--gpus N] [--steps K] ...    # CPU arm (oracle port, host cores)
-    torchrun --nproc-per-node N bench.py --gpus N ...              # one rank per GPU (x-slabs)
+    python bench.py --impl reference [--gpus N] [--steps K] ...    # CPU arm: the reference's torch path
+    torchrun --nproc-per-node N bench.py --gpus N ...              # one rank per GPU
 
-Workload (BASELINE.json configs[1], "cfg2"): 640x480 frames, 2 cm voxels over a 6x6x3 m room
-(+- trunc margin -> 304x304x154 = 14.2 M voxels), 768-d features, 5x7 tiled-patch feature image,
-frames of a 1000-pose orbit, all resident and visited in order.  A step = `--frames-per-step` frames (default
-100, so the default 10 timed steps are exactly the 1000-frame sequence).  With N > 1 ranks the scan is N such rooms
-side by side along x (a multi-room scan); rank r owns room r's x-slab, every rank is handed
-every frame (the camera visits the rooms round-robin) and culls the ones it cannot see -
-per-GPU work is fixed, "scaling": "weak", no collective in the data path.
+Workloads (BASELINE.json configs):
+  N = 1   configs[1] "cfg2": 640x480 frames, 2 cm voxels over a 6x6x3 m room (+- trunc margin -> 304x304x154 =
+          14.2 M voxels), 768-d features, 5x7 tiled-patch feature image, the 1000-pose orbit visited in order.
+  N > 1   configs[2] "cfg3": ONE 8x8x3 m room, 404x404x154 = 25.1 M voxels x 768-d, 5000-pose orbit, the grid
+          sharded over the ranks ("scaling": "strong"): block-cyclic x-slabs (stripes of 8 planes dealt round-robin,
+          --slab-layout contiguous for plain slabs), every rank is handed every frame
+          (clip_seem_fusion.py:305-313 has no notion of slabs), no collective in the fusion path.
+          --multi rooms keeps round 1's weak-scaling workload (N rooms side by side, one per rank).
+A step = `--frames-per-step` frames (default 100).  Both arms walk the same frame sequence: step s of the
+reference arm integrates the first frames of the native arm's step s.
 
-value  = voxel updates (feature-row read-modify-writes, sum over frames of `valid` voxels)
-         per second with all inputs resident in HBM, timed with CUDA events around K steps issued
-         through the C ABI (saf_integrate_sequence), max over ranks.
-e2e    = the same metric through the public Python API (ClipSeemFusion.integrate per frame) with
-         depth/rgb/pose/K copied from pinned host memory inside the timed region and the step's
-         counters read back to the host.
+value  = voxel updates (feature-row read-modify-writes, sum over frames of `valid` voxels) per second with all
+         inputs resident in HBM as the fp32 tensors the reference's integrate() takes, timed with CUDA events
+         around K steps issued through the C ABI (saf_integrate_sequence), max over ranks.
+e2e    = the same metric through the public Python API (ClipSeemFusion.integrate_sequence) with every frame's
+         depth + rgb copied from pinned host memory inside the timed region - in the sensor formats the reference's
+         datasets read from disk (uint16 mm depth, uint8 rgb; `e2e.f32` repeats it with fp32 host buffers) - and
+         the step's counters read back.  With N ranks every frame is uploaded ONCE (by rank i % N) and reaches the
+         other ranks by an NCCL all-gather over NVLink instead of N copies over PCIe.
 """
 import argparse
 import ctypes
@@ -39,59 +44,112 @@ from spatially_aware_ai_b200 import synth  # noqa: E402
 
 METRIC = "voxel_updates_per_s"
 UNIT = "voxel-updates/s"
+SLAB_SPAN = 8     # planes per stripe of the block-cyclic layout (= one 8^3 block)
 
 
-def parse_args():
+def parse_args(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "cfg1", "cfg2", "cfg3"])
+    ap.add_argument("--multi", default="strong", choices=["strong", "rooms"],
+                    help="N > 1: strong = one grid sharded over the ranks; rooms = N rooms side by side (weak)")
+    ap.add_argument("--slab-layout", default="cyclic", choices=["cyclic", "contiguous"])
     ap.add_argument("--frames-per-step", type=int, default=100)
-    ap.add_argument("--pool", type=int, default=1000,
-                    help="distinct frames kept resident per room (cycled); 1000 = cfg2's whole sequence, in order")
+    ap.add_argument("--pool", type=int, default=0,
+                    help="distinct frames kept resident (cycled); 0 = as many as the run visits, at most 2500")
     ap.add_argument("--feature-dim", type=int, default=768)
     ap.add_argument("--voxel-size", type=float, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--ref-frames-per-step", type=int, default=4)
-    ap.add_argument("--rooms", type=int, default=0, help="debug: emulate the N-room multi-GPU workload on this rank only")
+    ap.add_argument("--no-query", action="store_true")
+    ap.add_argument("--ref-kind", default="auto", choices=["auto", "torch", "port"],
+                    help="CPU arm: the reference's torch path (baseline/_ref) or the C/OpenMP port of it")
+    ap.add_argument("--ref-frames-per-step", type=int, default=0, help="0 = 1 (torch) / 4 (port)")
+    ap.add_argument("--rooms", type=int, default=0, help="debug: emulate the N-room workload on this rank only")
     ap.add_argument("--window", type=int, default=16, choices=list(range(1, 17)),
                     help="frames fused per launch trio by saf_integrate_sequence (1 = frame by frame)")
-    return ap.parse_args()
+    ap.add_argument("--resume-from", default=None, help="load_state() directory: fuse into an existing grid (config 5)")
+    return ap.parse_args(argv)
 
 
-def scene_config(args, n_rooms):
-    kw = dict(feature_dim=args.feature_dim)
-    if args.voxel_size:
-        kw["voxel_size"] = args.voxel_size
-    cfg = synth.baseline_config(args.workload, **kw)
-    return cfg
+# ------------------------------------------------------------------------------------------------
+# the workload, shared by both arms
+# ------------------------------------------------------------------------------------------------
 
+class Plan:
+    """Which grid, which frames, in which order - derived from the arguments only, so that the native and the
+    reference arm of the same command line describe the same job."""
 
-def workload_name(cfg, n_rooms):
-    o, nv = cfg.grid()
-    s = "%s: %dx%d frames, %.0f cm voxels, room %sx%sx%s m -> grid %dx%dx%d (%.1f M voxels), C=%d, table %dx%d" % (
-        cfg.name, cfg.width, cfg.height, cfg.voxel_size * 100, cfg.extent[0], cfg.extent[1], cfg.extent[2],
-        nv[0], nv[1], nv[2], np.prod(nv) / 1e6, cfg.feature_dim, cfg.npatches[0], cfg.npatches[1])
-    if n_rooms > 1:
-        s += "; %d rooms side by side along x (20 cm partition walls), one x-slab per rank" % n_rooms
-    return s
+    def __init__(self, args, world):
+        self.world = world
+        self.mode = "single" if world == 1 and not args.rooms else (args.multi if not args.rooms else "rooms")
+        which = args.workload
+        if which == "auto":
+            which = "cfg3" if self.mode == "strong" else "cfg2"
+        kw = dict(feature_dim=args.feature_dim)
+        if args.voxel_size:
+            kw["voxel_size"] = args.voxel_size
+        self.cfg = synth.baseline_config(which, **kw)
+        self.n_rooms = (args.rooms or world) if self.mode == "rooms" else 1
+        self.F = args.frames_per_step * self.n_rooms
+        self.K, self.W = args.steps, args.warmup
+        visits = self.F * (self.K + self.W)
+        cap = min(args.pool or 2500, self.cfg.frames) * self.n_rooms
+        self.P = max(self.n_rooms, min(cap, visits) // self.n_rooms * self.n_rooms)
+        self.n_base = self.P // self.n_rooms                       # distinct images (rooms share them)
+        self.stride = max(1, self.cfg.frames // self.n_base) if self.n_base < self.cfg.frames else 1
+        self.window = args.window
+        self.layout = args.slab_layout
+        origin, nvox_room = self.cfg.grid()
+        self.origin = origin
+        self.wall_vox = int(round(0.2 / self.cfg.voxel_size)) if self.mode == "rooms" else 0
+        self.slab_nx = int(nvox_room[0]) + self.wall_vox
+        self.nvox = nvox_room.copy()
+        if self.mode == "rooms":
+            self.nvox[0] = self.slab_nx * self.n_rooms
+        self.room_dx = self.slab_nx * self.cfg.voxel_size
 
+    def base_index(self, slot):
+        """Frame id (into the config's pose sequence) of resident image `slot`."""
+        return (slot * self.stride) % self.cfg.frames
 
-def frame_bytes(cfg, n_valid, n_tsdf_valid):
-    """Algorithmic bytes of one frame (SURVEY.md 8d / DESIGN.md): compulsory traffic only."""
-    C = cfg.feature_dim
-    R = cfg.npatches[0] * cfg.npatches[1]
-    return 16 * n_tsdf_valid + n_valid * (8 * C + 40) + cfg.height * cfg.width * 17 + R * C * 4
+    def position(self, step, j):
+        """(resident image slot, room) of the j-th frame of `step`."""
+        q = (step * self.F + j) % self.P
+        return q // self.n_rooms, q % self.n_rooms
 
+    def slab(self, rank):
+        """Constructor keywords of rank's volume."""
+        nx = int(self.nvox[0])
+        if self.mode == "single":
+            return {}
+        if self.mode == "rooms":
+            own = rank if self.world > 1 else 0
+            return dict(x_begin=own * self.slab_nx, x_end=(own + 1) * self.slab_nx)
+        if self.layout == "cyclic":
+            return dict(x_begin=rank * SLAB_SPAN, x_end=nx, x_span=SLAB_SPAN, x_stride=SLAB_SPAN * self.world)
+        from spatially_aware_ai_b200 import slab
+        xb, xe = slab.slab_bounds(nx, self.world, rank)
+        return dict(x_begin=xb, x_end=xe)
 
-def k3_bytes(cfg, n_valid):
-    """Algorithmic bytes of the feature-accumulate kernel alone."""
-    C = cfg.feature_dim
-    R = cfg.npatches[0] * cfg.npatches[1]
-    return n_valid * (8 * C + 40) + cfg.height * cfg.width * 13 + R * C * 4
+    def config(self):
+        cfg, nv = self.cfg, self.nvox
+        s = "%s: %dx%d frames, %.0f cm voxels, room %sx%sx%s m -> grid %dx%dx%d (%.1f M voxels), C=%d, table %dx%d" % (
+            cfg.name, cfg.width, cfg.height, cfg.voxel_size * 100, cfg.extent[0], cfg.extent[1], cfg.extent[2],
+            nv[0], nv[1], nv[2], np.prod(nv) / 1e6, cfg.feature_dim, cfg.npatches[0], cfg.npatches[1])
+        if self.mode == "rooms":
+            s += "; %d rooms side by side along x (20 cm partition walls), one x-slab per rank" % self.n_rooms
+        order = "poses %d, %d, ... of the %d-pose orbit, in order" % (0, self.stride, cfg.frames)
+        par = {"single": "single GPU",
+               "strong": "grid sharded over %d ranks (%s x-slabs%s), every rank handed every frame, no data-path "
+                         "collective" % (self.world, self.layout, ", stripes of %d planes" % SLAB_SPAN if self.layout == "cyclic" else ""),
+               "rooms": "one room (x-slab) per rank, every rank handed every frame, no data-path collective"}[self.mode]
+        return {"workload": s, "frames_per_step": self.F, "frame_pool": self.P, "frame_order": order,
+                "l2": "no flush needed: one window touches > 1 GB of feature rows, the L2 holds 126 MB",
+                "parallelism": par}
 
 
 class ClockSampler:
@@ -147,66 +205,164 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def host_frame(plan, slot, room=0):
+    fr = synth.make_frame(plan.cfg, plan.base_index(slot), table_layout="hwc")
+    if room:
+        fr["pose"] = fr["pose"].copy()
+        fr["pose"][0, 3] += room * plan.room_dx
+    return fr
+
+
+def mem_available_gb():
+    try:
+        with open("/proc/meminfo") as f:
+            for line in f:
+                if line.startswith("MemAvailable:"):
+                    return int(line.split()[1]) / 1e6
+    except OSError:
+        pass
+    return 0.0
+
+
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port on the host cores
+# CPU arm: the reference's own torch path (baseline/_ref), or the C/OpenMP port of it
 # ------------------------------------------------------------------------------------------------
 
-def cpu_leg(cfg, frames, n_frames, threads):
-    """Integrate `n_frames` frames with the oracle (all host threads); returns (updates, seconds)."""
-    from oracle import oracle as O
-    origin, nvox = cfg.grid()
-    vol = O.OracleVolume(origin, cfg.voxel_size, nvox, cfg.trunc, cfg.feature_dim, num_threads=threads)
-    fr = frames[0]
-    vol.integrate(fr["depth"][None], fr["rgb"][None], fr["pose"][None], fr["K"][None], fr["table"][None],
-                  fr["seg"][None], want_masks=False)  # warm-up: page in the state it touches
-    updates = 0
-    t0 = time.perf_counter()
-    for i in range(n_frames):
-        fr = frames[(i + 1) % len(frames)]
-        cnt = vol.integrate(fr["depth"][None], fr["rgb"][None], fr["pose"][None], fr["K"][None], fr["table"][None],
-                            fr["seg"][None], want_masks=False)
-        updates += int(cnt[0, 0])
-    return updates, time.perf_counter() - t0, vol
+class TorchReference:
+    """The UNMODIFIED reference ClipSeemFusion (clip_seem_fusion.py:611-822) on torch-CPU, all host threads,
+    imported from baseline/_ref through baseline/ref_loader.py; its CLIP / kMaX producers are stand-ins that
+    return the pre-generated feature image / class map, so only the fusion path is timed."""
+
+    kind = "reference"
+
+    def __init__(self, plan, threads, x_planes=None):
+        import torch
+        from baseline import ref_loader
+        torch.set_num_threads(threads)
+        _, csf, _ = ref_loader.load_reference()
+        self.torch = torch
+        cfg = plan.cfg
+        origin, nvox = plan.origin.copy(), plan.nvox.copy()
+        if x_planes is not None:          # bounded-memory sample: the first x_planes planes of the grid
+            nvox[0] = x_planes
+        outer = self
+
+        class _Clip(torch.nn.Module):
+            feature_dim = cfg.feature_dim
+
+            def img_inference_tiled(self, rgb_imgs, patch_size, patch_stride):
+                return outer.table
+
+        class _Seg:
+            def run_on_image(self, img):
+                return outer.seg
+
+        self.vol = csf.ClipSeemFusion(torch.from_numpy(origin), cfg.voxel_size, torch.from_numpy(nvox), cfg.trunc, False,
+                                      cfg.patch_size, cfg.patch_stride, _Clip(), _Seg())
+        self.n_voxels = int(np.prod(nvox))
+        self.source = ref_loader.reference_root()
+
+    def integrate(self, fr):
+        t = self.torch
+        self.table = t.from_numpy(fr["table"])[None]
+        self.seg = t.from_numpy(fr["seg"].astype(np.int64))
+        before = int(self.vol.weight.sum())
+        self.vol.integrate(t.from_numpy(fr["depth"])[None], t.from_numpy(fr["rgb"])[None], t.from_numpy(fr["pose"])[None],
+                           t.from_numpy(fr["K"])[None])
+        return int(self.vol.weight.sum()) - before
+
+
+class PortReference:
+    """The bit-exact C restatement of the same path (oracle/saf_oracle.c, OpenMP over voxels)."""
+
+    kind = "port"
+
+    def __init__(self, plan, threads, x_planes=None):
+        from oracle import oracle as O
+        O.build()
+        nvox = plan.nvox.copy()
+        self.vol = O.OracleVolume(plan.origin, plan.cfg.voxel_size, nvox, plan.cfg.trunc, plan.cfg.feature_dim,
+                                  num_threads=threads, x_begin=0, x_end=x_planes)
+        self.n_voxels = self.vol.n
+        self.source = "oracle/saf_oracle.c"
+
+    def integrate(self, fr):
+        cnt = self.vol.integrate(fr["depth"][None], fr["rgb"][None], fr["pose"][None], fr["K"][None], fr["table"][None],
+                                 fr["seg"][None], want_masks=False)
+        return int(cnt[0, 0])
+
+
+def make_cpu_reference(plan, kind, threads):
+    """(object, sample note).  The torch path needs the whole dense grid in host memory (3.7 KB per voxel at
+    C = 768); when that does not fit, it runs on the first x-planes of the grid that do and says so."""
+    from baseline import ref_loader
+    n_full = int(np.prod(plan.nvox))
+    per_voxel = 4 * plan.cfg.feature_dim + 4 * 143 + 64
+    if kind == "auto":
+        kind = "torch" if ref_loader.reference_root() else "port"
+    cls = TorchReference if kind == "torch" else PortReference
+    budget = 0.6 * mem_available_gb() * 1e9
+    planes = None
+    note = "the full grid"
+    if n_full * per_voxel > budget:
+        plane = int(plan.nvox[1]) * int(plan.nvox[2]) * per_voxel
+        planes = max(16, int(budget // plane))
+        note = ("the first %d of %d x-planes of the grid (host memory: %.0f GB available, the full dense grid needs "
+                "%.0f GB); the reference's cost is proportional to the voxels it holds" %
+                (planes, int(plan.nvox[0]), mem_available_gb(), n_full * per_voxel / 1e9))
+    return cls(plan, threads, planes), note
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    cfg = scene_config(args, 1)
+    plan = Plan(args, max(world, args.gpus if world == 1 else world))
     threads = os.cpu_count()
-    F = args.ref_frames_per_step
-    pool = [synth.make_frame(cfg, (i * 37) % cfg.frames, table_layout="hwc") for i in range(max(4, F))]
-    from oracle import oracle as O
-    O.build()
-    origin, nvox = cfg.grid()
-    vol = O.OracleVolume(origin, cfg.voxel_size, nvox, cfg.trunc, cfg.feature_dim, num_threads=threads)
+    ref, where = make_cpu_reference(plan, args.ref_kind, threads)
+    Fr = args.ref_frames_per_step or (1 if ref.kind == "reference" else 4)
+    Fr = min(Fr, plan.F)
+    cache = {}
 
-    def step(s):
+    def frame(step, j):
+        slot, room = plan.position(step, j)
+        if (slot, room) not in cache:
+            if len(cache) > 64:
+                cache.clear()
+            cache[(slot, room)] = host_frame(plan, slot, room)
+        return cache[(slot, room)]
+
+    def run_step(s):
         upd = 0
-        for j in range(F):
-            fr = pool[(s * F + j) % len(pool)]
-            upd += int(vol.integrate(fr["depth"][None], fr["rgb"][None], fr["pose"][None], fr["K"][None],
-                                     fr["table"][None], fr["seg"][None], want_masks=False)[0, 0])
+        for j in range(Fr):
+            upd += ref.integrate(frame(s, j))
         return upd
 
-    for s in range(args.warmup):
-        step(s)
-    t0 = time.perf_counter()
-    updates = sum(step(args.warmup + s) for s in range(args.steps))
-    dt = time.perf_counter() - t0
+    for s in range(plan.W):
+        for j in range(Fr):
+            frame(s, j)
+        run_step(s)
+    for s in range(plan.K):                      # frame synthesis stays outside the timed region
+        for j in range(Fr):
+            frame(plan.W + s, j)
+    dt, updates = 0.0, 0
+    for s in range(plan.K):
+        t0 = time.perf_counter()
+        updates += run_step(plan.W + s)
+        dt += time.perf_counter() - t0
     value = updates / dt
-    sample = "%d steps x %d frames of %s on the full grid" % (args.steps, F, cfg.name)
+    sample = ("each step integrates the first %d of the step's %d frames into %s; %s, %d threads" %
+              (Fr, plan.F, where, "unmodified reference ClipSeemFusion.integrate on torch-CPU (%s)" % ref.source
+               if ref.kind == "reference" else "C/OpenMP port of the reference path (%s)" % ref.source, threads))
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(cfg, 1), "frames_per_step": F},
-        "frames_per_s": args.steps * F / dt,
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": plan.world,
+        "steps": plan.K, "warmup": plan.W, "ms_per_step": dt / plan.K * 1e3,
+        "higher_is_better": True, "scaling": "strong" if plan.mode == "strong" else "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": plan.config(),
+        "frames_per_s": plan.K * Fr / dt, "voxel_visits_per_s": ref.n_voxels * plan.K * Fr / dt,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": ref.kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "reference has no native code; its path is stock torch on CPU and cannot travel to this box, "
-                "so this arm times the bit-exact C restatement (oracle/saf_oracle.c, OpenMP over voxels)",
     }))
 
 
@@ -219,8 +375,8 @@ def run_native_arm(args):
     import torch.distributed as dist
 
     import spatially_aware_ai_b200 as saf
-    from spatially_aware_ai_b200 import _lib
-    from tests.helpers import FakeClip, FakeSeg
+    from spatially_aware_ai_b200 import _lib, slab
+    from spatially_aware_ai_b200.synth import FakeClip, FakeSeg
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -238,100 +394,119 @@ def run_native_arm(args):
         json_fd = os.dup(1)
         os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
-    n_rooms = args.rooms if (args.rooms and world == 1) else world
-    cfg = scene_config(args, n_rooms)
-    origin, nvox_room = cfg.grid()
-    # multi-room scans: each slab is one room plus a 20 cm partition wall towards the next room
-    wall_vox = int(round(0.2 / cfg.voxel_size)) if n_rooms > 1 else 0
-    slab_nx = int(nvox_room[0]) + wall_vox
-    nvox = nvox_room.copy()
-    nvox[0] = slab_nx * n_rooms
-    room_dx = slab_nx * cfg.voxel_size            # world-space pitch of the rooms
-    own = rank if world > 1 else 0
-    x_begin, x_end = own * slab_nx, (own + 1) * slab_nx
+    plan = Plan(args, world)
+    cfg = plan.cfg
     lib = _lib.load()
-
-    clip, seg = FakeClip(cfg.feature_dim), FakeSeg()
-    vol = saf.ClipSeemFusion(torch.from_numpy(origin), cfg.voxel_size, torch.from_numpy(nvox), cfg.trunc, False,
-                             cfg.patch_size, cfg.patch_stride, clip, seg, x_begin=x_begin, x_end=x_end).to(dev)
-
-    # ---- frame pool: identical on every rank; frame i is taken in room (i % n_rooms) ----------------------
-    # weak scaling: every step visits every room `--frames-per-step` times, so the scan (and the frame count
-    # every rank is handed) grows with the number of rooms while the work inside each room stays fixed
-    F, K_steps, W_steps = args.frames_per_step * n_rooms, args.steps, args.warmup
-    P = min(args.pool * n_rooms, F * (K_steps + W_steps))
-    P = max(n_rooms, P - P % n_rooms)
-    stride = max(1, cfg.frames // (P // n_rooms))
-    # the n_rooms frames of one visit share their images (the rooms are identical): only the pose is shifted,
-    # so the resident pool is P / n_rooms images whatever the number of rooms
-    from concurrent.futures import ThreadPoolExecutor
-    n_threads = max(1, min(8, (os.cpu_count() or 1) // max(1, world)))   # numpy's generators release the GIL
-    with ThreadPoolExecutor(n_threads) as pool_ex:
-        base = list(pool_ex.map(lambda b: synth.make_frame(cfg, (b * stride) % cfg.frames, table_layout="hwc"),
-                                range(P // n_rooms)))
-    host = []
-    for i in range(P):
-        fr = dict(base[i // n_rooms])
-        fr["pose"] = fr["pose"].copy()
-        fr["pose"][0, 3] += (i % n_rooms) * room_dx
-        host.append(fr)
-    d_depth = torch.stack([torch.from_numpy(f["depth"]) for f in base]).to(dev)
-    d_rgb = torch.stack([torch.from_numpy(f["rgb"]) for f in base]).to(dev)
-    d_seg = torch.stack([torch.from_numpy(f["seg"]) for f in base]).to(dev)
-    d_table = torch.stack([torch.from_numpy(np.ascontiguousarray(f["table"].transpose(1, 2, 0))) for f in base]).to(dev)
     npy, npx = cfg.npatches
     H, Wd, C = cfg.height, cfg.width, cfg.feature_dim
-
-    def frame_struct(dst, i):
-        dst.depth = d_depth[i // n_rooms].data_ptr()
-        dst.rgb = d_rgb[i // n_rooms].data_ptr()
-        dst.seg = d_seg[i // n_rooms].data_ptr()
-        dst.seg_dtype = _lib.SAF_SEG_U8
-        dst.table = d_table[i // n_rooms].data_ptr()
-        dst.table_stride_c, dst.table_stride_r = 1, C
-        dst.npy, dst.npx = npy, npx
-        dst.pose[:] = host[i]["pose"].reshape(-1).tolist()
-        dst.K[:] = host[i]["K"].reshape(-1).tolist()
-
-    pool_structs = (_lib.Frame * P)()
-    for i in range(P):
-        frame_struct(pool_structs[i], i)
-
-    def step_structs(s):
-        arr = (_lib.Frame * F)()
-        for j in range(F):
-            ctypes.memmove(ctypes.byref(arr[j]), ctypes.byref(pool_structs[(s * F + j) % P]), ctypes.sizeof(_lib.Frame))
-        return arr
-
-    window = args.window
-    ws = vol._workspace(window, npy * npx * C)
-    calls_per_step = (F + window - 1) // window
-    grid_d, vol_d = vol._grid_desc(), vol._volume_desc()
-    stream = torch.cuda.current_stream(dev).cuda_stream
-    trunc = float(cfg.trunc)
-
-    def run_step(arr):
-        _lib.check(lib.saf_integrate_sequence(ctypes.byref(grid_d), ctypes.byref(vol_d), arr, F, H, Wd, trunc,
-                                              _lib.SAF_RGB_BILINEAR, ctypes.byref(ws), stream), "saf_integrate_sequence")
+    F, K_steps, W_steps, P, n_rooms, n_base = plan.F, plan.K, plan.W, plan.P, plan.n_rooms, plan.n_base
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def max_over_ranks(x):
+    def reduce_ranks(x, op):
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
+    def max_over_ranks(x):
+        return reduce_ranks(x, dist.ReduceOp.MAX) if world > 1 else x
+
     def sum_over_ranks(x):
+        return reduce_ranks(x, dist.ReduceOp.SUM) if world > 1 else x
+
+    def gather_ranks(x):
         if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+            return [x]
+        t = torch.zeros(world, dtype=torch.float64, device=dev)
+        t[rank] = x
+        dist.all_reduce(t)
+        return t.tolist()
+
+    clip, seg = FakeClip(C), FakeSeg()
+    vol = saf.ClipSeemFusion(torch.from_numpy(plan.origin), cfg.voxel_size, torch.from_numpy(plan.nvox), cfg.trunc, False,
+                             cfg.patch_size, cfg.patch_stride, clip, seg, **plan.slab(rank)).to(dev)
+    if args.resume_from:
+        saf.load_state(vol, os.path.join(args.resume_from, "rank%d" % rank) if world > 1 else args.resume_from)
+
+    # ---- resident frame pool: every rank synthesises its share of the images (sensor formats), the shares are
+    # all-gathered over NCCL, and the fp32 tensors the reference's integrate() takes are derived on the device
+    # with the dataset classes' own operations (clipfusion.py:185-188: float / 255, float / 1000) ----------------
+    from concurrent.futures import ThreadPoolExecutor
+    per = (n_base + world - 1) // world
+    mine = [min(n_base - 1, k * world + rank) for k in range(per)]
+    n_threads = max(1, min(16, (os.cpu_count() or 1) // max(1, world)))   # numpy's generators release the GIL
+    t_gen = time.time()
+    with ThreadPoolExecutor(n_threads) as ex:
+        frames_mine = list(ex.map(lambda b: host_frame(plan, b), mine))
+    sys.stderr.write("[bench] rank %d: %d frames synthesised in %.1f s (%d threads)\n" % (rank, per, time.time() - t_gen, n_threads))
+
+    def pooled(key, dtype):
+        local = torch.from_numpy(np.stack([f[key] for f in frames_mine])).to(dev)
+        if world == 1:
+            return local[:n_base]
+        flat = local.contiguous().view(torch.uint8).reshape(per, -1)
+        out = torch.empty((world, per, flat.shape[1]), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(out.view(world * per, -1), flat)
+        full = out.transpose(0, 1).reshape(world * per, -1)[:n_base].contiguous()
+        return full.view(dtype).reshape((n_base,) + tuple(local.shape[1:]))
+
+    d_depth_mm = pooled("depth_mm", torch.uint16)
+    d_rgb_u8 = pooled("rgb_u8", torch.uint8)
+    d_seg = pooled("seg", torch.uint8)
+    tab_local = torch.from_numpy(np.stack([np.ascontiguousarray(f["table"].transpose(1, 2, 0)) for f in frames_mine])).to(dev)
+    if world == 1:
+        d_table = tab_local[:n_base]
+    else:
+        flat = tab_local.view(torch.uint8).reshape(per, -1)
+        out = torch.empty((world * per, flat.shape[1]), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(out, flat)
+        d_table = out.view(world, per, -1).transpose(0, 1).reshape(world * per, -1)[:n_base].contiguous() \
+            .view(torch.float32).reshape(n_base, npy, npx, C)
+        del out
+    d_depth = d_depth_mm.to(torch.float32) / 1000
+    d_rgb = d_rgb_u8.to(torch.float32) / 255
+    # poses / intrinsics of every resident frame (cheap, computed by every rank)
+    pose_all = np.stack([synth.camera_pose(cfg, plan.base_index(b)) for b in range(n_base)])
+    K_one = synth.intrinsics(cfg)
+    e2e_host = frames_mine[:max(1, min(len(frames_mine), (64 + world - 1) // world))]   # pinned later
+    del frames_mine
+
+    frame_dt = _lib.frame_numpy_dtype()
+
+    def step_structs(s):
+        """saf_frame descriptors of step s: device-resident fp32 images, poses by value."""
+        arr = np.zeros(F, dtype=frame_dt)
+        pos = [plan.position(s, j) for j in range(F)]
+        slots = np.array([p[0] for p in pos], dtype=np.uint64)
+        rooms = np.array([p[1] for p in pos], dtype=np.float32)
+        arr["depth"] = d_depth.data_ptr() + slots * np.uint64(H * Wd * 4)
+        arr["rgb"] = d_rgb.data_ptr() + slots * np.uint64(H * Wd * 12)
+        arr["seg"] = d_seg.data_ptr() + slots * np.uint64(H * Wd)
+        arr["seg_dtype"] = _lib.SAF_SEG_U8
+        arr["table"] = d_table.data_ptr() + slots * np.uint64(npy * npx * C * 4)
+        arr["table_stride_c"], arr["table_stride_r"] = 1, C
+        arr["npy"], arr["npx"] = npy, npx
+        poses = pose_all[slots.astype(np.int64)].copy()
+        poses[:, 0, 3] += rooms * np.float32(plan.room_dx)
+        arr["pose"] = poses.reshape(F, 16)
+        arr["K"] = K_one.reshape(1, 9)
+        return arr
+
+    window = plan.window
+    ws = vol._workspace(window, npy * npx * C)
+    grid_d, vol_d = vol._grid_desc(), vol._volume_desc()
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    trunc = float(cfg.trunc)
+
+    def run_step(arr):
+        _lib.check(lib.saf_integrate_sequence(ctypes.byref(grid_d), ctypes.byref(vol_d),
+                                              arr.ctypes.data_as(ctypes.POINTER(_lib.Frame)), F, H, Wd, trunc,
+                                              _lib.SAF_RGB_BILINEAR, ctypes.byref(ws), stream), "saf_integrate_sequence")
 
     # ---- value: inputs resident, K steps through the C ABI -------------------------------------------------
     steps_arr = [step_structs(s) for s in range(W_steps + K_steps)]
@@ -359,115 +534,142 @@ def run_native_arm(args):
         best_burn = min(best_burn, dt_b)
         if settled >= 8 and time.time() - t_burn > 0.5:
             break
+    if world > 1:       # every rank leaves the burn-in after the same number of collectives: none inside it
+        barrier()
     for s in range(W_steps):
         run_step(steps_arr[s])
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    attempts = []
+    attempts, rank_ms = [], None
     for attempt in range(3):
         if rank == 0:
             sampler.lines.clear()            # keep only samples taken during the timed region
         st0 = vol.stats()
-        step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(K_steps + 1)] if os.environ.get("SAF_BENCH_STEPS") else None
         barrier()
         ev0.record()
         for s in range(K_steps):
-            if step_ev:
-                step_ev[s].record()
             run_step(steps_arr[W_steps + s])
-        if step_ev:
-            step_ev[K_steps].record()
         ev1.record()
         barrier()
-        attempts.append(max_over_ranks(ev0.elapsed_time(ev1)))
+        mine_ms = ev0.elapsed_time(ev1)
+        attempts.append(max_over_ranks(mine_ms))
+        rank_ms = gather_ranks(mine_ms)
         # a timed region whose steps took far longer than the settled burn-in step was perturbed: measure again
         # (at most twice; every attempt is reported in the JSON line)
         if attempts[-1] / K_steps <= 3.0 * max_over_ranks(best_burn):
             break
-    ms = min(attempts)
+    ms = attempts[-1] if len(attempts) == 1 else min(attempts)
     clocks = sampler.stop() if rank == 0 else None
     st1 = vol.stats()
-    if step_ev:
-        sys.stderr.write("[bench] per-step ms: %s\n" % " ".join("%.2f" % step_ev[i].elapsed_time(step_ev[i + 1]) for i in range(K_steps)))
     sys.stderr.write("[bench] rank %d: %.3f ms/step; depth_cull_on=%d last_blocks=%d last_processed=%d\n" %
                      (rank, ms / K_steps, st1["depth_cull_on"], st1["last_blocks"], st1["last_processed"]))
     upd = st1["total_valid"] - st0["total_valid"]
     tv = st1["total_tsdf_valid"] - st0["total_tsdf_valid"]
     blocks = st1["total_blocks"] - st0["total_blocks"]
+    union = st1["total_union"] - st0["total_union"]
+    calls = st1["total_calls"] - st0["total_calls"]
     total_upd = sum_over_ranks(upd)
+    rank_upd = gather_ranks(upd)
     n_frames = K_steps * F
     value = total_upd / (ms * 1e-3)
     frames_per_s = n_frames / (ms * 1e-3)
-    whole_bytes = 16 * tv + upd * (8 * C + 40) + n_frames * (H * Wd * 17 + npy * npx * C * 4)
+    # algorithmic bytes, SURVEY.md 8(d): frame-by-frame pricing (every update moves its row both ways) and the
+    # window formulation's own compulsory traffic (every row of a window's union list moves both ways once)
+    img_bytes = n_frames * (H * Wd * 17 + npy * npx * C * 4)
+    whole_bytes = 16 * tv + upd * (8 * C + 40) + img_bytes
+    whole_bytes_window = 16 * tv + union * 8 * C + upd * 40 + img_bytes
 
     # ---- e2e: public API, host buffers, H2D inside the timed region ---------------------------------------
     e2e = None
     if not args.no_e2e:
-        Pe = min(P, 64 - 64 % n_rooms if n_rooms > 1 else 64)
-        h_depth = torch.stack([torch.from_numpy(f["depth"]) for f in host[:Pe]]).pin_memory()
-        h_rgb = torch.stack([torch.from_numpy(f["rgb"]) for f in host[:Pe]]).pin_memory()
-        h_pose = torch.stack([torch.from_numpy(f["pose"]) for f in host[:Pe]])
-        h_K = torch.stack([torch.from_numpy(f["K"]) for f in host[:Pe]])
-        tables_chw = d_table.permute(0, 3, 1, 2)            # producer outputs stay on the device
-        chunk = window
+        Pe = len(e2e_host) * world                       # frames of the e2e pool: rank r holds frames k*world + r
+        Fe = min(F, Pe) // world * world or world        # frames per e2e step (every rank uploads Fe / world of them)
+        tables_chw = d_table.permute(0, 3, 1, 2)         # producer outputs stay on the device
         copy_stream = torch.cuda.Stream(dev)
+        n_loc = Fe // world
 
-        def stage(idx):
-            """H2D of one chunk's depth + rgb from pinned memory, on the copy stream (prefetch)."""
-            with torch.cuda.stream(copy_stream):
-                sel = torch.as_tensor(idx)
-                if idx[-1] - idx[0] == len(idx) - 1:       # consecutive pinned frames: one copy per tensor
-                    dd = h_depth[idx[0]:idx[-1] + 1].to(dev, non_blocking=True)
-                    rr = h_rgb[idx[0]:idx[-1] + 1].to(dev, non_blocking=True)
-                else:
-                    dd = torch.empty((len(idx), H, Wd), device=dev)
-                    rr = torch.empty((len(idx), H, Wd, 3), device=dev)
-                    for k, i in enumerate(idx):
-                        dd[k].copy_(h_depth[i], non_blocking=True)
-                        rr[k].copy_(h_rgb[i], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(copy_stream)
-            return dd, rr, sel, ev
+        def host_pool(fmt):
+            if fmt == "sensor":
+                hd = torch.from_numpy(np.stack([f["depth_mm"] for f in e2e_host])).pin_memory()
+                hr = torch.from_numpy(np.stack([f["rgb_u8"] for f in e2e_host])).pin_memory()
+            else:
+                hd = torch.from_numpy(np.stack([f["depth"] for f in e2e_host])).pin_memory()
+                hr = torch.from_numpy(np.stack([f["rgb"] for f in e2e_host])).pin_memory()
+            return hd, hr
 
-        def e2e_step(s):
-            ids = [(s * F + j) % Pe for j in range(F)]
-            chunks = [ids[k:k + chunk] for k in range(0, F, chunk)]
-            nxt = stage(chunks[0])
-            for ci, idx in enumerate(chunks):
-                dd, rr, sel, ev = nxt
-                if ci + 1 < len(chunks):
-                    nxt = stage(chunks[ci + 1])          # overlaps the fusion of this chunk
+        def run_e2e(fmt, n_steps):
+            hd, hr = host_pool(fmt)
+            bpf = (hd[0].numel() * hd.element_size() + hr[0].numel() * hr.element_size())
+            # frame g of the e2e pool is image (g % n_base-ish): rank r's k-th host frame is resident image mine[k]
+            slots_loc = [min(n_base - 1, k * world + rank) for k in range(len(e2e_host))]
+
+            def stage(s):
+                """H2D of this rank's share of step s from pinned memory + all-gather of the shares (copy stream)."""
+                k0 = (s * n_loc) % len(e2e_host)
+                ks = [(k0 + i) % len(e2e_host) for i in range(n_loc)]
+                with torch.cuda.stream(copy_stream):
+                    if ks[-1] - ks[0] == n_loc - 1:
+                        dd = hd[ks[0]:ks[-1] + 1].to(dev, non_blocking=True)
+                        rr = hr[ks[0]:ks[-1] + 1].to(dev, non_blocking=True)
+                    else:
+                        dd = torch.stack([hd[k] for k in ks]).pin_memory().to(dev, non_blocking=True)
+                        rr = torch.stack([hr[k] for k in ks]).pin_memory().to(dev, non_blocking=True)
+                    sl = torch.tensor([slots_loc[k] for k in ks], dtype=torch.int64)
+                    if world > 1:
+                        gd = torch.empty((world * n_loc,) + tuple(dd.shape[1:]), dtype=dd.dtype, device=dev)
+                        gr = torch.empty((world * n_loc,) + tuple(rr.shape[1:]), dtype=rr.dtype, device=dev)
+                        dist.all_gather_into_tensor(gd.view(torch.uint8).view(world * n_loc, -1),
+                                                    dd.view(torch.uint8).view(n_loc, -1))
+                        dist.all_gather_into_tensor(gr.view(torch.uint8).view(world * n_loc, -1),
+                                                    rr.view(torch.uint8).view(n_loc, -1))
+                        # rank q's k-th frame is resident image k*world + q (same k on every rank)
+                        sl_all = torch.stack([torch.clamp(sl // world * world + q, max=n_base - 1) for q in range(world)]).reshape(-1)
+                        dd, rr, sl = gd, gr, sl_all
+                    ev = torch.cuda.Event()
+                    ev.record(copy_stream)
+                return dd, rr, sl, ev
+
+            def step(s, nxt):
+                dd, rr, sl, ev = nxt
+                nxt = stage(s + 1)                                  # overlaps the fusion of this step
                 torch.cuda.current_stream(dev).wait_event(ev)
-                clip.next_table = tables_chw[(sel // n_rooms).to(dev)] if len(idx) > 1 else \
-                    tables_chw[idx[0] // n_rooms][None]
-                seg.queue = [d_seg[i // n_rooms] for i in idx]
-                if chunk > 1:
-                    vol.integrate_sequence(dd, rr, h_pose[sel], h_K[sel])
-                else:
-                    vol.integrate(dd, rr, h_pose[sel], h_K[sel])
+                sl_dev = sl.to(dev, non_blocking=True)
+                poses = torch.from_numpy(pose_all[sl.numpy()])
+                Ks = torch.from_numpy(np.broadcast_to(K_one, (len(sl), 3, 3)).copy())
+                vol.integrate_sequence(dd, rr, poses, Ks, clip_feat_img=tables_chw[sl_dev], seg_maps=d_seg[sl_dev])
                 dd.record_stream(torch.cuda.current_stream(dev))
                 rr.record_stream(torch.cuda.current_stream(dev))
-            return vol.stats()   # device -> host read of the step's counters (synchronises)
+                return vol.stats(), nxt   # device -> host read of the step's counters (synchronises)
 
-        e2e_steps = max(1, min(K_steps, 5))
-        e2e_step(0)
-        barrier()
-        s_before = vol.stats()
-        t0 = time.perf_counter()
-        for s in range(e2e_steps):
-            s_after = e2e_step(1 + s)
-        barrier()
-        dt = max_over_ranks(time.perf_counter() - t0)
-        e_upd = sum_over_ranks(s_after["total_valid"] - s_before["total_valid"])
-        h2d = F * (H * Wd * 4 + H * Wd * 12)
-        e2e = {"value": e_upd / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": ctypes.sizeof(_lib.Stats),
-               "frames_per_s": e2e_steps * F / dt, "steps": e2e_steps,
-               "note": "%s; depth+rgb of every frame copied H2D from pinned memory inside the timed region (prefetched "
-                       "one chunk ahead on a copy stream), pose/K passed as host tensors; feature image and class map "
-                       "come from device-resident stand-ins for the CLIP / kMaX producers (DNN inference is outside "
-                       "the path); the step's counters are read back to the host" %
-                       ("ClipSeemFusion.integrate_sequence on chunks of %d frames" % chunk if chunk > 1 else
-                        "ClipSeemFusion.integrate per frame")}
+            nxt = stage(0)
+            _, nxt = step(0, nxt)
+            barrier()
+            s_before = vol.stats()
+            t0 = time.perf_counter()
+            for s in range(n_steps):
+                s_after, nxt = step(1 + s, nxt)
+            barrier()
+            dt = max_over_ranks(time.perf_counter() - t0)
+            e_upd = sum_over_ranks(s_after["total_valid"] - s_before["total_valid"])
+            return {"value": e_upd / dt, "unit": UNIT, "h2d_bytes_per_step": Fe * bpf,
+                    "d2h_bytes_per_step": ctypes.sizeof(_lib.Stats) * world, "frames_per_s": n_steps * Fe / dt,
+                    "steps": n_steps, "frames_per_step": Fe, "host_format": fmt}
+
+        if plan.mode == "rooms":
+            e2e = None    # the rooms workload's feed was round 1's; the strong-scaling feed is the measured one
+        else:
+            e2e_steps = max(1, min(K_steps, 8))
+            e2e = run_e2e("sensor", e2e_steps)
+            e2e["note"] = ("ClipSeemFusion.integrate_sequence on whole steps; every frame's depth (uint16 mm) + rgb "
+                           "(uint8) - the formats the reference's datasets read from disk, converted in-kernel with "
+                           "the datasets' roundings - copied H2D from pinned memory inside the timed region, "
+                           "prefetched one step ahead on a copy stream%s; pose/K passed as host tensors; feature "
+                           "image and class map come from device-resident stand-ins for the CLIP / kMaX producers "
+                           "(DNN inference is outside the path); the step's counters are read back to the host" %
+                           ("; each frame is uploaded once (by rank i %% %d) and all-gathered over NCCL/NVLink" % world
+                            if world > 1 else ""))
+            if world == 1:
+                e2e["f32"] = run_e2e("f32", max(1, min(K_steps, 4)))
 
     # ---- roofline of the dominant kernel (feature accumulate), timed per launch with CUDA events -----------
     roof = None
@@ -478,12 +680,13 @@ def run_native_arm(args):
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         bw = window if window > 1 else 1
-        n_probe = max(1, min(P // bw, 6 if bw > 1 else 40))     # windows (or frames) timed one launch at a time
-        k3_ms, k3_b, k3_updates, k1_ms, k2_ms, timed = 0.0, 0, 0, 0.0, 0.0, 0
+        n_probe = max(1, min(n_base // bw, 6 if bw > 1 else 40))     # windows (or frames) timed one launch at a time
+        k3_ms, k3_upd, k3_union, k1_ms, k2_ms, timed = 0.0, 0, 0, 0.0, 0.0, 0
         ea, eb, e0, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+        probe = steps_arr[W_steps]
         for i in range(n_probe):
-            fr = ctypes.cast(ctypes.byref(pool_structs, i * bw * ctypes.sizeof(_lib.Frame)), ctypes.POINTER(_lib.Frame))
-            before = vol.stats()["total_valid"]
+            fr = ctypes.cast(probe.ctypes.data + i * bw * ctypes.sizeof(_lib.Frame), ctypes.POINTER(_lib.Frame))
+            sb = vol.stats()
             ea.record()
             _lib.check(lib.saf_frustum_cull(ctypes.byref(grid_d), fr, bw, H, Wd, trunc, ctypes.byref(ws), stream), "K1")
             eb.record()
@@ -502,64 +705,114 @@ def run_native_arm(args):
                                                       _lib.SAF_RGB_BILINEAR, ctypes.byref(ws), stream), "K3")
             e1.record()
             torch.cuda.synchronize(dev)
-            nv = vol.stats()["total_valid"] - before
+            sa = vol.stats()
+            nv = sa["total_valid"] - sb["total_valid"]
             if nv == 0:
                 continue
             timed += 1
             k1_ms += ea.elapsed_time(eb)
             k2_ms += eb.elapsed_time(e0)
             k3_ms += e0.elapsed_time(e1)
-            k3_b += nv * (8 * C + 40) + bw * (H * Wd * 13 + npy * npx * C * 4)
-            k3_updates += nv
+            k3_upd += nv
+            k3_union += (sa["total_union"] - sb["total_union"]) if bw > 1 else nv
+        timed = max(1, timed)
+        imgs = bw * (H * Wd * 13 + npy * npx * C * 4)
+        bytes_8d = k3_upd * (8 * C + 40) + timed * imgs              # per update, frame-by-frame
+        bytes_win = k3_union * 8 * C + k3_upd * 40 + timed * imgs    # per union row once per window
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "k3w_traffic.json" if bw > 1 else "k3_traffic.json")
-        if os.path.exists(tpath):
+        tpath = os.path.join(ROOT, "profiles", "r02_k3w_traffic.json" if bw > 1 else "k3_traffic.json")
+        if os.path.exists(tpath) and plan.mode == "single" and cfg.name == "cfg2" and C == 768:
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-        achieved = k3_b / (k3_ms * 1e-3) / 1e9 if k3_ms > 0 else 0.0
+        ach = bytes_win / (k3_ms * 1e-3) / 1e9 if k3_ms > 0 else 0.0
+        ach8 = bytes_8d / (k3_ms * 1e-3) / 1e9 if k3_ms > 0 else 0.0
         roof = {"bound": "hbm",
-                "kernel": "feature_accumulate_window_kernel (K3W, %d-frame window)" % bw if bw > 1 else
+                "kernel": "feature_accumulate_window_tile_kernel (K3W, %d-frame window)" % bw if bw > 1 else
                           "feature_accumulate_kernel (K3)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src, "launches_timed": timed, "avg_launch_us": k3_ms / max(1, timed) * 1e3,
-                "k1_avg_us": k1_ms / max(1, timed) * 1e3, "k2_avg_us": k2_ms / max(1, timed) * 1e3,
-                "avg_updates_per_launch": k3_updates / max(1, timed),
-                "algorithmic_bytes_per_update": 8 * C + 40,
-                "whole_step_gbs": whole_bytes / (ms * 1e-3) / 1e9, "whole_step_frac": whole_bytes / (ms * 1e-3) / 1e9 / peak,
-                "note": ("`achieved` counts SURVEY 8(d)'s algorithmic bytes (8C+40 per voxel update: what frame-by-frame "
-                         "fusion must move); the window kernel reads and writes each feature row once per window "
-                         "instead of once per frame, so its DRAM traffic (`traffic`, ncu) is a fraction of that and "
-                         "`frac` can exceed 1 - the kernel is bound by L1/issue, not HBM (profiles/)") if bw > 1 else None}
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                "peak_source": peak_src, "launches_timed": timed, "avg_launch_us": k3_ms / timed * 1e3,
+                "k1_avg_us": k1_ms / timed * 1e3, "k2_avg_us": k2_ms / timed * 1e3,
+                "avg_updates_per_launch": k3_upd / timed, "avg_union_rows_per_launch": k3_union / timed,
+                "ns_per_update": k3_ms * 1e6 / max(1, k3_upd),
+                "algorithmic_bytes_per_launch": bytes_win / timed,
+                "bytes_model": "window formulation (DESIGN.md section 4): 8C per union row (read + written once per "
+                               "window) + 40 per update (rgb, weight, one label counter) + the window's images and tables",
+                "achieved_8d": ach8, "frac_8d": ach8 / peak,
+                "bytes_model_8d": "SURVEY.md 8(d) frame-by-frame pricing: (8C + 40) per update; exceeds 1 because a "
+                                  "window moves each row once for all its frames",
+                "whole_step_gbs": whole_bytes_window / (ms * 1e-3) / 1e9,
+                "whole_step_frac": whole_bytes_window / (ms * 1e-3) / 1e9 / peak,
+                "whole_step_frac_8d": whole_bytes / (ms * 1e-3) / 1e9 / peak}
 
-    # ---- CPU baseline beside it (rank 0, N = 1 only) -------------------------------------------------------
+    # ---- language query over the fused grid (BASELINE config 4), rank slabs combined over NCCL ----------------
+    query = None
+    if not args.no_query:
+        T, k = 256, 100
+        gq = torch.Generator(device="cpu").manual_seed(4)
+        X = torch.nn.functional.normalize(torch.randn(T, C, generator=gq), dim=-1).to(dev)
+        M = vol.clip_feat.shape[0]
+        e0q, e1q, e2q = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+
+        def one_query():
+            ts, ti = saf.query_topk(vol.clip_feat, X, k, norm="nan_to_num", mode="dot", precision="tf32")
+            if world > 1:
+                ts, ti = slab.gather_topk(ts, slab.local_to_global_rows(vol, ti), k)
+            return ts, ti
+
+        one_query()
+        barrier()
+        e0q.record()
+        for _ in range(3):
+            one_query()
+        e1q.record()
+        barrier()
+        q_ms = max_over_ranks(e0q.elapsed_time(e1q) / 3)
+        M_all = sum_over_ranks(M)
+        q_bytes = M_all * C * 4
+        query = {"rows": int(M_all), "texts": T, "k": k, "feature_dim": C, "ms": q_ms, "rows_per_s": M_all / (q_ms * 1e-3),
+                 "read_gbs": q_bytes / (q_ms * 1e-3) / 1e9,
+                 "note": "exact top-%d rows for each of %d texts over the fused feature grid (cosine, rows normalised "
+                         "in-kernel), tcgen05 tf32 GEMM with a fused candidate filter + fp32 rescoring; %s" %
+                         (k, T, "per-rank lists all-gathered and merged over NCCL" if world > 1 else "one GPU")}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): the reference's torch path on a bounded sample ---------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import oracle as O
-        O.build()
         threads = os.cpu_count()
-        n_cpu = 12
-        c_upd, c_dt, _ = cpu_leg(cfg, host[:16], n_cpu, threads)
-        cpu = {"value": c_upd / c_dt, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "%d frames of the same workload on the full grid (oracle/saf_oracle.c, OpenMP)" % n_cpu,
-               "frames_per_s": n_cpu / c_dt}
+        try:
+            ref, where = make_cpu_reference(plan, args.ref_kind, threads)
+            n_cpu = 5 if ref.kind == "reference" else 12
+            frs = [host_frame(plan, plan.position(W_steps, j)[0]) for j in range(n_cpu + 1)]
+            ref.integrate(frs[0])                      # warm-up: pages in the state it touches
+            t0 = time.perf_counter()
+            c_upd = sum(ref.integrate(fr) for fr in frs[1:])
+            c_dt = time.perf_counter() - t0
+            cpu = {"value": c_upd / c_dt, "unit": UNIT, "cores": threads, "kind": ref.kind,
+                   "sample": "%d consecutive frames of the timed sequence integrated into %s (%s)" %
+                             (n_cpu, where, "unmodified reference on torch-CPU, " + ref.source if ref.kind == "reference"
+                              else "C/OpenMP port, " + ref.source),
+                   "frames_per_s": n_cpu / c_dt, "voxel_visits_per_s": ref.n_voxels * n_cpu / c_dt}
+            del ref
+        except Exception as exc:   # the baseline is a reported number, never a reason to lose the bench line
+            cpu = {"value": None, "unit": UNIT, "cores": threads, "kind": "unavailable", "sample": repr(exc)[:200]}
 
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K_steps, "warmup": W_steps,
-            "ms_per_step": ms / K_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(cfg, n_rooms), "frames_per_step": F, "frame_pool": P,
-                       "window": "%d consecutive frames per K1/K2/K3 launch trio (saf_integrate_sequence)" % window,
-                       "l2": "no flush needed: each frame's feature rows (%.0f MB) exceed the 126 MB L2" %
-                             (upd / max(1, n_frames) * (8 * C) / 1e6),
-                       "parallelism": "x-slab per rank, no data-path collective" if world > 1 else "single GPU"},
+            "ms_per_step": ms / K_steps, "higher_is_better": True,
+            "scaling": "strong" if plan.mode == "strong" else "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": plan.config(),
+            "window": "%d consecutive frames per K0/K1/K2/K3W launch quartet (saf_integrate_sequence)" % window,
             "frames_per_s": frames_per_s,
-            "updates_per_frame": total_upd / n_frames, "tsdf_updates_per_frame": sum_over_ranks(tv) / n_frames if world == 1 else None,
+            "updates_per_frame": total_upd / n_frames,
+            "tsdf_updates_per_frame": sum_over_ranks(tv) / n_frames if world == 1 else None,
+            "union_rows_per_window": union / max(1, calls), "updates_per_union_row": upd / max(1, union),
             "visible_blocks_per_frame": blocks / n_frames,
-            # rank 0's count: K0 + K1 + K2 + K3W per window the library launched (its own counter); sub-slab ranks
-            # add the frame-reach kernel and a counter kernel per sequence call
-            "gpu_launches": 4 * (st1["total_calls"] - st0["total_calls"]) + (2 * K_steps if n_rooms > 1 else 0),
+            "per_rank_ms_per_step": [x / K_steps for x in rank_ms], "per_rank_updates": rank_upd,
+            "rank_imbalance": max(rank_ms) / (sum(rank_ms) / len(rank_ms)),
+            # rank 0's count: K0 + K1 + K2 + K3W per window the library launched (its own counter)
+            "gpu_launches": 4 * calls,
             "timed_region_attempts_ms": attempts,
-            "clocks": clocks, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
+            "clocks": clocks, "e2e": e2e, "roofline": roof, "query": query, "cpu_baseline": cpu,
         }
         line = json.dumps(out) + "\n"
         if json_fd is not None:

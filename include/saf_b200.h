@@ -254,6 +254,23 @@ int saf_query_topk(const float *feats, int64_t M, int32_t C, int64_t ldf, const 
                    int32_t k, int64_t index_base, float *out_scores, int64_t *out_index, void *ws,
                    uint64_t ws_bytes, void *stream);
 
+/* Per-row consumers of the scores, computed chunk by chunk (64 Ki rows at a time, the chunk's score block stays
+ * in L2) so that the [M,T] matrix is never materialised.  ws: device scratch of saf_query_rows_workspace_bytes(T),
+ * 256-byte aligned.
+ * saf_query_row_labels: segment() of eval_scannet_segmentation.py:546-561 - out_labels[m, j] = the text with the
+ *   j-th largest softmax(100 cos) of row m, j < k (the reference returns the full argsort and its callers read
+ *   the first 1 / 5 columns; k = T reproduces it), ties to the lower text index; out_probs (optional, [M,k]) the
+ *   softmax values.  T <= 2048.
+ * saf_query_text_presence: hypersim_eval.py:80-89 - text = [n_background + n_targets, C]; out[i] = max over rows of
+ *   softmax(100 [s_bg.., s_target_i])[-1], the number the reference compares with its thresholds. */
+int saf_query_rows_workspace_bytes(int32_t T, uint64_t *bytes_out);
+int saf_query_row_labels(const float *feats, int64_t M, int32_t C, int64_t ldf, const float *text, int32_t T,
+                         int32_t norm_mode, int32_t precision, int32_t k, int64_t *out_labels, float *out_probs,
+                         void *ws, uint64_t ws_bytes, void *stream);
+int saf_query_text_presence(const float *feats, int64_t M, int32_t C, int64_t ldf, const float *text,
+                            int32_t n_background, int32_t n_targets, int32_t norm_mode, int32_t precision,
+                            float *out, void *ws, uint64_t ws_bytes, void *stream);
+
 /* ---- mesh: ClipSeemFusion.extract_mesh (clip_seem_fusion.py:824-888) and ClipFusion.extract_mesh
  *            (clipfusion.py:723-763) ------------------------------------------------------------
  * The reference masks unobserved voxels (weight == 0) to NaN, runs skimage.measure.marching_cubes

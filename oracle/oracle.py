@@ -211,6 +211,39 @@ def relevance_half(rel):
     return np.clip((np.asarray(rel, np.float32) - np.float32(0.5)) * np.float32(2), 0, 1)
 
 
+def minmax_per_text(sim):
+    """query_mesh.py:59-61: min-max over the rows, per text.  sim [M,T]."""
+    sim = np.asarray(sim, np.float32)
+    mn, mx = sim.min(axis=0, keepdims=True), sim.max(axis=0, keepdims=True)
+    return (sim - mn) / (mx - mn)
+
+
+def relevance_outliers(rel):
+    """query_mesh.py:63-73: keep entries above median + 2 sigma (torch.median = lower median, torch.std unbiased)."""
+    rel = np.asarray(rel, np.float32)
+    med = np.sort(rel)[(len(rel) - 1) // 2]
+    thr = med + np.float32(2) * rel.std(ddof=1, dtype=np.float32)
+    return np.where(rel > thr, rel, np.float32(0)).astype(np.float32)
+
+
+def segment_labels(feats, text):
+    """eval_scannet_segmentation.py:546-561: clamp_min(0.1) normalisation, argsort(descending) of softmax(100 cos);
+    ties towards the lower text index."""
+    F = normalize_rows(feats, "clamp_min")
+    rel = _softmax(np.float32(100) * (F @ np.asarray(text, np.float32).T), -1)
+    return np.argsort(-rel.astype(np.float64), axis=-1, kind="stable")
+
+
+def presence_scores(feats, background_text, target_text):
+    """hypersim_eval.py:50-51, 80-89: per target, max over rows of softmax(100 cos([background.., target]))[-1]."""
+    F = normalize_rows(feats, "clamp_min")
+    out = []
+    for i in range(len(target_text)):
+        tf = np.concatenate([background_text, target_text[i:i + 1]], 0).astype(np.float32)
+        out.append(_softmax(np.float32(100) * (F @ tf.T), -1)[:, -1].max())
+    return np.array(out, np.float32)
+
+
 def topk_indices(scores, k):
     """Top-k rows per text column, ties broken towards the lower row index.  scores [M,T] -> [T,k]."""
     M, T = scores.shape

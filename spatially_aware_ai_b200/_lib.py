@@ -47,6 +47,26 @@ class Frame(ctypes.Structure):
                 ("rgb_dtype", c_int32), ("pose_device", c_void_p), ("K_device", c_void_p)]
 
 
+def frame_numpy_dtype():
+    """numpy structured dtype with saf_frame's layout: lets callers fill an array of frames column-wise."""
+    import numpy as np
+    names, formats, offsets = [], [], []
+    for name, ctype in Frame._fields_:
+        names.append(name)
+        offsets.append(getattr(Frame, name).offset)
+        if name == "pose":
+            formats.append(("<f4", (16,)))
+        elif name == "K":
+            formats.append(("<f4", (9,)))
+        elif ctype is c_void_p:
+            formats.append("<u8")
+        elif ctype is c_int64:
+            formats.append("<i8")
+        else:
+            formats.append("<i4")
+    return np.dtype({"names": names, "formats": formats, "offsets": offsets, "itemsize": ctypes.sizeof(Frame)})
+
+
 class Stats(ctypes.Structure):
     _fields_ = [("total_frames", c_uint64), ("total_valid", c_uint64), ("total_tsdf_valid", c_uint64),
                 ("total_blocks", c_uint64), ("last_blocks", ctypes.c_uint32),
@@ -91,6 +111,11 @@ SIGNATURES = {
     "saf_query_topk": (ctypes.c_int, [c_void_p, c_int64, c_int32, c_int64, c_void_p, c_int32, c_int32, c_int32,
                                       c_void_p, c_int32, c_int32, c_int64, c_void_p, c_void_p, c_void_p, c_uint64,
                                       c_void_p]),
+    "saf_query_rows_workspace_bytes": (ctypes.c_int, [c_int32, P(c_uint64)]),
+    "saf_query_row_labels": (ctypes.c_int, [c_void_p, c_int64, c_int32, c_int64, c_void_p, c_int32, c_int32, c_int32,
+                                            c_int32, c_void_p, c_void_p, c_void_p, c_uint64, c_void_p]),
+    "saf_query_text_presence": (ctypes.c_int, [c_void_p, c_int64, c_int32, c_int64, c_void_p, c_int32, c_int32, c_int32,
+                                               c_int32, c_void_p, c_void_p, c_uint64, c_void_p]),
     "saf_label_components_workspace_bytes": (ctypes.c_int, [c_int64, P(c_uint64)]),
     "saf_label_components": (ctypes.c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
                                             c_uint64, P(ctypes.c_uint32), c_void_p]),

@@ -25,6 +25,7 @@ import torch
 
 from . import _lib
 
+_FRAME_DTYPE = _lib.frame_numpy_dtype()
 _SEG_DTYPES = {torch.uint8: _lib.SAF_SEG_U8, torch.int16: _lib.SAF_SEG_I16, torch.int32: _lib.SAF_SEG_I32,
                torch.int64: _lib.SAF_SEG_I64, torch.float32: _lib.SAF_SEG_F32}
 
@@ -168,41 +169,50 @@ class _FusionVolume(torch.nn.Module):
             table = table.contiguous()
             sb, sc, sy, sx = table.stride()
         sr = sx if npx > 1 else (sy if npy > 1 else max(1, self.n_clip_feats if sc == 1 else 1))
-        poses_dev = K_dev = None
+        # the B descriptors are filled column-wise (a Python loop over frames costs more than a window's kernels)
+        arr = np.zeros(B, dtype=_FRAME_DTYPE)
+        steps = np.arange(B, dtype=np.uint64)
+        arr["depth"] = depth.data_ptr() + steps * np.uint64(depth.stride(0) * depth.element_size())
+        arr["rgb"] = rgb.data_ptr() + steps * np.uint64(rgb.stride(0) * rgb.element_size())
+        arr["table"] = table.data_ptr() + steps * np.uint64(sb * table.element_size())
+        arr["depth_dtype"], arr["rgb_dtype"] = depth_dtype, rgb_dtype
+        arr["table_stride_c"], arr["table_stride_r"] = sc, sr
+        arr["npy"], arr["npx"] = npy, npx
+        keep = [depth, rgb, table, arr]
+        if seg_maps is not None:
+            if isinstance(seg_maps, torch.Tensor):       # stacked [B,H,W]
+                segs = seg_maps if seg_maps.dtype in _SEG_DTYPES else seg_maps.to(torch.int64)
+                segs = segs.contiguous()
+                if segs.device != dev:
+                    raise RuntimeError("segmentation maps are on %s but the volume is on %s" % (segs.device, dev))
+                if tuple(segs.shape) != (B, H, W):
+                    raise RuntimeError("segmentation maps shape %s != %s" % (tuple(segs.shape), (B, H, W)))
+                keep.append(segs)
+                arr["seg"] = segs.data_ptr() + steps * np.uint64(segs.stride(0) * segs.element_size())
+                arr["seg_dtype"] = _SEG_DTYPES[segs.dtype]
+            else:
+                for b in range(B):
+                    seg = seg_maps[b]
+                    if seg.device != dev:
+                        raise RuntimeError("segmentation map is on %s but the volume is on %s" % (seg.device, dev))
+                    if seg.dtype not in _SEG_DTYPES:
+                        seg = seg.to(torch.int64)
+                    seg = seg.contiguous()
+                    if tuple(seg.shape) != (H, W):
+                        raise RuntimeError("segmentation map shape %s != image %s" % (tuple(seg.shape), (H, W)))
+                    keep.append(seg)
+                    arr["seg"][b] = seg.data_ptr()
+                    arr["seg_dtype"][b] = _SEG_DTYPES[seg.dtype]
         if poses.is_cuda:
             poses_dev = poses.to(torch.float32).contiguous()
             K_dev = K.to(device=dev, dtype=torch.float32).contiguous()
+            keep += [poses_dev, K_dev]
+            arr["pose_device"] = poses_dev.data_ptr() + steps * np.uint64(64)
+            arr["K_device"] = K_dev.data_ptr() + steps * np.uint64(36)
         else:
-            poses_host = poses.to(torch.float32).contiguous().view(B, 16)
-            K_host = K.detach().cpu().to(torch.float32).contiguous().view(B, 9)
-        frames = (_lib.Frame * B)()
-        keep = [depth, rgb, table, poses_dev, K_dev]
-        for b in range(B):
-            f = frames[b]
-            f.depth = depth[b].data_ptr()
-            f.rgb = rgb[b].data_ptr()
-            f.depth_dtype, f.rgb_dtype = depth_dtype, rgb_dtype
-            f.table = table[b].data_ptr()
-            f.table_stride_c, f.table_stride_r = sc, sr
-            f.npy, f.npx = npy, npx
-            if seg_maps is not None:
-                seg = seg_maps[b]
-                if seg.device != dev:
-                    raise RuntimeError("segmentation map is on %s but the volume is on %s" % (seg.device, dev))
-                if seg.dtype not in _SEG_DTYPES:
-                    seg = seg.to(torch.int64)
-                seg = seg.contiguous()
-                if tuple(seg.shape) != (H, W):
-                    raise RuntimeError("segmentation map shape %s != image %s" % (tuple(seg.shape), (H, W)))
-                keep.append(seg)
-                f.seg = seg.data_ptr()
-                f.seg_dtype = _SEG_DTYPES[seg.dtype]
-            if poses_dev is not None:
-                f.pose_device = poses_dev[b].data_ptr()
-                f.K_device = K_dev[b].data_ptr()
-            else:
-                f.pose[:] = poses_host[b].tolist()
-                f.K[:] = K_host[b].tolist()
+            arr["pose"] = poses.detach().to(torch.float32).contiguous().view(B, 16).numpy()
+            arr["K"] = K.detach().cpu().to(torch.float32).contiguous().view(B, 9).numpy()
+        frames = arr.ctypes.data_as(ctypes.POINTER(_lib.Frame))
         return frames, keep, (B, H, W, npy * npx * self.n_clip_feats)
 
     def _integrate_frames(self, depth_imgs, rgb_imgs, poses, K, clip_feat_img, seg_maps, sequence=False):

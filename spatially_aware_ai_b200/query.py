@@ -104,12 +104,70 @@ def relevance_half(rel):
     return ((rel - 0.5) * 2).clamp(0, 1)
 
 
-def relevance_outliers(sim):
-    """query_mesh.py:59-73: per-text min-max, keep entries above median + 2 sigma.  sim [M,T] -> bool [M,T]."""
-    mn, mx = sim.min(dim=0, keepdim=True).values, sim.max(dim=0, keepdim=True).values
-    rel = (sim - mn) / (mx - mn)
-    thr = rel.median(dim=0, keepdim=True).values + 2 * rel.std(dim=0, keepdim=True)
-    return rel > thr
+def minmax_per_text(sim):
+    """query_mesh.py:59-61: per-text min-max normalisation of a similarity block [..., M, T] over the rows."""
+    mn, mx = sim.min(dim=-2, keepdim=True).values, sim.max(dim=-2, keepdim=True).values
+    return (sim - mn) / (mx - mn)
+
+
+def relevance_outliers(rel):
+    """query_mesh.py:63-73 for one relevance column [M] (already min-max normalised): entries above
+    median + 2 sigma keep their value, the rest become 0."""
+    thr = torch.median(rel) + 2 * torch.std(rel)
+    return torch.where(rel > thr, rel, torch.zeros_like(rel))
+
+
+def _rows_workspace(T, device):
+    nbytes = ctypes.c_uint64()
+    _lib.check(_lib.load().saf_query_rows_workspace_bytes(T, ctypes.byref(nbytes)), "saf_query_rows_workspace_bytes")
+    ws = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=device)
+    return ws, (ws.data_ptr() + 255) // 256 * 256, nbytes.value
+
+
+def segment_labels(feats, text, k=None, norm="clamp_min", precision="fp32", return_probs=False):
+    """The scorer of segment() (eval_scannet_segmentation.py:546-561): for every feature row the texts ordered
+    by descending softmax(100 * cos), as int64 [M, k].  The reference returns the full argsort (k = T, the
+    default) and its evaluation reads columns 0 (top-1) and 0..4 (top-5); pass k to get only those without ever
+    materialising [M, T] (M = 24 M voxels x T = 256 texts would be 24.6 GB).  norm="clamp_min" is segment()'s
+    feat_norm.clamp_min_(0.1).  Ties go to the lower text index."""
+    feats, text = _prep(feats, text)
+    M, C = feats.shape
+    T = text.shape[0]
+    k = T if k is None else int(k)
+    labels = torch.empty((M, k), dtype=torch.int64, device=feats.device)
+    probs = torch.empty((M, k), dtype=torch.float32, device=feats.device) if return_probs else None
+    ws, base, nbytes = _rows_workspace(T, feats.device)
+    stream = torch.cuda.current_stream(feats.device).cuda_stream
+    with torch.cuda.device(feats.device):
+        rc = _lib.load().saf_query_row_labels(feats.data_ptr(), M, C, feats.stride(0), text.data_ptr(), T,
+                                              NORM_MODES[norm], PRECISIONS[precision], k, labels.data_ptr(),
+                                              probs.data_ptr() if return_probs else None, base, nbytes, stream)
+    _lib.check(rc, "saf_query_row_labels")
+    return (labels, probs) if return_probs else labels
+
+
+def presence_scores(feats, background_text, target_text, norm="clamp_min", precision="fp32"):
+    """hypersim_eval.py:80-89: for every target text i, max over the rows of softmax(100 * cos([background..,
+    target_i]))[-1] - the number the reference compares with its 101 thresholds (`relevance.max() > thresholds`).
+    background_text [nb,C] (the four "a picture of an object / things / stuff / texture" embeddings), target_text
+    [L,C] -> float32 [L].  One pass over the features for all L targets instead of L passes."""
+    feats, text = _prep(feats, torch.cat([background_text, target_text.to(background_text.device)], dim=0))
+    M, C = feats.shape
+    nb, L = background_text.shape[0], target_text.shape[0]
+    out = torch.empty(L, dtype=torch.float32, device=feats.device)
+    ws, base, nbytes = _rows_workspace(nb + L, feats.device)
+    stream = torch.cuda.current_stream(feats.device).cuda_stream
+    with torch.cuda.device(feats.device):
+        rc = _lib.load().saf_query_text_presence(feats.data_ptr(), M, C, feats.stride(0), text.data_ptr(), nb, L,
+                                                 NORM_MODES[norm], PRECISIONS[precision], out.data_ptr(), base, nbytes,
+                                                 stream)
+    _lib.check(rc, "saf_query_text_presence")
+    return out
+
+
+# CLIP's image normalisation constants (clipfusion.py:773-780)
+CLIP_CHANNEL_MEAN = (0.48145466, 0.4578275, 0.40821073)
+CLIP_CHANNEL_STD = (0.26862954, 0.26130258, 0.27577711)
 
 
 class Clip(torch.nn.Module):
@@ -132,13 +190,58 @@ class Clip(torch.nn.Module):
             self.clip = backend
             self.tokenizer = backend.tokenizer
             self.feature_dim = backend.feature_dim
+        self.channel_mean = torch.nn.Parameter(torch.tensor(CLIP_CHANNEL_MEAN)[None, :, None, None], requires_grad=False)
+        self.channel_std = torch.nn.Parameter(torch.tensor(CLIP_CHANNEL_STD)[None, :, None, None], requires_grad=False)
+
+    def _model_device(self):
+        params = list(self.clip.parameters()) if hasattr(self.clip, "parameters") else []
+        return params[0].device if params else getattr(self.clip, "device", torch.device("cpu"))
+
+    def normalize_img(self, rgb_img_0_1):
+        """clipfusion.py:783-784."""
+        return (rgb_img_0_1 - self.channel_mean.to(rgb_img_0_1.device)) / self.channel_std.to(rgb_img_0_1.device)
+
+    def unnormalize_img(self, rgb_img_normed):
+        """clipfusion.py:786-787."""
+        return rgb_img_normed * self.channel_std.to(rgb_img_normed.device) + self.channel_mean.to(rgb_img_normed.device)
+
+    def get_patches(self, rgb_imgs, patch_size, patch_stride):
+        """clipfusion.py:789-806: [B,3,H,W] -> [B, npy, npx, 3, patch, patch] overlapping tiles."""
+        batch_size, _, imheight, imwidth = rgb_imgs.shape
+        assert (imheight - patch_size) % patch_stride == 0
+        assert (imwidth - patch_size) % patch_stride == 0
+        npatches_x = 1 + (imwidth - patch_size) // patch_stride
+        npatches_y = 1 + (imheight - patch_size) // patch_stride
+        # two unfolds are strided views of the image (no copy until the reshape below)
+        tiles = rgb_imgs.unfold(2, patch_size, patch_stride).unfold(3, patch_size, patch_stride)
+        assert tiles.shape[2] == npatches_y and tiles.shape[3] == npatches_x
+        return tiles.permute(0, 2, 3, 1, 4, 5)
 
     def img_inference_tiled(self, rgb_imgs, patch_size, patch_stride):
-        return self.clip.img_inference_tiled(rgb_imgs, patch_size, patch_stride)
+        """clipfusion.py:808-839: normalise, cut into tiles, resize every tile to 224 x 224 (bilinear,
+        align_corners=False), encode in batches of 8, return the feature image [B, C, npy, npx] as the permuted
+        view of [B, npy, npx, C] (the memory layout the fusion kernels read without repacking).  A backend that
+        brings its own img_inference_tiled is used instead."""
+        if hasattr(self.clip, "img_inference_tiled"):
+            return self.clip.img_inference_tiled(rgb_imgs, patch_size, patch_stride)
+        rgb_imgs = self.normalize_img(rgb_imgs)
+        patches = self.get_patches(rgb_imgs, patch_size, patch_stride)
+        batch_size, npatches_y, npatches_x = patches.shape[:3]
+        patches = patches.reshape(batch_size * npatches_y * npatches_x, 3, patch_size, patch_size)
+        patches = torch.nn.functional.interpolate(patches, size=(224, 224), mode="bilinear", align_corners=False)
+        clip_feats = torch.empty(len(patches), self.feature_dim, device=rgb_imgs.device)
+        max_patch_batch_size = 8
+        for start in range(0, len(patches), max_patch_batch_size):
+            stop = min(len(patches), start + max_patch_batch_size)
+            clip_feats[start:stop] = self.clip.encode_image(patches[start:stop])
+        return clip_feats.view(batch_size, npatches_y, npatches_x, self.feature_dim).permute(0, 3, 1, 2)
 
     def text_inference(self, str_list):
-        """clipfusion.py:892-897: unit-norm text embeddings [L, C]."""
-        feats = self.clip.encode_text(self.tokenizer(str_list))
+        """clipfusion.py:891-897: unit-norm text embeddings [L, C] (tokens moved to the model's device)."""
+        tokens = self.tokenizer(str_list)
+        if hasattr(tokens, "to"):
+            tokens = tokens.to(self._model_device())
+        feats = self.clip.encode_text(tokens)
         return feats / feats.norm(dim=-1, keepdim=True)
 
     def run_query(self, img_feats, labels, precision="fp32"):
@@ -171,14 +274,16 @@ class Clip(torch.nn.Module):
         if prompt_templates is None:
             prompt_templates = DEFAULT_PROMPT_TEMPLATES
         feats = []
+        model_device = self._model_device()
         for t in texts:
-            emb = self.clip.encode_text(self.tokenizer([tpl.format(t) for tpl in prompt_templates]))
+            tokens = self.tokenizer([tpl.format(t) for tpl in prompt_templates])
+            if hasattr(tokens, "to"):
+                tokens = tokens.to(model_device)
+            emb = self.clip.encode_text(tokens)
             emb = emb / emb.norm(dim=-1, keepdim=True)
             emb = emb.mean(dim=0)
             feats.append(emb / emb.norm())
         return torch.stack(feats, dim=1).to(device).t()
 
 
-# the reference's default ensemble is the 85-template ImageNet list (clipfusion.py:939-1025); its
-# own query driver passes ["a photo of {}"] (clip_seem_fusion.py:496-505), which is the default here.
-DEFAULT_PROMPT_TEMPLATES = ["a photo of {}"]
+from .prompt_templates import DEFAULT_PROMPT_TEMPLATES  # noqa: E402  (the reference's 85-template default)

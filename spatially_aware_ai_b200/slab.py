@@ -33,6 +33,27 @@ def slab_index_base(nvox, world_size, rank):
     return x_begin * int(nvox[1]) * int(nvox[2])
 
 
+def cyclic_slab(nx, world_size, rank, span=8):
+    """Block-cyclic split: rank r holds the stripes [r*span + k*world*span, ... + span) of the nx
+    x-planes.  Returns the constructor keywords of the fusion classes.  A camera sees a compact part of the grid
+    per frame; dealing the planes out in stripes gives every rank the same share of every view."""
+    if not (0 <= rank < world_size):
+        raise ValueError("rank %d outside world of %d" % (rank, world_size))
+    if rank * span >= nx:
+        raise ValueError("grid of %d planes has no stripe for rank %d (span %d)" % (nx, rank, span))
+    return dict(x_begin=rank * span, x_end=int(nx), x_span=span, x_stride=span * world_size)
+
+
+def local_to_global_rows(volume, rows):
+    """Slab-local flat voxel indices (rows of the volume's buffers; -1 = padding) -> global flat indices
+    (x*ny + y)*nz + z of the whole grid, for contiguous and block-cyclic slabs alike."""
+    plane = volume._dims[1] * volume._dims[2]
+    xs = torch.as_tensor(volume.global_x_planes(), dtype=torch.int64, device=rows.device)
+    lx = torch.div(rows.clamp(min=0), plane, rounding_mode="floor")
+    out = xs[lx] * plane + rows.clamp(min=0) % plane
+    return torch.where(rows < 0, rows, out)
+
+
 def merge_topk(scores, indices, k):
     """Merge candidate lists [..., T, n] -> top-k per text, descending score, ties to the lower index;
     entries with index < 0 are padding."""

@@ -337,6 +337,176 @@ def run_bounds_golden():
     print("bounds:", tuple(xyz.shape), "origin", minbound.tolist(), "nvox", nvox.tolist())
 
 
+def run_query_drivers_golden():
+    """The drivers around the scorers, executed from the unmodified reference where it offers a callable:
+      * InSituManager.clip_text_query (clip_seem_fusion.py:482-561), called unbound on a stand-in `self`: row
+        normalisation + nan_to_num, clip_feature_surgery, mean-subtract / clip / min-max relevance;
+      * segment() (eval_scannet_segmentation.py:546-561): clamp_min(0.1) normalisation, argsort of softmax(100 cos).
+    query_mesh.py and hypersim_eval.py are scripts without functions: their expressions (query_mesh.py:24-25, 39,
+    59-73; hypersim_eval.py:50-51, 80-89) are evaluated here with torch exactly as written there."""
+    import importlib
+    import tempfile
+    import types
+    rng = np.random.default_rng(2024)
+    M, C, T = 400, 24, 9
+    feats = (rng.standard_normal((M, C)) * rng.uniform(0.01, 3.0, size=(M, 1))).astype(np.float32)
+    feats[0] = rng.standard_normal(C).astype(np.float32)
+    feats[7] = 0.0           # unobserved vertex -> NaN after the division -> 0
+    feats[11] *= 0.001       # norm below clamp_min's 0.1
+    X = rng.standard_normal((T, C)).astype(np.float32)
+    X /= np.linalg.norm(X, axis=-1, keepdims=True)
+    Xt = torch.from_numpy(X)
+    out = dict(feats=feats, text=X)
+
+    # -- clip_text_query, unbound
+    class _ClipModel:
+        clip_feature_surgery = staticmethod(clipfusion.Clip.clip_feature_surgery)
+
+        def encode_text_with_prompt_ensemble(self, texts, device, prompt_templates=None):
+            assert prompt_templates == ["a photo of {}"]
+            return Xt[: len(texts)]
+
+    clip_seem_fusion.plt = types.SimpleNamespace(cm=types.SimpleNamespace(
+        turbo=lambda r: np.stack([r, r, r, np.ones_like(r)], axis=1)))
+    names = ["obj%d" % i for i in range(T - 1)]
+    me = types.SimpleNamespace(control_objects=list(names), control_text_features=None, clip_model=_ClipModel(),
+                               vert_clip_feat=feats.copy(), verts=[], faces=[], scene_knowledge=None)
+    mesh_json = clip_seem_fusion.InSituManager.clip_text_query(me, "the query")
+    colors = np.asarray(mesh_json["colors"], dtype=np.float64)
+    out["text_query_relevance"] = colors[:, 0].astype(np.float32)       # turbo stand-in passes the relevance through
+    out["text_query_alpha"] = colors[:, 3].astype(np.float32)           # relevance * 0.5
+    out["text_query_column"] = np.int64(T - 1)
+
+    # -- segment()
+    ess = importlib.import_module("eval_scannet_segmentation")
+
+    class _ClipSeg:
+        def text_inference(self, prompts):
+            return Xt
+
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "vertex_clip_feats.npy")
+        seg_feats = feats.copy()
+        seg_feats[7] = rng.standard_normal(C).astype(np.float32) * 1e-3   # segment() raises on NaN rows
+        np.save(path, seg_feats)
+        out["segment_feats"] = seg_feats
+        out["segment_labels"] = ess.segment(_ClipSeg(), path, ["p"] * T).numpy().astype(np.int64)
+
+    # -- query_mesh.py:24-25, 39 (run_query relevance of the last of five labels) and :59-73 (surgery + outliers)
+    F = torch.from_numpy(seg_feats.copy())
+    F /= F.norm(dim=-1, keepdim=True)
+
+    class _Self:
+        def text_inference(self, labels):
+            return Xt[:5]
+
+    relevance = clipfusion.Clip.run_query(_Self(), F, ["x"] * 5)[:, -1]
+    out["query_mesh_half"] = ((relevance - 0.5) * 2).clamp(0, 1).numpy()
+    similarity = clipfusion.Clip.clip_feature_surgery(F[None], Xt)
+    similarity = (similarity - similarity.min(1, keepdim=True)[0]) / (
+        similarity.max(1, keepdim=True)[0] - similarity.min(1, keepdim=True)[0])
+    out["query_mesh_minmax"] = similarity[0].numpy()
+    clipped = []
+    for n in range(T):
+        rel = similarity[0, :, n]
+        median, std = torch.median(rel), torch.std(rel)
+        clipped.append(torch.where(rel > median + 2 * std, rel, torch.zeros_like(rel)))
+    out["query_mesh_outliers"] = torch.stack(clipped, dim=1).numpy()
+
+    # -- hypersim_eval.py:50-51, 80-89: 4 background texts + one target at a time, presence = max relevance
+    G = torch.from_numpy(feats.copy())
+    G /= torch.clamp_min(G.norm(dim=-1, keepdim=True), 0.1)
+    bg, targets = Xt[:4], Xt[4:]
+    thresholds = torch.linspace(0, 1, 101)
+    pres, preds = [], []
+    for i in range(len(targets)):
+        tf = torch.cat((bg, targets[i, None]), dim=0)
+        rel = (100 * (G @ tf.T)).softmax(dim=-1)[..., -1]
+        pres.append(rel.max())
+        preds.append(rel.max() > thresholds)
+    out["hypersim_presence"] = torch.stack(pres).numpy()
+    out["hypersim_preds"] = torch.stack(preds).numpy()
+    path = os.path.join(HERE, "query_drivers.npz")
+    np.savez_compressed(path, **out)
+    print("query_drivers ->", os.path.getsize(path) // 1024, "KiB")
+
+
+def run_tiled_golden():
+    """Clip.get_patches / Clip.img_inference_tiled (clipfusion.py:789-839) of the unmodified reference with a
+    deterministic stand-in for open_clip's encode_image (a fixed projection of the 224x224 tile pooled to 4x4)."""
+    rng = np.random.default_rng(606)
+    C = 16
+    proj = torch.from_numpy(rng.standard_normal((3 * 16, C)).astype(np.float32))
+
+    class _Encoder:
+        @staticmethod
+        def encode_image(x):
+            pooled = torch.nn.functional.adaptive_avg_pool2d(x, 4).reshape(len(x), -1)
+            return pooled @ proj
+
+    clip = clipfusion.Clip.__new__(clipfusion.Clip)
+    torch.nn.Module.__init__(clip)
+    clip.clip = _Encoder()
+    clip.feature_dim = C
+    clip.channel_mean = torch.nn.Parameter(torch.tensor([0.48145466, 0.4578275, 0.40821073])[None, :, None, None],
+                                           requires_grad=False)
+    clip.channel_std = torch.nn.Parameter(torch.tensor([0.26862954, 0.26130258, 0.27577711])[None, :, None, None],
+                                          requires_grad=False)
+    rgb = torch.from_numpy(rng.random((2, 3, 96, 128)).astype(np.float32))
+    patches = clip.get_patches(rgb, 64, 32)
+    feat_img = clip.img_inference_tiled(rgb, 64, 32)
+    path = os.path.join(HERE, "tiled.npz")
+    np.savez_compressed(path, rgb=rgb.numpy(), proj=proj.numpy(), patch_size=np.int64(64), patch_stride=np.int64(32),
+                        patches_shape=np.array(patches.shape), patches_sha256=np.array(
+                            hashlib.sha256(np.ascontiguousarray(patches.numpy()).tobytes()).hexdigest()),
+                        patch_1_2=patches[1, 0, 2].numpy(), feat_img=feat_img.numpy(),
+                        feat_img_strides=np.array(feat_img.stride()))
+    print("tiled:", tuple(patches.shape), tuple(feat_img.shape), "->", os.path.getsize(path) // 1024, "KiB")
+
+
+def run_sensor_golden():
+    """ScanNetDataset.__getitem__ (clipfusion.py:243-256) of the unmodified reference on a two-frame scan directory
+    written here: 640x480 JPEG colour (decoded to uint8 by cv2) and 16-bit PNG depth in millimetres.  The depth
+    image holds every uint16 value and the colour image every uint8 value, so the golden is the complete table of
+    the dataset's conversions rgb = float(u8) / 255 and depth = float(u16) / 1000."""
+    import tempfile
+
+    import cv2
+    rng = np.random.default_rng(31337)
+    with tempfile.TemporaryDirectory() as d:
+        for sub in ("color", "depth", "pose", "intrinsic"):
+            os.makedirs(os.path.join(d, sub))
+        np.savetxt(os.path.join(d, "intrinsic", "intrinsic_depth.txt"), np.eye(4))
+        depth_in, rgb_in = [], []
+        for i in range(2):
+            dimg = rng.permutation(np.arange(640 * 480, dtype=np.int64) % 65536).astype(np.uint16).reshape(480, 640)
+            cimg = rng.integers(0, 256, size=(480, 640, 3), dtype=np.uint8)
+            cimg[0, :256, 0] = np.arange(256)
+            cv2.imwrite(os.path.join(d, "depth", "%d.png" % i), dimg)
+            cv2.imwrite(os.path.join(d, "color", "%d.jpg" % i), cimg)
+            pose = np.eye(4)
+            pose[0, 3] = i          # 1 m apart: both frames are key frames (clipfusion.py:226-233)
+            np.savetxt(os.path.join(d, "pose", "%d.txt" % i), pose)
+            depth_in.append(cv2.imread(os.path.join(d, "depth", "%d.png" % i), cv2.IMREAD_ANYDEPTH))
+            rgb_in.append(cv2.cvtColor(cv2.imread(os.path.join(d, "color", "%d.jpg" % i)), cv2.COLOR_BGR2RGB))
+        ds = clipfusion.ScanNetDataset(d)
+        assert len(ds) == 2
+        depth_lut = np.full(65536, np.nan, np.float32)
+        rgb_lut = np.full(256, np.nan, np.float32)
+        for i in range(2):
+            rgb_f, depth_f, _, _, _ = ds[i]
+            assert depth_in[i].dtype == np.uint16 and rgb_in[i].dtype == np.uint8
+            depth_lut[depth_in[i].reshape(-1)] = depth_f.numpy().reshape(-1)
+            rgb_lut[rgb_in[i].reshape(-1)] = rgb_f.numpy().reshape(-1)
+            # consistency: one output value per input value
+            assert np.array_equal(depth_lut[depth_in[i]], depth_f.numpy())
+            assert np.array_equal(rgb_lut[rgb_in[i]], rgb_f.numpy())
+    assert not np.isnan(depth_lut).any() and not np.isnan(rgb_lut).any()
+    path = os.path.join(HERE, "sensor.npz")
+    np.savez_compressed(path, depth_lut=depth_lut, rgb_lut=rgb_lut)
+    print("sensor ->", os.path.getsize(path) // 1024, "KiB")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     only = sys.argv[1:]
@@ -351,3 +521,9 @@ if __name__ == "__main__":
         run_objects_golden()
     if not only or "bounds" in only:
         run_bounds_golden()
+    if not only or "query_drivers" in only:
+        run_query_drivers_golden()
+    if not only or "tiled" in only:
+        run_tiled_golden()
+    if not only or "sensor" in only:
+        run_sensor_golden()
