@@ -209,13 +209,20 @@ int saf_integrate(const saf_grid_desc *grid, const saf_volume *vol, const saf_fr
                   int32_t batch, int32_t height, int32_t width, float trunc, int32_t rgb_mode,
                   const saf_workspace *ws, void *stream);
 
+/* Host-side, pose-only test: 1 if the camera frustum of a frame (pose: camera->world row-major 4x4, K: row-major
+ * 3x3, both HOST pointers) may contain a voxel centre of the slab `grid` describes, 0 if it cannot (conservative),
+ * < 0 on bad arguments.  No device work: a multi-GPU feeder calls it to decide whether a frame needs to be copied
+ * to this rank at all.  Block-cyclic slabs always answer 1. */
+int saf_frame_reaches_slab(const saf_grid_desc *grid, const float *pose, const float *K, int32_t height, int32_t width);
+
 /* n_frames successive single-frame integrate() calls (the reference's frame loop,
  * clip_seem_fusion.py:305-313) issued from one host call.  With a workspace sized for max_batch >= 2 the
  * frames are fused in windows of max_batch frames (see the window-mode calls above) and
  * K1 + K2 of the next window overlap the feature kernel of the current one; a max_batch = 1 workspace runs
- * frame by frame.  Either way the result equals the frame loop's.  For a sub-slab volume (x_begin > 0 or
- * x_end < nvox[0]) and n_frames >= 16 the call first drops the frames that cannot touch the slab (a small
- * pre-pass kernel; this variant synchronises `stream` once before it launches the windows). */
+ * frame by frame.  Either way the result equals the frame loop's.  For a contiguous sub-slab volume (x_begin > 0 or
+ * x_end < nvox[0], x_span = 0) the call first drops the frames that cannot touch the slab: by the host test above
+ * for frames whose pose is passed by value, and for >= 16 survivors additionally by a depth-aware pre-pass kernel
+ * (this variant synchronises `stream` once before it launches the windows; SAF_REACH_PREPASS=0 disables it). */
 int saf_integrate_sequence(const saf_grid_desc *grid, const saf_volume *vol, const saf_frame *frames,
                            int32_t n_frames, int32_t height, int32_t width, float trunc,
                            int32_t rgb_mode, const saf_workspace *ws, void *stream);

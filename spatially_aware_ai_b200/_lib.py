@@ -102,6 +102,7 @@ SIGNATURES = {
                                                      c_int32, P(Workspace), c_void_p]),
     "saf_integrate": (ctypes.c_int, [P(GridDesc), P(Volume), P(Frame), c_int32, c_int32, c_int32, c_float, c_int32,
                                      P(Workspace), c_void_p]),
+    "saf_frame_reaches_slab": (ctypes.c_int, [P(GridDesc), P(c_float), P(c_float), c_int32, c_int32]),
     "saf_integrate_sequence": (ctypes.c_int, [P(GridDesc), P(Volume), P(Frame), c_int32, c_int32, c_int32, c_float,
                                               c_int32, P(Workspace), c_void_p]),
     "saf_label_argmax": (ctypes.c_int, [c_void_p, c_int64, c_int32, c_void_p, c_void_p]),

@@ -29,7 +29,8 @@ def backproject_samples(depth_imgs, poses, K, max_depth=float("inf"), uv_size=7)
     us, vs = u.to(device=dev, dtype=torch.int32), v.to(device=dev, dtype=torch.int32)
     xyz = torch.empty((F, uv_size * uv_size, 3), dtype=torch.float32, device=dev)
     valid = torch.empty((F, uv_size * uv_size), dtype=torch.uint8, device=dev)
-    _lib.check(_lib.load().saf_backproject_samples(depth.data_ptr(), P.data_ptr(), Kinv.data_ptr(), us.data_ptr(),
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().saf_backproject_samples(depth.data_ptr(), P.data_ptr(), Kinv.data_ptr(), us.data_ptr(),
                                                    vs.data_ptr(), F, H, W, uv_size, uv_size, float(max_depth),
                                                    xyz.data_ptr(), valid.data_ptr(),
                                                    torch.cuda.current_stream(dev).cuda_stream), "saf_backproject_samples")

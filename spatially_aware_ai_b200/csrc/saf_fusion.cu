@@ -2541,9 +2541,79 @@ int saf_integrate(const saf_grid_desc* grid, const saf_volume* vol, const saf_fr
     return integrate_call(grid, vol, frames, batch, H, W, trunc, rgb_mode, ws, 0, sms, smem_optin, st, st, nullptr, nullptr);
 }
 
+// Host-side reach test for contiguous sub-slabs: can the camera frustum of a frame (pose and intrinsics only, no
+// depth) contain any voxel centre of the slab?  The five half-spaces of block_maybe_visible, taken to world space,
+// against the slab's axis-aligned box of voxel centres (padded by a voxel).  Conservative (NaN -> keep); costs
+// nothing on the device and needs no synchronisation, so it runs before any frame is handed to the kernels -
+// a caller can use saf_frame_reaches_slab to decide BEFORE copying a frame to the device at all.
+static bool frame_may_reach_slab_host(const saf_grid_desc& g, const float* pose, const float* K, int H, int W)
+{
+    const double vs = g.voxel_size;
+    const double lo[3] = {g.origin[0] + vs * (g.x_begin - 1), g.origin[1] - vs, g.origin[2] - vs};
+    const double hi[3] = {g.origin[0] + vs * g.x_end, g.origin[1] + vs * g.nvox[1], g.origin[2] + vs * g.nvox[2]};
+    const double t[3] = {pose[3], pose[7], pose[11]};
+    double n[5][3];
+    for (int k = 0; k < 3; ++k) {
+        n[0][k] = K[6 + k];
+        n[1][k] = K[k] + 0.5 * K[6 + k];
+        n[2][k] = (W - 0.5) * K[6 + k] - K[k];
+        n[3][k] = K[3 + k] + 0.5 * K[6 + k];
+        n[4][k] = (H - 0.5) * K[6 + k] - K[3 + k];
+    }
+    for (int i = 0; i < 5; ++i) {
+        double best = 0.0, scale = 0.0, nlen = 0.0;
+        for (int a = 0; a < 3; ++a) {
+            // world-space normal m = R n_i, R = pose[0:3, 0:3] (camera -> world)
+            const double m = pose[4 * a] * n[i][0] + pose[4 * a + 1] * n[i][1] + pose[4 * a + 2] * n[i][2];
+            const double v0 = m * (lo[a] - t[a]), v1 = m * (hi[a] - t[a]);
+            best += v0 > v1 ? v0 : v1;
+            scale += fabs(m) * (fabs(lo[a] - t[a]) + fabs(hi[a] - t[a]));
+            nlen += m * m;
+        }
+        if (best + 1e-3 * scale + 1e-6 * sqrt(nlen) < 0.0) return false;   // NaN compares false -> kept
+    }
+    return true;
+}
+
+// Side stream and events of saf_integrate_sequence's two-slot overlap: created once per (host thread, device) and
+// kept (creating and destroying a stream and five events per call cost more than a window's kernels).
+struct SeqStreams {
+    cudaStream_t side = nullptr;
+    cudaEvent_t fork = nullptr, geo_done[2] = {nullptr, nullptr}, feat_done[2] = {nullptr, nullptr}, join = nullptr;
+    bool ok = false;
+};
+static int seq_streams(SeqStreams** out)
+{
+    static thread_local SeqStreams cache[64];
+    int dev = 0;
+    SAF_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return SAF_ERR_DEVICE;
+    SeqStreams& s = cache[dev];
+    if (!s.ok) {
+        SAF_CUDA_TRY(cudaStreamCreateWithFlags(&s.side, cudaStreamNonBlocking));
+        SAF_CUDA_TRY(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
+        SAF_CUDA_TRY(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
+        for (int i = 0; i < 2; ++i) {
+            SAF_CUDA_TRY(cudaEventCreateWithFlags(&s.geo_done[i], cudaEventDisableTiming));
+            SAF_CUDA_TRY(cudaEventCreateWithFlags(&s.feat_done[i], cudaEventDisableTiming));
+        }
+        s.ok = true;
+    }
+    *out = &s;
+    return 0;
+}
+
+int saf_frame_reaches_slab(const saf_grid_desc* grid, const float* pose, const float* K, int32_t H, int32_t W)
+{
+    if (!grid || !pose || !K) return SAF_ERR_NULL;
+    if (!slab_desc_ok(*grid) || H <= 0 || W <= 0) return SAF_ERR_GRID;
+    if (grid->x_span != 0) return 1;   // block-cyclic stripes span the grid: a frame that sees the grid sees the slab
+    return frame_may_reach_slab_host(*grid, pose, K, H, W) ? 1 : 0;
+}
+
 // The reference's frame loop.  Frames are independent except through the volume, and K1/K2 touch only the
-// TSDF state while K3 touches only weight / rgb / features / labels, so K1+K2 of frame i+1 run on a side
-// stream underneath K3 of frame i (the two scratch slots of the workspace alternate).
+// TSDF state while K3 touches only weight / rgb / features / labels, so K1+K2 of window i+1 run on a side
+// stream underneath K3W of window i (the two scratch slots of the workspace alternate).
 int saf_integrate_sequence(const saf_grid_desc* grid, const saf_volume* vol, const saf_frame* frames, int32_t n_frames,
                            int32_t H, int32_t W, float trunc, int32_t rgb_mode, const saf_workspace* ws, void* stream)
 {
@@ -2553,36 +2623,46 @@ int saf_integrate_sequence(const saf_grid_desc* grid, const saf_volume* vol, con
     if (rc) return rc;
     if (!(trunc > 0.f)) return SAF_ERR_SHAPE;
     cudaStream_t st = (cudaStream_t)stream;
-    // Window mode: up to 8 consecutive frames share one K1 / K2 / K3W launch trio (per-voxel updates are applied
-    // frame by frame inside the kernels, so the result is that of the single-frame calls).  The window is the
-    // workspace's max_batch; a max_batch = 1 workspace runs frame by frame.
+    // Window mode: up to SAF_MAX_BATCH consecutive frames share one K0 / K1 / K2 / K3W launch quartet (per-voxel
+    // updates are applied frame by frame inside the kernels, so the result is that of the single-frame calls).  The
+    // window is the workspace's max_batch; a max_batch = 1 workspace runs frame by frame.
     const int32_t window = ws ? std::max<int32_t>(1, std::min<int32_t>(SAF_MAX_BATCH, ws->max_batch)) : 1;
-    // Sub-slab volumes (multi-GPU): drop the frames that cannot touch this slab before forming windows.  Costs
-    // one small kernel, a copy of the frame descriptors into the workspace and one stream synchronisation per
-    // call, so it is only done when the slab is a strict part of the grid and the sequence is long enough to
-    // amortise it.
+    // Contiguous sub-slab volumes (multi-GPU): drop the frames that cannot touch this slab before forming windows.
+    // First on the host from the pose alone (no device work, no synchronisation); then, for long sequences, the
+    // depth-aware pre-pass kernel (walls between the camera and the slab), which costs one small kernel, a copy
+    // of the frame descriptors into the workspace and one stream synchronisation.  SAF_REACH_PREPASS=0 in the
+    // environment keeps only the host test.
     std::vector<saf_frame> kept;
-    if (grid && frames && ws && ws->base && (grid->x_begin > 0 || grid->x_end < grid->nvox[0]) && n_frames >= 16) {
+    if (grid && frames && ws && ws->base && grid->x_span == 0 && (grid->x_begin > 0 || grid->x_end < grid->nvox[0])) {
         FusionParams p;
         rc = build_params(grid, vol, frames, 1, H, W, trunc, rgb_mode, ws, &p, 0);
         if (rc) return rc;
-        // scratch: the (idle) list region of slot 0 holds the frame descriptors and the flags - no allocation
-        const size_t fbytes = sizeof(saf_frame) * (size_t)n_frames, rbytes = sizeof(uint32_t) * (size_t)n_frames;
-        const bool fits = fbytes + rbytes <= (size_t)p.list_cap * sizeof(ValidEntry);   // else: keep every frame
-        unsigned char* dbuf = reinterpret_cast<unsigned char*>(p.lists);
-        std::vector<uint32_t> reach((size_t)n_frames, 1u);
-        if (fits) {
-            SAF_CUDA_TRY(cudaMemcpyAsync(dbuf, frames, fbytes, cudaMemcpyHostToDevice, st));
-            frame_reach_kernel<<<n_frames, 256, 0, st>>>(p, (const saf_frame*)dbuf, n_frames, (uint32_t*)(dbuf + fbytes));
-            SAF_CHECK_LAUNCH("frame_reach_kernel", st);
-            SAF_CUDA_TRY(cudaMemcpyAsync(reach.data(), dbuf + fbytes, rbytes, cudaMemcpyDeviceToHost, st));
-            SAF_CUDA_TRY(cudaStreamSynchronize(st));
-        }
         kept.reserve((size_t)n_frames);
         for (int32_t i = 0; i < n_frames; ++i)
-            if (reach[(size_t)i]) kept.push_back(frames[i]);
+            if (frames[i].pose_device || frame_may_reach_slab_host(*grid, frames[i].pose, frames[i].K, H, W))
+                kept.push_back(frames[i]);
+        static const bool prepass = !(getenv("SAF_REACH_PREPASS") && getenv("SAF_REACH_PREPASS")[0] == '0');
+        const int32_t n_host = (int32_t)kept.size();
+        if (prepass && n_host >= 16) {
+            // scratch: the (idle) list region of slot 0 holds the frame descriptors and the flags - no allocation
+            const size_t fbytes = sizeof(saf_frame) * (size_t)n_host, rbytes = sizeof(uint32_t) * (size_t)n_host;
+            if (fbytes + rbytes <= (size_t)p.list_cap * sizeof(ValidEntry)) {   // else: keep every frame
+                unsigned char* dbuf = reinterpret_cast<unsigned char*>(p.lists);
+                std::vector<uint32_t> reach((size_t)n_host, 1u);
+                SAF_CUDA_TRY(cudaMemcpyAsync(dbuf, kept.data(), fbytes, cudaMemcpyHostToDevice, st));
+                frame_reach_kernel<<<n_host, 256, 0, st>>>(p, (const saf_frame*)dbuf, n_host, (uint32_t*)(dbuf + fbytes));
+                SAF_CHECK_LAUNCH("frame_reach_kernel", st);
+                SAF_CUDA_TRY(cudaMemcpyAsync(reach.data(), dbuf + fbytes, rbytes, cudaMemcpyDeviceToHost, st));
+                SAF_CUDA_TRY(cudaStreamSynchronize(st));
+                size_t o = 0;
+                for (int32_t i = 0; i < n_host; ++i)
+                    if (reach[(size_t)i]) kept[o++] = kept[(size_t)i];
+                kept.resize(o);
+            }
+        }
         const unsigned long long skipped = (unsigned long long)n_frames - kept.size();
-        if (getenv("SAF_DEBUG_REACH")) fprintf(stderr, "[saf] reach pre-pass: %d frames, %zu kept\n", n_frames, kept.size());
+        if (getenv("SAF_DEBUG_REACH"))
+            fprintf(stderr, "[saf] reach: %d frames, %d after the pose test, %zu kept\n", n_frames, n_host, kept.size());
         if (skipped) {
             add_skipped_frames_kernel<<<1, 1, 0, st>>>(p.hdr, skipped);
             SAF_CHECK_LAUNCH("add_skipped_frames_kernel", st);
@@ -2601,49 +2681,25 @@ int saf_integrate_sequence(const saf_grid_desc* grid, const saf_volume* vol, con
         }
         return 0;
     }
-    cudaStream_t side = nullptr;
-    cudaEvent_t fork = nullptr, geo_done[2] = {nullptr, nullptr}, feat_done[2] = {nullptr, nullptr};
-    auto cleanup = [&]() {
-        if (fork) cudaEventDestroy(fork);
-        for (int s = 0; s < 2; ++s) {
-            if (geo_done[s]) cudaEventDestroy(geo_done[s]);
-            if (feat_done[s]) cudaEventDestroy(feat_done[s]);
-        }
-        if (side) cudaStreamDestroy(side);
-    };
-#define SAF_SEQ_TRY(expr)                      \
-    do {                                       \
-        cudaError_t _e = (expr);               \
-        if (_e != cudaSuccess) {               \
-            cleanup();                         \
-            return (int)_e;                    \
-        }                                      \
-    } while (0)
-    SAF_SEQ_TRY(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
-    SAF_SEQ_TRY(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
-    for (int s = 0; s < 2; ++s) {
-        SAF_SEQ_TRY(cudaEventCreateWithFlags(&geo_done[s], cudaEventDisableTiming));
-        SAF_SEQ_TRY(cudaEventCreateWithFlags(&feat_done[s], cudaEventDisableTiming));
-    }
+    SeqStreams* ss = nullptr;
+    if ((rc = seq_streams(&ss))) return rc;
     // the side stream starts after everything already queued on the caller's stream
-    SAF_SEQ_TRY(cudaEventRecord(fork, st));
-    SAF_SEQ_TRY(cudaStreamWaitEvent(side, fork, 0));
-    for (int32_t c = 0; c < n_calls; ++c) {
+    SAF_CUDA_TRY(cudaEventRecord(ss->fork, st));
+    SAF_CUDA_TRY(cudaStreamWaitEvent(ss->side, ss->fork, 0));
+    for (int32_t c = 0; c < n_calls && rc == 0; ++c) {
         const uint32_t slot = (uint32_t)(c & 1);
         const int32_t i0 = c * window, nb = std::min(window, n_frames - i0);
         // slot reuse: the feature kernel of call c-2 must have finished reading this slot's lists
-        if (c >= 2) SAF_SEQ_TRY(cudaStreamWaitEvent(side, feat_done[slot], 0));
-        rc = integrate_call(grid, vol, frames + i0, nb, H, W, trunc, rgb_mode, ws, slot, sms, smem_optin, side, st,
-                            geo_done[slot], feat_done[slot], true);
-        if (rc) {
-            cleanup();
-            return rc;
-        }
+        if (c >= 2) rc = (int)cudaStreamWaitEvent(ss->side, ss->feat_done[slot], 0);
+        if (rc == 0)
+            rc = integrate_call(grid, vol, frames + i0, nb, H, W, trunc, rgb_mode, ws, slot, sms, smem_optin, ss->side, st,
+                                ss->geo_done[slot], ss->feat_done[slot], true);
     }
-#undef SAF_SEQ_TRY
-    // the caller's stream already waits on the last K2 through geo_done; nothing else runs on `side`
-    cleanup();
-    return 0;
+    // Whatever happened, the caller's stream must not run ahead of the kernels already queued on the side stream
+    // (after an error the caller drops the frame tensors and the workspace; the last K2 is otherwise awaited
+    // through geo_done).
+    if (cudaEventRecord(ss->join, ss->side) == cudaSuccess) cudaStreamWaitEvent(st, ss->join, 0);
+    return rc;
 }
 
 int saf_label_argmax(const int32_t* labels, int64_t n, int32_t n_classes, int64_t* out, void* stream)

@@ -140,8 +140,9 @@ class _FusionVolume(torch.nn.Module):
         base = (self._ws_tensor.data_ptr() + 255) // 256 * 256
         ws = _lib.Workspace()
         ws.base, ws.bytes, ws.max_batch, ws.max_table_elems = base, nbytes.value, max_batch, max_table
-        _lib.check(lib.saf_workspace_init(ctypes.byref(ws), ctypes.byref(self._grid_desc()),
-                                          torch.cuda.current_stream(dev).cuda_stream), "saf_workspace_init")
+        with torch.cuda.device(dev):     # the library launches on the CURRENT device (stream 0 is valid on all)
+            _lib.check(lib.saf_workspace_init(ctypes.byref(ws), ctypes.byref(self._grid_desc()),
+                                              torch.cuda.current_stream(dev).cuda_stream), "saf_workspace_init")
         self._ws, self._ws_key = ws, (dev, max_batch, max_table)
         self._stats_carry = old_stats
         return ws
@@ -222,6 +223,11 @@ class _FusionVolume(torch.nn.Module):
         frames, keep, (B, H, W, table_elems) = self._make_frames(depth_imgs, rgb_imgs, poses, K, clip_feat_img, seg_maps)
         vol = self._volume_desc()
         stream = torch.cuda.current_stream(self.tsdf.device).cuda_stream
+        with torch.cuda.device(self.tsdf.device):
+            self._launch_integrate(frames, vol, B, H, W, table_elems, stream, sequence)
+        del keep
+
+    def _launch_integrate(self, frames, vol, B, H, W, table_elems, stream, sequence):
         if sequence:
             # B successive single-frame calls; a max_batch = SAF_MAX_BATCH workspace lets the library fuse them 16 at a time
             ws = self._workspace(_lib.SAF_MAX_BATCH, table_elems)
@@ -235,7 +241,6 @@ class _FusionVolume(torch.nn.Module):
             rc = _lib.load().saf_integrate(ctypes.byref(self._grid_desc()), ctypes.byref(vol), frames, B, H, W,
                                            float(self.trunc), self._rgb_mode, ctypes.byref(ws), stream)
             _lib.check(rc, "saf_integrate")
-        del keep
 
     @staticmethod
     def _producer_inputs(depth_imgs, rgb_imgs):
@@ -273,7 +278,8 @@ class _FusionVolume(torch.nn.Module):
                         last_valid=[], last_tsdf_valid=[], error_flags=0, total_union=0, last_union=0)
         st = _lib.Stats()
         stream = torch.cuda.current_stream(self.tsdf.device).cuda_stream
-        _lib.check(_lib.load().saf_read_stats(ctypes.byref(self._ws), ctypes.byref(st), stream), "saf_read_stats")
+        with torch.cuda.device(self.tsdf.device):
+            _lib.check(_lib.load().saf_read_stats(ctypes.byref(self._ws), ctypes.byref(st), stream), "saf_read_stats")
         out = dict(total_frames=st.total_frames, total_valid=st.total_valid, total_tsdf_valid=st.total_tsdf_valid,
                    total_blocks=st.total_blocks, last_blocks=st.last_blocks, last_valid=list(st.last_valid),
                    last_tsdf_valid=list(st.last_tsdf_valid), error_flags=st.error_flags,
@@ -295,8 +301,9 @@ class _FusionVolume(torch.nn.Module):
         """argmax_with_check_2d_efficient (clip_seem_fusion.py:315-325): int64 [N], -1 where unobserved."""
         out = torch.empty(self.labels_one_hot.shape[0], dtype=torch.int64, device=self.tsdf.device)
         stream = torch.cuda.current_stream(self.tsdf.device).cuda_stream
-        _lib.check(_lib.load().saf_label_argmax(self.labels_one_hot.data_ptr(), out.numel(), self.n_classes,
-                                                out.data_ptr(), stream), "saf_label_argmax")
+        with torch.cuda.device(self.tsdf.device):
+            _lib.check(_lib.load().saf_label_argmax(self.labels_one_hot.data_ptr(), out.numel(), self.n_classes,
+                                                    out.data_ptr(), stream), "saf_label_argmax")
         return out
 
 

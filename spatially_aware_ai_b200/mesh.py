@@ -87,14 +87,16 @@ def marching_cubes_device(volume, halo=None, return_edge_ids=False):
     n_plane = volume._dims[1] * volume._dims[2]
     h_tsdf, keep0 = _halo_ptr(halo, "tsdf", n_plane, torch.float32, dev)
     h_weight, keep1 = _halo_ptr(halo, "weight", n_plane, torch.int32, dev)
-    _lib.check(lib.saf_mesh_count(ctypes.byref(grid), volume.tsdf.data_ptr(), volume.weight.data_ptr(), h_tsdf, h_weight,
+    with torch.cuda.device(dev):
+        _lib.check(lib.saf_mesh_count(ctypes.byref(grid), volume.tsdf.data_ptr(), volume.weight.data_ptr(), h_tsdf, h_weight,
                                   base, nbytes.value, ctypes.byref(nv), ctypes.byref(nf), stream), "saf_mesh_count")
     verts = torch.empty((nv.value, 3), dtype=torch.float32, device=dev)
     verts_world = torch.empty((nv.value, 3), dtype=torch.float32, device=dev)
     faces = torch.empty((nf.value, 3), dtype=torch.int64, device=dev)
     edge_ids = torch.empty(nv.value, dtype=torch.int64, device=dev) if return_edge_ids else None
     if nv.value or nf.value:
-        _lib.check(lib.saf_mesh_emit(ctypes.byref(grid), volume.tsdf.data_ptr(), volume.weight.data_ptr(), h_tsdf,
+        with torch.cuda.device(dev):
+            _lib.check(lib.saf_mesh_emit(ctypes.byref(grid), volume.tsdf.data_ptr(), volume.weight.data_ptr(), h_tsdf,
                                      h_weight, base, nbytes.value, verts.data_ptr(), verts_world.data_ptr(),
                                      edge_ids.data_ptr() if return_edge_ids else None, faces.data_ptr(), stream),
                    "saf_mesh_emit")
@@ -116,7 +118,8 @@ def sample_vertices(volume, verts, field, mode="bilinear", clamp01=False, halo_f
     out = torch.empty((verts.shape[0], field.shape[1]), dtype=torch.float32, device=dev)
     m = {"bilinear": _lib.SAF_SAMPLE_TRILINEAR, "nearest": _lib.SAF_SAMPLE_NEAREST}[mode]
     h_ptr, keep = _halo_ptr({"f": halo_field}, "f", volume._dims[1] * volume._dims[2], torch.float32, dev, field.shape[1])
-    _lib.check(_lib.load().saf_mesh_sample(ctypes.byref(volume._grid_desc()), verts.data_ptr(), verts.shape[0],
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().saf_mesh_sample(ctypes.byref(volume._grid_desc()), verts.data_ptr(), verts.shape[0],
                                            field.data_ptr(), h_ptr, field.shape[1], m, int(bool(clamp01)),
                                            out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream),
                "saf_mesh_sample")

@@ -35,7 +35,8 @@ def label_objects(class_grid, null_class=NULL_CLASS, min_voxels=MIN_VOXELS):
     base = (scratch.data_ptr() + 255) // 256 * 256
     out = torch.empty((nx, ny, nz), dtype=torch.int32, device=dev)
     n_obj = ctypes.c_uint32()
-    _lib.check(lib.saf_label_components(labels.data_ptr(), nx, ny, nz, int(null_class), int(min_voxels), out.data_ptr(),
+    with torch.cuda.device(dev):
+        _lib.check(lib.saf_label_components(labels.data_ptr(), nx, ny, nz, int(null_class), int(min_voxels), out.data_ptr(),
                                         base, nbytes.value, ctypes.byref(n_obj),
                                         torch.cuda.current_stream(dev).cuda_stream), "saf_label_components")
     del scratch

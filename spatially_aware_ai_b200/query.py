@@ -57,8 +57,9 @@ def query_scores(feats, text, norm=None, mode="dot", surgery_w=None, precision="
         surgery_w = surgery_w.to(device=feats.device, dtype=torch.float32).contiguous()
         w_ptr = surgery_w.data_ptr()
     stream = torch.cuda.current_stream(feats.device).cuda_stream
-    rc = _lib.load().saf_query_scores(feats.data_ptr(), M, C, feats.stride(0), text.data_ptr(), T, NORM_MODES[norm],
-                                      SCORE_MODES[mode], w_ptr, PRECISIONS[precision], out.data_ptr(), stream)
+    with torch.cuda.device(feats.device):
+        rc = _lib.load().saf_query_scores(feats.data_ptr(), M, C, feats.stride(0), text.data_ptr(), T, NORM_MODES[norm],
+                                          SCORE_MODES[mode], w_ptr, PRECISIONS[precision], out.data_ptr(), stream)
     _lib.check(rc, "saf_query_scores")
     return out
 
@@ -83,9 +84,10 @@ def query_topk(feats, text, k, norm=None, mode="dot", surgery_w=None, precision=
         surgery_w = surgery_w.to(device=feats.device, dtype=torch.float32).contiguous()
         w_ptr = surgery_w.data_ptr()
     stream = torch.cuda.current_stream(feats.device).cuda_stream
-    rc = lib.saf_query_topk(feats.data_ptr(), M, C, feats.stride(0), text.data_ptr(), T, NORM_MODES[norm],
-                            SCORE_MODES[mode], w_ptr, PRECISIONS[precision], k, index_base, out_s.data_ptr(),
-                            out_i.data_ptr(), base, nbytes.value, stream)
+    with torch.cuda.device(feats.device):
+        rc = lib.saf_query_topk(feats.data_ptr(), M, C, feats.stride(0), text.data_ptr(), T, NORM_MODES[norm],
+                                SCORE_MODES[mode], w_ptr, PRECISIONS[precision], k, index_base, out_s.data_ptr(),
+                                out_i.data_ptr(), base, nbytes.value, stream)
     _lib.check(rc, "saf_query_topk")
     return out_s, out_i
 

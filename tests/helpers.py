@@ -73,17 +73,17 @@ def cosine_rows(a, b):
 from spatially_aware_ai_b200.synth import FakeClip, FakeSeg  # noqa: E402,F401
 
 
-def make_gpu_volume(g, device="cuda", x_begin=0, x_end=None):
+def make_gpu_volume(g, device="cuda", x_begin=0, x_end=None, **slab_kw):
     import torch
     import spatially_aware_ai_b200 as saf
     clip, seg = FakeClip(g["feature_dim"]), FakeSeg()
     origin, nvox = torch.from_numpy(g["origin"]), torch.from_numpy(g["nvox"])
     if g["cls"] == "ClipSeemFusion":
         vol = saf.ClipSeemFusion(origin, g["voxel_size"], nvox, g["trunc"], False, 0, 0, clip, seg,
-                                 x_begin=x_begin, x_end=x_end)
+                                 x_begin=x_begin, x_end=x_end, **slab_kw)
     else:
         vol = saf.ClipFusion(origin, g["voxel_size"], nvox, g["trunc"], False, clip, None, 0, 0,
-                             x_begin=x_begin, x_end=x_end)
+                             x_begin=x_begin, x_end=x_end, **slab_kw)
     return vol.to(device), clip, seg
 
 

@@ -123,3 +123,41 @@ def test_cyclic_slab_layout_host_side():
         assert glob[0].item() == xs[0] * ny * nz and glob[1].item() == xs[9] * ny * nz + 7 and glob[2].item() == -1
         assert torch.allclose(vol.xyz_world[:, 0].reshape(len(xs), -1)[:, 0], torch.tensor(xs) * 0.05)
     assert sorted(seen) == list(range(nx))
+
+
+def test_host_reach_test_is_conservative_and_useful():
+    """saf_frame_reaches_slab (pose only, host): never 0 for a frame that updates a voxel of the slab (oracle), and
+    0 for a good share of the frames that look away from it."""
+    import ctypes
+    from spatially_aware_ai_b200 import _lib, synth
+    cfg = synth.SceneConfig(extent=(4.0, 2.0, 1.6), voxel_size=0.1, height=48, width=64, patch_size=32, patch_stride=16,
+                            feature_dim=4, frames=40, seed=3)
+    origin, nvox = cfg.grid()
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    dropped = 0
+    for xb, xe in ((0, 8), (16, 24), (int(nvox[0]) - 8, int(nvox[0]))):
+        g = _lib.GridDesc()
+        g.origin[:] = origin.tolist()
+        g.voxel_size = cfg.voxel_size
+        g.nvox[:] = [int(v) for v in nvox]
+        g.x_begin, g.x_end = xb, xe
+        for i in range(cfg.frames):
+            fr = synth.make_frame(cfg, i)
+            if i % 3 == 1:
+                fr["pose"] = synth.perturbed_pose(cfg, i, rng)
+            orc = O.OracleVolume(origin, cfg.voxel_size, nvox, cfg.trunc, 4, x_begin=xb, x_end=xe, num_threads=0)
+            cnt = orc.integrate(fr["depth"][None] * 0 + 50.0, fr["rgb"][None], fr["pose"][None], fr["K"][None],
+                                fr["table"][None], fr["seg"][None], want_masks=False)   # far surface: all in-view voxels
+            pose = np.ascontiguousarray(fr["pose"], np.float32).reshape(-1)
+            K = np.ascontiguousarray(fr["K"], np.float32).reshape(-1)
+            r = lib.saf_frame_reaches_slab(ctypes.byref(g), pose.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
+                                           K.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), cfg.height, cfg.width)
+            assert r in (0, 1)
+            if cnt[0, 1] > 0:
+                assert r == 1, (xb, i)
+            dropped += (r == 0)
+    assert dropped >= 10
+    g.x_span, g.x_stride = 8, 16
+    assert lib.saf_frame_reaches_slab(ctypes.byref(g), pose.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
+                                      K.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), cfg.height, cfg.width) == 1

@@ -1,0 +1,217 @@
+"""GPU: round-2 additions - the window tile kernel at every compiled width, sensor-format inputs, block-cyclic
+slabs, the query drivers and the per-row / per-text scorers - against the oracle and the reference's goldens."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+from spatially_aware_ai_b200 import slab, synth
+from tests import helpers as Hh
+from tests.test_parity_gpu import _check_against, _np
+
+pytestmark = pytest.mark.gpu
+
+
+def _scene(C, seed=21, frames=60, h=96, w=128, patch=64, stride=32, extent=(2.2, 2.0, 1.6)):
+    cfg = synth.SceneConfig(extent=extent, voxel_size=0.05, height=h, width=w, patch_size=patch, patch_stride=stride,
+                            feature_dim=C, frames=frames, seed=seed)
+    origin, nvox = cfg.grid()
+    g = dict(cls="ClipSeemFusion", feature_dim=C, origin=origin, nvox=nvox, voxel_size=cfg.voxel_size, trunc=cfg.trunc)
+    return cfg, origin, nvox, g
+
+
+def _oracle_run(cfg, origin, nvox, C, frames, **kw):
+    orc = O.OracleVolume(origin, cfg.voxel_size, nvox, cfg.trunc, C, num_threads=0, **kw)
+    for fr in frames:
+        orc.integrate(fr["depth"][None], fr["rgb"][None], fr["pose"][None], fr["K"][None], fr["table"][None],
+                      fr["seg"][None], want_masks=False)
+    return orc
+
+
+def _sequence(vol, clip, seg, frames, sensor=False, pass_producers=False):
+    tables = torch.stack([torch.from_numpy(f["table"]) for f in frames]).cuda()
+    segs = [torch.from_numpy(f["seg"]).cuda() for f in frames]
+    if sensor:
+        depth = torch.stack([torch.from_numpy(f["depth_mm"]) for f in frames]).cuda()
+        rgb = torch.stack([torch.from_numpy(f["rgb_u8"]) for f in frames]).cuda()
+    else:
+        depth = torch.stack([torch.from_numpy(f["depth"]) for f in frames]).cuda()
+        rgb = torch.stack([torch.from_numpy(f["rgb"]) for f in frames]).cuda()
+    poses = torch.stack([torch.from_numpy(f["pose"]) for f in frames])
+    Ks = torch.stack([torch.from_numpy(f["K"]) for f in frames])
+    if pass_producers:
+        vol.integrate_sequence(depth, rgb, poses, Ks, clip_feat_img=tables, seg_maps=torch.stack(segs))
+    else:
+        clip.next_table, seg.queue = tables, segs
+        vol.integrate_sequence(depth, rgb, poses, Ks)
+
+
+@pytest.mark.parametrize("C,n_frames,step", [(1024, 21, 1), (768, 37, 2), (512, 18, 5), (6, 11, 3), (132, 9, 4)])
+def test_window_kernels_every_width(C, n_frames, step):
+    """Window mode for the tile kernel (C = 512 / 768 / 1024, incl. ragged last tiles and windows), the generic
+    16-byte kernel (C = 132) and the scalar one (C = 6: rows are not 16-byte multiples), bit-exact vs the oracle."""
+    cfg, origin, nvox, g = _scene(C)
+    vol, clip, seg = Hh.make_gpu_volume(g)
+    frames = [synth.make_frame(cfg, (i * step) % cfg.frames) for i in range(n_frames)]
+    orc = _oracle_run(cfg, origin, nvox, C, frames)
+    _sequence(vol, clip, seg, frames)
+    _check_against(vol, orc.tsdf, orc.weight, orc.tsdf_weight, orc.rgb, orc.clip_feat, orc.labels_one_hot, exact=True)
+    st = vol.stats()
+    assert st["total_valid"] == int(orc.weight.sum()) and 0 < st["total_union"] <= st["total_valid"]
+
+
+@pytest.mark.parametrize("variant", ["0", "1"])
+def test_older_window_kernels_still_exact(variant, monkeypatch):
+    """SAF_K3W_VARIANT selects the one-voxel / pair kernels (kept for A/B timing).  The variable is read once per
+    process, so this runs in a subprocess."""
+    import os
+    import subprocess
+    import sys
+    code = ("import os, sys; sys.path.insert(0, %r)\n"
+            "import tests.test_round2_gpu as T\nT.test_window_kernels_every_width(768, 19, 1)\nprint('ok')\n"
+            % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ, SAF_K3W_VARIANT=variant)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("cls", ["ClipSeemFusion", "ClipFusion"])
+def test_sensor_format_inputs_equal_fp32_inputs(cls):
+    """uint16-mm depth + uint8 rgb through integrate() and integrate_sequence() == the fp32 tensors the reference's
+    dataset classes would have produced from them (clipfusion.py:185-188), bit for bit, for both rgb samplers."""
+    C = 512
+    cfg, origin, nvox, g = _scene(C, seed=8)
+    g["cls"] = cls
+    frames = [synth.make_frame(cfg, i) for i in range(20)]
+    a, clip_a, seg_a = Hh.make_gpu_volume(g)
+    b, clip_b, seg_b = Hh.make_gpu_volume(g)
+    # first three frames one by one, the rest as a sequence
+    for vol, clip, seg, sensor in ((a, clip_a, seg_a, False), (b, clip_b, seg_b, True)):
+        for fr in frames[:3]:
+            clip.next_table = torch.from_numpy(fr["table"]).cuda()[None]
+            seg.queue = [torch.from_numpy(fr["seg"]).cuda()]
+            d = torch.from_numpy(fr["depth_mm"] if sensor else fr["depth"]).cuda()[None]
+            r = torch.from_numpy(fr["rgb_u8"] if sensor else fr["rgb"]).cuda()[None]
+            vol.integrate(d, r, torch.from_numpy(fr["pose"])[None], torch.from_numpy(fr["K"])[None])
+        _sequence(vol, clip, seg, frames[3:], sensor=sensor, pass_producers=sensor)
+    for name in ("tsdf", "weight", "tsdf_weight", "rgb", "clip_feat") + (("labels_one_hot",) if cls == "ClipSeemFusion" else ()):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    assert int(a.weight.sum()) > 0
+    orc = O.OracleVolume(origin, cfg.voxel_size, nvox, cfg.trunc, C, with_labels=(cls == "ClipSeemFusion"), num_threads=0)
+    for fr in frames:
+        orc.integrate(O.depth_from_mm(fr["depth_mm"])[None], O.rgb_from_u8(fr["rgb_u8"])[None], fr["pose"][None],
+                      fr["K"][None], fr["table"][None], fr["seg"][None] if cls == "ClipSeemFusion" else None,
+                      want_masks=False)
+    _check_against(b, orc.tsdf, orc.weight, orc.tsdf_weight, orc.rgb, orc.clip_feat, orc.labels_one_hot, exact=True)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_block_cyclic_slabs_concatenate_to_the_full_grid(world):
+    """Every rank's block-cyclic volume (emulated in one process) holds exactly the oracle's rows of its stripes,
+    through single-frame calls and window mode; the stripes cover the grid once."""
+    C = 768
+    cfg, origin, nvox, g = _scene(C, seed=5, extent=(2.6, 1.8, 1.5))
+    frames = [synth.make_frame(cfg, i * 3 % cfg.frames) for i in range(22)]
+    orc = _oracle_run(cfg, origin, nvox, C, frames)
+    nx, plane = int(nvox[0]), int(nvox[1]) * int(nvox[2])
+    covered = np.zeros(nx, int)
+    for r in range(world):
+        kw = slab.cyclic_slab(nx, world, r)
+        vol, clip, seg = Hh.make_gpu_volume(g, **kw)
+        fr = frames[0]
+        clip.next_table = torch.from_numpy(fr["table"]).cuda()[None]
+        seg.queue = [torch.from_numpy(fr["seg"]).cuda()]
+        vol.integrate(torch.from_numpy(fr["depth"]).cuda()[None], torch.from_numpy(fr["rgb"]).cuda()[None],
+                      torch.from_numpy(fr["pose"])[None], torch.from_numpy(fr["K"])[None])
+        _sequence(vol, clip, seg, frames[1:])
+        xs = np.array(vol.global_x_planes())
+        covered[xs] += 1
+        rows = (xs[:, None] * plane + np.arange(plane)[None]).reshape(-1)
+        _check_against(vol, orc.tsdf[rows], orc.weight[rows], orc.tsdf_weight[rows], orc.rgb[rows], orc.clip_feat[rows],
+                       orc.labels_one_hot[rows], exact=True)
+        # query rows map back to global voxel ids
+        X = torch.nn.functional.normalize(torch.randn(3, C, generator=torch.Generator().manual_seed(1)), dim=-1).cuda()
+        import spatially_aware_ai_b200 as saf
+        ts, ti = saf.query_topk(vol.clip_feat, X, 4, norm="nan_to_num", mode="dot")
+        gi = _np(slab.local_to_global_rows(vol, ti))
+        ref = O.normalize_rows(orc.clip_feat[rows]) @ _np(X).T
+        assert np.array_equal(gi, rows[O.topk_indices(ref, 4)])
+    assert (covered == 1).all()
+
+
+def test_text_query_driver_on_device():
+    """clip_text_query (clip_seem_fusion.py:507-533) through the kernels: nan_to_num normalisation fused into the
+    scorer, surgery epilogue, relevance post-processing - against the unmodified driver's output."""
+    import spatially_aware_ai_b200 as saf
+    g = Hh.load_golden("query_drivers")
+    F, X = torch.from_numpy(g["feats"]).cuda(), torch.from_numpy(g["text"]).cuda()
+    Fn = torch.nan_to_num(F / F.norm(dim=-1, keepdim=True))
+    sim = saf.Clip.clip_feature_surgery(Fn[None], X)
+    rel = saf.relevance_minmax(sim[0, :, int(g["text_query_column"])])
+    assert np.abs(_np(rel) - g["text_query_relevance"]).max() <= 2e-5
+    # the same with the normalisation inside the kernel (row 0's weights from the normalised row 0)
+    w = saf.surgery_weights(Fn[0], X)
+    sim2 = saf.query_scores(F, X, norm="nan_to_num", mode="surgery", surgery_w=w)
+    assert np.abs(_np(saf.relevance_minmax(sim2[:, int(g["text_query_column"])])) - g["text_query_relevance"]).max() <= 2e-5
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_segment_labels_match_reference(precision):
+    """segment() (eval_scannet_segmentation.py:546-561): clamp_min normalisation in-kernel, labels per row."""
+    import spatially_aware_ai_b200 as saf
+    g = Hh.load_golden("query_drivers")
+    F, X = torch.from_numpy(g["segment_feats"]).cuda(), torch.from_numpy(g["text"]).cuda()
+    ref = g["segment_labels"]
+    full = _np(saf.segment_labels(F, X, precision=precision))
+    assert full.shape == ref.shape
+    if precision == "fp32":
+        assert np.array_equal(full[:, :5], ref[:, :5]) and (full == ref).mean() > 0.999
+    else:
+        assert (full[:, 0] == ref[:, 0]).mean() > 0.99
+    top5, probs = saf.segment_labels(F, X, k=5, precision=precision, return_probs=True)
+    assert np.array_equal(_np(top5), full[:, :5])
+    rel = O._softmax(np.float32(100) * (O.normalize_rows(g["segment_feats"], "clamp_min") @ g["text"].T), -1)
+    want = np.take_along_axis(rel, ref[:, :5], axis=1)
+    assert np.abs(_np(probs) - want).max() <= (2e-5 if precision == "fp32" else 5e-2)
+    # many rows: several 64 Ki-row chunks, ragged tail
+    M = 150_001
+    big = torch.randn(M, 24, generator=torch.Generator().manual_seed(3)).cuda()
+    lab = _np(saf.segment_labels(big, X, k=3, precision="fp32"))
+    want = O.segment_labels(_np(big), g["text"])[:, :3]
+    assert (lab == want).mean() > 0.9999
+
+
+def test_presence_scores_match_reference():
+    """hypersim_eval.py:80-89: max relevance per target label in one pass."""
+    import spatially_aware_ai_b200 as saf
+    g = Hh.load_golden("query_drivers")
+    F, X = torch.from_numpy(g["feats"]).cuda(), torch.from_numpy(g["text"]).cuda()
+    pres = _np(saf.presence_scores(F, X[:4], X[4:]))
+    assert np.abs(pres - g["hypersim_presence"]).max() <= 2e-5
+
+
+def test_query_mesh_post_processing_on_device():
+    import spatially_aware_ai_b200 as saf
+    g = Hh.load_golden("query_drivers")
+    sim = torch.from_numpy(g["query_mesh_minmax"]).cuda()
+    for n in range(sim.shape[1]):
+        out = _np(saf.relevance_outliers(sim[:, n]))
+        assert np.array_equal(out, g["query_mesh_outliers"][:, n])
+    F = torch.from_numpy(g["segment_feats"]).cuda()
+    F = F / F.norm(dim=-1, keepdim=True)
+    X = torch.from_numpy(g["text"]).cuda()
+    s = saf.Clip.clip_feature_surgery(F[None], X)
+    assert np.abs(_np(saf.minmax_per_text(s)[0]) - g["query_mesh_minmax"]).max() <= 2e-5
+    rel = saf.query_scores(F, X[:5], mode="softmax100")[:, -1]
+    assert np.abs(_np(saf.relevance_half(rel)) - g["query_mesh_half"]).max() <= 2e-5
+
+
+def test_volume_on_a_non_current_device_is_refused_or_correct():
+    """Every ctypes call runs with the tensors' device current (a volume on cuda:1 while cuda:0 is current)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    g = Hh.load_golden("seem_a")
+    torch.cuda.set_device(0)
+    vol, _ = Hh.replay_gpu(g, device="cuda:1")
+    _check_against(vol, g["tsdf"], g["weight"], g["tsdf_weight"], g["rgb_state"], g["clip_feat"], Hh.golden_labels(g),
+                   exact=True)
