@@ -63,6 +63,18 @@ extern "C" {
 #define SAF_RGB_F32      0   /* [0,1]                                   */
 #define SAF_RGB_U8       1   /* uint8, rgb = v / 255                    */
 
+/* Feature source of a frame (saf_frame.table_mode).
+ * SAF_TABLE_PATCH_GRID: the reference's - `table` is the tiled-patch CLIP feature image [C,npy,npx], sampled
+ *   bilinearly with zeros padding at the voxel's projection (clip_seem_fusion.py:800-805).  The default.
+ * SAF_TABLE_SEGMENTS: BASELINE.json north_star's "segment -> CLIP table" (an extension, the
+ *   reference has no such mode): `table` holds one embedding per segment / class id, npy = 1, npx = n_segments,
+ *   and a voxel's sample is the row of its nearest-sampled class id - the id of saf_frame.seg that also feeds the
+ *   label histogram (clip_seem_fusion.py:786-791; id 0 for a pixel outside the image).  Same kernels, a one-tap
+ *   generator (row id, weight 1) instead of the four bilinear taps; needs seg.  An id outside [0, npx) samples
+ *   zeros and sets SAF_FLAG_BAD_CLASS_ID. */
+#define SAF_TABLE_PATCH_GRID 0
+#define SAF_TABLE_SEGMENTS   1
+
 /* rgb sampling: clipfusion.py:701-706 (nearest) / clip_seem_fusion.py:793-798 (bilinear) */
 #define SAF_RGB_NEAREST  0
 #define SAF_RGB_BILINEAR 1
@@ -120,6 +132,8 @@ typedef struct saf_frame {
     const float *pose_device; /* optional device copies of pose[16] / K[9]: when non-NULL the kernels  */
     const float *K_device;    /* read these instead (the reference's callers hand integrate() CUDA     */
                               /* tensors, clip_seem_fusion.py:308-311; no host sync needed this way)   */
+    int32_t      table_mode;  /* SAF_TABLE_*                                                         */
+    int32_t      reserved;
 } saf_frame;
 
 /* Counters kept in the workspace (device) and copied out by saf_read_stats. */

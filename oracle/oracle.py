@@ -42,6 +42,7 @@ def lib():
             build()
         _lib = ctypes.CDLL(_LIB_PATH)
         _lib.saf_oracle_integrate.restype = ctypes.c_int
+        _lib.saf_oracle_integrate_ex.restype = ctypes.c_int
         _lib.saf_oracle_label_argmax.restype = None
     return _lib
 
@@ -94,9 +95,10 @@ class OracleVolume:
         self.last_tsdf_valid = None
         self.last_counts = None
 
-    def integrate(self, depth, rgb, poses, K, table, seg=None, want_masks=True):
+    def integrate(self, depth, rgb, poses, K, table, seg=None, want_masks=True, table_mode=0):
         """depth [B,H,W], rgb [B,H,W,3], poses [B,4,4], K [B,3,3], table [B,C,npy,npx] (any strides),
-        seg [B,H,W] class ids (any dtype) or None."""
+        seg [B,H,W] class ids (any dtype) or None.  table_mode 1: table [B,C,1,n_segments], the sample is the row
+        of the voxel's class id (north_star's segment table; saf_oracle.c saf_oracle_integrate_ex)."""
         depth = np.ascontiguousarray(depth, np.float32)
         rgb = np.ascontiguousarray(rgb, np.float32)
         poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 16)
@@ -113,20 +115,21 @@ class OracleVolume:
             sb, sc, sy, sx = (s // es for s in table.strides)
         sr = sx if npx > 1 else (sy if npy > 1 else 1)
         segf = None
-        if self.with_labels:
+        if self.with_labels or table_mode == 1:
             assert seg is not None
             segf = np.ascontiguousarray(seg, np.float32)  # pano_seg.float(), clip_seem_fusion.py:760
         valid = np.zeros((B, self.n), np.uint8) if want_masks else None
         tvalid = np.zeros((B, self.n), np.uint8) if want_masks else None
         counts = np.zeros(2 * B, np.int64)
-        rc = lib().saf_oracle_integrate(
+        rc = lib().saf_oracle_integrate_ex(
             _p(self.origin), ctypes.c_float(self.voxel_size), _p(self.nvox), ctypes.c_int(self.x_begin),
             ctypes.c_int(self.x_end), ctypes.c_float(self.trunc), ctypes.c_int(B), ctypes.c_int(H),
             ctypes.c_int(W), _p(depth), _p(rgb), _p(segf), _p(table), ctypes.c_ssize_t(sb),
             ctypes.c_ssize_t(sc), ctypes.c_ssize_t(sr), ctypes.c_int(npy), ctypes.c_int(npx),
             ctypes.c_int(self.C), _p(poses), _p(K), ctypes.c_int(self.rgb_mode), ctypes.c_int(N_CLASSES),
             _p(self.tsdf), _p(self.tsdf_weight), _p(self.weight), _p(self.rgb), _p(self.clip_feat),
-            _p(self.labels_one_hot), _p(valid), _p(tvalid), _p(counts), ctypes.c_int(self.num_threads))
+            _p(self.labels_one_hot), _p(valid), _p(tvalid), _p(counts), ctypes.c_int(self.num_threads),
+            ctypes.c_int(table_mode))
         if rc < 0:
             raise ValueError("saf_oracle_integrate: bad argument (%d)" % rc)
         if rc == 1:

@@ -129,6 +129,14 @@ static inline void project(const float *pose, const float *K, float xw, float yw
  * Returns 0, or a negative code for bad arguments, or 1 if a class id was outside [0, n_classes)
  * (the reference's one_hot raises there).
  */
+int saf_oracle_integrate_ex(const float *origin, float voxel_size, const int *nvox, int x_begin, int x_end,
+                            float trunc, int B, int H, int W, const float *depth, const float *rgb,
+                            const float *seg, const float *table, ptrdiff_t table_sb, ptrdiff_t table_sc,
+                            ptrdiff_t table_sr, int npy, int npx, int C, const float *poses, const float *K,
+                            int rgb_mode, int n_classes, float *tsdf, int32_t *tsdf_weight, int32_t *weight,
+                            float *rgb_state, float *clip_feat, int32_t *labels, uint8_t *valid_out,
+                            uint8_t *tsdf_valid_out, int64_t *counts, int num_threads, int table_mode);
+
 int saf_oracle_integrate(const float *origin, float voxel_size, const int *nvox, int x_begin, int x_end,
                          float trunc, int B, int H, int W, const float *depth, const float *rgb,
                          const float *seg, const float *table, ptrdiff_t table_sb, ptrdiff_t table_sc,
@@ -137,6 +145,29 @@ int saf_oracle_integrate(const float *origin, float voxel_size, const int *nvox,
                          float *rgb_state, float *clip_feat, int32_t *labels, uint8_t *valid_out,
                          uint8_t *tsdf_valid_out, int64_t *counts, int num_threads)
 {
+    return saf_oracle_integrate_ex(origin, voxel_size, nvox, x_begin, x_end, trunc, B, H, W, depth, rgb, seg, table,
+                                   table_sb, table_sc, table_sr, npy, npx, C, poses, K, rgb_mode, n_classes, tsdf,
+                                   tsdf_weight, weight, rgb_state, clip_feat, labels, valid_out, tsdf_valid_out, counts,
+                                   num_threads, 0);
+}
+
+/* table_mode 0: the reference's feature source, a [C,npy,npx] tiled-patch feature image sampled bilinearly
+ * (clip_seem_fusion.py:800-805).  table_mode 1: BASELINE.json north_star's "segment -> CLIP table" (SURVEY.md 7.2,
+ * NOT in the reference, so nothing pins it but this definition): table = [n_segments = npx, C] rows (npy = 1), the
+ * sample of a voxel is the row of its nearest-sampled class id (the id that also feeds the label histogram,
+ * clip_seem_fusion.py:786-791; 0 when the pixel is outside the image), expressed as the same four-tap chain with
+ * taps (id, -, -, -) and weights (1, 0, 0, 0).  An id outside [0, n_segments) samples zeros and raises the
+ * bad-label flag. */
+int saf_oracle_integrate_ex(const float *origin, float voxel_size, const int *nvox, int x_begin, int x_end,
+                            float trunc, int B, int H, int W, const float *depth, const float *rgb,
+                            const float *seg, const float *table, ptrdiff_t table_sb, ptrdiff_t table_sc,
+                            ptrdiff_t table_sr, int npy, int npx, int C, const float *poses, const float *K,
+                            int rgb_mode, int n_classes, float *tsdf, int32_t *tsdf_weight, int32_t *weight,
+                            float *rgb_state, float *clip_feat, int32_t *labels, uint8_t *valid_out,
+                            uint8_t *tsdf_valid_out, int64_t *counts, int num_threads, int table_mode)
+{
+    if (table_mode == 1 && (!seg || npy != 1))
+        return -3;
     if (B < 1 || B > SAF_ORACLE_MAX_BATCH)
         return -1;
     if (x_begin < 0 || x_end > nvox[0] || x_begin > x_end)
@@ -237,7 +268,21 @@ int saf_oracle_integrate(const float *origin, float voxel_size, const int *nvox,
                 rgb_state[v * 3 + k] = s[k] * a + rgb_state[v * 3 + k] * bb;
 
             bilinear_taps t;
-            bilinear_setup(gx, gy, npx, npy, &t);
+            if (table_mode == 1) {
+                int px = nearest_index(gx, W), py = nearest_index(gy, H);
+                float lf = (px >= 0 && py >= 0) ? seg[b * npix + (int64_t)py * W + px] : 0.0f;
+                long id = (long)lf;
+                if (id < 0 || id >= npx) {
+                    bad_label |= 1;
+                    id = -1;
+                }
+                t.idx[0] = (int)id;
+                t.idx[1] = t.idx[2] = t.idx[3] = -1;
+                t.w[0] = 1.0f;
+                t.w[1] = t.w[2] = t.w[3] = 0.0f;
+            } else {
+                bilinear_setup(gx, gy, npx, npy, &t);
+            }
             const float *tab = table + b * table_sb;
             float *f = clip_feat + v * (int64_t)C;
             for (int c = 0; c < C; ++c) {

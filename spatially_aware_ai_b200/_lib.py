@@ -18,6 +18,7 @@ SAF_SEG_NONE, SAF_SEG_U8, SAF_SEG_I16, SAF_SEG_I32, SAF_SEG_I64, SAF_SEG_F32 = r
 SAF_RGB_NEAREST, SAF_RGB_BILINEAR = 0, 1
 SAF_DEPTH_F32, SAF_DEPTH_U16_MM = 0, 1
 SAF_RGB_F32, SAF_RGB_U8 = 0, 1
+SAF_TABLE_PATCH_GRID, SAF_TABLE_SEGMENTS = 0, 1
 SAF_BLOCK_EDGE = 8
 SAF_FLAG_BAD_CLASS_ID = 1
 SAF_NORM_NONE, SAF_NORM_NAN_TO_NUM, SAF_NORM_CLAMP_MIN = 0, 1, 2
@@ -44,7 +45,8 @@ class Frame(ctypes.Structure):
     _fields_ = [("depth", c_void_p), ("rgb", c_void_p), ("seg", c_void_p), ("table", c_void_p),
                 ("table_stride_c", c_int64), ("table_stride_r", c_int64), ("npy", c_int32), ("npx", c_int32),
                 ("seg_dtype", c_int32), ("depth_dtype", c_int32), ("pose", c_float * 16), ("K", c_float * 9),
-                ("rgb_dtype", c_int32), ("pose_device", c_void_p), ("K_device", c_void_p)]
+                ("rgb_dtype", c_int32), ("pose_device", c_void_p), ("K_device", c_void_p), ("table_mode", c_int32),
+                ("reserved", c_int32)]
 
 
 def frame_numpy_dtype():

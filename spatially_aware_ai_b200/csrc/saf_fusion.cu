@@ -196,6 +196,45 @@ __device__ __forceinline__ float load_class_id(const void* seg, int dtype, int p
     }
 }
 
+// Feature taps of one (voxel, frame): the reference's bilinear taps over the patch grid, or - segment-table mode,
+// see SAF_TABLE_SEGMENTS - the single row of the voxel's nearest-sampled class id with weight 1.  Both feed the same
+// four-tap mul/fma chain.  `flags`: the workspace's error word (a bad id samples zeros and is reported).
+__device__ __forceinline__ int segment_row(const saf_frame& f, float gx, float gy, int W, int H, uint32_t* flags)
+{
+    const int px = nearest_index(gx, W), py = nearest_index(gy, H);
+    const float lf = (px >= 0 && py >= 0) ? load_class_id(f.seg, f.seg_dtype, py * W + px) : 0.0f;
+    const long long id = (long long)lf;
+    if (id < 0 || id >= f.npx) {
+        atomicOr(flags, SAF_FLAG_BAD_CLASS_ID);
+        return -1;
+    }
+    return (int)id;
+}
+__device__ __forceinline__ void feature_taps(const saf_frame& f, float gx, float gy, int W, int H, uint32_t* flags, Taps& t)
+{
+    if (f.table_mode == SAF_TABLE_SEGMENTS) {
+        t.idx[0] = segment_row(f, gx, gy, W, H, flags);
+        t.idx[1] = t.idx[2] = t.idx[3] = -1;
+        t.w[0] = 1.0f;
+        t.w[1] = t.w[2] = t.w[3] = 0.0f;
+    } else {
+        bilinear_setup(gx, gy, f.npx, f.npy, t);
+    }
+}
+// ... for the window kernels' repacked tables: zero-bordered patch grid, or [zero row, segment rows]
+__device__ __forceinline__ void feature_taps_padded(const saf_frame& f, float gx, float gy, int W, int H, uint32_t* flags,
+                                                    Taps& t)
+{
+    if (f.table_mode == SAF_TABLE_SEGMENTS) {
+        t.idx[0] = segment_row(f, gx, gy, W, H, flags) + 1;
+        t.idx[1] = t.idx[2] = t.idx[3] = 0;
+        t.w[0] = 1.0f;
+        t.w[1] = t.w[2] = t.w[3] = 0.0f;
+    } else {
+        bilinear_setup_padded(gx, gy, f.npx, f.npy, t);
+    }
+}
+
 // Sensor-format inputs: what the reference's dataset classes hold before they convert
 // (clipfusion.py:185-188, 245, 254, 355, 362): rgb = float(u8) / 255, depth = float(u16 millimetres) / 1000.
 // Both quotients are produced without a division: q0 = x * fl(1/d), r = fma(-d, q0, x), q = fma(r, fl(1/d), q0)
@@ -419,10 +458,11 @@ __global__ void __launch_bounds__(kK1Threads) frame_setup_kernel(const FusionPar
             if (p.sequential) {
                 // window mode: [(npy+2)*(npx+2), C] rows with a zero border, so that the feature kernel's four
                 // taps are always in range (dropped taps land on a zero row: grid_sample's zeros padding)
+                const bool segs = f.table_mode == SAF_TABLE_SEGMENTS;   // [zero row, one row per segment]
                 const int pw = f.npx + 2;
-                const int Rp = (f.npy + 2) * pw;
+                const int Rp = segs ? f.npx + 1 : (f.npy + 2) * pw;
                 for (int r = (int)(blockIdx.x - cull_ctas); r < Rp; r += (int)pack_ctas) {   // one padded row per CTA pass
-                    const int py = r / pw - 1, px = r % pw - 1;
+                    const int py = segs ? 0 : r / pw - 1, px = segs ? r - 1 : r % pw - 1;
                     const bool in = py >= 0 && py < f.npy && px >= 0 && px < f.npx;
                     const float* src = f.table + ((int64_t)py * f.npx + px) * f.table_stride_r;
                     for (int c = threadIdx.x; c < C; c += kK1Threads)
@@ -1069,7 +1109,7 @@ feature_accumulate_kernel(const FusionParams p, const float* __restrict__ table,
             const float a = __frcp_rn(__int2float_rn(w + 1));
             const float b = __fmul_rn(__int2float_rn(w), a);
             Taps t;
-            bilinear_setup(gx, gy, f.npx, f.npy, t);
+            feature_taps(f, gx, gy, p.W, p.H, &p.hdr->error_flags, t);
             float4* row = reinterpret_cast<float4*>(p.vol.clip_feat + (size_t)vq * C);
             const float4* old4 = reinterpret_cast<const float4*>(my_ring + (size_t)s * C);
             const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1119,7 +1159,7 @@ __global__ void __launch_bounds__(kK3Threads) feature_accumulate_generic_kernel(
         const float a = __frcp_rn(__int2float_rn(w + 1));
         const float b = __fmul_rn(__int2float_rn(w), a);
         Taps t;
-        bilinear_setup(e.gx, e.gy, f.npx, f.npy, t);
+        feature_taps(f, e.gx, e.gy, p.W, p.H, &p.hdr->error_flags, t);
         float* row = p.vol.clip_feat + (size_t)e.voxel * C;
         if (VEC == 4) {
             const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1348,7 +1388,7 @@ feature_accumulate_window_kernel(const __grid_constant__ FusionParams p, const _
                 const float a = __frcp_rn(__int2float_rn(w + 1));
                 const float bb = __fmul_rn(__int2float_rn(w), a);
                 Taps t;
-                bilinear_setup_padded(g.x, g.y, p.frames[b].npx, p.frames[b].npy, t);
+                feature_taps_padded(p.frames[b], g.x, g.y, p.W, p.H, &p.hdr->error_flags, t);
                 const float4* tab4 = reinterpret_cast<const float4*>(wt.ptr[b]) + lane;   // zero-bordered [R',C] rows
                 const float4* r0 = tab4 + t.idx[0] * (C / 4);
                 const float4* r1 = tab4 + t.idx[1] * (C / 4);
@@ -1538,14 +1578,14 @@ feature_accumulate_window_pair_kernel(const __grid_constant__ FusionParams p, co
                 float a0 = 0.f, b0 = 0.f, a1 = 0.f, b1 = 0.f;
                 if (in0) {   // clip_seem_fusion.py:808-810
                     const float2 g = my_coords[q * SAF_MAX_BATCH + b];
-                    bilinear_setup_padded(g.x, g.y, p.frames[b].npx, p.frames[b].npy, t0);
+                    feature_taps_padded(p.frames[b], g.x, g.y, p.W, p.H, &p.hdr->error_flags, t0);
                     a0 = __frcp_rn(__int2float_rn(w0 + 1));
                     b0 = __fmul_rn(__int2float_rn(w0), a0);
                     ++w0;
                 }
                 if (in1) {
                     const float2 g = my_coords[(q + 1) * SAF_MAX_BATCH + b];
-                    bilinear_setup_padded(g.x, g.y, p.frames[b].npx, p.frames[b].npy, t1);
+                    feature_taps_padded(p.frames[b], g.x, g.y, p.W, p.H, &p.hdr->error_flags, t1);
                     a1 = __frcp_rn(__int2float_rn(w1 + 1));
                     b1 = __fmul_rn(__int2float_rn(w1), a1);
                     ++w1;
@@ -1786,7 +1826,7 @@ feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, co
                     const float a = __frcp_rn(__int2float_rn(w + 1));
                     const float bb = __fmul_rn(__int2float_rn(w), a);
                     Taps t;
-                    bilinear_setup_padded(g.x, g.y, f.npx, f.npy, t);
+                    feature_taps_padded(f, g.x, g.y, p.W, p.H, &p.hdr->error_flags, t);
                     const uint32_t rows = (uint32_t)t.idx[0] | ((uint32_t)t.idx[1] << 8) | ((uint32_t)t.idx[2] << 16) |
                                           ((uint32_t)t.idx[3] << 24);
                     TileUpdate u;
@@ -1943,7 +1983,7 @@ __global__ void __launch_bounds__(kK3Threads) feature_accumulate_window_generic_
             const float a = __frcp_rn(__int2float_rn(w + 1));
             const float bb = __fmul_rn(__int2float_rn(w), a);
             Taps t;
-            bilinear_setup_padded(g.x, g.y, p.frames[b].npx, p.frames[b].npy, t);
+            feature_taps_padded(p.frames[b], g.x, g.y, p.W, p.H, &p.hdr->error_flags, t);
             const float* table = wt.ptr[b];   // zero-bordered [R',C] rows
             const int64_t sr = wt.stride_r[b];
             if (VEC == 4) {
@@ -2150,6 +2190,8 @@ static int check_feature_args(const saf_volume* vol, const saf_frame* frames, in
         if (f.npy <= 0 || f.npx <= 0) return SAF_ERR_SHAPE;
         if (f.seg && (f.seg_dtype < SAF_SEG_U8 || f.seg_dtype > SAF_SEG_F32)) return SAF_ERR_DTYPE;
         if (f.rgb_dtype != SAF_RGB_F32 && f.rgb_dtype != SAF_RGB_U8) return SAF_ERR_DTYPE;
+        if (f.table_mode != SAF_TABLE_PATCH_GRID && f.table_mode != SAF_TABLE_SEGMENTS) return SAF_ERR_UNSUPPORTED;
+        if (f.table_mode == SAF_TABLE_SEGMENTS && (!f.seg || f.npy != 1)) return SAF_ERR_NULL;
         const int64_t elems = (int64_t)f.npy * f.npx * vol->feature_dim;
         if (f.table_stride_c != 1) {
             if (elems > ws->max_table_elems) return SAF_ERR_WORKSPACE;
@@ -2314,7 +2356,9 @@ static int launch_k3w(const FusionParams& p, int sms, cudaStream_t st)
     if (rows16) {
         // the tile kernel addresses table rows with one byte each
         bool small_tables = true;
-        for (int b = 0; b < p.batch; ++b) small_tables &= (p.frames[b].npy + 2) * (p.frames[b].npx + 2) <= 256;
+        for (int b = 0; b < p.batch; ++b)
+            small_tables &= (p.frames[b].table_mode == SAF_TABLE_SEGMENTS ? p.frames[b].npx + 1
+                                                                          : (p.frames[b].npy + 2) * (p.frames[b].npx + 2)) <= 256;
         if (k3w_variant() == 2 && small_tables) {
             switch (C) {
                 case 512: return launch_k3w_tile<4, 3, 3>(p, wt, sms, st);

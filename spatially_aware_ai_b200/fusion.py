@@ -41,6 +41,10 @@ class _FusionVolume(torch.nn.Module):
 
     _with_labels = True
     _rgb_mode = _lib.SAF_RGB_BILINEAR
+    # "patch_grid": the reference's feature source (bilinear sample of the tiled-patch CLIP image).
+    # "segment_table": one embedding per class id, a voxel takes the row of its nearest-sampled id
+    # (BASELINE.json north_star / SURVEY.md 7.2; include/saf_b200.h SAF_TABLE_SEGMENTS).  Set on the instance.
+    feature_source = "patch_grid"
 
     def _init_volume(self, origin, voxel_size, nvox, trunc, feature_dim, x_begin=0, x_end=None, x_span=0, x_stride=0):
         self.origin = origin
@@ -150,6 +154,15 @@ class _FusionVolume(torch.nn.Module):
     def _make_frames(self, depth_imgs, rgb_imgs, poses, K, clip_feat_img, seg_maps):
         B, H, W, _ = rgb_imgs.shape
         dev = self.tsdf.device
+        table_mode = _lib.SAF_TABLE_PATCH_GRID
+        if self.feature_source == "segment_table":
+            # [B, n_segments, C] rows -> the [B, C, 1, n_segments] view the kernels index as a one-row patch grid
+            if clip_feat_img.dim() != 3:
+                raise RuntimeError("segment-table mode takes per-frame tables [B, n_segments, C]")
+            if seg_maps is None:
+                raise RuntimeError("segment-table mode needs the class maps")
+            clip_feat_img = clip_feat_img.permute(0, 2, 1)[:, :, None, :]
+            table_mode = _lib.SAF_TABLE_SEGMENTS
         for name, t in (("depth_imgs", depth_imgs), ("rgb_imgs", rgb_imgs), ("clip feature image", clip_feat_img)):
             if t.device != dev:
                 raise RuntimeError("%s is on %s but the volume is on %s" % (name, t.device, dev))
@@ -178,6 +191,7 @@ class _FusionVolume(torch.nn.Module):
         arr["table"] = table.data_ptr() + steps * np.uint64(sb * table.element_size())
         arr["depth_dtype"], arr["rgb_dtype"] = depth_dtype, rgb_dtype
         arr["table_stride_c"], arr["table_stride_r"] = sc, sr
+        arr["table_mode"] = table_mode
         arr["npy"], arr["npx"] = npy, npx
         keep = [depth, rgb, table, arr]
         if seg_maps is not None:
@@ -328,6 +342,9 @@ class ClipSeemFusion(_FusionVolume):
         """clip_seem_fusion.py:683-695, 753-757: tiled-patch CLIP feature image and one class map per frame."""
         batch_size = rgb_imgs.shape[0]
         rgb_chw = rgb_imgs.permute(0, 3, 1, 2)
+        if self.feature_source == "segment_table":
+            seg_maps = [self.segmentation_model.run_on_image(rgb_chw[i]) for i in range(batch_size)]
+            return self.clip.segment_features(rgb_chw, seg_maps), seg_maps     # [B, n_segments, C]
         if self.scale_patches_by_depth:
             clip_feat_img = self.clip.img_inference_tiled_depthscaled(rgb_chw, depth_imgs, K,
                                                                       patch_stride=self.clip_patch_stride)

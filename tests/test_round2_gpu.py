@@ -215,3 +215,50 @@ def test_volume_on_a_non_current_device_is_refused_or_correct():
     vol, _ = Hh.replay_gpu(g, device="cuda:1")
     _check_against(vol, g["tsdf"], g["weight"], g["tsdf_weight"], g["rgb_state"], g["clip_feat"], Hh.golden_labels(g),
                    exact=True)
+
+
+@pytest.mark.parametrize("C", [768, 20])
+def test_segment_table_mode(C):
+    """north_star's segment -> CLIP table (SAF_TABLE_SEGMENTS): a voxel's sample is the row of its nearest-sampled
+    class id.  Single-frame kernels and window mode (tile kernel at C = 768, generic at C = 20) against the
+    oracle's definition of the mode, bit for bit; a bad class id is reported."""
+    cfg, origin, nvox, g = _scene(C, seed=13)
+    n_seg = 134
+    rng = np.random.default_rng(5)
+    frames = [synth.make_frame(cfg, i) for i in range(19)]
+    tables = [rng.standard_normal((n_seg, C), dtype=np.float32) for _ in frames]
+    orc = O.OracleVolume(origin, cfg.voxel_size, nvox, cfg.trunc, C, num_threads=0)
+    for fr, tab in zip(frames, tables):
+        orc.integrate(fr["depth"][None], fr["rgb"][None], fr["pose"][None], fr["K"][None],
+                      np.ascontiguousarray(tab.T)[None, :, None, :], fr["seg"][None], want_masks=False, table_mode=1)
+    vol, clip, seg = Hh.make_gpu_volume(g)
+    vol.feature_source = "segment_table"
+    dev_tables = torch.from_numpy(np.stack(tables)).cuda()
+
+    class _SegClip:
+        def segment_features(self, rgb_chw, seg_maps):
+            return self.next
+
+    vol.clip = _SegClip()
+    for i in range(3):          # the reference's call pattern: one frame per integrate()
+        fr = frames[i]
+        vol.clip.next = dev_tables[i:i + 1]
+        seg.queue = [torch.from_numpy(fr["seg"]).cuda()]
+        vol.integrate(torch.from_numpy(fr["depth"]).cuda()[None], torch.from_numpy(fr["rgb"]).cuda()[None],
+                      torch.from_numpy(fr["pose"])[None], torch.from_numpy(fr["K"])[None])
+    rest = frames[3:]
+    vol.integrate_sequence(torch.stack([torch.from_numpy(f["depth"]) for f in rest]).cuda(),
+                           torch.stack([torch.from_numpy(f["rgb"]) for f in rest]).cuda(),
+                           torch.stack([torch.from_numpy(f["pose"]) for f in rest]),
+                           torch.stack([torch.from_numpy(f["K"]) for f in rest]),
+                           clip_feat_img=dev_tables[3:], seg_maps=torch.stack([torch.from_numpy(f["seg"]) for f in rest]).cuda())
+    _check_against(vol, orc.tsdf, orc.weight, orc.tsdf_weight, orc.rgb, orc.clip_feat, orc.labels_one_hot, exact=True)
+    assert int(orc.weight.sum()) > 0
+    # a table with fewer rows than the class map's ids: zeros are sampled and the sticky flag is raised
+    vol.integrate_sequence(torch.from_numpy(frames[0]["depth"]).cuda()[None].repeat(2, 1, 1),
+                           torch.from_numpy(frames[0]["rgb"]).cuda()[None].repeat(2, 1, 1, 1),
+                           torch.from_numpy(frames[0]["pose"])[None].repeat(2, 1, 1),
+                           torch.from_numpy(frames[0]["K"])[None].repeat(2, 1, 1),
+                           clip_feat_img=dev_tables[:2, :40], seg_maps=torch.from_numpy(frames[0]["seg"]).cuda()[None].repeat(2, 1, 1))
+    with pytest.raises(RuntimeError):
+        vol.check_errors()
