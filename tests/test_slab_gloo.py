@@ -161,3 +161,49 @@ def test_exchange_halo_world2(tmp_path):
     assert np.array_equal(h0["clip_feat"], np.arange(first * 5, (first + 12) * 5, dtype=np.float32).reshape(12, 5))
     assert np.array_equal(h0["voxel_obj_idx"].reshape(-1), np.arange(first, first + 12, dtype=np.int32))
     assert set(h1.files) == {"rank"}                                    # the last rank has no successor
+
+
+def _worker_cyclic(rank, world, port, F, X, k, nx, plane, out_dir):
+    """Block-cyclic rows: rank-local top-k -> global voxel ids -> merged over the ranks; plus the bench's
+    interleaved frame sharing."""
+    import types
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        kw = slab.cyclic_slab(nx, world, rank)
+        xs = []
+        for start in range(kw["x_begin"], kw["x_end"], kw["x_stride"]):
+            xs.extend(range(start, min(start + kw["x_span"], kw["x_end"])))
+        vol = types.SimpleNamespace(_dims=[nx, plane, 1], global_x_planes=lambda: xs)
+        rows = (np.array(xs)[:, None] * plane + np.arange(plane)[None]).reshape(-1)
+        local = O.normalize_rows(F[rows]) @ X.T
+        li = O.topk_indices(local, k)
+        ls = np.take_along_axis(local.T, li, axis=1)
+        gi_local = slab.local_to_global_rows(vol, torch.from_numpy(li))
+        gs, gi = slab.gather_topk(torch.from_numpy(ls.astype(np.float32)), gi_local, k)
+        # interleaved sharing: rank r holds items r, r + world, ...
+        n_total, per = 11, (11 + world - 1) // world
+        items = torch.arange(n_total * 6, dtype=torch.int16).reshape(n_total, 2, 3)
+        mine = torch.stack([items[min(n_total - 1, j * world + rank)] for j in range(per)])
+        whole = bench.share_interleaved(mine, n_total, world, dist.all_gather_into_tensor)
+        np.savez(os.path.join(out_dir, "c%d.npz" % rank), gs=gs.numpy(), gi=gi.numpy(), whole=whole.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_cyclic_topk_and_frame_sharing_world2(tmp_path):
+    rng = np.random.default_rng(8)
+    nx, plane, C, T, k = 44, 7, 12, 4, 6
+    F = rng.standard_normal((nx * plane, C)).astype(np.float32)
+    X = rng.standard_normal((T, C)).astype(np.float32)
+    mp.spawn(_worker_cyclic, args=(2, _free_port(), F, X, k, nx, plane, str(tmp_path)), nprocs=2, join=True)
+    full = O.normalize_rows(F) @ X.T
+    want = O.topk_indices(full, k)
+    for r in range(2):
+        z = np.load(tmp_path / ("c%d.npz" % r))
+        assert np.array_equal(z["gi"], want)
+        assert np.allclose(z["gs"], np.take_along_axis(full.T, want, axis=1), atol=1e-6)
+        assert np.array_equal(z["whole"], np.arange(11 * 6, dtype=np.int16).reshape(11, 2, 3))
