@@ -261,7 +261,8 @@ int saf_label_argmax(const int32_t *labels_one_hot, int64_t n, int32_t n_classes
  *   feats  device [M, ldf] f32 (first C columns used), text device [T,C] f32,
  *   surgery_w device [T] f32: the class weights w (required for SAF_SCORE_SURGERY),
  *   out    device [M,T] f32.
- * precision: 0 = fp32 CUDA-core FMA, 1 = tf32 tensor cores (tcgen05), 2 = 3xTF32 split (tcgen05). */
+ * precision: 0 = fp32 CUDA-core FMA, 1 = tf32 tensor cores (tcgen05).  (Exact rankings on the tensor cores come
+ * from saf_query_topk, which filters with the tf32 scores and rescoring the survivors in fp32.) */
 int saf_query_scores(const float *feats, int64_t M, int32_t C, int64_t ldf, const float *text, int32_t T,
                      int32_t norm_mode, int32_t score_mode, const float *surgery_w, int32_t precision,
                      float *out, void *stream);

@@ -23,7 +23,7 @@ SAF_BLOCK_EDGE = 8
 SAF_FLAG_BAD_CLASS_ID = 1
 SAF_NORM_NONE, SAF_NORM_NAN_TO_NUM, SAF_NORM_CLAMP_MIN = 0, 1, 2
 SAF_SCORE_DOT, SAF_SCORE_SOFTMAX100, SAF_SCORE_SURGERY = 0, 1, 2
-SAF_PRECISION_FP32, SAF_PRECISION_TF32, SAF_PRECISION_3XTF32 = 0, 1, 2
+SAF_PRECISION_FP32, SAF_PRECISION_TF32 = 0, 1
 SAF_SAMPLE_TRILINEAR, SAF_SAMPLE_NEAREST = 0, 1
 
 c_void_p, c_int32, c_int64, c_uint64, c_float = (ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64,

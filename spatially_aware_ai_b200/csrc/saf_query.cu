@@ -7,7 +7,7 @@
 //
 // precision 0: fp32 CUDA-core kernel (this file): one warp per feature row, the text block staged
 //              in shared memory, butterfly reduction that leaves 32 scores in 32 lanes.
-// precision 1/2: tcgen05 tensor-core kernels (saf_query_tc.cu).
+// precision 1: tcgen05 tensor-core kernel (saf_query_tc.cu).
 #include <limits.h>
 #include <math.h>
 #include <algorithm>
@@ -258,7 +258,7 @@ int saf_query_scores(const float* feats, int64_t M, int32_t C, int64_t ldf, cons
     cudaStream_t st = (cudaStream_t)stream;
     if (precision == 0)
         rc = query_scores_fp32(feats, M, C, ldf, text, T, norm_mode, out, sms, smem_optin, st);
-    else if (precision == 1 || precision == 2)
+    else if (precision == 1)
         rc = query_scores_tc(feats, M, C, ldf, text, T, norm_mode, precision, out, st);
     else
         rc = SAF_ERR_UNSUPPORTED;

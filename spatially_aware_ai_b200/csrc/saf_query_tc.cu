@@ -14,6 +14,7 @@
 //   warps 2-5   per-row sum of squares from the A tiles; epilogue tcgen05.ld -> scale -> store
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -27,7 +28,7 @@ namespace tc {
 constexpr int BM = 128;          // rows of F per CTA (UMMA M)
 constexpr int BK = 32;           // fp32 per k-block = one 128-byte swizzle row
 constexpr int UMMA_K = 8;        // tf32 MMA K
-constexpr int STAGES = 4;
+constexpr int MAX_STAGES = 4;   // k-block ring depth (2 for the wide fused top-k kernel: two CTAs per SM)
 constexpr int THREADS = 192;
 constexpr uint32_t A_BYTES = BM * BK * 4;
 
@@ -134,7 +135,7 @@ template <bool FILTER>
 __global__ void __launch_bounds__(THREADS, 1)
 query_gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int64_t M,
                        int C, int n_pad, int t_valid, int t0, uint32_t tmem_cols, int norm_mode, float* __restrict__ out,
-                       int64_t ldo, int64_t tile0, const FilterArgs fa)
+                       int64_t ldo, int64_t tile0, const FilterArgs fa, const int STAGES)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t stage_bytes = A_BYTES + (uint32_t)n_pad * BK * 4;
@@ -362,19 +363,25 @@ static int launch_gemm(bool filter, const float* feats, int64_t M, int32_t C, in
         rc = make_map(enc, &map_b, text, (uint64_t)T, (uint64_t)C, (uint64_t)C, (uint32_t)n_pad);
         if (rc) return rc;
         const size_t stage_bytes = A_BYTES + (size_t)n_pad * BK * 4;
+        // The fused top-k kernel with more than 128 texts runs TWO CTAs per SM on a 2-deep ring each (2 x 96 KB of
+        // shared memory, 2 x 256 TMEM columns): one CTA's filter epilogue overlaps the other's main loop.  The
+        // scores kernel parks its output tile in the ring buffers and keeps 4 stages.  SAF_QUERY_STAGES overrides.
+        static const int stages_env = getenv("SAF_QUERY_STAGES") ? atoi(getenv("SAF_QUERY_STAGES")) : 0;
+        int STAGES = (filter && n_pad > 128) ? 2 : MAX_STAGES;
+        if (filter && stages_env >= 2 && stages_env <= MAX_STAGES) STAGES = stages_env;
         const size_t smem = (size_t)STAGES * stage_bytes + (2 * STAGES + 1) * 8 + 16;
         if (filter) {
             SAF_CUDA_TRY(cudaFuncSetAttribute(query_gemm_tf32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               (int)smem));
             query_gemm_tf32_kernel<true><<<(unsigned)tiles, THREADS, smem, st>>>(map_a, map_b, M, C, n_pad, t_valid, t0,
                                                                                 tmem_cols, norm_mode, out, (int64_t)T,
-                                                                                tile0, fa);
+                                                                                tile0, fa, STAGES);
         } else {
             SAF_CUDA_TRY(cudaFuncSetAttribute(query_gemm_tf32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               (int)smem));
             query_gemm_tf32_kernel<false><<<(unsigned)tiles, THREADS, smem, st>>>(map_a, map_b, M, C, n_pad, t_valid, t0,
                                                                                  tmem_cols, norm_mode, out, (int64_t)T,
-                                                                                 tile0, fa);
+                                                                                 tile0, fa, STAGES);
         }
         SAF_CHECK_LAUNCH("query_gemm_tf32_kernel", st);
     }
@@ -584,7 +591,7 @@ int query_topk_tc(const float* feats, int64_t M, int32_t C, int64_t ldf, const f
 int query_scores_tc(const float* feats, int64_t M, int32_t C, int64_t ldf, const float* text, int32_t T,
                     int32_t norm_mode, int32_t precision, float* out, cudaStream_t st)
 {
-    if (precision != 1) return SAF_ERR_UNSUPPORTED;  // 3xTF32 split: not implemented, use precision 0 (fp32)
+    if (precision != 1) return SAF_ERR_UNSUPPORTED;
     tc::FilterArgs fa;
     memset(&fa, 0, sizeof(fa));
     return tc::launch_gemm(false, feats, M, C, ldf, text, T, norm_mode, out, 0, M, fa, st);

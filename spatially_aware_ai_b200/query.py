@@ -14,7 +14,7 @@ from . import _lib
 NORM_MODES = {None: _lib.SAF_NORM_NONE, "none": _lib.SAF_NORM_NONE, "nan_to_num": _lib.SAF_NORM_NAN_TO_NUM,
               "clamp_min": _lib.SAF_NORM_CLAMP_MIN}
 SCORE_MODES = {"dot": _lib.SAF_SCORE_DOT, "softmax100": _lib.SAF_SCORE_SOFTMAX100, "surgery": _lib.SAF_SCORE_SURGERY}
-PRECISIONS = {"fp32": _lib.SAF_PRECISION_FP32, "tf32": _lib.SAF_PRECISION_TF32, "3xtf32": _lib.SAF_PRECISION_3XTF32}
+PRECISIONS = {"fp32": _lib.SAF_PRECISION_FP32, "tf32": _lib.SAF_PRECISION_TF32}
 
 
 def _prep(feats, text):
@@ -44,7 +44,7 @@ def query_scores(feats, text, norm=None, mode="dot", surgery_w=None, precision="
     """[M,T] scores of feature rows against text embeddings.
 
     norm: None | "nan_to_num" | "clamp_min" row normalisation fused into the kernel;
-    mode: "dot" | "softmax100" | "surgery"; precision: "fp32" | "tf32" | "3xtf32"."""
+    mode: "dot" | "softmax100" | "surgery"; precision: "fp32" | "tf32"."""
     feats, text = _prep(feats, text)
     M, C = feats.shape
     T = text.shape[0]
