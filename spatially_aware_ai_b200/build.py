@@ -53,18 +53,23 @@ def _fingerprint():
     return h.hexdigest()
 
 
-def build_library(force=False, verbose=False):
-    stamp = os.path.join(OBJ_DIR, "fingerprint.txt")
-    fp = _fingerprint()
-    if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp) and open(stamp).read() == fp:
-        return LIB_PATH
+def build_library(force=False, verbose=False, variant=None, defines=()):
+    """variant / defines: an experimental build of the same ABI next to the product library
+    (libsaf_b200_<variant>.so, compiled with -D<define>...; selected at run time with SAF_LIB_PATH for A/B timing)."""
+    obj_dir = OBJ_DIR if not variant else os.path.join(OBJ_DIR, variant)
+    lib_path = LIB_PATH if not variant else os.path.join(HERE, "libsaf_b200_%s.so" % variant)
+    stamp = os.path.join(obj_dir, "fingerprint.txt")
+    fp = _fingerprint() + repr(tuple(defines))
+    if not force and os.path.exists(lib_path) and os.path.exists(stamp) and open(stamp).read() == fp:
+        return lib_path
     nvcc = _nvcc()
-    os.makedirs(OBJ_DIR, exist_ok=True)
+    os.makedirs(obj_dir, exist_ok=True)
     objs = []
     procs = []
     for src in _sources():
-        obj = os.path.join(OBJ_DIR, src[:-3] + ".o")
+        obj = os.path.join(obj_dir, src[:-3] + ".o")
         cmd = [nvcc] + _host_compiler_flags() + ARCH_FLAGS + COMMON_FLAGS + PER_FILE_FLAGS.get(src, []) + \
+              ["-D" + d for d in defines] + \
               (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
@@ -78,12 +83,15 @@ def build_library(force=False, verbose=False):
             sys.stderr.write(out)
     if failed:
         raise RuntimeError("building libsaf_b200.so failed")
-    cmd = [nvcc] + _host_compiler_flags() + ARCH_FLAGS + ["-shared", "-o", LIB_PATH] + objs + ["-lcudart_static", "-lrt", "-lpthread", "-ldl"]
+    cmd = [nvcc] + _host_compiler_flags() + ARCH_FLAGS + ["-shared", "-o", lib_path] + objs + ["-lcudart_static", "-lrt", "-lpthread", "-ldl"]
     subprocess.run(cmd, check=True)
     with open(stamp, "w") as f:
         f.write(fp)
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    # python -m spatially_aware_ai_b200.build [--force] [-v] [--variant NAME -DNAME=VALUE ...]
+    variant = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else None
+    defs = [a[2:] for a in sys.argv if a.startswith("-D")]
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=variant, defines=defs))

@@ -1668,6 +1668,9 @@ feature_accumulate_window_pair_kernel(const __grid_constant__ FusionParams p, co
 // with n_rows = 0.  Arithmetic per voxel = the single-frame calls in frame order (clip_seem_fusion.py:800-814).
 // ---------------------------------------------------------------------------------------------
 
+#ifndef SAF_TILE_PRODUCER
+#define SAF_TILE_PRODUCER 1     // 2: cell-parallel producer (see the kernel)
+#endif
 constexpr int kTileSlots = 8;    // voxels per set (accumulator registers: 8 x float4 per thread)
 
 struct __align__(16) TileUpdate {   // one (frame, voxel) feature update
@@ -1731,7 +1734,8 @@ feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, co
 
     float* rows_buf = reinterpret_cast<float*>(smem_raw);                                   // [NBUF][G][C]
     Meta* metas = reinterpret_cast<Meta*>(smem_raw + (size_t)NBUF * G * C * sizeof(float));  // [2*NBUF]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(metas + 2 * NBUF);
+    float4* smp_buf = reinterpret_cast<float4*>(metas + 2 * NBUF);                           // [NBUF][G][16]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smp_buf + (size_t)NBUF * G * SAF_MAX_BATCH);
     uint64_t* full = bars;                    // [2*NBUF]
     uint64_t* meta_free = bars + 2 * NBUF;    // [2*NBUF]
     uint64_t* rows_free = bars + 4 * NBUF;    // [NBUF]
@@ -1745,6 +1749,171 @@ feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, co
     }
     __syncthreads();
 
+#if SAF_TILE_PRODUCER == 2
+    if (warp < NBUF) {
+        // ------------------------------- producer -------------------------------
+        // Nothing below is a chain of dependent memory round trips per (voxel, frame): the valid (voxel, frame)
+        // CELLS of the tile are spread over the 32 lanes and handled independently (the weight a cell sees is the
+        // voxel's weight plus the number of its earlier valid frames; label counters are fire-and-forget
+        // reductions), and only the rgb running average - pure arithmetic on samples parked in shared memory -
+        // walks a voxel's frames in order.
+        const uint32_t n_blocks = sc->n_blocks;
+        const uint32_t* __restrict__ off = p.blk_offset;
+        const int B = p.batch;
+        float* my_rows = rows_buf + (size_t)warp * G * C;
+        float4* my_smp = smp_buf + (size_t)warp * G * SAF_MAX_BATCH;   // [voxel][frame] rgb sample
+        const int set = lane / kTileSlots, slot = lane % kTileSlots;
+        constexpr int kCellIters = G * SAF_MAX_BATCH / 32;
+        for (uint32_t j = 0;; ++j) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&sc->k3_next, (uint32_t)G);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const uint32_t cnt = base < n ? min((uint32_t)G, n - base) : 0u;
+            const uint32_t ms = (uint32_t)warp + (uint32_t)NBUF * (j & 1u);
+            Meta* M = metas + ms;
+            if (cnt == 0) {
+                mbar_wait(&meta_free[ms], ((j >> 1) & 1u) ^ 1u);
+                if (lane == 0) {
+                    M->n_rows = 0;
+                    mbar_arrive(&full[ms]);
+                }
+                break;
+            }
+            // block rank of the tile's first entry: 32-ary search by the whole warp (off[lo] <= base < off[hi])
+            uint32_t lo = 0, hi = n_blocks;
+            while (hi - lo > 1) {
+                const uint32_t step = (hi - lo + 31u) / 32u;
+                const uint32_t probe = lo + (uint32_t)lane * step;
+                const bool le = probe < hi && __ldg(off + probe) <= base;
+                const uint32_t k = (uint32_t)__popc(__ballot_sync(0xffffffffu, le));   // >= 1: lane 0 probes lo
+                lo += (k - 1u) * step;
+                hi = min(hi, lo + step);
+            }
+            uint32_t my_voxel = 0, my_mask = 0, my_local = 0, my_rank = 0;
+            int my_w0 = 0;
+            float rgb0[3] = {0.f, 0.f, 0.f};
+            if (lane < cnt) {
+                const uint32_t i = base + lane;
+                uint32_t r = lo;
+                while (r + 1u < n_blocks && __ldg(off + r + 1u) <= i) ++r;   // the tile spans a few blocks at most
+                const WinEntry e = p.ulist[(uint64_t)r * kBlockVoxels + (i - __ldg(off + r))];
+                my_voxel = e.voxel;
+                my_mask = e.mask_local & 0xffffu;
+                my_local = e.mask_local >> 16;
+                my_rank = r;
+                my_w0 = p.vol.weight[my_voxel];
+                const float* src3 = p.vol.rgb + (size_t)my_voxel * 3;
+                rgb0[0] = src3[0];
+                rgb0[1] = src3[1];
+                rgb0[2] = src3[2];
+            }
+            // the landing buffer was handed back when the compute warps took its rows to registers
+            mbar_wait(&rows_free[warp], (j & 1u) ^ 1u);
+            if (lane == 0) mbar_expect_tx(&full[ms], cnt * (uint32_t)C * 4u);
+            __syncwarp();
+            if (lane < cnt)
+                tma_bulk_g2s(my_rows + (size_t)lane * C, p.vol.clip_feat + (size_t)my_voxel * C, (uint32_t)C * 4u, &full[ms]);
+            // which voxel of each set comes first in every frame (its rows are the ones prefetched for the set)
+            uint32_t first_bits = 0, my_ballot = 0;
+#pragma unroll
+            for (int b = 0; b < SAF_MAX_BATCH; ++b) {
+                const uint32_t bal = __ballot_sync(0xffffffffu, (my_mask >> b) & 1u);
+                if (((bal >> (set * kTileSlots)) & ((1u << slot) - 1u)) == 0u) first_bits |= 1u << b;
+                if (lane == b) my_ballot = bal;
+            }
+            // the metadata slot was last read two of this producer's tiles ago
+            mbar_wait(&meta_free[ms], ((j >> 1) & 1u) ^ 1u);
+            if (lane < SAF_MAX_BATCH) {
+#pragma unroll
+                for (int s = 0; s < NSET; ++s) M->vmask[s][lane] = (uint8_t)((my_ballot >> (s * kTileSlots)) & 0xffu);
+            }
+#pragma unroll
+            for (int s = 0; s < NSET; ++s) {
+                const uint32_t fm = __ballot_sync(0xffffffffu, lane < SAF_MAX_BATCH &&
+                                                                   ((my_ballot >> (s * kTileSlots)) & 0xffu) != 0u);
+                if (lane == 0) M->fmask[s] = fm;
+            }
+            if (lane == 0) M->n_rows = cnt;
+            if (lane < cnt) M->voxel[lane] = my_voxel;
+            // cells: c -> (frame c / G, voxel c % G).  Pass 1 requests every valid cell's image coordinates.
+            float2 cg[kCellIters];
+#pragma unroll
+            for (int it = 0; it < kCellIters; ++it) {
+                const int c = it * 32 + lane, b = c / G, v = c % G;
+                const uint32_t mv = __shfl_sync(0xffffffffu, my_mask, v);
+                const uint32_t rk = __shfl_sync(0xffffffffu, my_rank, v);
+                const uint32_t lc = __shfl_sync(0xffffffffu, my_local, v);
+                cg[it] = make_float2(0.f, 0.f);
+                if ((mv >> b) & 1u) cg[it] = p.wcoords[((uint64_t)rk * B + b) * kBlockVoxels + lc];
+            }
+            // Pass 2: per valid cell the compute warps' update record (clip_seem_fusion.py:800-810), the rgb sample
+            // and the label counter (:786-798, 820-822).
+#pragma unroll
+            for (int it = 0; it < kCellIters; ++it) {
+                const int c = it * 32 + lane, b = c / G, v = c % G;
+                const uint32_t mv = __shfl_sync(0xffffffffu, my_mask, v);
+                const uint32_t vx = __shfl_sync(0xffffffffu, my_voxel, v);
+                const int w0 = __shfl_sync(0xffffffffu, my_w0, v);
+                const uint32_t fb = __shfl_sync(0xffffffffu, first_bits, v);
+                if ((mv >> b) & 1u) {
+                    const saf_frame& f = p.frames[b];
+                    const float2 g = cg[it];
+                    const int w = w0 + __popc(mv & ((1u << b) - 1u));   // single-frame calls before this one
+                    const float a = __frcp_rn(__int2float_rn(w + 1));
+                    const float bb = __fmul_rn(__int2float_rn(w), a);
+                    Taps t;
+                    feature_taps_padded(f, g.x, g.y, p.W, p.H, &p.hdr->error_flags, t);
+                    const uint32_t rows = (uint32_t)t.idx[0] | ((uint32_t)t.idx[1] << 8) | ((uint32_t)t.idx[2] << 16) |
+                                          ((uint32_t)t.idx[3] << 24);
+                    TileUpdate u;
+                    u.w[0] = t.w[0];
+                    u.w[1] = t.w[1];
+                    u.w[2] = t.w[2];
+                    u.w[3] = t.w[3];
+                    u.a = a;
+                    u.b = bb;
+                    u.rows = rows;
+                    u.pad = 0;
+                    M->upd[v / kTileSlots][b][v % kTileSlots] = u;
+                    if ((fb >> b) & 1u) M->prim_rows[v / kTileSlots][b] = rows;
+                    const int px = nearest_index(g.x, p.W), py = nearest_index(g.y, p.H);
+                    float smp[3];
+                    sample_rgb(p, f, g.x, g.y, px, py, smp);
+                    my_smp[v * SAF_MAX_BATCH + b] = make_float4(smp[0], smp[1], smp[2], 0.f);
+                    if (p.vol.labels_one_hot && f.seg) {
+                        const float lf = (px >= 0 && py >= 0) ? load_class_id(f.seg, f.seg_dtype, py * p.W + px) : 0.0f;
+                        const long long id = (long long)lf;
+                        if (id >= 0 && id < p.vol.n_classes)
+                            atomicAdd(p.vol.labels_one_hot + (size_t)vx * p.vol.n_classes + id, 1);   // RED: no round trip
+                        else
+                            atomicOr(&p.hdr->error_flags, SAF_FLAG_BAD_CLASS_ID);
+                    }
+                }
+            }
+            __syncwarp();   // samples and update records of every cell are in shared memory
+            if (lane < cnt) {
+                // the rgb running average walks the voxel's frames in order (clip_seem_fusion.py:808-813)
+                float acc[3] = {rgb0[0], rgb0[1], rgb0[2]};
+                for (uint32_t mm = my_mask; mm; mm &= mm - 1u) {
+                    const int b = __ffs(mm) - 1;
+                    const float4 sm = my_smp[lane * SAF_MAX_BATCH + b];
+                    const float a = M->upd[set][b][slot].a, bb = M->upd[set][b][slot].b;
+                    acc[0] = __fadd_rn(__fmul_rn(sm.x, a), __fmul_rn(acc[0], bb));
+                    acc[1] = __fadd_rn(__fmul_rn(sm.y, a), __fmul_rn(acc[1], bb));
+                    acc[2] = __fadd_rn(__fmul_rn(sm.z, a), __fmul_rn(acc[2], bb));
+                }
+                float* dst = p.vol.rgb + (size_t)my_voxel * 3;
+                dst[0] = acc[0];
+                dst[1] = acc[1];
+                dst[2] = acc[2];
+                p.vol.weight[my_voxel] = my_w0 + __popc(my_mask);
+            }
+            __syncwarp();   // every lane's metadata is written (and my_smp read) before the arrival publishes it
+            if (lane == 0) mbar_arrive(&full[ms]);
+        }
+        return;
+    }
+#else   // lane-per-voxel producer: each lane walks its voxel's frames one after the other
     if (warp < NBUF) {
         // ------------------------------- producer -------------------------------
         const uint32_t n_blocks = sc->n_blocks;
@@ -1865,6 +2034,7 @@ feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, co
         return;
     }
 
+#endif
     // ------------------------------- compute -------------------------------
     const int cw = warp - NBUF;
     const int set = cw / CHUNKS, chunk = cw % CHUNKS;
@@ -2323,7 +2493,10 @@ static int launch_k3w_tile(const FusionParams& p, const WindowTables& wt, int sm
 {
     constexpr int kThreads = (CHUNKS * NSET + NBUF) * 32;
     constexpr size_t smem = (size_t)NBUF * NSET * kTileSlots * CHUNKS * 128 * sizeof(float) +
-                            2 * (size_t)NBUF * sizeof(TileMeta<NSET>) + 5 * (size_t)NBUF * sizeof(uint64_t);
+                            2 * (size_t)NBUF * sizeof(TileMeta<NSET>) +
+                            (size_t)NBUF * NSET * kTileSlots * SAF_MAX_BATCH * sizeof(float4) +
+                            5 * (size_t)NBUF * sizeof(uint64_t);
+    static_assert(smem <= 227 * 1024, "tile kernel shared memory");
     auto kern = feature_accumulate_window_tile_kernel<CHUNKS, NSET, NBUF>;
     SAF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<sms, kThreads, smem, st>>>(p, wt);
@@ -2361,7 +2534,7 @@ static int launch_k3w(const FusionParams& p, int sms, cudaStream_t st)
                                                                           : (p.frames[b].npy + 2) * (p.frames[b].npx + 2)) <= 256;
         if (k3w_variant() == 2 && small_tables) {
             switch (C) {
-                case 512: return launch_k3w_tile<4, 3, 3>(p, wt, sms, st);
+                case 512: return launch_k3w_tile<4, 2, 3>(p, wt, sms, st);
                 case 768: return launch_k3w_tile<6, 2, 3>(p, wt, sms, st);
                 case 1024: return launch_k3w_tile<8, 2, 2>(p, wt, sms, st);
                 default: break;

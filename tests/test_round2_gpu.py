@@ -134,8 +134,10 @@ def test_block_cyclic_slabs_concatenate_to_the_full_grid(world):
         import spatially_aware_ai_b200 as saf
         ts, ti = saf.query_topk(vol.clip_feat, X, 4, norm="nan_to_num", mode="dot")
         gi = _np(slab.local_to_global_rows(vol, ti))
-        ref = O.normalize_rows(orc.clip_feat[rows]) @ _np(X).T
-        assert np.array_equal(gi, rows[O.topk_indices(ref, 4)])
+        # neighbouring voxels can score within an ulp of each other: rank the kernel's own fp32 scores
+        scores = _np(saf.query_scores(vol.clip_feat, X, norm="nan_to_num", mode="dot"))
+        assert np.abs(scores - O.normalize_rows(orc.clip_feat[rows]) @ _np(X).T).max() <= 1e-5
+        assert np.array_equal(gi, rows[O.topk_indices(scores, 4)])
     assert (covered == 1).all()
 
 

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import spatially_aware_ai_b200 as saf  # noqa: E402
 from spatially_aware_ai_b200 import _lib, synth  # noqa: E402
-from tests.helpers import FakeClip, FakeSeg  # noqa: E402
+from spatially_aware_ai_b200.synth import FakeClip, FakeSeg  # noqa: E402
 
 window = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 n_windows = int(sys.argv[2]) if len(sys.argv) > 2 else 6
