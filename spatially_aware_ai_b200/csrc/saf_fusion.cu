@@ -1671,6 +1671,9 @@ feature_accumulate_window_pair_kernel(const __grid_constant__ FusionParams p, co
 #ifndef SAF_TILE_PRODUCER
 #define SAF_TILE_PRODUCER 1     // 2: cell-parallel producer (see the kernel)
 #endif
+#ifndef SAF_TILE_PREFETCH
+#define SAF_TILE_PREFETCH 1     // frames whose table rows are requested ahead of the arithmetic (1 or 2)
+#endif
 constexpr int kTileSlots = 8;    // voxels per set (accumulator registers: 8 x float4 per thread)
 
 struct __align__(16) TileUpdate {   // one (frame, voxel) feature update
@@ -2071,18 +2074,8 @@ feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, co
 
         const uint32_t fm = M->fmask[set];
         if (fm) {
-            RowRegs T, Tn;
-            int b = __ffs(fm) - 1;
-            uint32_t cur_rows = M->prim_rows[set][b];
-            load_rows(T, wt.ptr[b], cur_rows, C, col4);
-            for (uint32_t rest = fm & (fm - 1u);; rest &= rest - 1u) {
-                // the next frame's rows are requested before this frame's arithmetic starts
-                const int bn = rest ? __ffs(rest) - 1 : -1;
-                uint32_t nxt_rows = 0;
-                if (bn >= 0) {
-                    nxt_rows = M->prim_rows[set][bn];
-                    load_rows(Tn, wt.ptr[bn], nxt_rows, C, col4);
-                }
+            // one frame of the window: every voxel of the set that the frame sees, with the frame's rows in T
+            auto frame_updates = [&](int b, RowRegs& T, uint32_t& cur_rows) {
                 const uint32_t vm = M->vmask[set][b];
 #pragma unroll
                 for (int s = 0; s < kTileSlots; ++s) {
@@ -2101,11 +2094,57 @@ feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, co
                         acc_hi[s] = mix_blend2(T.hi, wp, ap, bp, acc_hi[s]);
                     }
                 }
+            };
+            uint32_t rest = fm;
+            auto next_frame = [&]() {
+                const int b = rest ? __ffs(rest) - 1 : -1;
+                rest &= rest - 1u;
+                return b;
+            };
+            auto request = [&](int b, RowRegs& T, uint32_t& rows) {
+                if (b >= 0) {
+                    rows = M->prim_rows[set][b];
+                    load_rows(T, wt.ptr[b], rows, C, col4);
+                }
+            };
+#if SAF_TILE_PREFETCH == 2
+            // the rows of the next TWO frames are in flight while a frame's arithmetic runs (an L2 round trip is
+            // longer than the arithmetic of one frame): three register sets in rotation, no copies
+            RowRegs Ta, Tb, Tc;
+            uint32_t ra = 0, rb = 0, rc = 0;
+            int fa = next_frame(), fb = next_frame(), fc;
+            request(fa, Ta, ra);
+            request(fb, Tb, rb);
+            for (;;) {
+                fc = next_frame();
+                request(fc, Tc, rc);
+                frame_updates(fa, Ta, ra);
+                if (fb < 0) break;
+                fa = next_frame();
+                request(fa, Ta, ra);
+                frame_updates(fb, Tb, rb);
+                if (fc < 0) break;
+                fb = next_frame();
+                request(fb, Tb, rb);
+                frame_updates(fc, Tc, rc);
+                if (fa < 0) break;
+            }
+#else
+            RowRegs T, Tn;
+            uint32_t cur_rows = 0, nxt_rows = 0;
+            int b = next_frame();
+            request(b, T, cur_rows);
+            for (;;) {
+                // the next frame's rows are requested before this frame's arithmetic starts
+                const int bn = next_frame();
+                request(bn, Tn, nxt_rows);
+                frame_updates(b, T, cur_rows);
                 if (bn < 0) break;
                 T = Tn;
                 cur_rows = nxt_rows;
                 b = bn;
             }
+#endif
 #pragma unroll
             for (int s = 0; s < kTileSlots; ++s) {
                 if ((uint32_t)(set * kTileSlots + s) < n_rows) {
