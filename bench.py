@@ -9,8 +9,8 @@ Workloads (BASELINE.json configs):
   N = 1   configs[1] "cfg2": 640x480 frames, 2 cm voxels over a 6x6x3 m room (+- trunc margin -> 304x304x154 =
           14.2 M voxels), 768-d features, 5x7 tiled-patch feature image, the 1000-pose orbit visited in order.
   N > 1   configs[2] "cfg3": ONE 8x8x3 m room, 404x404x154 = 25.1 M voxels x 768-d, 5000-pose orbit, the grid
-          sharded over the ranks ("scaling": "strong"): block-cyclic x-slabs (stripes of 8 planes dealt round-robin,
-          --slab-layout contiguous for plain slabs), every rank is handed every frame
+          sharded over the ranks ("scaling": "strong"): sheared block columns (8x8xnz column (bx, by) on rank
+          (bx + by) % N; --slab-layout cyclic / contiguous for x-stripes / x-slabs), every rank is handed every frame
           (clip_seem_fusion.py:305-313 has no notion of slabs), no collective in the fusion path.
           --multi rooms keeps round 1's weak-scaling workload (N rooms side by side, one per rank).
 A step = `--frames-per-step` frames (default 100).  Both arms walk the same frame sequence: step s of the
@@ -56,7 +56,8 @@ def parse_args(argv=None):
     ap.add_argument("--workload", default="auto", choices=["auto", "cfg1", "cfg2", "cfg3"])
     ap.add_argument("--multi", default="strong", choices=["strong", "rooms"],
                     help="N > 1: strong = one grid sharded over the ranks; rooms = N rooms side by side (weak)")
-    ap.add_argument("--slab-layout", default="cyclic", choices=["cyclic", "contiguous"])
+    ap.add_argument("--slab-layout", default="sheared", choices=["sheared", "cyclic", "contiguous"],
+                    help="N > 1, strong: sheared block columns ((bx + by) %% N), block-cyclic x-stripes, or x-slabs")
     ap.add_argument("--frames-per-step", type=int, default=100)
     ap.add_argument("--pool", type=int, default=0,
                     help="distinct frames kept resident (cycled); 0 = as many as the run visits, at most 2500")
@@ -129,6 +130,8 @@ class Plan:
         if self.mode == "rooms":
             own = rank if self.world > 1 else 0
             return dict(x_begin=own * self.slab_nx, x_end=(own + 1) * self.slab_nx)
+        if self.layout == "sheared":
+            return dict(y_ranks=self.world, y_rank=rank)
         if self.layout == "cyclic":
             return dict(x_begin=rank * SLAB_SPAN, x_end=nx, x_span=SLAB_SPAN, x_stride=SLAB_SPAN * self.world)
         from spatially_aware_ai_b200 import slab
@@ -144,8 +147,10 @@ class Plan:
             s += "; %d rooms side by side along x (20 cm partition walls), one x-slab per rank" % self.n_rooms
         order = "poses %d, %d, ... of the %d-pose orbit, in order" % (0, self.stride, cfg.frames)
         par = {"single": "single GPU",
-               "strong": "grid sharded over %d ranks (%s x-slabs%s), every rank handed every frame, no data-path "
-                         "collective" % (self.world, self.layout, ", stripes of %d planes" % SLAB_SPAN if self.layout == "cyclic" else ""),
+               "strong": "grid sharded over %d ranks (%s), every rank handed every frame, no data-path collective" %
+                         (self.world, {"sheared": "sheared block columns: 8x8xnz column (bx, by) on rank (bx + by) mod N",
+                                       "cyclic": "block-cyclic x-stripes of %d planes" % SLAB_SPAN,
+                                       "contiguous": "contiguous x-slabs"}[self.layout]),
                "rooms": "one room (x-slab) per rank, every rank handed every frame, no data-path collective"}[self.mode]
         return {"workload": s, "frames_per_step": self.F, "frame_pool": self.P, "frame_order": order,
                 "l2": "no flush needed: one window touches > 1 GB of feature rows, the L2 holds 126 MB",

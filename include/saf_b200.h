@@ -90,7 +90,12 @@ extern "C" {
  * [x_begin + k*x_stride, x_begin + k*x_stride + x_span) for k = 0, 1, ... clipped to x_end, concatenated in
  * order (rank r of n: x_begin = r*x_span, x_stride = n*x_span, x_end = nvox[0]).  x_span and x_stride are
  * multiples of SAF_BLOCK_EDGE.  Fusion, label argmax and the query accept such slabs; the mesh and object
- * entry points need contiguous slabs (x_span = 0) and return SAF_ERR_UNSUPPORTED otherwise. */
+ * entry points need contiguous slabs (x_span = 0) and return SAF_ERR_UNSUPPORTED otherwise.
+ * Sheared block columns (y_ranks = n > 1; x_begin = 0, x_end = nvox[0], x_span = 0): the grid is cut into columns
+ * of 8 x 8 x nz voxels and column (bx, by) belongs to rank (bx + by) mod n, so that a surface lying in ONE x-plane or
+ * ONE y-plane (a wall of an axis-aligned room) is spread over all ranks - x-stripes leave it on one.  A rank's
+ * buffers are a dense [nvox[0], ny_local, nz] grid, ny_local = 8 * ceil(ceil(ny / 8) / n): local y-block j of
+ * x-block bx is global y-block j*n + ((y_rank - bx) mod n); local columns beyond the grid are never touched. */
 typedef struct saf_grid_desc {
     float   origin[3];
     float   voxel_size;
@@ -99,6 +104,8 @@ typedef struct saf_grid_desc {
     int32_t x_end;
     int32_t x_span;    /* 0 = one contiguous slab [x_begin, x_end) */
     int32_t x_stride;
+    int32_t y_ranks;   /* > 1: sheared block-column layout over this many ranks (below), else 0 */
+    int32_t y_rank;    /* this rank's index in it */
 } saf_grid_desc;
 
 /* Device buffers of one slab; names, dtypes and shapes are the reference's registered buffers

@@ -32,7 +32,8 @@ c_void_p, c_int32, c_int64, c_uint64, c_float = (ctypes.c_void_p, ctypes.c_int32
 
 class GridDesc(ctypes.Structure):
     _fields_ = [("origin", c_float * 3), ("voxel_size", c_float), ("nvox", c_int32 * 3),
-                ("x_begin", c_int32), ("x_end", c_int32), ("x_span", c_int32), ("x_stride", c_int32)]
+                ("x_begin", c_int32), ("x_end", c_int32), ("x_span", c_int32), ("x_stride", c_int32),
+                ("y_ranks", c_int32), ("y_rank", c_int32)]
 
 
 class Volume(ctypes.Structure):

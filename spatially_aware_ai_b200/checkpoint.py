@@ -30,7 +30,7 @@ _STATE_FILES = {
 
 def _grid_shape(volume, tensor):
     nxs = len(volume.global_x_planes())
-    return (nxs, volume._dims[1], volume._dims[2]) + tuple(tensor.shape[1:])
+    return (nxs, volume.ny_local, volume._dims[2]) + tuple(tensor.shape[1:])
 
 
 def _stream_out(tensor, path, shape):
@@ -81,7 +81,8 @@ def save_state(volume, directory):
     meta = dict(format_version=FORMAT_VERSION, cls=type(volume).__name__, origin=[float(v) for v in origin],
                 voxel_size=float(volume.voxel_size), nvox=[int(v) for v in volume._dims], trunc=float(volume.trunc),
                 x_begin=int(volume.x_begin), x_end=int(volume.x_end), x_span=int(volume.x_span),
-                x_stride=int(volume.x_stride), feature_dim=int(volume.n_clip_feats), files=written, stats=volume.stats(check=False) if volume.tsdf.is_cuda else None)
+                x_stride=int(volume.x_stride), y_ranks=int(volume.y_ranks), y_rank=int(volume.y_rank),
+                feature_dim=int(volume.n_clip_feats), files=written, stats=volume.stats(check=False) if volume.tsdf.is_cuda else None)
     with open(os.path.join(directory, "volume_state.json"), "w") as f:
         json.dump(meta, f, indent=1, default=str)
     return meta
@@ -94,7 +95,8 @@ def load_state(volume, directory):
     if meta.get("format_version") != FORMAT_VERSION:
         raise ValueError("unsupported checkpoint format %r" % meta.get("format_version"))
     mine = dict(nvox=[int(v) for v in volume._dims], x_begin=int(volume.x_begin), x_end=int(volume.x_end),
-                x_span=int(volume.x_span), x_stride=int(volume.x_stride), feature_dim=int(volume.n_clip_feats))
+                x_span=int(volume.x_span), x_stride=int(volume.x_stride), y_ranks=int(volume.y_ranks),
+                y_rank=int(volume.y_rank), feature_dim=int(volume.n_clip_feats))
     for key, val in mine.items():
         if meta.get(key, 0) != val:
             raise ValueError("checkpoint %s = %r does not match the volume's %r" % (key, meta[key], val))

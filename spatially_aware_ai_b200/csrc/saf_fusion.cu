@@ -49,6 +49,7 @@ struct FusionParams {
     uint32_t nb[3];
     uint32_t nblocks_total;
     uint32_t nxs;              // slab extent in x
+    uint32_t nyl;              // slab extent in y (the grid's ny, or the sheared layout's local extent)
     uint64_t nslab;
     uint64_t list_cap;
     uint64_t max_table_elems;
@@ -304,8 +305,10 @@ __device__ __forceinline__ bool block_maybe_visible(const Geom& g, float cx, flo
 __device__ __forceinline__ void block_sphere(const FusionParams& p, uint32_t bx, uint32_t by, uint32_t bz, float& cx,
                                              float& cy, float& cz, float& r, float* half = nullptr)
 {
-    const int x0 = (int)bx * kBlockEdge, y0 = (int)by * kBlockEdge, z0 = (int)bz * kBlockEdge;
-    const int ex = min(kBlockEdge, (int)p.nxs - x0), ey = min(kBlockEdge, p.grid.nvox[1] - y0),
+    const int x0 = (int)bx * kBlockEdge, z0 = (int)bz * kBlockEdge;
+    const int y0 = slab_global_y(p.grid, x0, (int)by * kBlockEdge);   // global y of the block's first row
+    // (a local block column of the sheared layout that lies beyond the grid gets ey <= 0: see block_in_grid)
+    const int ex = min(kBlockEdge, (int)p.nxs - x0), ey = max(1, min(kBlockEdge, p.grid.nvox[1] - y0)),
               ez = min(kBlockEdge, p.grid.nvox[2] - z0);
     const float vs = p.grid.voxel_size;
     const float hx = 0.5f * vs * (float)(ex - 1), hy = 0.5f * vs * (float)(ey - 1), hz = 0.5f * vs * (float)(ez - 1);
@@ -318,6 +321,12 @@ __device__ __forceinline__ void block_sphere(const FusionParams& p, uint32_t bx,
         half[1] = hy + 0.01f * vs;
         half[2] = hz + 0.01f * vs;
     }
+}
+
+// sheared layout: the last local block column of an x-block may lie beyond the grid's y extent
+__device__ __forceinline__ bool block_in_grid(const FusionParams& p, uint32_t bx, uint32_t by)
+{
+    return slab_global_y(p.grid, (int)bx * kBlockEdge, (int)by * kBlockEdge) < p.grid.nvox[1];
 }
 
 // smallest camera-space z = K[2,:] . R^T (x - t) over the block's box of voxel centres (exact minimum of a
@@ -510,7 +519,7 @@ __global__ void __launch_bounds__(kK1Threads) frame_setup_kernel(const FusionPar
     }
     uint32_t vis = 0;       // bit b: the block may be touched by frame b
     uint32_t frustum = 0;   // ... before the depth test
-    if (blk < p.nblocks_total) {
+    if (blk < p.nblocks_total && block_in_grid(p, blk / (p.nb[2] * p.nb[1]), (blk / p.nb[2]) % p.nb[1])) {
         const uint32_t bz = blk % p.nb[2];
         const uint32_t by = (blk / p.nb[2]) % p.nb[1];
         const uint32_t bx = blk / (p.nb[2] * p.nb[1]);
@@ -575,7 +584,7 @@ __global__ void __launch_bounds__(kK2Threads, SEQ ? 8 : 1) tsdf_update_kernel(co
     __shared__ uint32_t s_rank;                // list segment claimed for the block being processed
     const int B = BATCH1 ? 1 : p.batch;
     const float fW = (float)p.W, fH = (float)p.H;
-    const int ny = p.grid.nvox[1], nz = p.grid.nvox[2];
+    const int ny = p.grid.nvox[1], nz = p.grid.nvox[2], nyl = (int)p.nyl;
     uint32_t tv_count[BATCH1 ? 1 : SAF_MAX_BATCH];
 #pragma unroll
     for (int b = 0; b < (BATCH1 ? 1 : SAF_MAX_BATCH); ++b) tv_count[b] = 0;
@@ -611,10 +620,11 @@ __global__ void __launch_bounds__(kK2Threads, SEQ ? 8 : 1) tsdf_update_kernel(co
         for (int j = 0; j < kK2Iter; ++j) {
             const int local = threadIdx.x + j * kK2Threads;
             const int lx = (int)bx * kBlockEdge + (local >> 6);  // slab-local x
-            const int iy = (int)by * kBlockEdge + ((local >> 3) & 7);
+            const int ly = (int)by * kBlockEdge + ((local >> 3) & 7);   // slab-local y
+            const int iy = slab_global_y(p.grid, lx, ly);
             const int iz = (int)bz * kBlockEdge + (local & 7);
             inside[j] = lx < (int)p.nxs && iy < ny && iz < nz;
-            v[j] = inside[j] ? (uint32_t)(((uint64_t)lx * ny + iy) * nz + iz) : 0u;
+            v[j] = inside[j] ? (uint32_t)(((uint64_t)lx * nyl + ly) * nz + iz) : 0u;
             xw[j] = voxel_centre(slab_global_x(p.grid, lx), p.grid.voxel_size, p.grid.origin[0]);
             yw[j] = voxel_centre(iy, p.grid.voxel_size, p.grid.origin[1]);
             zw[j] = voxel_centre(iz, p.grid.voxel_size, p.grid.origin[2]);
@@ -2334,7 +2344,8 @@ static int build_params(const saf_grid_desc* grid, const saf_volume* vol, const 
     p->nblocks_total = L.nblocks_total;
     p->n_k1 = L.n_k1;
     p->nxs = (uint32_t)slab_planes(*grid);
-    p->nslab = (uint64_t)p->nxs * (uint64_t)grid->nvox[1] * (uint64_t)grid->nvox[2];
+    p->nyl = (uint32_t)slab_ny_local(*grid);
+    p->nslab = (uint64_t)p->nxs * (uint64_t)p->nyl * (uint64_t)grid->nvox[2];
     p->list_cap = L.list_cap;
     p->max_table_elems = (uint64_t)ws->max_table_elems;
     p->table_slot_elems = L.table_slot_elems;
@@ -2840,7 +2851,7 @@ int saf_frame_reaches_slab(const saf_grid_desc* grid, const float* pose, const f
 {
     if (!grid || !pose || !K) return SAF_ERR_NULL;
     if (!slab_desc_ok(*grid) || H <= 0 || W <= 0) return SAF_ERR_GRID;
-    if (grid->x_span != 0) return 1;   // block-cyclic stripes span the grid: a frame that sees the grid sees the slab
+    if (grid->x_span != 0 || grid->y_ranks > 1) return 1;   // stripes / block columns span the grid
     return frame_may_reach_slab_host(*grid, pose, K, H, W) ? 1 : 0;
 }
 

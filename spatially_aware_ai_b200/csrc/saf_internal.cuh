@@ -116,9 +116,26 @@ __host__ __device__ inline int slab_global_x(const saf_grid_desc& g, int lx)
     if (g.x_span <= 0) return g.x_begin + lx;
     return g.x_begin + (lx / g.x_span) * g.x_stride + (lx % g.x_span);
 }
+// sheared block-column layout (saf_grid_desc.y_ranks): local y extent and the global y of a local (x, y)
+__host__ __device__ inline int slab_ny_local(const saf_grid_desc& g)
+{
+    if (g.y_ranks <= 1) return g.nvox[1];
+    const int nby = (g.nvox[1] + SAF_BLOCK_EDGE - 1) / SAF_BLOCK_EDGE;
+    return SAF_BLOCK_EDGE * ((nby + g.y_ranks - 1) / g.y_ranks);
+}
+__host__ __device__ inline int slab_global_y(const saf_grid_desc& g, int lx, int ly)
+{
+    if (g.y_ranks <= 1) return ly;
+    const int n = g.y_ranks;
+    const int shift = ((g.y_rank - lx / SAF_BLOCK_EDGE) % n + n) % n;
+    return ((ly / SAF_BLOCK_EDGE) * n + shift) * SAF_BLOCK_EDGE + ly % SAF_BLOCK_EDGE;
+}
 inline bool slab_desc_ok(const saf_grid_desc& g)
 {
     if (g.x_begin < 0 || g.x_end > g.nvox[0] || g.x_begin >= g.x_end) return false;
+    if (g.y_ranks > 1)
+        return g.x_begin == 0 && g.x_end == g.nvox[0] && g.x_span == 0 && g.y_rank >= 0 && g.y_rank < g.y_ranks;
+    if (g.y_ranks < 0) return false;
     if (g.x_span == 0) return true;
     return g.x_span > 0 && g.x_span % SAF_BLOCK_EDGE == 0 && g.x_stride >= g.x_span && g.x_stride % SAF_BLOCK_EDGE == 0;
 }
@@ -131,10 +148,11 @@ inline int compute_layout(const saf_grid_desc* g, int32_t max_batch, int64_t max
         return SAF_ERR_GRID;
     if (max_table_elems < 0) return SAF_ERR_SHAPE;
     const uint64_t nxs = (uint64_t)slab_planes(*g);
-    const uint64_t n = nxs * (uint64_t)g->nvox[1] * (uint64_t)g->nvox[2];
+    const uint64_t nyl = (uint64_t)slab_ny_local(*g);
+    const uint64_t n = nxs * nyl * (uint64_t)g->nvox[2];
     if (n >= (1ull << 31)) return SAF_ERR_GRID;  // voxel indices are 32-bit
     L->nb[0] = (uint32_t)((nxs + kBlockEdge - 1) / kBlockEdge);
-    L->nb[1] = (uint32_t)((g->nvox[1] + kBlockEdge - 1) / kBlockEdge);
+    L->nb[1] = (uint32_t)((nyl + kBlockEdge - 1) / kBlockEdge);
     L->nb[2] = (uint32_t)((g->nvox[2] + kBlockEdge - 1) / kBlockEdge);
     const uint64_t nblocks = (uint64_t)L->nb[0] * L->nb[1] * L->nb[2];
     L->n_k1 = (uint32_t)((nblocks + kK1Threads - 1) / kK1Threads);

@@ -376,7 +376,7 @@ int mc_layout(const saf_grid_desc* g, McLayout* L)
     if (g->nvox[0] <= 0 || g->nvox[1] <= 0 || g->nvox[2] <= 0 || g->x_begin < 0 || g->x_end > g->nvox[0] ||
         g->x_begin >= g->x_end)
         return SAF_ERR_GRID;
-    if (g->x_span != 0) return SAF_ERR_UNSUPPORTED;   // block-cyclic slabs: redistribute to contiguous slabs first
+    if (g->x_span != 0 || g->y_ranks > 1) return SAF_ERR_UNSUPPORTED;   // cyclic layouts: contiguous slabs only
     L->n = (int64_t)(g->x_end - g->x_begin + 1) * g->nvox[1] * g->nvox[2];   // the slab plus one halo plane
     if (L->n * 3 >= (1ll << 32)) return SAF_ERR_GRID;   // edge -> vertex map is 32-bit
     L->nblk = (uint32_t)((L->n + kMcThreads - 1) / kMcThreads);

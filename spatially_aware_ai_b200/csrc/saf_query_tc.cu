@@ -226,11 +226,16 @@ query_gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             // less than 2^-9 relative, so |exact - tf32| <= 2^-9 |f| |x| (Cauchy-Schwarz) plus fp32 slack.
             const float eps_row = 0.001953125f * sqrtf(norm2) * scale;
             const int64_t m = m0 + row;
+            // An all-zero row (an unobserved voxel: most of a fused grid) scores exactly 0 against every text.  It
+            // is never a candidate here - millions of rows tied at 0 would flood the buckets - and only noted:
+            // the final kernel asks for the exact path in the rare case that a text's k-th best score is <= 0.
+            const bool zero_row = m < M && norm2 == 0.0f;
+            if (__any_sync(0xffffffffu, zero_row) && lane == 0) fa.flags[1] = 1u;
             const uint32_t lane_base_f = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
             for (int c0 = 0; c0 < n_pad; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld32(lane_base_f + (uint32_t)c0, r);
-                if (m < M) {
+                if (m < M && !zero_row) {
 #pragma unroll
                     for (int c = 0; c < 32; ++c) {
                         const int t = t0 + c0 + c;
@@ -428,7 +433,10 @@ __global__ void __launch_bounds__(128) topk_tc_init_kernel(const float* __restri
         thr[t] = -INFINITY;
         counts_a[t] = 0;
         counts_b[t] = 0;
-        if (t == 0) flags[0] = 0;
+        if (t == 0) {
+            flags[0] = 0;
+            flags[1] = 0;   // set by the filter when it skipped an all-zero row
+        }
     }
 }
 
@@ -531,14 +539,17 @@ __global__ void __launch_bounds__(256) topk_tc_final_kernel(const Candidate* __r
             out_s[(size_t)t * k + rank] = sa;
             out_i[(size_t)t * k + rank] = (long long)ra + index_base;
         }
+        // zero rows were left out of the buckets: they belong in the answer iff the k-th best score is not positive
+        if (rank == k - 1 && !(sa > 0.0f) && flags[1]) atomicOr(flags, 1u);
     }
+    if (threadIdx.x == 0 && n < (uint32_t)k && flags[1]) atomicOr(flags, 1u);
 }
 
 }  // namespace tc
 
 uint64_t query_topk_tc_workspace_bytes(int32_t T)
 {
-    return 2ull * (uint64_t)T * tc::kBucketCap * sizeof(tc::Candidate) + 4ull * (uint64_t)T * 4 + 256;
+    return 2ull * (uint64_t)T * tc::kBucketCap * sizeof(tc::Candidate) + 4ull * (uint64_t)T * 4 + 256;   // + flags[2]
 }
 
 // returns 0 on success, 1 when the caller must fall back to the exact chunked path (bucket overflow:

@@ -13,8 +13,9 @@ Differences a caller can observe:
     as a lazily computed property.
   * optional ``x_begin`` / ``x_end`` keyword arguments hold only an x-slab of the grid
     (multi-GPU partitioning); buffers then cover that slab, coordinates stay global.  ``x_span`` /
-    ``x_stride`` make the slab block-cyclic (stripes of x_span planes every x_stride planes), which
-    balances the ranks when a camera sees only part of the grid per frame.
+    ``x_stride`` make the slab block-cyclic (stripes of x_span planes every x_stride planes); ``y_ranks`` /
+    ``y_rank`` select the sheared block-column layout (column (bx, by) of 8 x 8 x nz voxels on rank
+    (bx + by) % y_ranks), which gives every rank the same share of every view AND of every axis-aligned wall.
   * class ids outside [0, n_classes) cannot raise inside a kernel; they set a sticky flag that
     ``check_errors()`` (and ``stats()``) turn into the RuntimeError torch's one_hot would raise.
 """
@@ -46,7 +47,8 @@ class _FusionVolume(torch.nn.Module):
     # (BASELINE.json north_star / SURVEY.md 7.2; include/saf_b200.h SAF_TABLE_SEGMENTS).  Set on the instance.
     feature_source = "patch_grid"
 
-    def _init_volume(self, origin, voxel_size, nvox, trunc, feature_dim, x_begin=0, x_end=None, x_span=0, x_stride=0):
+    def _init_volume(self, origin, voxel_size, nvox, trunc, feature_dim, x_begin=0, x_end=None, x_span=0, x_stride=0,
+                     y_ranks=0, y_rank=0):
         self.origin = origin
         self.voxel_size = voxel_size
         self.nvox = nvox
@@ -62,8 +64,12 @@ class _FusionVolume(torch.nn.Module):
         if self.x_span and (self.x_span % _lib.SAF_BLOCK_EDGE or self.x_stride % _lib.SAF_BLOCK_EDGE or
                             self.x_stride < self.x_span or self.x_span < 0):
             raise ValueError("x_span / x_stride must be multiples of %d with x_stride >= x_span" % _lib.SAF_BLOCK_EDGE)
+        # sheared block columns: 8 x 8 x nz columns, column (bx, by) on rank (bx + by) % y_ranks (saf_grid_desc)
+        self.y_ranks, self.y_rank = int(y_ranks), int(y_rank)
+        if self.y_ranks > 1 and (self.x_span or self.x_begin or self.x_end != dims[0] or not 0 <= self.y_rank < self.y_ranks):
+            raise ValueError("the sheared block-column layout holds the whole x range and needs 0 <= y_rank < y_ranks")
         self._dims = dims
-        n = len(self.global_x_planes()) * dims[1] * dims[2]
+        n = len(self.global_x_planes()) * self.ny_local * dims[2]
         self.register_buffer("tsdf", torch.zeros(n, dtype=torch.float32))
         self.register_buffer("rgb", torch.zeros((n, 3), dtype=torch.float32))
         self.register_buffer("clip_feat", torch.zeros((n, self.n_clip_feats), dtype=torch.float32))
@@ -90,8 +96,35 @@ class _FusionVolume(torch.nn.Module):
             g.nvox[:] = self._dims
             g.x_begin, g.x_end = self.x_begin, self.x_end
             g.x_span, g.x_stride = self.x_span, self.x_stride
+            g.y_ranks, g.y_rank = (self.y_ranks, self.y_rank) if self.y_ranks > 1 else (0, 0)
             self._grid = g
         return self._grid
+
+    @property
+    def ny_local(self):
+        """Rows of the slab's y axis: the grid's ny, or the sheared layout's 8 * ceil(n_y_blocks / y_ranks)."""
+        if self.y_ranks <= 1:
+            return self._dims[1]
+        e = _lib.SAF_BLOCK_EDGE
+        nby = (self._dims[1] + e - 1) // e
+        return e * ((nby + self.y_ranks - 1) // self.y_ranks)
+
+    def global_rows(self, device=None):
+        """Global flat voxel index (x*ny + y)*nz + z of every row of the slab's buffers, int64 [n]; -1 for the
+        sheared layout's padding rows (local columns beyond the grid)."""
+        nx, ny, nz = self._dims
+        e = _lib.SAF_BLOCK_EDGE
+        xs = torch.as_tensor(self.global_x_planes(), dtype=torch.int64, device=device)
+        ly = torch.arange(self.ny_local, dtype=torch.int64, device=device)
+        if self.y_ranks > 1:
+            lx = torch.arange(len(xs), dtype=torch.int64, device=device)
+            shift = (self.y_rank - lx // e) % self.y_ranks
+            gy = ((ly[None, :] // e) * self.y_ranks + shift[:, None]) * e + ly[None, :] % e       # [nx, ny_local]
+        else:
+            gy = ly[None, :].expand(len(xs), -1)
+        rows = (xs[:, None] * ny + gy)[:, :, None] * nz + torch.arange(nz, dtype=torch.int64, device=device)
+        rows = torch.where((gy < ny)[:, :, None], rows, torch.full_like(rows, -1))
+        return rows.reshape(-1)
 
     def global_x_planes(self):
         """Global x index of every slab-local plane (a contiguous range, or the rank's block-cyclic stripes)."""
@@ -106,11 +139,16 @@ class _FusionVolume(torch.nn.Module):
     def xyz_world(self):
         """World coordinates of the slab's voxel centres, computed like clip_seem_fusion.py:664-669."""
         dev = self.tsdf.device
-        x = torch.as_tensor(self.global_x_planes(), device=dev)
-        y = torch.arange(self._dims[1], device=dev)
-        z = torch.arange(self._dims[2], device=dev)
-        xx, yy, zz = torch.meshgrid(x, y, z, indexing="ij")
-        xyz_idx = torch.stack((xx, yy, zz), dim=-1).view(-1, 3)
+        if self.y_ranks > 1:
+            rows = self.global_rows(dev).clamp(min=0)     # padding rows report voxel 0's centre
+            nx, ny, nz = self._dims
+            xyz_idx = torch.stack((rows // (ny * nz), rows // nz % ny, rows % nz), dim=-1)
+        else:
+            x = torch.as_tensor(self.global_x_planes(), device=dev)
+            y = torch.arange(self._dims[1], device=dev)
+            z = torch.arange(self._dims[2], device=dev)
+            xx, yy, zz = torch.meshgrid(x, y, z, indexing="ij")
+            xyz_idx = torch.stack((xx, yy, zz), dim=-1).view(-1, 3)
         origin = self.origin if isinstance(self.origin, torch.Tensor) else torch.as_tensor(self.origin)
         return xyz_idx * self.voxel_size + origin.to(dev)
 
@@ -328,14 +366,15 @@ class ClipSeemFusion(_FusionVolume):
     _rgb_mode = _lib.SAF_RGB_BILINEAR
 
     def __init__(self, origin, voxel_size, nvox, trunc, scale_patches_by_depth, clip_patch_size, clip_patch_stride,
-                 clip_model, seg_model, x_begin=0, x_end=None, x_span=0, x_stride=0):
+                 clip_model, seg_model, x_begin=0, x_end=None, x_span=0, x_stride=0, y_ranks=0, y_rank=0):
         super().__init__()
         self.clip = clip_model
         self.clip_patch_size = clip_patch_size
         self.clip_patch_stride = clip_patch_stride
         self.scale_patches_by_depth = scale_patches_by_depth
         self.segmentation_model = seg_model
-        self._init_volume(origin, voxel_size, nvox, trunc, self.clip.feature_dim, x_begin, x_end, x_span, x_stride)
+        self._init_volume(origin, voxel_size, nvox, trunc, self.clip.feature_dim, x_begin, x_end, x_span, x_stride,
+                          y_ranks, y_rank)
         self.debug_counter = 0
 
     def _run_producers(self, depth_imgs, rgb_imgs, K):
@@ -374,7 +413,7 @@ class ClipFusion(_FusionVolume):
     _rgb_mode = _lib.SAF_RGB_NEAREST
 
     def __init__(self, origin, voxel_size, nvox, trunc, scale_patches_by_depth, clip_model, clip_pretraining,
-                 clip_patch_size, clip_patch_stride, x_begin=0, x_end=None, x_span=0, x_stride=0):
+                 clip_patch_size, clip_patch_stride, x_begin=0, x_end=None, x_span=0, x_stride=0, y_ranks=0, y_rank=0):
         super().__init__()
         if isinstance(clip_model, str):
             from .query import Clip
@@ -386,7 +425,8 @@ class ClipFusion(_FusionVolume):
         self.clip_patch_size = clip_patch_size
         self.clip_patch_stride = clip_patch_stride
         self.scale_patches_by_depth = scale_patches_by_depth
-        self._init_volume(origin, voxel_size, nvox, trunc, self.clip.feature_dim, x_begin, x_end, x_span, x_stride)
+        self._init_volume(origin, voxel_size, nvox, trunc, self.clip.feature_dim, x_begin, x_end, x_span, x_stride,
+                          y_ranks, y_rank)
 
     def _run_producers(self, depth_imgs, rgb_imgs, K):
         """clipfusion.py:634-646."""

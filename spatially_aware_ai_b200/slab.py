@@ -44,14 +44,78 @@ def cyclic_slab(nx, world_size, rank, span=8):
     return dict(x_begin=rank * span, x_end=int(nx), x_span=span, x_stride=span * world_size)
 
 
+def sheared_slab(world_size, rank):
+    """Sheared block-column split: column (bx, by) of 8 x 8 x nz voxels lives on rank (bx + by) % world_size.
+    Returns the constructor keywords of the fusion classes.  Unlike x-stripes it also spreads a surface that
+    lies in a single x-plane (a wall of an axis-aligned room) over all ranks."""
+    if not (0 <= rank < world_size):
+        raise ValueError("rank %d outside world of %d" % (rank, world_size))
+    return dict(y_ranks=world_size, y_rank=rank) if world_size > 1 else {}
+
+
 def local_to_global_rows(volume, rows):
     """Slab-local flat voxel indices (rows of the volume's buffers; -1 = padding) -> global flat indices
-    (x*ny + y)*nz + z of the whole grid, for contiguous and block-cyclic slabs alike."""
+    (x*ny + y)*nz + z of the whole grid, for contiguous, block-cyclic and sheared slabs alike."""
+    if getattr(volume, "y_ranks", 0) > 1:
+        table = volume.global_rows(rows.device)
+        return torch.where(rows < 0, rows, table[rows.clamp(min=0)])
     plane = volume._dims[1] * volume._dims[2]
     xs = torch.as_tensor(volume.global_x_planes(), dtype=torch.int64, device=rows.device)
     lx = torch.div(rows.clamp(min=0), plane, rounding_mode="floor")
     out = xs[lx] * plane + rows.clamp(min=0) % plane
     return torch.where(rows < 0, rows, out)
+
+
+def redistribute_to_contiguous(volume, group=None):
+    """Block-cyclic slabs -> contiguous slabs (rank r gets slab_bounds(nx, world, r)): the volume of every rank is
+    replaced by a new one of the same class holding the contiguous slab, filled from the ranks that fused its
+    planes (one all_to_all per state buffer, NCCL over NVLink on GPUs).  Fusion balances best on block-cyclic
+    slabs; extract_mesh / label_objects want contiguous ones.  Returns the new volume."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    nx, ny, nz = volume._dims
+    plane = ny * nz
+    xs = volume.global_x_planes()
+    bounds = [slab_bounds(nx, world, q) for q in range(world)]
+    dest_of = lambda x: next(q for q, (a, b) in enumerate(bounds) if a <= x < b)   # noqa: E731
+    send_planes = [0] * world
+    for x in xs:                       # local planes are in ascending x: the planes for a destination are one run
+        send_planes[dest_of(x)] += 1
+    # what every rank holds, derived from the layout (no communication): planes of my new range per source rank
+    if not volume.x_span:
+        raise ValueError("redistribute_to_contiguous expects block-cyclic slabs")
+
+    def planes_of(r):
+        out = []
+        for start in range(r * volume.x_span, nx, volume.x_stride):
+            out.extend(range(start, min(start + volume.x_span, nx)))
+        return out
+    xb, xe = bounds[rank]
+    recv_x = [[x for x in planes_of(r) if xb <= x < xe] for r in range(world)]
+    recv_planes = [len(v) for v in recv_x]
+    order = torch.as_tensor(np.argsort(np.concatenate([np.asarray(v, np.int64) for v in recv_x]), kind="stable"),
+                            device=volume.tsdf.device)
+    kw = dict(x_begin=xb, x_end=xe)
+    cls = type(volume)
+    if hasattr(volume, "segmentation_model"):
+        new = cls(volume.origin, volume.voxel_size, volume.nvox, volume.trunc, volume.scale_patches_by_depth,
+                  volume.clip_patch_size, volume.clip_patch_stride, volume.clip, volume.segmentation_model, **kw)
+    else:
+        new = cls(volume.origin, volume.voxel_size, volume.nvox, volume.trunc, volume.scale_patches_by_depth, volume.clip,
+                  None, volume.clip_patch_size, volume.clip_patch_stride, **kw)
+    new = new.to(volume.tsdf.device)
+    new.feature_source = volume.feature_source
+    for name in ("tsdf", "weight", "tsdf_weight", "rgb", "clip_feat", "labels_one_hot"):
+        src = getattr(volume, name, None)
+        if src is None:
+            continue
+        width = src[0].numel() if src.dim() > 1 else 1
+        flat = src.reshape(len(xs), plane * width)
+        out = torch.empty((sum(recv_planes), plane * width), dtype=src.dtype, device=src.device)
+        dist.all_to_all_single(out, flat.contiguous(), output_split_sizes=recv_planes, input_split_sizes=send_planes,
+                               group=group)
+        getattr(new, name).copy_(out.index_select(0, order).reshape(getattr(new, name).shape))
+        del out
+    return new
 
 
 def merge_topk(scores, indices, k):
@@ -175,14 +239,38 @@ def extract_mesh_distributed(volume, extra=(), dst=0, group=None):
     rank = dist.get_rank(group)
     halo = exchange_halo(volume, extra, group)
     out = volume.extract_mesh(halo=halo, return_edge_ids=True)
-    verts, faces, ids = out[0], out[1], out[-1]
-    attrs = tuple(a.detach().cpu().numpy() for a in out[2:-1])
-    pieces = [None] * dist.get_world_size(group) if rank == dst else None
-    dist.gather_object((verts, faces, ids, attrs), pieces, dst=dst, group=group)
+    dev = volume.tsdf.device
+    # every array travels as a device tensor through gather_rows (sizes first, then padded payloads: NCCL over
+    # NVLink on GPUs) - per-vertex features are [V, C] floats, far too much for a pickled object gather
+    arrays = [torch.as_tensor(np.asarray(out[0], np.float32)), torch.as_tensor(np.asarray(out[1], np.int64)),
+              torch.as_tensor(np.asarray(out[-1], np.int64))] + [a.detach() for a in out[2:-1]]
+    gathered = [gather_rows(a.to(dev), dst=dst, group=group) for a in arrays]
     if rank != dst:
         return None
+    world = dist.get_world_size(group)
+    pieces = [(gathered[0][r].cpu().numpy(), gathered[1][r].cpu().numpy(), gathered[2][r].cpu().numpy(),
+               tuple(g[r].cpu().numpy() for g in gathered[3:])) for r in range(world)]
     wv, wf, wattrs = weld_slab_meshes(pieces)
     return (wv, wf) + tuple(wattrs)
+
+
+def gather_rows(t, dst=0, group=None):
+    """Variable-length gather of one tensor per rank ([n_r, ...], same trailing shape and dtype everywhere) to rank
+    `dst`: the row counts are all-gathered, the payloads padded to the longest and gathered as tensors on the
+    device the group communicates on.  Returns the list of per-rank tensors on `dst`, None elsewhere."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    counts = [torch.empty_like(n) for _ in range(world)]
+    dist.all_gather(counts, n, group=group)
+    counts = [int(c.item()) for c in counts]
+    nmax = max(1, max(counts))
+    pad = torch.zeros((nmax,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[: t.shape[0]] = t
+    bufs = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+    dist.gather(pad, bufs, dst=dst, group=group)
+    if rank != dst:
+        return None
+    return [bufs[r][: counts[r]] for r in range(world)]
 
 
 def gather_mesh(verts, faces, dst=0, group=None):

@@ -161,3 +161,29 @@ def test_host_reach_test_is_conservative_and_useful():
     g.x_span, g.x_stride = 8, 16
     assert lib.saf_frame_reaches_slab(ctypes.byref(g), pose.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
                                       K.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), cfg.height, cfg.width) == 1
+
+
+def test_sheared_block_column_layout_host_side():
+    """Column (bx, by) on rank (bx + by) % n: the ranks' rows cover every voxel exactly once, a single x-plane and a
+    single y-plane are both spread over all ranks, padding rows are marked."""
+    import spatially_aware_ai_b200 as saf
+    from spatially_aware_ai_b200 import slab, synth
+    nx, ny, nz, world = 44, 30, 5, 3
+    seen = torch.zeros(nx * ny * nz, dtype=torch.int64)
+    for r in range(world):
+        vol = saf.ClipSeemFusion(torch.zeros(3), 0.05, torch.tensor([nx, ny, nz]), 0.1, False, 0, 0, synth.FakeClip(4),
+                                 synth.FakeSeg(), **slab.sheared_slab(world, r))
+        rows = vol.global_rows()
+        assert vol.ny_local == 8 * 2 and vol.tsdf.shape[0] == nx * vol.ny_local * nz == rows.numel()
+        real = rows[rows >= 0]
+        seen[real] += 1
+        x, y = real // (ny * nz), real // nz % ny
+        assert bool(((x // 8 + y // 8) % world == r).all())
+        assert (x == 17).sum() > 0 and (y == 3).sum() > 0           # every rank holds part of any x- or y-plane
+        local = torch.tensor([0, 5 * vol.ny_local * nz + 7, -1])
+        out = slab.local_to_global_rows(vol, local)
+        assert out[2].item() == -1 and out[0].item() == rows[0].item() and out[1].item() == rows[5 * vol.ny_local * nz + 7].item()
+        xyz = vol.xyz_world
+        ok = rows >= 0
+        assert torch.allclose(xyz[ok][:, 1], (rows[ok] // nz % ny) * 0.05)
+    assert bool((seen == 1).all())

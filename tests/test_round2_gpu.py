@@ -264,3 +264,59 @@ def test_segment_table_mode(C):
                            clip_feat_img=dev_tables[:2, :40], seg_maps=torch.from_numpy(frames[0]["seg"]).cuda()[None].repeat(2, 1, 1))
     with pytest.raises(RuntimeError):
         vol.check_errors()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sheared_block_columns_concatenate_to_the_full_grid(world):
+    """Sheared block-column layout (column (bx, by) on rank (bx + by) % n): every rank's volume holds exactly the
+    oracle's rows of its columns, padding rows stay zero, query rows map back to global voxel ids."""
+    import spatially_aware_ai_b200 as saf
+    C = 768
+    cfg, origin, nvox, g = _scene(C, seed=6, extent=(2.6, 1.9, 1.5))
+    frames = [synth.make_frame(cfg, i * 3 % cfg.frames) for i in range(21)]
+    orc = _oracle_run(cfg, origin, nvox, C, frames)
+    covered = np.zeros(orc.n, int)
+    for r in range(world):
+        vol, clip, seg = Hh.make_gpu_volume(g, **slab.sheared_slab(world, r))
+        fr = frames[0]
+        clip.next_table = torch.from_numpy(fr["table"]).cuda()[None]
+        seg.queue = [torch.from_numpy(fr["seg"]).cuda()]
+        vol.integrate(torch.from_numpy(fr["depth"]).cuda()[None], torch.from_numpy(fr["rgb"]).cuda()[None],
+                      torch.from_numpy(fr["pose"])[None], torch.from_numpy(fr["K"])[None])
+        _sequence(vol, clip, seg, frames[1:])
+        rows = vol.global_rows().numpy()
+        real = rows >= 0
+        covered[rows[real]] += 1
+        sel = np.where(real, rows, 0)
+        pad0 = lambda a: np.where(real.reshape((-1,) + (1,) * (a.ndim - 1)), a[sel], 0).astype(a.dtype)   # noqa: E731
+        _check_against(vol, pad0(orc.tsdf), pad0(orc.weight), pad0(orc.tsdf_weight), pad0(orc.rgb), pad0(orc.clip_feat),
+                       pad0(orc.labels_one_hot), exact=True)
+        X = torch.nn.functional.normalize(torch.randn(3, C, generator=torch.Generator().manual_seed(2)), dim=-1).cuda()
+        ts, ti = saf.query_topk(vol.clip_feat, X, 4, norm="nan_to_num", mode="dot")
+        scores = _np(saf.query_scores(vol.clip_feat, X, norm="nan_to_num", mode="dot"))
+        assert np.array_equal(_np(slab.local_to_global_rows(vol, ti)), rows[O.topk_indices(scores, 4)])
+    assert (covered == 1).all()
+
+
+def test_fused_topk_on_a_mostly_unobserved_grid():
+    """A fused grid is mostly all-zero rows (unobserved voxels).  The tensor-core top-k must neither rank them above
+    positive scores nor drown in them (they are skipped by the filter, and asked for only when needed)."""
+    import spatially_aware_ai_b200 as saf
+    gen = torch.Generator().manual_seed(9)
+    M, C, T, k = 300_000, 768, 40, 100
+    F = torch.zeros(M, C)
+    obs = torch.randperm(M, generator=gen)[:20_000]
+    obs = obs[obs > 150_000]                       # the first half of the rows is entirely unobserved
+    F[obs] = torch.randn(len(obs), C, generator=gen)
+    X = torch.nn.functional.normalize(torch.randn(T, C, generator=gen), dim=-1)
+    Fd, Xd = F.cuda(), X.cuda()
+    ts, ti = saf.query_topk(Fd, Xd, k, norm="nan_to_num", mode="dot", precision="tf32")
+    scores = _np(saf.query_scores(Fd, Xd, norm="nan_to_num", mode="dot"))
+    assert np.array_equal(_np(ti), O.topk_indices(scores, k))
+    assert float(ts.min()) > 0
+    # fewer positive rows than k: zero rows (lowest indices first) complete the list, through the exact path
+    F2 = torch.zeros(5000, C)
+    F2[4000:4030] = torch.randn(30, C, generator=gen)
+    ts2, ti2 = saf.query_topk(F2.cuda(), Xd, k, norm="nan_to_num", mode="dot", precision="tf32")
+    s2 = _np(saf.query_scores(F2.cuda(), Xd, norm="nan_to_num", mode="dot"))
+    assert np.array_equal(_np(ti2), O.topk_indices(s2, k))

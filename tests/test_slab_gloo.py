@@ -207,3 +207,39 @@ def test_cyclic_topk_and_frame_sharing_world2(tmp_path):
         assert np.array_equal(z["gi"], want)
         assert np.allclose(z["gs"], np.take_along_axis(full.T, want, axis=1), atol=1e-6)
         assert np.array_equal(z["whole"], np.arange(11 * 6, dtype=np.int16).reshape(11, 2, 3))
+
+
+def _worker_redistribute(rank, world, port, nx, ny, nz, C, out_dir):
+    import spatially_aware_ai_b200 as saf
+    from spatially_aware_ai_b200 import synth
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        vol = saf.ClipSeemFusion(torch.zeros(3), 0.05, torch.tensor([nx, ny, nz]), 0.1, False, 0, 0, synth.FakeClip(C),
+                                 synth.FakeSeg(), **slab.cyclic_slab(nx, world, rank))
+        plane = ny * nz
+        gid = (torch.tensor(vol.global_x_planes())[:, None] * plane + torch.arange(plane)[None]).reshape(-1)
+        vol.tsdf.copy_(gid.float() * 0.5)
+        vol.weight.copy_(gid.int())
+        vol.tsdf_weight.copy_(gid.int() + 7)
+        vol.rgb.copy_(gid.float()[:, None] + torch.tensor([0.0, 0.25, 0.5]))
+        vol.clip_feat.copy_(gid.float()[:, None] * 2 + torch.arange(C))
+        vol.labels_one_hot.copy_((gid[:, None] + torch.arange(vol.n_classes)).int())
+        new = slab.redistribute_to_contiguous(vol)
+        xb, xe = slab.slab_bounds(nx, world, rank)
+        assert (new.x_begin, new.x_end, new.x_span) == (xb, xe, 0)
+        want = torch.arange(xb * plane, xe * plane)
+        assert torch.equal(new.weight, want.int()) and torch.equal(new.tsdf, want.float() * 0.5)
+        assert torch.equal(new.tsdf_weight, want.int() + 7)
+        assert torch.equal(new.rgb, want.float()[:, None] + torch.tensor([0.0, 0.25, 0.5]))
+        assert torch.equal(new.clip_feat, want.float()[:, None] * 2 + torch.arange(C))
+        assert torch.equal(new.labels_one_hot, (want[:, None] + torch.arange(vol.n_classes)).int())
+        open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_redistribute_cyclic_to_contiguous(tmp_path, world):
+    mp.spawn(_worker_redistribute, args=(world, _free_port(), 44, 5, 3, 6, str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / ("ok%d" % r)).exists() for r in range(world))
