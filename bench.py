@@ -70,6 +70,8 @@ def parse_args(argv=None):
                     help="CPU arm: the reference's torch path (baseline/_ref) or the C/OpenMP port of it")
     ap.add_argument("--ref-frames-per-step", type=int, default=0, help="0 = 1 (torch) / 4 (port)")
     ap.add_argument("--rooms", type=int, default=0, help="debug: emulate the N-room workload on this rank only")
+    ap.add_argument("--emulate-world", type=int, default=0,
+                    help="debug: on ONE GPU, run rank 0's share of the N-rank strong-scaling job (per-kernel times of a shard)")
     ap.add_argument("--window", type=int, default=16, choices=list(range(1, 17)),
                     help="frames fused per launch trio by saf_integrate_sequence (1 = frame by frame)")
     ap.add_argument("--resume-from", default=None, help="load_state() directory: fuse into an existing grid (config 5)")
@@ -86,7 +88,10 @@ class Plan:
 
     def __init__(self, args, world):
         self.world = world
-        self.mode = "single" if world == 1 and not args.rooms else (args.multi if not args.rooms else "rooms")
+        self.shards = world                   # ranks the grid is cut into (differs from world only with --emulate-world)
+        if world == 1 and getattr(args, "emulate_world", 0) > 1 and not args.rooms:
+            self.shards = args.emulate_world
+        self.mode = "single" if self.shards == 1 and not args.rooms else (args.multi if not args.rooms else "rooms")
         which = args.workload
         if which == "auto":
             which = "cfg3" if self.mode == "strong" else "cfg2"
@@ -131,11 +136,11 @@ class Plan:
             own = rank if self.world > 1 else 0
             return dict(x_begin=own * self.slab_nx, x_end=(own + 1) * self.slab_nx)
         if self.layout == "sheared":
-            return dict(y_ranks=self.world, y_rank=rank)
+            return dict(y_ranks=self.shards, y_rank=rank)
         if self.layout == "cyclic":
-            return dict(x_begin=rank * SLAB_SPAN, x_end=nx, x_span=SLAB_SPAN, x_stride=SLAB_SPAN * self.world)
+            return dict(x_begin=rank * SLAB_SPAN, x_end=nx, x_span=SLAB_SPAN, x_stride=SLAB_SPAN * self.shards)
         from spatially_aware_ai_b200 import slab
-        xb, xe = slab.slab_bounds(nx, self.world, rank)
+        xb, xe = slab.slab_bounds(nx, self.shards, rank)
         return dict(x_begin=xb, x_end=xe)
 
     def config(self):
@@ -148,7 +153,7 @@ class Plan:
         order = "poses %d, %d, ... of the %d-pose orbit, in order" % (0, self.stride, cfg.frames)
         par = {"single": "single GPU",
                "strong": "grid sharded over %d ranks (%s), every rank handed every frame, no data-path collective" %
-                         (self.world, {"sheared": "sheared block columns: 8x8xnz column (bx, by) on rank (bx + by) mod N",
+                         (self.shards, {"sheared": "sheared block columns: 8x8xnz column (bx, by) on rank (bx + by) mod N",
                                        "cyclic": "block-cyclic x-stripes of %d planes" % SLAB_SPAN,
                                        "contiguous": "contiguous x-slabs"}[self.layout]),
                "rooms": "one room (x-slab) per rank, every rank handed every frame, no data-path collective"}[self.mode]

@@ -27,6 +27,8 @@
 #include <limits.h>
 #include <math.h>
 #include <algorithm>
+#include <mutex>
+#include <unordered_map>
 #include <vector>
 #include <stdio.h>
 #include <stdlib.h>
@@ -2302,14 +2304,50 @@ __global__ void __launch_bounds__(256) label_argmax_kernel(const int32_t* __rest
 
 int device_sm_count(int* sms, int* smem_optin)
 {
+    // per-device attributes are constants: queried once per device
+    struct Info { int ok, major, sms, smem; };
+    static Info cache[64] = {};
     int dev = 0;
     SAF_CUDA_TRY(cudaGetDevice(&dev));
-    int major = 0;
-    SAF_CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
-    if (major != 10) return SAF_ERR_DEVICE;
-    SAF_CUDA_TRY(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev));
-    if (smem_optin) SAF_CUDA_TRY(cudaDeviceGetAttribute(smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    Info local;
+    Info& info = (dev >= 0 && dev < 64) ? cache[dev] : local;
+    if (&info == &local || !info.ok) {
+        Info q = {};
+        SAF_CUDA_TRY(cudaDeviceGetAttribute(&q.major, cudaDevAttrComputeCapabilityMajor, dev));
+        SAF_CUDA_TRY(cudaDeviceGetAttribute(&q.sms, cudaDevAttrMultiProcessorCount, dev));
+        SAF_CUDA_TRY(cudaDeviceGetAttribute(&q.smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        q.ok = 1;
+        info = q;
+    }
+    if (info.major != 10) return SAF_ERR_DEVICE;
+    *sms = info.sms;
+    if (smem_optin) *smem_optin = info.smem;
     return 0;
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device, size) instead of once per launch
+static int ensure_dynamic_smem_impl(const void* kern, size_t smem)
+{
+    static std::mutex mu;
+    static std::unordered_map<const void*, size_t> granted[64];
+    int dev = 0;
+    SAF_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) {
+        SAF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        return 0;
+    }
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& g = granted[dev][kern];
+    if (g < smem) {
+        SAF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        g = smem;
+    }
+    return 0;
+}
+template <typename K>
+static int ensure_dynamic_smem(K kern, size_t smem)
+{
+    return ensure_dynamic_smem_impl(reinterpret_cast<const void*>(kern), smem);
 }
 
 static int build_params(const saf_grid_desc* grid, const saf_volume* vol, const saf_frame* frames, int32_t batch,
@@ -2414,7 +2452,7 @@ static int launch_k1(const FusionParams& p, cudaStream_t st)
     SAF_CHECK_LAUNCH("depth_tiles_kernel (K0)", st);
     const size_t k1_smem = (size_t)p.batch * ntiles * sizeof(float);
     if (k1_smem > 48u * 1024u)
-        SAF_CUDA_TRY(cudaFuncSetAttribute(frame_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem));
+        { int rc_ = ensure_dynamic_smem(frame_setup_kernel, k1_smem); if (rc_) return rc_; }
     frame_setup_kernel<<<p.n_k1 + pack_ctas, kK1Threads, k1_smem, st>>>(p, p.n_k1);
     SAF_CHECK_LAUNCH("frame_setup_kernel (K1)", st);
     return 0;
@@ -2438,7 +2476,7 @@ static int launch_k3_fixed(const FusionParams& p, const float* table, int64_t st
                            int sms, cudaStream_t st)
 {
     auto kern = feature_accumulate_kernel<CHUNKS, NST, SMEM>;
-    SAF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { int rc_ = ensure_dynamic_smem(kern, smem); if (rc_) return rc_; }
     kern<<<sms, kK3Threads, smem, st>>>(p, table, stride_r, table_tma);
     SAF_CHECK_LAUNCH("feature_accumulate_kernel (K3)", st);
     return 0;
@@ -2495,7 +2533,7 @@ static int launch_k3w_pair(const FusionParams& p, const WindowTables& wt, int sm
     const size_t smem = (size_t)kW3Warps * 2 * row + (size_t)kW3Warps * kW3Chunk * SAF_MAX_BATCH * sizeof(float2) +
                         8 * (size_t)kW3Warps;
     auto kern = feature_accumulate_window_pair_kernel<CHUNKS, kW3Warps>;
-    SAF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { int rc_ = ensure_dynamic_smem(kern, smem); if (rc_) return rc_; }
     kern<<<sms, kW3Threads, smem, st>>>(p, wt);
     SAF_CHECK_LAUNCH("feature_accumulate_window_pair_kernel (K3W)", st);
     return 0;
@@ -2509,7 +2547,7 @@ static int launch_k3w_fixed(const FusionParams& p, const WindowTables& wt, int s
     const size_t smem = (size_t)kW3Warps * row + (size_t)kW3Warps * kW3Chunk * SAF_MAX_BATCH * sizeof(float2) +
                         8 * (size_t)kW3Warps;
     auto kern = feature_accumulate_window_kernel<CHUNKS, kW3Warps>;
-    SAF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { int rc_ = ensure_dynamic_smem(kern, smem); if (rc_) return rc_; }
     kern<<<sms, kW3Threads, smem, st>>>(p, wt);
     SAF_CHECK_LAUNCH("feature_accumulate_window_kernel (K3W)", st);
     return 0;
@@ -2525,7 +2563,7 @@ static int launch_k3w_tile(const FusionParams& p, const WindowTables& wt, int sm
                             5 * (size_t)NBUF * sizeof(uint64_t);
     static_assert(smem <= 227 * 1024, "tile kernel shared memory");
     auto kern = feature_accumulate_window_tile_kernel<CHUNKS, NSET, NBUF>;
-    SAF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { int rc_ = ensure_dynamic_smem(kern, smem); if (rc_) return rc_; }
     kern<<<sms, kThreads, smem, st>>>(p, wt);
     SAF_CHECK_LAUNCH("feature_accumulate_window_tile_kernel (K3W)", st);
     return 0;

@@ -404,8 +404,12 @@ static int launch_gemm(bool filter, const float* feats, int64_t M, int32_t C, in
 // rejected row can be in the exact top-k.  topk_tc_final_kernel rescoring the survivors in fp32
 // (same arithmetic as the fp32 query kernel) therefore yields the exact top-k.
 
-constexpr uint32_t kBucketCap = 8192;
-constexpr int kFinalMax = 4096;
+// Fused grids are smooth: thousands of neighbouring voxels can score within the tf32 error radius of a text's k-th
+// best row.  The buckets are therefore generous, the waves stop growing at kWaveMax rows (the thresholds tighten after
+// every wave, so a late wave admits few rows) and the final ranking takes a whole bucket.
+constexpr uint32_t kBucketCap = 16384;
+constexpr int kFinalMax = 16384;
+constexpr int64_t kWaveMax = 1 << 20;
 
 __device__ __forceinline__ uint32_t float_key(float f)
 {
@@ -492,8 +496,9 @@ __global__ void __launch_bounds__(256) topk_tc_final_kernel(const Candidate* __r
                                                             int64_t index_base, float* __restrict__ out_s,
                                                             long long* __restrict__ out_i, uint32_t* flags)
 {
-    __shared__ float ex_s[kFinalMax];
-    __shared__ uint32_t ex_r[kFinalMax];
+    extern __shared__ __align__(16) unsigned char final_smem[];
+    float* ex_s = reinterpret_cast<float*>(final_smem);                 // [kFinalMax]
+    uint32_t* ex_r = reinterpret_cast<uint32_t*>(ex_s + kFinalMax);     // [kFinalMax]
     const int t = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const Candidate* b = buckets + (size_t)t * cap;
@@ -588,9 +593,10 @@ int query_topk_tc(const float* feats, int64_t M, int32_t C, int64_t ldf, const f
         SAF_CHECK_LAUNCH("topk_tc_threshold_kernel", st);
         cur ^= 1;
         r0 = r1;
-        wave *= 8;
+        wave = std::min<int64_t>(wave * 8, kWaveMax);
     }
-    topk_tc_final_kernel<<<T, 256, 0, st>>>(bucket[cur], counts[cur], kBucketCap, feats, C, ldf, text, norm_mode, k,
+    SAF_CUDA_TRY(cudaFuncSetAttribute(topk_tc_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinalMax * 8));
+    topk_tc_final_kernel<<<T, 256, kFinalMax * 8, st>>>(bucket[cur], counts[cur], kBucketCap, feats, C, ldf, text, norm_mode, k,
                                             index_base, out_scores, (long long*)out_index, flags);
     SAF_CHECK_LAUNCH("topk_tc_final_kernel", st);
     uint32_t h_flags = 0;
