@@ -2564,7 +2564,15 @@ static int launch_k3w_tile(const FusionParams& p, const WindowTables& wt, int sm
     static_assert(smem <= 227 * 1024, "tile kernel shared memory");
     auto kern = feature_accumulate_window_tile_kernel<CHUNKS, NSET, NBUF>;
     { int rc_ = ensure_dynamic_smem(kern, smem); if (rc_) return rc_; }
-    kern<<<sms, kThreads, smem, st>>>(p, wt);
+    // A shard of a grid (multi-GPU) has small windows: their cost is the chain of dependent launches, not
+    // throughput.  K3W then leaves some SMs free (it holds one CTA per SM and fills every SM it is given), so that
+    // K0 / K1 / K2 of the NEXT window - already queued on the side stream - run beside it instead of after it.
+    // Whole grids keep all SMs: there both kernels are throughput-bound and sharing would only slow K3W.
+    static const int reserve_env = getenv("SAF_K3W_RESERVE_SMS") ? atoi(getenv("SAF_K3W_RESERVE_SMS")) : -1;
+    const bool shard = p.grid.y_ranks > 1 || p.grid.x_span > 0 || p.grid.x_begin > 0 || p.grid.x_end < p.grid.nvox[0];
+    const int reserve = reserve_env >= 0 ? reserve_env : (shard ? sms / 8 : 0);
+    const int grid = std::max(1, sms - std::min(reserve, sms - 1));
+    kern<<<grid, kThreads, smem, st>>>(p, wt);
     SAF_CHECK_LAUNCH("feature_accumulate_window_tile_kernel (K3W)", st);
     return 0;
 }
