@@ -53,7 +53,7 @@ def parse_args(argv=None):
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="auto", choices=["auto", "cfg1", "cfg2", "cfg3"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "cfg1", "cfg2", "cfg3", "cfg5"])
     ap.add_argument("--multi", default="strong", choices=["strong", "rooms"],
                     help="N > 1: strong = one grid sharded over the ranks; rooms = N rooms side by side (weak)")
     ap.add_argument("--slab-layout", default="sheared", choices=["sheared", "cyclic", "contiguous"],
@@ -95,6 +95,7 @@ class Plan:
         which = args.workload
         if which == "auto":
             which = "cfg3" if self.mode == "strong" else "cfg2"
+        # an explicit workload on several ranks is sharded like cfg3 (e.g. the 1 cm cells of config 5)
         kw = dict(feature_dim=args.feature_dim)
         if args.voxel_size:
             kw["voxel_size"] = args.voxel_size

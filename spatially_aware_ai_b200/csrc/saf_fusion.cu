@@ -1702,6 +1702,7 @@ struct __align__(128) TileMeta {
     uint32_t voxel[NSET * kTileSlots];
     uint32_t prim_rows[NSET][SAF_MAX_BATCH];        // rows of the set's first valid voxel in the frame
     uint8_t vmask[NSET][SAF_MAX_BATCH];             // voxels of the set valid in the frame
+    uint8_t uniform[NSET][SAF_MAX_BATCH];           // 1: every valid voxel of the set uses prim_rows in the frame
     TileUpdate upd[NSET][SAF_MAX_BATCH][kTileSlots];
 };
 
@@ -1828,12 +1829,11 @@ feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, co
             __syncwarp();
             if (lane < cnt)
                 tma_bulk_g2s(my_rows + (size_t)lane * C, p.vol.clip_feat + (size_t)my_voxel * C, (uint32_t)C * 4u, &full[ms]);
-            // which voxel of each set comes first in every frame (its rows are the ones prefetched for the set)
-            uint32_t first_bits = 0, my_ballot = 0;
+            // per frame: which voxels of the tile are valid (lane b keeps frame b's ballot)
+            uint32_t my_ballot = 0;
 #pragma unroll
             for (int b = 0; b < SAF_MAX_BATCH; ++b) {
                 const uint32_t bal = __ballot_sync(0xffffffffu, (my_mask >> b) & 1u);
-                if (((bal >> (set * kTileSlots)) & ((1u << slot) - 1u)) == 0u) first_bits |= 1u << b;
                 if (lane == b) my_ballot = bal;
             }
             // the metadata slot was last read two of this producer's tiles ago
@@ -1869,8 +1869,9 @@ feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, co
                 const uint32_t mv = __shfl_sync(0xffffffffu, my_mask, v);
                 const uint32_t vx = __shfl_sync(0xffffffffu, my_voxel, v);
                 const int w0 = __shfl_sync(0xffffffffu, my_w0, v);
-                const uint32_t fb = __shfl_sync(0xffffffffu, first_bits, v);
-                if ((mv >> b) & 1u) {
+                const bool cell_valid = (mv >> b) & 1u;
+                uint32_t cell_rows = 0;
+                if (cell_valid) {
                     const saf_frame& f = p.frames[b];
                     const float2 g = cg[it];
                     const int w = w0 + __popc(mv & ((1u << b) - 1u));   // single-frame calls before this one
@@ -1890,7 +1891,7 @@ feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, co
                     u.rows = rows;
                     u.pad = 0;
                     M->upd[v / kTileSlots][b][v % kTileSlots] = u;
-                    if ((fb >> b) & 1u) M->prim_rows[v / kTileSlots][b] = rows;
+                    cell_rows = rows;
                     const int px = nearest_index(g.x, p.W), py = nearest_index(g.y, p.H);
                     float smp[3];
                     sample_rgb(p, f, g.x, g.y, px, py, smp);
@@ -1903,6 +1904,20 @@ feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, co
                         else
                             atomicOr(&p.hdr->error_flags, SAF_FLAG_BAD_CLASS_ID);
                     }
+                }
+                // The 8 lanes of a group hold one set's voxels for one frame (G = 16: two frames per iteration).  The
+                // group's first valid voxel provides the rows the compute warps prefetch for (set, frame); if every
+                // valid voxel of the group uses those rows - nearly always - the frame takes the compare-free path.
+                static_assert(G == 16, "cell groups assume 16 voxels per tile");
+                const uint32_t vb = __ballot_sync(0xffffffffu, cell_valid);
+                const int group = lane >> 3;
+                const uint32_t gb = (vb >> (group * 8)) & 0xffu;
+                const int first = group * 8 + (gb ? __ffs(gb) - 1 : 0);
+                const uint32_t prim = __shfl_sync(0xffffffffu, cell_rows, first);
+                const uint32_t mb = __ballot_sync(0xffffffffu, cell_valid && cell_rows != prim);
+                if (gb && lane == first) {
+                    M->prim_rows[v / kTileSlots][b] = prim;
+                    M->uniform[v / kTileSlots][b] = ((mb >> (group * 8)) & 0xffu) == 0u ? 1 : 0;
                 }
             }
             __syncwarp();   // samples and update records of every cell are in shared memory
@@ -1986,7 +2001,10 @@ feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, co
             mbar_wait(&meta_free[ms], ((j >> 1) & 1u) ^ 1u);
             if (lane < SAF_MAX_BATCH) {
 #pragma unroll
-                for (int s = 0; s < NSET; ++s) M->vmask[s][lane] = (uint8_t)((my_ballot >> (s * kTileSlots)) & 0xffu);
+                for (int s = 0; s < NSET; ++s) {
+                    M->vmask[s][lane] = (uint8_t)((my_ballot >> (s * kTileSlots)) & 0xffu);
+                    M->uniform[s][lane] = 0;   // this producer does not classify frames: always the checked path
+                }
             }
 #pragma unroll
             for (int s = 0; s < NSET; ++s) {
@@ -2089,6 +2107,23 @@ feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, co
             // one frame of the window: every voxel of the set that the frame sees, with the frame's rows in T
             auto frame_updates = [&](int b, RowRegs& T, uint32_t& cur_rows) {
                 const uint32_t vm = M->vmask[set][b];
+                if (M->uniform[set][b]) {
+                    // every valid voxel of the set samples the prefetched rows: no per-voxel row check
+#pragma unroll
+                    for (int s = 0; s < kTileSlots; ++s) {
+                        if ((vm >> s) & 1u) {
+                            const uint4 m0 = *reinterpret_cast<const uint4*>(&M->upd[set][b][s]);
+                            const uint2 m1 = *reinterpret_cast<const uint2*>(&M->upd[set][b][s].a);
+                            const float w0 = __uint_as_float(m0.x), w1 = __uint_as_float(m0.y), w2 = __uint_as_float(m0.z),
+                                        w3 = __uint_as_float(m0.w), a = __uint_as_float(m1.x), bb = __uint_as_float(m1.y);
+                            const f32x2_t wp[4] = {pack2(w0, w0), pack2(w1, w1), pack2(w2, w2), pack2(w3, w3)};
+                            const f32x2_t ap = pack2(a, a), bp = pack2(bb, bb);
+                            acc_lo[s] = mix_blend2(T.lo, wp, ap, bp, acc_lo[s]);
+                            acc_hi[s] = mix_blend2(T.hi, wp, ap, bp, acc_hi[s]);
+                        }
+                    }
+                    return;
+                }
 #pragma unroll
                 for (int s = 0; s < kTileSlots; ++s) {
                     if ((vm >> s) & 1u) {
@@ -2569,8 +2604,11 @@ static int launch_k3w_tile(const FusionParams& p, const WindowTables& wt, int sm
     // K0 / K1 / K2 of the NEXT window - already queued on the side stream - run beside it instead of after it.
     // Whole grids keep all SMs: there both kernels are throughput-bound and sharing would only slow K3W.
     static const int reserve_env = getenv("SAF_K3W_RESERVE_SMS") ? atoi(getenv("SAF_K3W_RESERVE_SMS")) : -1;
-    const bool shard = p.grid.y_ranks > 1 || p.grid.x_span > 0 || p.grid.x_begin > 0 || p.grid.x_end < p.grid.nvox[0];
-    const int reserve = reserve_env >= 0 ? reserve_env : (shard ? sms / 8 : 0);
+    // share of the grid this volume holds; measured on the cfg3 grid (one GPU running one rank's shard): a 1/8 shard
+    // is fastest with ~40 of 148 SMs left free (step -11 %), a 1/2 shard with ~10-18 (-4 %)
+    const double share = (double)p.nslab / ((double)p.grid.nvox[0] * p.grid.nvox[1] * p.grid.nvox[2]);
+    const int reserve = reserve_env >= 0 ? reserve_env
+                                         : (share < 0.75 ? (int)(sms * std::min(0.28, 0.035 / std::max(share, 1e-3))) : 0);
     const int grid = std::max(1, sms - std::min(reserve, sms - 1));
     kern<<<grid, kThreads, smem, st>>>(p, wt);
     SAF_CHECK_LAUNCH("feature_accumulate_window_tile_kernel (K3W)", st);

@@ -76,6 +76,10 @@ def baseline_config(which, **overrides):
         # cfg-3: large multi-room scan, slab-sharded
         "cfg3": dict(extent=(8.0, 8.0, 3.0), voxel_size=0.02, height=480, width=640, patch_size=160,
                      patch_stride=80, frames=5000, laps=16, name="cfg3"),
+        # cfg-5: Scene Manager v00 -> v01 incremental re-fusion: the cfg-1 extent, 60 + 500 frames at 640x480
+        # (SURVEY.md 8d); swept over feature_dim and voxel_size by the caller
+        "cfg5": dict(extent=(4.0, 4.0, 3.0), voxel_size=0.02, height=480, width=640, patch_size=160,
+                     patch_stride=80, frames=560, laps=4, name="cfg5"),
         # small case for unit tests
         "tiny": dict(extent=(1.6, 1.4, 1.2), voxel_size=0.08, height=48, width=64, patch_size=32,
                      patch_stride=16, frames=6, feature_dim=16, seg_block=8, name="tiny"),
