@@ -69,6 +69,8 @@ struct FusionParams {
     WinEntry* ulist;           // window mode: [nblocks_total*512] voxels valid in any frame, rank r's start at r*512
     float2* wcoords;           // window mode: [nblocks_total][batch][512] (gx, gy) per (block rank, frame, local voxel)
     float* tables;
+    void* tile_meta;           // window mode: [tile_meta_cap] TileMeta<2> written by K2T for K3W's tiles (idle list regions)
+    uint32_t tile_meta_cap;    // tiles of the union list K2T prepares; later tiles are prepared inside K3W
     uint8_t* valid_out;
     uint8_t* tsdf_valid_out;
 };
@@ -1686,13 +1688,22 @@ feature_accumulate_window_pair_kernel(const __grid_constant__ FusionParams p, co
 #ifndef SAF_TILE_NBUF
 #define SAF_TILE_NBUF 3         // producer warps = landing buffers per CTA (C = 512 / 768)
 #endif
+#ifndef SAF_TILE_NLAND
+#define SAF_TILE_NLAND SAF_TILE_NBUF        // landing buffers per CTA at C = 768
+#endif
+#ifndef SAF_TILE_LW
+#define SAF_TILE_LW 4           // floats per compute lane at C = 768 (2: 24 compute warps of 64 channels)
+#endif
+#ifndef SAF_TILE_TDEPTH
+#define SAF_TILE_TDEPTH 0       // frames of table rows staged ahead per compute warp at C = 768 (0: register ping-pong)
+#endif
 constexpr int kTileSlots = 8;    // voxels per set (accumulator registers: 8 x float4 per thread)
 
 struct __align__(16) TileUpdate {   // one (frame, voxel) feature update
     float w[4];                     // bilinear weights nw, ne, sw, se
     float a, b;                     // clip_seem_fusion.py:808-810
     uint32_t rows;                  // the four rows of the frame's zero-bordered table, one byte each
-    uint32_t pad;
+    float one;                      // 1.0f, a multiplicand ptxas cannot see through (mix_blend2_if)
 };
 
 template <int NSET>
@@ -1710,21 +1721,71 @@ struct RowRegs {   // this thread's 4-float column of the four table rows of one
     f32x2_t lo[4], hi[4];
 };
 
-__device__ __forceinline__ void load_rows(RowRegs& T, const float* __restrict__ table, uint32_t rows, int C, int col4)
+// a thread's LW-float column (LW = 4: lo and hi pairs, LW = 2: lo only) of a row at `base`, column index `col`
+template <int LW>
+__device__ __forceinline__ void ld_col_global(const float* __restrict__ base, int col, f32x2_t& lo, f32x2_t& hi)
+{
+    if constexpr (LW == 4) {
+        const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(base) + col);
+        lo = v.x;
+        hi = v.y;
+    } else {
+        lo = __ldg(reinterpret_cast<const unsigned long long*>(base) + col);
+        hi = 0ull;
+    }
+}
+template <int LW>
+__device__ __forceinline__ void ld_col_shared(const float* base, int col, f32x2_t& lo, f32x2_t& hi)
+{
+    if constexpr (LW == 4) {
+        const ulonglong2 v = reinterpret_cast<const ulonglong2*>(base)[col];
+        lo = v.x;
+        hi = v.y;
+    } else {
+        lo = reinterpret_cast<const unsigned long long*>(base)[col];
+        hi = 0ull;
+    }
+}
+template <int LW>
+__device__ __forceinline__ void load_rows(RowRegs& T, const float* __restrict__ table, uint32_t rows, int C, int col)
 {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(table + (size_t)((rows >> (8 * k)) & 0xffu) * C) + col4);
-        T.lo[k] = v.x;
-        T.hi[k] = v.y;
-    }
+    for (int k = 0; k < 4; ++k)
+        ld_col_global<LW>(table + (size_t)((rows >> (8 * k)) & 0xffu) * C, col, T.lo[k], T.hi[k]);
 }
 
 // bilinear_mix + blend4 on one packed pair: ((t0 w0 + t1 w1) + t2 w2) + t3 w3 as mul / fma / fma / fma, then
 // smp a + old b as mul, mul, add - each lane of the pair rounded like the scalar code
-__device__ __forceinline__ f32x2_t mix_blend2(const f32x2_t (&t)[4], const f32x2_t (&w)[4], f32x2_t a, f32x2_t b, f32x2_t old)
+#ifndef SAF_TILE_DENSE
+#define SAF_TILE_DENSE 0    // N > 0: frames that see at least N of a set's 8 voxels take the branch-free path (measured: no gain)
+#endif
+#ifndef SAF_TILE_ADD2
+#define SAF_TILE_ADD2 1     // 1: the blend's final add is fma.rn.f32x2(x, 1.0, y) with an opaque 1.0 (exactly x + y)
+#endif
+
+// Branch-free form for frames that see most of a set: the update is computed for every slot and committed under a
+// predicate, so the eight slots' chains interleave instead of serialising behind one branch per voxel.  `one` is
+// 1.0f read from the update record (opaque to ptxas, which would otherwise turn mul + add into one FFMA2 and drop a
+// rounding): fma(x, 1, y) is x + y correctly rounded, signed zeros included.
+__device__ __forceinline__ f32x2_t mix_blend2_if(const f32x2_t (&t)[4], const f32x2_t (&w)[4], f32x2_t a, f32x2_t b,
+                                                 f32x2_t one, f32x2_t old, uint32_t commit)
 {
     const f32x2_t smp = fma2_rn(t[3], w[3], fma2_rn(t[2], w[2], fma2_rn(t[1], w[1], mul2_rn(t[0], w[0]))));
+    const f32x2_t x = mul2_rn(smp, a), y = mul2_rn(old, b);
+    f32x2_t r = old;
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %4, 0;\n\t@p fma.rn.f32x2 %0, %1, %2, %3;\n\t}"
+        : "+l"(r)
+        : "l"(x), "l"(one), "l"(y), "r"(commit));
+    return r;
+}
+
+__device__ __forceinline__ f32x2_t mix_blend2(const f32x2_t (&t)[4], const f32x2_t (&w)[4], f32x2_t a, f32x2_t b,
+                                              f32x2_t one, f32x2_t old)
+{
+    const f32x2_t smp = fma2_rn(t[3], w[3], fma2_rn(t[2], w[2], fma2_rn(t[1], w[1], mul2_rn(t[0], w[0]))));
+#if SAF_TILE_ADD2
+    return fma2_rn(mul2_rn(smp, a), one, mul2_rn(old, b));
+#endif
     // ptxas (12.9) contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with --fmad false and explicit .rn, which
     // would drop one of the reference's three roundings: the final add is therefore two scalar add.rn
     float xl, xh, yl, yh;
@@ -1733,34 +1794,229 @@ __device__ __forceinline__ f32x2_t mix_blend2(const f32x2_t (&t)[4], const f32x2
     return pack2(__fadd_rn(xl, yl), __fadd_rn(xh, yh));
 }
 
-template <int CHUNKS, int NSET, int NBUF>
+// One lane's voxel of a tile of the window's union list (tile = G consecutive entries starting at `base`).
+struct TileLane {
+    uint32_t voxel, mask, local, rank;   // slab-local voxel, frames that see it, index in its block, block rank
+    int w0;                              // the voxel's weight before the window
+    float rgb0[3];
+};
+
+__device__ __forceinline__ TileLane load_tile_lane(const FusionParams& p, uint32_t n_blocks, uint32_t base, uint32_t cnt,
+                                                   int lane)
+{
+    const uint32_t* __restrict__ off = p.blk_offset;
+    // block rank of the tile's first entry: 32-ary search by the whole warp (off[lo] <= base < off[hi])
+    uint32_t lo = 0, hi = n_blocks;
+    while (hi - lo > 1) {
+        const uint32_t step = (hi - lo + 31u) / 32u;
+        const uint32_t probe = lo + (uint32_t)lane * step;
+        const bool le = probe < hi && __ldg(off + probe) <= base;
+        const uint32_t k = (uint32_t)__popc(__ballot_sync(0xffffffffu, le));   // >= 1: lane 0 probes lo
+        lo += (k - 1u) * step;
+        hi = min(hi, lo + step);
+    }
+    TileLane L = {0u, 0u, 0u, 0u, 0, {0.f, 0.f, 0.f}};
+    if (lane < cnt) {
+        const uint32_t i = base + lane;
+        uint32_t r = lo;
+        while (r + 1u < n_blocks && __ldg(off + r + 1u) <= i) ++r;   // the tile spans a few blocks at most
+        const WinEntry e = p.ulist[(uint64_t)r * kBlockVoxels + (i - __ldg(off + r))];
+        L.voxel = e.voxel;
+        L.mask = e.mask_local & 0xffffu;
+        L.local = e.mask_local >> 16;
+        L.rank = r;
+        L.w0 = p.vol.weight[L.voxel];
+        const float* src3 = p.vol.rgb + (size_t)L.voxel * 3;
+        L.rgb0[0] = src3[0];
+        L.rgb0[1] = src3[1];
+        L.rgb0[2] = src3[2];
+    }
+    return L;
+}
+
+// The tile's metadata for the compute warps (update records, masks, prefetch rows) into M - shared memory when K3W's
+// producer prepares the tile itself, global memory when K2T prepares it ahead - and the tile's small state: rgb
+// running average, label counters, weight.  my_smp: G x SAF_MAX_BATCH float4 of shared-memory scratch of this warp.
+// The valid (voxel, frame) CELLS of the tile are spread over the 32 lanes and handled independently.
+template <int NSET>
+__device__ __forceinline__ void fill_tile_meta(const FusionParams& p, const TileLane& L, uint32_t cnt, TileMeta<NSET>* M,
+                                               float4* my_smp, int lane)
+{
+    constexpr int G = NSET * kTileSlots;
+    constexpr int kCellIters = G * SAF_MAX_BATCH / 32;
+    const int B = p.batch;
+    // per frame: which voxels of the tile are valid (lane b keeps frame b's ballot)
+    uint32_t my_ballot = 0;
+#pragma unroll
+    for (int b = 0; b < SAF_MAX_BATCH; ++b) {
+        const uint32_t bal = __ballot_sync(0xffffffffu, (L.mask >> b) & 1u);
+        if (lane == b) my_ballot = bal;
+    }
+    if (lane < SAF_MAX_BATCH) {
+#pragma unroll
+        for (int s = 0; s < NSET; ++s) M->vmask[s][lane] = (uint8_t)((my_ballot >> (s * kTileSlots)) & 0xffu);
+    }
+#pragma unroll
+    for (int s = 0; s < NSET; ++s) {
+        const uint32_t fm = __ballot_sync(0xffffffffu, lane < SAF_MAX_BATCH &&
+                                                           ((my_ballot >> (s * kTileSlots)) & 0xffu) != 0u);
+        if (lane == 0) M->fmask[s] = fm;
+    }
+    if (lane == 0) M->n_rows = cnt;
+    if (lane < cnt) M->voxel[lane] = L.voxel;
+    // cells: c -> (frame c / G, voxel c % G).  Pass 1 requests every valid cell's image coordinates.
+    float2 cg[kCellIters];
+#pragma unroll
+    for (int it = 0; it < kCellIters; ++it) {
+        const int c = it * 32 + lane, b = c / G, v = c % G;
+        const uint32_t mv = __shfl_sync(0xffffffffu, L.mask, v);
+        const uint32_t rk = __shfl_sync(0xffffffffu, L.rank, v);
+        const uint32_t lc = __shfl_sync(0xffffffffu, L.local, v);
+        cg[it] = make_float2(0.f, 0.f);
+#ifndef SAF_DBG_FAST_PRODUCER
+        if ((mv >> b) & 1u) cg[it] = p.wcoords[((uint64_t)rk * B + b) * kBlockVoxels + lc];
+#endif
+    }
+    // Pass 2: per valid cell the compute warps' update record (clip_seem_fusion.py:800-810), the rgb sample
+    // and the label counter (:786-798, 820-822).
+#pragma unroll
+    for (int it = 0; it < kCellIters; ++it) {
+        const int c = it * 32 + lane, b = c / G, v = c % G;
+        const uint32_t mv = __shfl_sync(0xffffffffu, L.mask, v);
+        const uint32_t vx = __shfl_sync(0xffffffffu, L.voxel, v);
+        const int w0 = __shfl_sync(0xffffffffu, L.w0, v);
+        const bool cell_valid = (mv >> b) & 1u;
+        uint32_t cell_rows = 0;
+        if (cell_valid) {
+            const saf_frame& f = p.frames[b];
+            const float2 g = cg[it];
+            const int w = w0 + __popc(mv & ((1u << b) - 1u));   // single-frame calls before this one
+            const float a = __frcp_rn(__int2float_rn(w + 1));
+            const float bb = __fmul_rn(__int2float_rn(w), a);
+            Taps t;
+#ifdef SAF_DBG_FAST_PRODUCER
+            t.idx[0] = 1; t.idx[1] = 2; t.idx[2] = 8; t.idx[3] = 9;   // timing experiment only
+            t.w[0] = t.w[1] = t.w[2] = t.w[3] = 0.25f;
+#else
+            feature_taps_padded(f, g.x, g.y, p.W, p.H, &p.hdr->error_flags, t);
+#endif
+            const uint32_t rows = (uint32_t)t.idx[0] | ((uint32_t)t.idx[1] << 8) | ((uint32_t)t.idx[2] << 16) |
+                                  ((uint32_t)t.idx[3] << 24);
+            TileUpdate u;
+            u.w[0] = t.w[0];
+            u.w[1] = t.w[1];
+            u.w[2] = t.w[2];
+            u.w[3] = t.w[3];
+            u.a = a;
+            u.b = bb;
+            u.rows = rows;
+            u.one = 1.0f;
+            M->upd[v / kTileSlots][b][v % kTileSlots] = u;
+            cell_rows = rows;
+            const int px = nearest_index(g.x, p.W), py = nearest_index(g.y, p.H);
+            float smp[3];
+#ifdef SAF_DBG_SKIP_SMALL
+            smp[0] = smp[1] = smp[2] = 0.f;   // timing experiment only
+#else
+            sample_rgb(p, f, g.x, g.y, px, py, smp);
+#endif
+            my_smp[v * SAF_MAX_BATCH + b] = make_float4(smp[0], smp[1], smp[2], 0.f);
+#ifdef SAF_DBG_SKIP_SMALL
+            if (false) {
+#else
+            if (p.vol.labels_one_hot && f.seg) {
+#endif
+                const float lf = (px >= 0 && py >= 0) ? load_class_id(f.seg, f.seg_dtype, py * p.W + px) : 0.0f;
+                const long long id = (long long)lf;
+                if (id >= 0 && id < p.vol.n_classes)
+                    atomicAdd(p.vol.labels_one_hot + (size_t)vx * p.vol.n_classes + id, 1);   // RED: no round trip
+                else
+                    atomicOr(&p.hdr->error_flags, SAF_FLAG_BAD_CLASS_ID);
+            }
+        }
+        // The 8 lanes of a group hold one set's voxels for one frame (G = 16: two frames per iteration).  The
+        // group's first valid voxel provides the rows the compute warps prefetch for (set, frame); if every
+        // valid voxel of the group uses those rows - nearly always - the frame takes the compare-free path.
+        static_assert(G == 16, "cell groups assume 16 voxels per tile");
+        const uint32_t vb = __ballot_sync(0xffffffffu, cell_valid);
+        const int group = lane >> 3;
+        const uint32_t gb = (vb >> (group * 8)) & 0xffu;
+        const int first = group * 8 + (gb ? __ffs(gb) - 1 : 0);
+        const uint32_t prim = __shfl_sync(0xffffffffu, cell_rows, first);
+        const uint32_t mb = __ballot_sync(0xffffffffu, cell_valid && cell_rows != prim);
+        if (gb && lane == first) {
+            M->prim_rows[v / kTileSlots][b] = prim;
+            M->uniform[v / kTileSlots][b] = ((mb >> (group * 8)) & 0xffu) == 0u ? 1 : 0;
+        }
+    }
+    __syncwarp();   // samples and update records of every cell are in shared memory
+    if (lane < cnt) {
+        // the rgb running average walks the voxel's frames in order (clip_seem_fusion.py:808-813)
+        float acc[3] = {L.rgb0[0], L.rgb0[1], L.rgb0[2]};
+        int w = L.w0;
+        for (uint32_t mm = L.mask; mm; mm &= mm - 1u, ++w) {
+            const int b = __ffs(mm) - 1;
+            const float4 sm = my_smp[lane * SAF_MAX_BATCH + b];
+            const float a = __frcp_rn(__int2float_rn(w + 1)), bb = __fmul_rn(__int2float_rn(w), a);   // the records' a, b
+            acc[0] = __fadd_rn(__fmul_rn(sm.x, a), __fmul_rn(acc[0], bb));
+            acc[1] = __fadd_rn(__fmul_rn(sm.y, a), __fmul_rn(acc[1], bb));
+            acc[2] = __fadd_rn(__fmul_rn(sm.z, a), __fmul_rn(acc[2], bb));
+        }
+        float* dst = p.vol.rgb + (size_t)L.voxel * 3;
+        dst[0] = acc[0];
+        dst[1] = acc[1];
+        dst[2] = acc[2];
+        p.vol.weight[L.voxel] = L.w0 + __popc(L.mask);
+    }
+    __syncwarp();   // every lane's metadata is written (and my_smp read) before the arrival publishes it
+}
+
+// NLAND landing buffers (default: one per producer).  With NLAND < NBUF tile t of the CTA (t = j * NBUF + producer)
+// lands in buffer t % NLAND: a buffer is only in use from its TMA until the compute warps have taken the rows to
+// registers, and a tile is worked on ~10 us, so one or two buffers keep the copies ahead - the freed shared memory
+// holds the table-row rings below.
+// TDEPTH > 0: every compute warp stages its 128-channel slice of a frame's four table rows in a private shared-memory
+// ring (4 x 512 B per frame) with its own cp.async.bulk copies, TDEPTH frames ahead, instead of holding the next
+// frame's rows in a second register set: the L2 round trip of a frame's rows is covered by TDEPTH frames of
+// arithmetic instead of one, and the frame code exists once.
+// LW: floats of a row per compute lane (4: a warp owns 128 channels; 2: 64 channels - half the registers per thread,
+// twice the compute warps per set for the same C).
+template <int CHUNKS, int NSET, int NBUF, int NLAND = NBUF, int TDEPTH = 0, int LW = 4>
 __global__ void __launch_bounds__((CHUNKS * NSET + NBUF) * 32, 1)
 feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, const __grid_constant__ WindowTables wt)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int C = CHUNKS * 128;
+    static_assert(LW == 4 || LW == 2, "lane width");
+    constexpr int CW = 32 * LW;        // channels per compute warp
+    constexpr int C = CHUNKS * CW;
     constexpr int G = NSET * kTileSlots;
     constexpr int NCW = CHUNKS * NSET;
+    constexpr bool kSharedLanding = NLAND != NBUF;
+    constexpr int kRingDepth = TDEPTH > 0 ? TDEPTH : 1;
     static_assert(G <= 32, "one producer lane per voxel of the tile");
+    static_assert(NLAND >= 1 && NLAND <= NBUF, "landing buffers");
     using Meta = TileMeta<NSET>;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     SlotCounters* sc = &p.hdr->slot[p.slot];
     const uint32_t n = sc->n_union;
     if (n == 0) return;
 
-    float* rows_buf = reinterpret_cast<float*>(smem_raw);                                   // [NBUF][G][C]
-    Meta* metas = reinterpret_cast<Meta*>(smem_raw + (size_t)NBUF * G * C * sizeof(float));  // [2*NBUF]
+    float* rows_buf = reinterpret_cast<float*>(smem_raw);                                   // [NLAND][G][C]
+    Meta* metas = reinterpret_cast<Meta*>(smem_raw + (size_t)NLAND * G * C * sizeof(float));  // [2*NBUF]
     float4* smp_buf = reinterpret_cast<float4*>(metas + 2 * NBUF);                           // [NBUF][G][16]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smp_buf + (size_t)NBUF * G * SAF_MAX_BATCH);
+    float* tring = reinterpret_cast<float*>(smp_buf + (size_t)NBUF * G * SAF_MAX_BATCH);     // [NCW][TDEPTH][4][CW]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tring + (size_t)NCW * TDEPTH * 4 * CW);
     uint64_t* full = bars;                    // [2*NBUF]
     uint64_t* meta_free = bars + 2 * NBUF;    // [2*NBUF]
-    uint64_t* rows_free = bars + 4 * NBUF;    // [NBUF]
+    uint64_t* rows_free = bars + 4 * NBUF;    // [NLAND]
+    uint64_t* tbar = rows_free + NLAND;       // [NCW][TDEPTH]
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2 * NBUF; ++i) {
             mbar_init(&full[i], 1);
             mbar_init(&meta_free[i], NCW);
         }
-        for (int i = 0; i < NBUF; ++i) mbar_init(&rows_free[i], NCW);
+        for (int i = 0; i < NLAND; ++i) mbar_init(&rows_free[i], NCW);
+        for (int i = 0; i < NCW * TDEPTH; ++i) mbar_init(&tbar[i], 1);
         fence_mbar_init();
     }
     __syncthreads();
@@ -1774,12 +2030,8 @@ feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, co
         // reductions), and only the rgb running average - pure arithmetic on samples parked in shared memory -
         // walks a voxel's frames in order.
         const uint32_t n_blocks = sc->n_blocks;
-        const uint32_t* __restrict__ off = p.blk_offset;
-        const int B = p.batch;
-        float* my_rows = rows_buf + (size_t)warp * G * C;
         float4* my_smp = smp_buf + (size_t)warp * G * SAF_MAX_BATCH;   // [voxel][frame] rgb sample
-        const int set = lane / kTileSlots, slot = lane % kTileSlots;
-        constexpr int kCellIters = G * SAF_MAX_BATCH / 32;
+        const Meta* prepared = reinterpret_cast<const Meta*>(p.tile_meta);
         for (uint32_t j = 0;; ++j) {
             uint32_t base = 0;
             if (lane == 0) base = atomicAdd(&sc->k3_next, (uint32_t)G);
@@ -1795,150 +2047,54 @@ feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, co
                 }
                 break;
             }
-            // block rank of the tile's first entry: 32-ary search by the whole warp (off[lo] <= base < off[hi])
-            uint32_t lo = 0, hi = n_blocks;
-            while (hi - lo > 1) {
-                const uint32_t step = (hi - lo + 31u) / 32u;
-                const uint32_t probe = lo + (uint32_t)lane * step;
-                const bool le = probe < hi && __ldg(off + probe) <= base;
-                const uint32_t k = (uint32_t)__popc(__ballot_sync(0xffffffffu, le));   // >= 1: lane 0 probes lo
-                lo += (k - 1u) * step;
-                hi = min(hi, lo + step);
+            if (NSET == 2 && base / (uint32_t)G < p.tile_meta_cap) {
+                // K2T prepared this tile (metadata in global memory, small state already updated): one bulk copy of
+                // the metadata next to the feature rows'
+                static_assert(!kSharedLanding || NSET != 2, "prepared tiles use the producer's own landing buffer");
+                const Meta* GM = prepared + base / (uint32_t)G;
+                const uint32_t vox = lane < cnt ? __ldg(&GM->voxel[lane]) : 0u;
+                mbar_wait(&rows_free[warp], (j & 1u) ^ 1u);
+                mbar_wait(&meta_free[ms], ((j >> 1) & 1u) ^ 1u);
+                if (lane == 0) {
+                    mbar_expect_tx(&full[ms], cnt * (uint32_t)C * 4u + (uint32_t)sizeof(Meta));
+                    tma_bulk_g2s(M, GM, (uint32_t)sizeof(Meta), &full[ms]);
+                }
+                __syncwarp();
+                if (lane < cnt)
+                    tma_bulk_g2s(rows_buf + ((size_t)warp * G + lane) * C, p.vol.clip_feat + (size_t)vox * C,
+                                 (uint32_t)C * 4u, &full[ms]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[ms]);
+                continue;
             }
-            uint32_t my_voxel = 0, my_mask = 0, my_local = 0, my_rank = 0;
-            int my_w0 = 0;
-            float rgb0[3] = {0.f, 0.f, 0.f};
-            if (lane < cnt) {
-                const uint32_t i = base + lane;
-                uint32_t r = lo;
-                while (r + 1u < n_blocks && __ldg(off + r + 1u) <= i) ++r;   // the tile spans a few blocks at most
-                const WinEntry e = p.ulist[(uint64_t)r * kBlockVoxels + (i - __ldg(off + r))];
-                my_voxel = e.voxel;
-                my_mask = e.mask_local & 0xffffu;
-                my_local = e.mask_local >> 16;
-                my_rank = r;
-                my_w0 = p.vol.weight[my_voxel];
-                const float* src3 = p.vol.rgb + (size_t)my_voxel * 3;
-                rgb0[0] = src3[0];
-                rgb0[1] = src3[1];
-                rgb0[2] = src3[2];
-            }
-            // the landing buffer was handed back when the compute warps took its rows to registers
-            mbar_wait(&rows_free[warp], (j & 1u) ^ 1u);
-            if (lane == 0) mbar_expect_tx(&full[ms], cnt * (uint32_t)C * 4u);
-            __syncwarp();
-            if (lane < cnt)
-                tma_bulk_g2s(my_rows + (size_t)lane * C, p.vol.clip_feat + (size_t)my_voxel * C, (uint32_t)C * 4u, &full[ms]);
-            // per frame: which voxels of the tile are valid (lane b keeps frame b's ballot)
-            uint32_t my_ballot = 0;
-#pragma unroll
-            for (int b = 0; b < SAF_MAX_BATCH; ++b) {
-                const uint32_t bal = __ballot_sync(0xffffffffu, (my_mask >> b) & 1u);
-                if (lane == b) my_ballot = bal;
-            }
+            const TileLane L = load_tile_lane(p, n_blocks, base, cnt, lane);
+            const uint32_t my_voxel = L.voxel;
+            // the landing buffer was handed back when the compute warps took its rows to registers.  Shared landing
+            // buffers: tile t may only land once tile t - NLAND has been taken, which is about when tile t's
+            // metadata is due - so (after the first round) the copies start when the metadata is done instead of
+            // blocking this warp before it
+            const uint32_t tseq = j * (uint32_t)NBUF + (uint32_t)warp;
+            const uint32_t lb = kSharedLanding ? tseq % (uint32_t)NLAND : (uint32_t)warp;
+            const uint32_t lphase = kSharedLanding ? ((tseq / (uint32_t)NLAND) & 1u) ^ 1u : (j & 1u) ^ 1u;
+            float* my_rows = rows_buf + (size_t)lb * G * C;
+            const bool land_early = !kSharedLanding || tseq < (uint32_t)NLAND;
+            auto start_rows = [&]() {
+                mbar_wait(&rows_free[lb], lphase);
+                if (lane == 0) mbar_expect_tx(&full[ms], cnt * (uint32_t)C * 4u);
+                __syncwarp();
+                if (lane < cnt)
+                    tma_bulk_g2s(my_rows + (size_t)lane * C, p.vol.clip_feat + (size_t)my_voxel * C, (uint32_t)C * 4u,
+                                 &full[ms]);
+            };
+            if (land_early) start_rows();
             // the metadata slot was last read two of this producer's tiles ago
             mbar_wait(&meta_free[ms], ((j >> 1) & 1u) ^ 1u);
-            if (lane < SAF_MAX_BATCH) {
-#pragma unroll
-                for (int s = 0; s < NSET; ++s) M->vmask[s][lane] = (uint8_t)((my_ballot >> (s * kTileSlots)) & 0xffu);
-            }
-#pragma unroll
-            for (int s = 0; s < NSET; ++s) {
-                const uint32_t fm = __ballot_sync(0xffffffffu, lane < SAF_MAX_BATCH &&
-                                                                   ((my_ballot >> (s * kTileSlots)) & 0xffu) != 0u);
-                if (lane == 0) M->fmask[s] = fm;
-            }
-            if (lane == 0) M->n_rows = cnt;
-            if (lane < cnt) M->voxel[lane] = my_voxel;
-            // cells: c -> (frame c / G, voxel c % G).  Pass 1 requests every valid cell's image coordinates.
-            float2 cg[kCellIters];
-#pragma unroll
-            for (int it = 0; it < kCellIters; ++it) {
-                const int c = it * 32 + lane, b = c / G, v = c % G;
-                const uint32_t mv = __shfl_sync(0xffffffffu, my_mask, v);
-                const uint32_t rk = __shfl_sync(0xffffffffu, my_rank, v);
-                const uint32_t lc = __shfl_sync(0xffffffffu, my_local, v);
-                cg[it] = make_float2(0.f, 0.f);
-                if ((mv >> b) & 1u) cg[it] = p.wcoords[((uint64_t)rk * B + b) * kBlockVoxels + lc];
-            }
-            // Pass 2: per valid cell the compute warps' update record (clip_seem_fusion.py:800-810), the rgb sample
-            // and the label counter (:786-798, 820-822).
-#pragma unroll
-            for (int it = 0; it < kCellIters; ++it) {
-                const int c = it * 32 + lane, b = c / G, v = c % G;
-                const uint32_t mv = __shfl_sync(0xffffffffu, my_mask, v);
-                const uint32_t vx = __shfl_sync(0xffffffffu, my_voxel, v);
-                const int w0 = __shfl_sync(0xffffffffu, my_w0, v);
-                const bool cell_valid = (mv >> b) & 1u;
-                uint32_t cell_rows = 0;
-                if (cell_valid) {
-                    const saf_frame& f = p.frames[b];
-                    const float2 g = cg[it];
-                    const int w = w0 + __popc(mv & ((1u << b) - 1u));   // single-frame calls before this one
-                    const float a = __frcp_rn(__int2float_rn(w + 1));
-                    const float bb = __fmul_rn(__int2float_rn(w), a);
-                    Taps t;
-                    feature_taps_padded(f, g.x, g.y, p.W, p.H, &p.hdr->error_flags, t);
-                    const uint32_t rows = (uint32_t)t.idx[0] | ((uint32_t)t.idx[1] << 8) | ((uint32_t)t.idx[2] << 16) |
-                                          ((uint32_t)t.idx[3] << 24);
-                    TileUpdate u;
-                    u.w[0] = t.w[0];
-                    u.w[1] = t.w[1];
-                    u.w[2] = t.w[2];
-                    u.w[3] = t.w[3];
-                    u.a = a;
-                    u.b = bb;
-                    u.rows = rows;
-                    u.pad = 0;
-                    M->upd[v / kTileSlots][b][v % kTileSlots] = u;
-                    cell_rows = rows;
-                    const int px = nearest_index(g.x, p.W), py = nearest_index(g.y, p.H);
-                    float smp[3];
-                    sample_rgb(p, f, g.x, g.y, px, py, smp);
-                    my_smp[v * SAF_MAX_BATCH + b] = make_float4(smp[0], smp[1], smp[2], 0.f);
-                    if (p.vol.labels_one_hot && f.seg) {
-                        const float lf = (px >= 0 && py >= 0) ? load_class_id(f.seg, f.seg_dtype, py * p.W + px) : 0.0f;
-                        const long long id = (long long)lf;
-                        if (id >= 0 && id < p.vol.n_classes)
-                            atomicAdd(p.vol.labels_one_hot + (size_t)vx * p.vol.n_classes + id, 1);   // RED: no round trip
-                        else
-                            atomicOr(&p.hdr->error_flags, SAF_FLAG_BAD_CLASS_ID);
-                    }
-                }
-                // The 8 lanes of a group hold one set's voxels for one frame (G = 16: two frames per iteration).  The
-                // group's first valid voxel provides the rows the compute warps prefetch for (set, frame); if every
-                // valid voxel of the group uses those rows - nearly always - the frame takes the compare-free path.
-                static_assert(G == 16, "cell groups assume 16 voxels per tile");
-                const uint32_t vb = __ballot_sync(0xffffffffu, cell_valid);
-                const int group = lane >> 3;
-                const uint32_t gb = (vb >> (group * 8)) & 0xffu;
-                const int first = group * 8 + (gb ? __ffs(gb) - 1 : 0);
-                const uint32_t prim = __shfl_sync(0xffffffffu, cell_rows, first);
-                const uint32_t mb = __ballot_sync(0xffffffffu, cell_valid && cell_rows != prim);
-                if (gb && lane == first) {
-                    M->prim_rows[v / kTileSlots][b] = prim;
-                    M->uniform[v / kTileSlots][b] = ((mb >> (group * 8)) & 0xffu) == 0u ? 1 : 0;
-                }
-            }
-            __syncwarp();   // samples and update records of every cell are in shared memory
-            if (lane < cnt) {
-                // the rgb running average walks the voxel's frames in order (clip_seem_fusion.py:808-813)
-                float acc[3] = {rgb0[0], rgb0[1], rgb0[2]};
-                for (uint32_t mm = my_mask; mm; mm &= mm - 1u) {
-                    const int b = __ffs(mm) - 1;
-                    const float4 sm = my_smp[lane * SAF_MAX_BATCH + b];
-                    const float a = M->upd[set][b][slot].a, bb = M->upd[set][b][slot].b;
-                    acc[0] = __fadd_rn(__fmul_rn(sm.x, a), __fmul_rn(acc[0], bb));
-                    acc[1] = __fadd_rn(__fmul_rn(sm.y, a), __fmul_rn(acc[1], bb));
-                    acc[2] = __fadd_rn(__fmul_rn(sm.z, a), __fmul_rn(acc[2], bb));
-                }
-                float* dst = p.vol.rgb + (size_t)my_voxel * 3;
-                dst[0] = acc[0];
-                dst[1] = acc[1];
-                dst[2] = acc[2];
-                p.vol.weight[my_voxel] = my_w0 + __popc(my_mask);
-            }
+            fill_tile_meta<NSET>(p, L, cnt, M, my_smp, lane);
             __syncwarp();   // every lane's metadata is written (and my_smp read) before the arrival publishes it
+            if (!land_early) {
+                start_rows();
+                __syncwarp();
+            }
             if (lane == 0) mbar_arrive(&full[ms]);
         }
         return;
@@ -1946,6 +2102,7 @@ feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, co
 #else   // lane-per-voxel producer: each lane walks its voxel's frames one after the other
     if (warp < NBUF) {
         // ------------------------------- producer -------------------------------
+        static_assert(!kSharedLanding, "the lane-per-voxel producer owns its landing buffer");
         const uint32_t n_blocks = sc->n_blocks;
         const uint32_t* __restrict__ off = p.blk_offset;
         const int B = p.batch;
@@ -2039,7 +2196,7 @@ feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, co
                     u.a = a;
                     u.b = bb;
                     u.rows = rows;
-                    u.pad = 0;
+                    u.one = 1.0f;
                     M->upd[set][b][slot] = u;
                     if ((first_bits >> b) & 1u) M->prim_rows[set][b] = rows;
                     const int px = nearest_index(g.x, p.W), py = nearest_index(g.y, p.H);
@@ -2071,28 +2228,36 @@ feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, co
     // ------------------------------- compute -------------------------------
     const int cw = warp - NBUF;
     const int set = cw / CHUNKS, chunk = cw % CHUNKS;
-    const int col4 = chunk * 32 + lane;   // this thread's float4 column of every row
+    const int col4 = chunk * 32 + lane;   // this thread's LW-float column of every row
     uint32_t done = 0;                    // producers that have published their last tile
+    // table-row ring of this warp (TDEPTH > 0): requests issued / taken so far
+    float* my_ring = tring + (size_t)cw * kRingDepth * 4 * CW;
+    uint64_t* my_tbar = tbar + cw * kRingDepth;
+    uint32_t ring_issued = 0, ring_taken = 0;
     for (uint32_t t = 0; done != (1u << NBUF) - 1u; ++t) {
         const uint32_t pi = t % NBUF, j = t / NBUF;
-        if ((done >> pi) & 1u) continue;
+        const uint32_t lb = kSharedLanding ? t % (uint32_t)NLAND : pi;
+        if ((done >> pi) & 1u) {
+            // shared landing buffers are handed on in tile order: a tile that never lands still takes its turn
+            if (kSharedLanding && lane == 0) mbar_arrive(&rows_free[lb]);
+            continue;
+        }
         const uint32_t ms = pi + (uint32_t)NBUF * (j & 1u);
         mbar_wait(&full[ms], (j >> 1) & 1u);
         const Meta* M = metas + ms;
         const uint32_t n_rows = M->n_rows;
         if (n_rows == 0) {
             done |= 1u << pi;
+            if (kSharedLanding && lane == 0) mbar_arrive(&rows_free[lb]);
             continue;
         }
         // accumulators of the set's voxels: landing buffer -> registers, then the buffer goes back to the producer
         f32x2_t acc_lo[kTileSlots], acc_hi[kTileSlots];
-        const ulonglong2* land = reinterpret_cast<const ulonglong2*>(rows_buf + (size_t)pi * G * C) + col4;
+        const float* land = rows_buf + (size_t)lb * G * C;
 #pragma unroll
         for (int s = 0; s < kTileSlots; ++s) {
             if ((uint32_t)(set * kTileSlots + s) < n_rows) {
-                const ulonglong2 v = land[(size_t)(set * kTileSlots + s) * (C / 4)];
-                acc_lo[s] = v.x;
-                acc_hi[s] = v.y;
+                ld_col_shared<LW>(land + (size_t)(set * kTileSlots + s) * C, col4, acc_lo[s], acc_hi[s]);
             } else {
                 acc_lo[s] = 0ull;
                 acc_hi[s] = 0ull;
@@ -2100,26 +2265,49 @@ feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, co
         }
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&rows_free[pi]);
+        if (lane == 0) mbar_arrive(&rows_free[lb]);
 
+#ifdef SAF_DBG_SKIP_COMPUTE
+        const uint32_t fm = M->fmask[set] & SAF_DBG_SKIP_COMPUTE;   // timing experiment only
+#else
         const uint32_t fm = M->fmask[set];
+#endif
         if (fm) {
             // one frame of the window: every voxel of the set that the frame sees, with the frame's rows in T
             auto frame_updates = [&](int b, RowRegs& T, uint32_t& cur_rows) {
                 const uint32_t vm = M->vmask[set][b];
                 if (M->uniform[set][b]) {
                     // every valid voxel of the set samples the prefetched rows: no per-voxel row check
+#if SAF_TILE_DENSE > 0
+                    if (__popc(vm) >= SAF_TILE_DENSE) {
+#pragma unroll
+                        for (int s = 0; s < kTileSlots; ++s) {
+                            const uint4 m0 = *reinterpret_cast<const uint4*>(&M->upd[set][b][s]);
+                            const uint4 m1 = *(reinterpret_cast<const uint4*>(&M->upd[set][b][s]) + 1);
+                            const float w0 = __uint_as_float(m0.x), w1 = __uint_as_float(m0.y), w2 = __uint_as_float(m0.z),
+                                        w3 = __uint_as_float(m0.w), a = __uint_as_float(m1.x), bb = __uint_as_float(m1.y),
+                                        one = __uint_as_float(m1.w);
+                            const f32x2_t wp[4] = {pack2(w0, w0), pack2(w1, w1), pack2(w2, w2), pack2(w3, w3)};
+                            const f32x2_t ap = pack2(a, a), bp = pack2(bb, bb), op = pack2(one, one);
+                            const uint32_t commit = (vm >> s) & 1u;
+                            acc_lo[s] = mix_blend2_if(T.lo, wp, ap, bp, op, acc_lo[s], commit);
+                            if constexpr (LW == 4) acc_hi[s] = mix_blend2_if(T.hi, wp, ap, bp, op, acc_hi[s], commit);
+                        }
+                        return;
+                    }
+#endif
 #pragma unroll
                     for (int s = 0; s < kTileSlots; ++s) {
                         if ((vm >> s) & 1u) {
                             const uint4 m0 = *reinterpret_cast<const uint4*>(&M->upd[set][b][s]);
-                            const uint2 m1 = *reinterpret_cast<const uint2*>(&M->upd[set][b][s].a);
+                            const uint4 m1 = *(reinterpret_cast<const uint4*>(&M->upd[set][b][s]) + 1);
                             const float w0 = __uint_as_float(m0.x), w1 = __uint_as_float(m0.y), w2 = __uint_as_float(m0.z),
-                                        w3 = __uint_as_float(m0.w), a = __uint_as_float(m1.x), bb = __uint_as_float(m1.y);
+                                        w3 = __uint_as_float(m0.w), a = __uint_as_float(m1.x), bb = __uint_as_float(m1.y),
+                                        one = __uint_as_float(m1.w);
                             const f32x2_t wp[4] = {pack2(w0, w0), pack2(w1, w1), pack2(w2, w2), pack2(w3, w3)};
-                            const f32x2_t ap = pack2(a, a), bp = pack2(bb, bb);
-                            acc_lo[s] = mix_blend2(T.lo, wp, ap, bp, acc_lo[s]);
-                            acc_hi[s] = mix_blend2(T.hi, wp, ap, bp, acc_hi[s]);
+                            const f32x2_t ap = pack2(a, a), bp = pack2(bb, bb), op = pack2(one, one);
+                            acc_lo[s] = mix_blend2(T.lo, wp, ap, bp, op, acc_lo[s]);
+                            if constexpr (LW == 4) acc_hi[s] = mix_blend2(T.hi, wp, ap, bp, op, acc_hi[s]);
                         }
                     }
                     return;
@@ -2131,17 +2319,55 @@ feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, co
                         const uint4 m1 = *(reinterpret_cast<const uint4*>(&M->upd[set][b][s]) + 1);
                         if (m1.z != cur_rows) {   // a voxel of the set straddles a table cell boundary: rare
                             cur_rows = m1.z;
-                            load_rows(T, wt.ptr[b], cur_rows, C, col4);
+                            load_rows<LW>(T, wt.ptr[b], cur_rows, C, col4);
                         }
                         const float w0 = __uint_as_float(m0.x), w1 = __uint_as_float(m0.y), w2 = __uint_as_float(m0.z),
-                                    w3 = __uint_as_float(m0.w), a = __uint_as_float(m1.x), bb = __uint_as_float(m1.y);
+                                    w3 = __uint_as_float(m0.w), a = __uint_as_float(m1.x), bb = __uint_as_float(m1.y),
+                                    one = __uint_as_float(m1.w);
                         const f32x2_t wp[4] = {pack2(w0, w0), pack2(w1, w1), pack2(w2, w2), pack2(w3, w3)};
-                        const f32x2_t ap = pack2(a, a), bp = pack2(bb, bb);
-                        acc_lo[s] = mix_blend2(T.lo, wp, ap, bp, acc_lo[s]);
-                        acc_hi[s] = mix_blend2(T.hi, wp, ap, bp, acc_hi[s]);
+                        const f32x2_t ap = pack2(a, a), bp = pack2(bb, bb), op = pack2(one, one);
+                        acc_lo[s] = mix_blend2(T.lo, wp, ap, bp, op, acc_lo[s]);
+                        if constexpr (LW == 4) acc_hi[s] = mix_blend2(T.hi, wp, ap, bp, op, acc_hi[s]);
                     }
                 }
             };
+            if constexpr (TDEPTH > 0) {
+                // frames of the set in order; the rows of frame i + TDEPTH are requested when frame i's have been
+                // taken to registers
+                uint32_t use_rest = fm, req_rest = fm;
+                auto request_next = [&]() {
+                    const int b = __ffs(req_rest) - 1;
+                    req_rest &= req_rest - 1u;
+                    const uint32_t slot = ring_issued % (uint32_t)kRingDepth;
+                    const uint32_t rows = M->prim_rows[set][b];
+                    if (lane == 0) mbar_arrive_expect_tx(&my_tbar[slot], 4u * CW * 4u);
+                    __syncwarp();
+                    if (lane < 4)
+                        tma_bulk_g2s(my_ring + ((size_t)slot * 4 + lane) * CW,
+                                     wt.ptr[b] + (size_t)((rows >> (8 * lane)) & 0xffu) * C + chunk * CW, CW * 4u,
+                                     &my_tbar[slot]);
+                    ++ring_issued;
+                };
+#pragma unroll
+                for (int i = 0; i < kRingDepth; ++i)
+                    if (req_rest) request_next();
+                RowRegs T;
+                while (use_rest) {
+                    const int b = __ffs(use_rest) - 1;
+                    use_rest &= use_rest - 1u;
+                    const uint32_t slot = ring_taken % (uint32_t)kRingDepth;
+                    mbar_wait(&my_tbar[slot], (ring_taken / (uint32_t)kRingDepth) & 1u);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        ld_col_shared<LW>(my_ring + ((size_t)slot * 4 + k) * CW, lane, T.lo[k], T.hi[k]);
+                    ++ring_taken;
+                    fence_proxy_async();
+                    __syncwarp();   // every lane has its slice before the slot is refilled
+                    if (req_rest) request_next();
+                    uint32_t cur_rows = M->prim_rows[set][b];
+                    frame_updates(b, T, cur_rows);
+                }
+            } else {
             uint32_t rest = fm;
             auto next_frame = [&]() {
                 const int b = rest ? __ffs(rest) - 1 : -1;
@@ -2151,7 +2377,7 @@ feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, co
             auto request = [&](int b, RowRegs& T, uint32_t& rows) {
                 if (b >= 0) {
                     rows = M->prim_rows[set][b];
-                    load_rows(T, wt.ptr[b], rows, C, col4);
+                    load_rows<LW>(T, wt.ptr[b], rows, C, col4);
                 }
             };
             // the next frame's rows are requested before a frame's arithmetic starts; two register sets take turns
@@ -2169,16 +2395,50 @@ feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, co
                 frame_updates(b1, T1, rows1);
                 if (b0 < 0) break;
             }
+            }
 #pragma unroll
             for (int s = 0; s < kTileSlots; ++s) {
                 if ((uint32_t)(set * kTileSlots + s) < n_rows) {
                     const uint32_t v = M->voxel[set * kTileSlots + s];
-                    st_stream_b64x2(reinterpret_cast<ulonglong2*>(p.vol.clip_feat + (size_t)v * C) + col4, acc_lo[s], acc_hi[s]);
+                    if constexpr (LW == 4)
+                        st_stream_b64x2(reinterpret_cast<ulonglong2*>(p.vol.clip_feat + (size_t)v * C) + col4, acc_lo[s],
+                                        acc_hi[s]);
+                    else
+                        st_stream_b64(reinterpret_cast<unsigned long long*>(p.vol.clip_feat + (size_t)v * C) + col4,
+                                      acc_lo[s]);
                 }
             }
         }
+        fence_proxy_async();   // prepared tiles: the slot is refilled by a bulk copy
         __syncwarp();
         if (lane == 0) mbar_arrive(&meta_free[ms]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2T: prepares K3W's tiles ahead of it.  Inside K3W the three producer warps of a CTA do this work one tile at a
+// time, each a chain of memory round trips (union entries, image coordinates, rgb taps, class ids) that 3 warps per
+// SM cannot hide: measured on cfg2, K3W takes 461 us with its producers doing everything, 251 us with the compute
+// warps idle, 323 us with the producers reduced to nothing.  Here the same per-tile routine (fill_tile_meta) runs
+// one warp per tile over the whole GPU, tens of warps per SM, writes the tile's metadata to global memory and
+// updates the small state; K3W's producers then only start two bulk copies per tile.
+// ---------------------------------------------------------------------------------------------
+constexpr int kK2TWarps = 8;
+
+__global__ void __launch_bounds__(kK2TWarps * 32) window_tile_setup_kernel(const __grid_constant__ FusionParams p)
+{
+    constexpr int NSET = 2, G = NSET * kTileSlots;
+    __shared__ float4 s_smp[kK2TWarps][G * SAF_MAX_BATCH];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const SlotCounters* sc = &p.hdr->slot[p.slot];
+    const uint32_t n = sc->n_union, n_blocks = sc->n_blocks;
+    const uint32_t n_tiles = min((n + G - 1) / G, p.tile_meta_cap);
+    TileMeta<NSET>* metas = reinterpret_cast<TileMeta<NSET>*>(p.tile_meta);
+    for (uint32_t tile = blockIdx.x * kK2TWarps + warp; tile < n_tiles; tile += gridDim.x * kK2TWarps) {
+        const uint32_t base = tile * G, cnt = min((uint32_t)G, n - base);
+        const TileLane L = load_tile_lane(p, n_blocks, base, cnt, lane);
+        fill_tile_meta<NSET>(p, L, cnt, metas + tile, s_smp[warp], lane);
+        __syncwarp();   // s_smp is reused by the warp's next tile
     }
 }
 
@@ -2443,6 +2703,16 @@ static int build_params(const saf_grid_desc* grid, const saf_volume* vol, const 
     p->ulist = (WinEntry*)p->lists;
     p->wcoords = (float2*)(p->lists + L.list_cap);
     p->tables = (float*)(sb + L.off_tables);
+    // a window workspace's list regions past the coordinates are idle in window mode: K2T's tile metadata
+    {
+        const uint64_t used = (uint64_t)L.list_cap * (sizeof(ValidEntry) + (uint64_t)batch * sizeof(float2));
+        const uint64_t total = (uint64_t)ws->max_batch * L.list_cap * sizeof(ValidEntry);
+        const uint64_t start = align_up(used, 128);
+        p->tile_meta = (unsigned char*)p->lists + start;
+        static const bool setup_on = !(getenv("SAF_TILE_SETUP") && atoi(getenv("SAF_TILE_SETUP")) == 0);
+        p->tile_meta_cap = (setup_on && total > start)
+                               ? (uint32_t)std::min<uint64_t>((total - start) / sizeof(TileMeta<2>), 0x7fffffffu) : 0u;
+    }
     return 0;
 }
 
@@ -2588,16 +2858,18 @@ static int launch_k3w_fixed(const FusionParams& p, const WindowTables& wt, int s
     return 0;
 }
 
-template <int CHUNKS, int NSET, int NBUF>
+template <int CHUNKS, int NSET, int NBUF, int NLAND = NBUF, int TDEPTH = 0, int LW = 4>
 static int launch_k3w_tile(const FusionParams& p, const WindowTables& wt, int sms, cudaStream_t st)
 {
     constexpr int kThreads = (CHUNKS * NSET + NBUF) * 32;
-    constexpr size_t smem = (size_t)NBUF * NSET * kTileSlots * CHUNKS * 128 * sizeof(float) +
+    constexpr size_t smem = (size_t)NLAND * NSET * kTileSlots * CHUNKS * 32 * LW * sizeof(float) +
                             2 * (size_t)NBUF * sizeof(TileMeta<NSET>) +
                             (size_t)NBUF * NSET * kTileSlots * SAF_MAX_BATCH * sizeof(float4) +
-                            5 * (size_t)NBUF * sizeof(uint64_t);
+                            (size_t)CHUNKS * NSET * TDEPTH * 4 * 32 * LW * sizeof(float) +
+                            (4 * (size_t)NBUF + NLAND + (size_t)CHUNKS * NSET * TDEPTH) * sizeof(uint64_t);
     static_assert(smem <= 227 * 1024, "tile kernel shared memory");
-    auto kern = feature_accumulate_window_tile_kernel<CHUNKS, NSET, NBUF>;
+    static_assert(kThreads <= 1024, "tile kernel threads");
+    auto kern = feature_accumulate_window_tile_kernel<CHUNKS, NSET, NBUF, NLAND, TDEPTH, LW>;
     { int rc_ = ensure_dynamic_smem(kern, smem); if (rc_) return rc_; }
     // A shard of a grid (multi-GPU) has small windows: their cost is the chain of dependent launches, not
     // throughput.  K3W then leaves some SMs free (it holds one CTA per SM and fills every SM it is given), so that
@@ -2610,6 +2882,10 @@ static int launch_k3w_tile(const FusionParams& p, const WindowTables& wt, int sm
     const int reserve = reserve_env >= 0 ? reserve_env
                                          : (share < 0.75 ? (int)(sms * std::min(0.28, 0.035 / std::max(share, 1e-3))) : 0);
     const int grid = std::max(1, sms - std::min(reserve, sms - 1));
+    if (NSET == 2 && p.tile_meta_cap > 0) {
+        window_tile_setup_kernel<<<sms * 4, kK2TWarps * 32, 0, st>>>(p);
+        SAF_CHECK_LAUNCH("window_tile_setup_kernel (K2T)", st);
+    }
     kern<<<grid, kThreads, smem, st>>>(p, wt);
     SAF_CHECK_LAUNCH("feature_accumulate_window_tile_kernel (K3W)", st);
     return 0;
@@ -2646,7 +2922,9 @@ static int launch_k3w(const FusionParams& p, int sms, cudaStream_t st)
         if (k3w_variant() == 2 && small_tables) {
             switch (C) {
                 case 512: return launch_k3w_tile<4, 2, SAF_TILE_NBUF>(p, wt, sms, st);
-                case 768: return launch_k3w_tile<6, 2, SAF_TILE_NBUF>(p, wt, sms, st);
+                case 768:
+                    return launch_k3w_tile<768 / (32 * SAF_TILE_LW), 2, SAF_TILE_NBUF, SAF_TILE_NLAND, SAF_TILE_TDEPTH,
+                                           SAF_TILE_LW>(p, wt, sms, st);
                 case 1024: return launch_k3w_tile<8, 2, 2>(p, wt, sms, st);
                 default: break;
             }

@@ -271,6 +271,10 @@ __device__ __forceinline__ void st_stream_b64x2(void* p, f32x2_t lo, f32x2_t hi)
 {
     asm volatile("st.global.L1::no_allocate.v2.b64 [%0], {%1,%2};" ::"l"(p), "l"(lo), "l"(hi) : "memory");
 }
+__device__ __forceinline__ void st_stream_b64(void* p, f32x2_t v)
+{
+    asm volatile("st.global.L1::no_allocate.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 
 // ---- exact fp32 scoring helpers shared by the fp32 query kernel and the top-k rescoring kernel, so that
 // both produce bit-identical scores -------------------------------------------------------------------
