@@ -73,7 +73,7 @@ def parse_args(argv=None):
     ap.add_argument("--emulate-world", type=int, default=0,
                     help="debug: on ONE GPU, run rank 0's share of the N-rank strong-scaling job (per-kernel times of a shard)")
     ap.add_argument("--window", type=int, default=16, choices=list(range(1, 17)),
-                    help="frames fused per launch trio by saf_integrate_sequence (1 = frame by frame)")
+                    help="frames fused per launch set by saf_integrate_sequence (1 = frame by frame)")
     ap.add_argument("--resume-from", default=None, help="load_state() directory: fuse into an existing grid (config 5)")
     return ap.parse_args(argv)
 
@@ -691,8 +691,8 @@ def run_native_arm(args):
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         bw = window if window > 1 else 1
         n_probe = max(1, min(n_base // bw, 6 if bw > 1 else 40))     # windows (or frames) timed one launch at a time
-        k3_ms, k3_upd, k3_union, k1_ms, k2_ms, timed = 0.0, 0, 0, 0.0, 0.0, 0
-        ea, eb, e0, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+        k3_ms, k3_upd, k3_union, k1_ms, k2_ms, k2t_ms, timed = 0.0, 0, 0, 0.0, 0.0, 0.0, 0
+        ea, eb, e0, et, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(5))
         probe = steps_arr[W_steps]
         for i in range(n_probe):
             fr = ctypes.cast(probe.ctypes.data + i * bw * ctypes.sizeof(_lib.Frame), ctypes.POINTER(_lib.Frame))
@@ -708,9 +708,15 @@ def run_native_arm(args):
                                                ctypes.byref(ws), None, None, stream), "K2")
             e0.record()
             if bw > 1:
-                _lib.check(lib.saf_feature_accumulate_window(ctypes.byref(grid_d), ctypes.byref(vol_d), fr, bw, H, Wd,
-                                                             _lib.SAF_RGB_BILINEAR, ctypes.byref(ws), stream), "K3W")
+                # K2T (tile metadata + rgb / weight / label counters) and K3W (the feature rows), timed separately
+                for stage, ev in ((1, et), (2, None)):
+                    _lib.check(lib.saf_feature_accumulate_window_stages(
+                        ctypes.byref(grid_d), ctypes.byref(vol_d), fr, bw, H, Wd, _lib.SAF_RGB_BILINEAR, ctypes.byref(ws),
+                        stage, stream), "K2T" if stage == 1 else "K3W")
+                    if ev is not None:
+                        ev.record()
             else:
+                et.record()
                 _lib.check(lib.saf_feature_accumulate(ctypes.byref(grid_d), ctypes.byref(vol_d), fr, 1, 0, H, Wd,
                                                       _lib.SAF_RGB_BILINEAR, ctypes.byref(ws), stream), "K3")
             e1.record()
@@ -722,7 +728,8 @@ def run_native_arm(args):
             timed += 1
             k1_ms += ea.elapsed_time(eb)
             k2_ms += eb.elapsed_time(e0)
-            k3_ms += e0.elapsed_time(e1)
+            k2t_ms += e0.elapsed_time(et)
+            k3_ms += et.elapsed_time(e1)
             k3_upd += nv
             k3_union += (sa["total_union"] - sb["total_union"]) if bw > 1 else nv
         timed = max(1, timed)
@@ -740,7 +747,7 @@ def run_native_arm(args):
                           "feature_accumulate_kernel (K3)",
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "peak_source": peak_src, "launches_timed": timed, "avg_launch_us": k3_ms / timed * 1e3,
-                "k1_avg_us": k1_ms / timed * 1e3, "k2_avg_us": k2_ms / timed * 1e3,
+                "k1_avg_us": k1_ms / timed * 1e3, "k2_avg_us": k2_ms / timed * 1e3, "k2t_avg_us": k2t_ms / timed * 1e3,
                 "avg_updates_per_launch": k3_upd / timed, "avg_union_rows_per_launch": k3_union / timed,
                 "ns_per_update": k3_ms * 1e6 / max(1, k3_upd),
                 "algorithmic_bytes_per_launch": bytes_win / timed,
@@ -815,7 +822,7 @@ def run_native_arm(args):
             "ms_per_step": ms / K_steps, "higher_is_better": True,
             "scaling": "strong" if plan.mode == "strong" else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": plan.config(),
-            "window": "%d consecutive frames per K0/K1/K2/K3W launch quartet (saf_integrate_sequence)" % window,
+            "window": "up to %d consecutive frames per K0/K1/K2/K2T/K3W launch quintet (saf_integrate_sequence)" % window,
             "frames_per_s": frames_per_s,
             "updates_per_frame": total_upd / n_frames,
             "tsdf_updates_per_frame": sum_over_ranks(tv) / n_frames if world == 1 else None,
@@ -823,8 +830,8 @@ def run_native_arm(args):
             "visible_blocks_per_frame": blocks / n_frames,
             "per_rank_ms_per_step": [x / K_steps for x in rank_ms], "per_rank_updates": rank_upd,
             "rank_imbalance": max(rank_ms) / (sum(rank_ms) / len(rank_ms)),
-            # rank 0's count: K0 + K1 + K2 + K3W per window the library launched (its own counter)
-            "gpu_launches": 4 * calls,
+            # rank 0's count: K0 + K1 + K2 + K2T + K3W per window the library launched (its own counter)
+            "gpu_launches": (5 if window > 1 else 4) * calls,
             "timed_region_attempts_ms": attempts,
             "clocks": clocks, "e2e": e2e, "roofline": roof, "query": query, "cpu_baseline": cpu,
         }

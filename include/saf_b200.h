@@ -225,6 +225,18 @@ int saf_feature_accumulate_window(const saf_grid_desc *grid, const saf_volume *v
                                   int32_t batch, int32_t height, int32_t width, int32_t rgb_mode,
                                   const saf_workspace *ws, void *stream);
 
+/* The two stages of saf_feature_accumulate_window, separately (what the bench times one by one):
+ * SAF_STAGE_TILE_SETUP   repacks the frames' feature images and runs K2T, which prepares the update metadata of the
+ *                        window's tiles and applies the window's rgb / weight / label-counter updates
+ *                        (clip_seem_fusion.py:786-798, 808-813, 820-822);
+ * SAF_STAGE_ACCUMULATE   K3W, the running average of the feature rows (clip_seem_fusion.py:800-814).
+ * SAF_STAGE_ACCUMULATE alone is only valid after SAF_STAGE_TILE_SETUP on the same window. */
+#define SAF_STAGE_TILE_SETUP 1
+#define SAF_STAGE_ACCUMULATE 2
+int saf_feature_accumulate_window_stages(const saf_grid_desc *grid, const saf_volume *vol, const saf_frame *frames,
+                                         int32_t batch, int32_t height, int32_t width, int32_t rgb_mode,
+                                         const saf_workspace *ws, int32_t stages, void *stream);
+
 /* One reference integrate() call: K1, K2, then K3 for each frame of the batch in order. */
 int saf_integrate(const saf_grid_desc *grid, const saf_volume *vol, const saf_frame *frames,
                   int32_t batch, int32_t height, int32_t width, float trunc, int32_t rgb_mode,

@@ -103,6 +103,8 @@ SIGNATURES = {
                                               P(Workspace), c_void_p]),
     "saf_feature_accumulate_window": (ctypes.c_int, [P(GridDesc), P(Volume), P(Frame), c_int32, c_int32, c_int32,
                                                      c_int32, P(Workspace), c_void_p]),
+    "saf_feature_accumulate_window_stages": (ctypes.c_int, [P(GridDesc), P(Volume), P(Frame), c_int32, c_int32, c_int32,
+                                                            c_int32, P(Workspace), c_int32, c_void_p]),
     "saf_integrate": (ctypes.c_int, [P(GridDesc), P(Volume), P(Frame), c_int32, c_int32, c_int32, c_float, c_int32,
                                      P(Workspace), c_void_p]),
     "saf_frame_reaches_slab": (ctypes.c_int, [P(GridDesc), P(c_float), P(c_float), c_int32, c_int32]),

@@ -1665,11 +1665,13 @@ feature_accumulate_window_pair_kernel(const __grid_constant__ FusionParams p, co
 // the whole window and the frames are walked in order, so the four table rows of a frame are loaded once per
 // (frame, set of 8 voxels) and reused by every voxel of the set that the frame sees.
 //
-//   warps [0, NBUF)              producers: claim G consecutive union-list entries, start the TMA bulk copies of
-//                                their feature rows into a landing buffer, do the voxels' small state (rgb average,
-//                                label counters, weight) one lane per voxel, and write the tile's update metadata
-//                                (per valid (frame, voxel): bilinear weights, a = 1/(w+1), b = w*a, table rows) into
-//                                shared memory - computed ONCE per update instead of redundantly by 32 lanes
+//   warps [0, NBUF)              producers: claim G consecutive union-list entries and start the TMA bulk copies of
+//                                their feature rows into a landing buffer and of the tile's update metadata (per
+//                                valid (frame, voxel): bilinear weights, a = 1/(w+1), b = w*a, table rows - computed
+//                                ONCE per update instead of redundantly by 32 lanes) into shared memory.  The
+//                                metadata was prepared, and the voxels' small state (rgb average, label counters,
+//                                weight) updated, by K2T (window_tile_setup_kernel, below) just before this kernel;
+//                                tiles past K2T's capacity are prepared here by the same routine (fill_tile_meta)
 //   warps [NBUF, NBUF+NSET*CHUNKS)  compute: warp (set, chunk) owns the 128-channel slice `chunk` of the set's 8
 //                                voxels: accumulators from the landing buffer to registers (the buffer is handed back
 //                                to the producer at once), then for every frame of the window in order the exact
@@ -1682,20 +1684,8 @@ feature_accumulate_window_pair_kernel(const __grid_constant__ FusionParams p, co
 // with n_rows = 0.  Arithmetic per voxel = the single-frame calls in frame order (clip_seem_fusion.py:800-814).
 // ---------------------------------------------------------------------------------------------
 
-#ifndef SAF_TILE_PRODUCER
-#define SAF_TILE_PRODUCER 2     // 2: cell-parallel producer (default; 0.77 -> 0.62 ns per update), 1: lane per voxel
-#endif
 #ifndef SAF_TILE_NBUF
 #define SAF_TILE_NBUF 3         // producer warps = landing buffers per CTA (C = 512 / 768)
-#endif
-#ifndef SAF_TILE_NLAND
-#define SAF_TILE_NLAND SAF_TILE_NBUF        // landing buffers per CTA at C = 768
-#endif
-#ifndef SAF_TILE_LW
-#define SAF_TILE_LW 4           // floats per compute lane at C = 768 (2: 24 compute warps of 64 channels)
-#endif
-#ifndef SAF_TILE_TDEPTH
-#define SAF_TILE_TDEPTH 0       // frames of table rows staged ahead per compute warp at C = 768 (0: register ping-pong)
 #endif
 constexpr int kTileSlots = 8;    // voxels per set (accumulator registers: 8 x float4 per thread)
 
@@ -1703,7 +1693,7 @@ struct __align__(16) TileUpdate {   // one (frame, voxel) feature update
     float w[4];                     // bilinear weights nw, ne, sw, se
     float a, b;                     // clip_seem_fusion.py:808-810
     uint32_t rows;                  // the four rows of the frame's zero-bordered table, one byte each
-    float one;                      // 1.0f, a multiplicand ptxas cannot see through (mix_blend2_if)
+    float one;                      // 1.0f, a multiplicand ptxas cannot see through (mix_blend2)
 };
 
 template <int NSET>
@@ -1721,77 +1711,26 @@ struct RowRegs {   // this thread's 4-float column of the four table rows of one
     f32x2_t lo[4], hi[4];
 };
 
-// a thread's LW-float column (LW = 4: lo and hi pairs, LW = 2: lo only) of a row at `base`, column index `col`
-template <int LW>
-__device__ __forceinline__ void ld_col_global(const float* __restrict__ base, int col, f32x2_t& lo, f32x2_t& hi)
-{
-    if constexpr (LW == 4) {
-        const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(base) + col);
-        lo = v.x;
-        hi = v.y;
-    } else {
-        lo = __ldg(reinterpret_cast<const unsigned long long*>(base) + col);
-        hi = 0ull;
-    }
-}
-template <int LW>
-__device__ __forceinline__ void ld_col_shared(const float* base, int col, f32x2_t& lo, f32x2_t& hi)
-{
-    if constexpr (LW == 4) {
-        const ulonglong2 v = reinterpret_cast<const ulonglong2*>(base)[col];
-        lo = v.x;
-        hi = v.y;
-    } else {
-        lo = reinterpret_cast<const unsigned long long*>(base)[col];
-        hi = 0ull;
-    }
-}
-template <int LW>
-__device__ __forceinline__ void load_rows(RowRegs& T, const float* __restrict__ table, uint32_t rows, int C, int col)
+__device__ __forceinline__ void load_rows(RowRegs& T, const float* __restrict__ table, uint32_t rows, int C, int col4)
 {
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-        ld_col_global<LW>(table + (size_t)((rows >> (8 * k)) & 0xffu) * C, col, T.lo[k], T.hi[k]);
+    for (int k = 0; k < 4; ++k) {
+        const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(table + (size_t)((rows >> (8 * k)) & 0xffu) * C) + col4);
+        T.lo[k] = v.x;
+        T.hi[k] = v.y;
+    }
 }
 
 // bilinear_mix + blend4 on one packed pair: ((t0 w0 + t1 w1) + t2 w2) + t3 w3 as mul / fma / fma / fma, then
-// smp a + old b as mul, mul, add - each lane of the pair rounded like the scalar code
-#ifndef SAF_TILE_DENSE
-#define SAF_TILE_DENSE 0    // N > 0: frames that see at least N of a set's 8 voxels take the branch-free path (measured: no gain)
-#endif
-#ifndef SAF_TILE_ADD2
-#define SAF_TILE_ADD2 1     // 1: the blend's final add is fma.rn.f32x2(x, 1.0, y) with an opaque 1.0 (exactly x + y)
-#endif
-
-// Branch-free form for frames that see most of a set: the update is computed for every slot and committed under a
-// predicate, so the eight slots' chains interleave instead of serialising behind one branch per voxel.  `one` is
-// 1.0f read from the update record (opaque to ptxas, which would otherwise turn mul + add into one FFMA2 and drop a
-// rounding): fma(x, 1, y) is x + y correctly rounded, signed zeros included.
-__device__ __forceinline__ f32x2_t mix_blend2_if(const f32x2_t (&t)[4], const f32x2_t (&w)[4], f32x2_t a, f32x2_t b,
-                                                 f32x2_t one, f32x2_t old, uint32_t commit)
-{
-    const f32x2_t smp = fma2_rn(t[3], w[3], fma2_rn(t[2], w[2], fma2_rn(t[1], w[1], mul2_rn(t[0], w[0]))));
-    const f32x2_t x = mul2_rn(smp, a), y = mul2_rn(old, b);
-    f32x2_t r = old;
-    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %4, 0;\n\t@p fma.rn.f32x2 %0, %1, %2, %3;\n\t}"
-        : "+l"(r)
-        : "l"(x), "l"(one), "l"(y), "r"(commit));
-    return r;
-}
-
+// smp a + old b as mul, mul, add - each lane of the pair rounded like the scalar code.  The add is
+// fma(x, 1.0f, y) = x + y correctly rounded (signed zeros included) with the 1.0f read from the update record: ptxas
+// (12.9) contracts a packed mul + add pair into one FFMA2 even with --fmad false and explicit .rn, which would drop
+// one of the reference's three roundings, and it cannot see through a multiplicand that comes from memory.
 __device__ __forceinline__ f32x2_t mix_blend2(const f32x2_t (&t)[4], const f32x2_t (&w)[4], f32x2_t a, f32x2_t b,
                                               f32x2_t one, f32x2_t old)
 {
     const f32x2_t smp = fma2_rn(t[3], w[3], fma2_rn(t[2], w[2], fma2_rn(t[1], w[1], mul2_rn(t[0], w[0]))));
-#if SAF_TILE_ADD2
     return fma2_rn(mul2_rn(smp, a), one, mul2_rn(old, b));
-#endif
-    // ptxas (12.9) contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with --fmad false and explicit .rn, which
-    // would drop one of the reference's three roundings: the final add is therefore two scalar add.rn
-    float xl, xh, yl, yh;
-    unpack2(mul2_rn(smp, a), xl, xh);
-    unpack2(mul2_rn(old, b), yl, yh);
-    return pack2(__fadd_rn(xl, yl), __fadd_rn(xh, yh));
 }
 
 // One lane's voxel of a tile of the window's union list (tile = G consecutive entries starting at `base`).
@@ -1873,9 +1812,7 @@ __device__ __forceinline__ void fill_tile_meta(const FusionParams& p, const Tile
         const uint32_t rk = __shfl_sync(0xffffffffu, L.rank, v);
         const uint32_t lc = __shfl_sync(0xffffffffu, L.local, v);
         cg[it] = make_float2(0.f, 0.f);
-#ifndef SAF_DBG_FAST_PRODUCER
         if ((mv >> b) & 1u) cg[it] = p.wcoords[((uint64_t)rk * B + b) * kBlockVoxels + lc];
-#endif
     }
     // Pass 2: per valid cell the compute warps' update record (clip_seem_fusion.py:800-810), the rgb sample
     // and the label counter (:786-798, 820-822).
@@ -1894,12 +1831,7 @@ __device__ __forceinline__ void fill_tile_meta(const FusionParams& p, const Tile
             const float a = __frcp_rn(__int2float_rn(w + 1));
             const float bb = __fmul_rn(__int2float_rn(w), a);
             Taps t;
-#ifdef SAF_DBG_FAST_PRODUCER
-            t.idx[0] = 1; t.idx[1] = 2; t.idx[2] = 8; t.idx[3] = 9;   // timing experiment only
-            t.w[0] = t.w[1] = t.w[2] = t.w[3] = 0.25f;
-#else
             feature_taps_padded(f, g.x, g.y, p.W, p.H, &p.hdr->error_flags, t);
-#endif
             const uint32_t rows = (uint32_t)t.idx[0] | ((uint32_t)t.idx[1] << 8) | ((uint32_t)t.idx[2] << 16) |
                                   ((uint32_t)t.idx[3] << 24);
             TileUpdate u;
@@ -1915,17 +1847,9 @@ __device__ __forceinline__ void fill_tile_meta(const FusionParams& p, const Tile
             cell_rows = rows;
             const int px = nearest_index(g.x, p.W), py = nearest_index(g.y, p.H);
             float smp[3];
-#ifdef SAF_DBG_SKIP_SMALL
-            smp[0] = smp[1] = smp[2] = 0.f;   // timing experiment only
-#else
             sample_rgb(p, f, g.x, g.y, px, py, smp);
-#endif
             my_smp[v * SAF_MAX_BATCH + b] = make_float4(smp[0], smp[1], smp[2], 0.f);
-#ifdef SAF_DBG_SKIP_SMALL
-            if (false) {
-#else
             if (p.vol.labels_one_hot && f.seg) {
-#endif
                 const float lf = (px >= 0 && py >= 0) ? load_class_id(f.seg, f.seg_dtype, py * p.W + px) : 0.0f;
                 const long long id = (long long)lf;
                 if (id >= 0 && id < p.vol.n_classes)
@@ -1971,65 +1895,42 @@ __device__ __forceinline__ void fill_tile_meta(const FusionParams& p, const Tile
     __syncwarp();   // every lane's metadata is written (and my_smp read) before the arrival publishes it
 }
 
-// NLAND landing buffers (default: one per producer).  With NLAND < NBUF tile t of the CTA (t = j * NBUF + producer)
-// lands in buffer t % NLAND: a buffer is only in use from its TMA until the compute warps have taken the rows to
-// registers, and a tile is worked on ~10 us, so one or two buffers keep the copies ahead - the freed shared memory
-// holds the table-row rings below.
-// TDEPTH > 0: every compute warp stages its 128-channel slice of a frame's four table rows in a private shared-memory
-// ring (4 x 512 B per frame) with its own cp.async.bulk copies, TDEPTH frames ahead, instead of holding the next
-// frame's rows in a second register set: the L2 round trip of a frame's rows is covered by TDEPTH frames of
-// arithmetic instead of one, and the frame code exists once.
-// LW: floats of a row per compute lane (4: a warp owns 128 channels; 2: 64 channels - half the registers per thread,
-// twice the compute warps per set for the same C).
-template <int CHUNKS, int NSET, int NBUF, int NLAND = NBUF, int TDEPTH = 0, int LW = 4>
+template <int CHUNKS, int NSET, int NBUF>
 __global__ void __launch_bounds__((CHUNKS * NSET + NBUF) * 32, 1)
 feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, const __grid_constant__ WindowTables wt)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    static_assert(LW == 4 || LW == 2, "lane width");
-    constexpr int CW = 32 * LW;        // channels per compute warp
-    constexpr int C = CHUNKS * CW;
+    constexpr int C = CHUNKS * 128;
     constexpr int G = NSET * kTileSlots;
     constexpr int NCW = CHUNKS * NSET;
-    constexpr bool kSharedLanding = NLAND != NBUF;
-    constexpr int kRingDepth = TDEPTH > 0 ? TDEPTH : 1;
     static_assert(G <= 32, "one producer lane per voxel of the tile");
-    static_assert(NLAND >= 1 && NLAND <= NBUF, "landing buffers");
     using Meta = TileMeta<NSET>;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     SlotCounters* sc = &p.hdr->slot[p.slot];
     const uint32_t n = sc->n_union;
     if (n == 0) return;
 
-    float* rows_buf = reinterpret_cast<float*>(smem_raw);                                   // [NLAND][G][C]
-    Meta* metas = reinterpret_cast<Meta*>(smem_raw + (size_t)NLAND * G * C * sizeof(float));  // [2*NBUF]
+    float* rows_buf = reinterpret_cast<float*>(smem_raw);                                   // [NBUF][G][C]
+    Meta* metas = reinterpret_cast<Meta*>(smem_raw + (size_t)NBUF * G * C * sizeof(float));  // [2*NBUF]
     float4* smp_buf = reinterpret_cast<float4*>(metas + 2 * NBUF);                           // [NBUF][G][16]
-    float* tring = reinterpret_cast<float*>(smp_buf + (size_t)NBUF * G * SAF_MAX_BATCH);     // [NCW][TDEPTH][4][CW]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(tring + (size_t)NCW * TDEPTH * 4 * CW);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smp_buf + (size_t)NBUF * G * SAF_MAX_BATCH);
     uint64_t* full = bars;                    // [2*NBUF]
     uint64_t* meta_free = bars + 2 * NBUF;    // [2*NBUF]
-    uint64_t* rows_free = bars + 4 * NBUF;    // [NLAND]
-    uint64_t* tbar = rows_free + NLAND;       // [NCW][TDEPTH]
+    uint64_t* rows_free = bars + 4 * NBUF;    // [NBUF]
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2 * NBUF; ++i) {
             mbar_init(&full[i], 1);
             mbar_init(&meta_free[i], NCW);
         }
-        for (int i = 0; i < NLAND; ++i) mbar_init(&rows_free[i], NCW);
-        for (int i = 0; i < NCW * TDEPTH; ++i) mbar_init(&tbar[i], 1);
+        for (int i = 0; i < NBUF; ++i) mbar_init(&rows_free[i], NCW);
         fence_mbar_init();
     }
     __syncthreads();
 
-#if SAF_TILE_PRODUCER == 2
     if (warp < NBUF) {
         // ------------------------------- producer -------------------------------
-        // Nothing below is a chain of dependent memory round trips per (voxel, frame): the valid (voxel, frame)
-        // CELLS of the tile are spread over the 32 lanes and handled independently (the weight a cell sees is the
-        // voxel's weight plus the number of its earlier valid frames; label counters are fire-and-forget
-        // reductions), and only the rgb running average - pure arithmetic on samples parked in shared memory -
-        // walks a voxel's frames in order.
         const uint32_t n_blocks = sc->n_blocks;
+        float* my_rows = rows_buf + (size_t)warp * G * C;
         float4* my_smp = smp_buf + (size_t)warp * G * SAF_MAX_BATCH;   // [voxel][frame] rgb sample
         const Meta* prepared = reinterpret_cast<const Meta*>(p.tile_meta);
         for (uint32_t j = 0;; ++j) {
@@ -2049,8 +1950,7 @@ feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, co
             }
             if (NSET == 2 && base / (uint32_t)G < p.tile_meta_cap) {
                 // K2T prepared this tile (metadata in global memory, small state already updated): one bulk copy of
-                // the metadata next to the feature rows'
-                static_assert(!kSharedLanding || NSET != 2, "prepared tiles use the producer's own landing buffer");
+                // the metadata next to those of the feature rows
                 const Meta* GM = prepared + base / (uint32_t)G;
                 const uint32_t vox = lane < cnt ? __ldg(&GM->voxel[lane]) : 0u;
                 mbar_wait(&rows_free[warp], (j & 1u) ^ 1u);
@@ -2061,203 +1961,53 @@ feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, co
                 }
                 __syncwarp();
                 if (lane < cnt)
-                    tma_bulk_g2s(rows_buf + ((size_t)warp * G + lane) * C, p.vol.clip_feat + (size_t)vox * C,
-                                 (uint32_t)C * 4u, &full[ms]);
+                    tma_bulk_g2s(my_rows + (size_t)lane * C, p.vol.clip_feat + (size_t)vox * C, (uint32_t)C * 4u, &full[ms]);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full[ms]);
                 continue;
             }
+            // a tile past K2T's capacity (or a build without it): prepared here, one tile at a time
             const TileLane L = load_tile_lane(p, n_blocks, base, cnt, lane);
-            const uint32_t my_voxel = L.voxel;
-            // the landing buffer was handed back when the compute warps took its rows to registers.  Shared landing
-            // buffers: tile t may only land once tile t - NLAND has been taken, which is about when tile t's
-            // metadata is due - so (after the first round) the copies start when the metadata is done instead of
-            // blocking this warp before it
-            const uint32_t tseq = j * (uint32_t)NBUF + (uint32_t)warp;
-            const uint32_t lb = kSharedLanding ? tseq % (uint32_t)NLAND : (uint32_t)warp;
-            const uint32_t lphase = kSharedLanding ? ((tseq / (uint32_t)NLAND) & 1u) ^ 1u : (j & 1u) ^ 1u;
-            float* my_rows = rows_buf + (size_t)lb * G * C;
-            const bool land_early = !kSharedLanding || tseq < (uint32_t)NLAND;
-            auto start_rows = [&]() {
-                mbar_wait(&rows_free[lb], lphase);
-                if (lane == 0) mbar_expect_tx(&full[ms], cnt * (uint32_t)C * 4u);
-                __syncwarp();
-                if (lane < cnt)
-                    tma_bulk_g2s(my_rows + (size_t)lane * C, p.vol.clip_feat + (size_t)my_voxel * C, (uint32_t)C * 4u,
-                                 &full[ms]);
-            };
-            if (land_early) start_rows();
-            // the metadata slot was last read two of this producer's tiles ago
-            mbar_wait(&meta_free[ms], ((j >> 1) & 1u) ^ 1u);
-            fill_tile_meta<NSET>(p, L, cnt, M, my_smp, lane);
-            __syncwarp();   // every lane's metadata is written (and my_smp read) before the arrival publishes it
-            if (!land_early) {
-                start_rows();
-                __syncwarp();
-            }
-            if (lane == 0) mbar_arrive(&full[ms]);
-        }
-        return;
-    }
-#else   // lane-per-voxel producer: each lane walks its voxel's frames one after the other
-    if (warp < NBUF) {
-        // ------------------------------- producer -------------------------------
-        static_assert(!kSharedLanding, "the lane-per-voxel producer owns its landing buffer");
-        const uint32_t n_blocks = sc->n_blocks;
-        const uint32_t* __restrict__ off = p.blk_offset;
-        const int B = p.batch;
-        float* my_rows = rows_buf + (size_t)warp * G * C;
-        const int set = lane / kTileSlots, slot = lane % kTileSlots;
-        for (uint32_t j = 0;; ++j) {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(&sc->k3_next, (uint32_t)G);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            const uint32_t cnt = base < n ? min((uint32_t)G, n - base) : 0u;
-            const uint32_t ms = (uint32_t)warp + (uint32_t)NBUF * (j & 1u);
-            Meta* M = metas + ms;
-            if (cnt == 0) {
-                mbar_wait(&meta_free[ms], ((j >> 1) & 1u) ^ 1u);
-                if (lane == 0) {
-                    M->n_rows = 0;
-                    mbar_arrive(&full[ms]);
-                }
-                break;
-            }
-            uint32_t my_voxel = 0, my_mask = 0, my_local = 0, my_rank = 0;
-            if (lane < cnt) {
-                const uint32_t i = base + lane;
-                uint32_t lo = 0, hi = n_blocks;  // off[lo] <= i < off[hi]
-                while (hi - lo > 1) {
-                    const uint32_t mid = (lo + hi) >> 1;
-                    if (__ldg(off + mid) <= i)
-                        lo = mid;
-                    else
-                        hi = mid;
-                }
-                const WinEntry e = p.ulist[(uint64_t)lo * kBlockVoxels + (i - __ldg(off + lo))];
-                my_voxel = e.voxel;
-                my_mask = e.mask_local & 0xffffu;
-                my_local = e.mask_local >> 16;
-                my_rank = lo;
-            }
             // the landing buffer was handed back when the compute warps took its rows to registers
             mbar_wait(&rows_free[warp], (j & 1u) ^ 1u);
             if (lane == 0) mbar_expect_tx(&full[ms], cnt * (uint32_t)C * 4u);
             __syncwarp();
             if (lane < cnt)
-                tma_bulk_g2s(my_rows + (size_t)lane * C, p.vol.clip_feat + (size_t)my_voxel * C, (uint32_t)C * 4u, &full[ms]);
-            // which voxel of each set comes first in every frame (its rows are the ones prefetched for the set)
-            uint32_t first_bits = 0, my_ballot = 0;
-#pragma unroll
-            for (int b = 0; b < SAF_MAX_BATCH; ++b) {
-                const uint32_t bal = __ballot_sync(0xffffffffu, (my_mask >> b) & 1u);
-                if (((bal >> (set * kTileSlots)) & ((1u << slot) - 1u)) == 0u) first_bits |= 1u << b;
-                if (lane == b) my_ballot = bal;
-            }
+                tma_bulk_g2s(my_rows + (size_t)lane * C, p.vol.clip_feat + (size_t)L.voxel * C, (uint32_t)C * 4u, &full[ms]);
             // the metadata slot was last read two of this producer's tiles ago
             mbar_wait(&meta_free[ms], ((j >> 1) & 1u) ^ 1u);
-            if (lane < SAF_MAX_BATCH) {
-#pragma unroll
-                for (int s = 0; s < NSET; ++s) {
-                    M->vmask[s][lane] = (uint8_t)((my_ballot >> (s * kTileSlots)) & 0xffu);
-                    M->uniform[s][lane] = 0;   // this producer does not classify frames: always the checked path
-                }
-            }
-#pragma unroll
-            for (int s = 0; s < NSET; ++s) {
-                const uint32_t fm = __ballot_sync(0xffffffffu, lane < SAF_MAX_BATCH &&
-                                                                   ((my_ballot >> (s * kTileSlots)) & 0xffu) != 0u);
-                if (lane == 0) M->fmask[s] = fm;
-            }
-            if (lane == 0) M->n_rows = cnt;
-            if (lane < cnt) {
-                M->voxel[lane] = my_voxel;
-                // per valid frame: update metadata for the compute warps, and this voxel's small state
-                // (clip_seem_fusion.py:786-798, 808-822)
-                const float2* src = p.wcoords + (uint64_t)my_rank * B * kBlockVoxels + my_local;
-                float* dst = p.vol.rgb + (size_t)my_voxel * 3;
-                float acc[3] = {dst[0], dst[1], dst[2]};
-                int w = p.vol.weight[my_voxel];
-                for (uint32_t mm = my_mask; mm; mm &= mm - 1u) {
-                    const int b = __ffs(mm) - 1;
-                    const saf_frame& f = p.frames[b];
-                    const float2 g = src[(size_t)b * kBlockVoxels];
-                    const float a = __frcp_rn(__int2float_rn(w + 1));
-                    const float bb = __fmul_rn(__int2float_rn(w), a);
-                    Taps t;
-                    feature_taps_padded(f, g.x, g.y, p.W, p.H, &p.hdr->error_flags, t);
-                    const uint32_t rows = (uint32_t)t.idx[0] | ((uint32_t)t.idx[1] << 8) | ((uint32_t)t.idx[2] << 16) |
-                                          ((uint32_t)t.idx[3] << 24);
-                    TileUpdate u;
-                    u.w[0] = t.w[0];
-                    u.w[1] = t.w[1];
-                    u.w[2] = t.w[2];
-                    u.w[3] = t.w[3];
-                    u.a = a;
-                    u.b = bb;
-                    u.rows = rows;
-                    u.one = 1.0f;
-                    M->upd[set][b][slot] = u;
-                    if ((first_bits >> b) & 1u) M->prim_rows[set][b] = rows;
-                    const int px = nearest_index(g.x, p.W), py = nearest_index(g.y, p.H);
-                    float smp[3];
-                    sample_rgb(p, f, g.x, g.y, px, py, smp);
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) acc[c] = __fadd_rn(__fmul_rn(smp[c], a), __fmul_rn(acc[c], bb));
-                    if (p.vol.labels_one_hot && f.seg) {
-                        const float lf = (px >= 0 && py >= 0) ? load_class_id(f.seg, f.seg_dtype, py * p.W + px) : 0.0f;
-                        const long long id = (long long)lf;
-                        if (id >= 0 && id < p.vol.n_classes)
-                            p.vol.labels_one_hot[(size_t)my_voxel * p.vol.n_classes + id] += 1;
-                        else
-                            atomicOr(&p.hdr->error_flags, SAF_FLAG_BAD_CLASS_ID);
-                    }
-                    ++w;
-                }
-#pragma unroll
-                for (int c = 0; c < 3; ++c) dst[c] = acc[c];
-                p.vol.weight[my_voxel] = w;
-            }
-            __syncwarp();   // every lane's metadata is written before the arrival publishes it
+            fill_tile_meta<NSET>(p, L, cnt, M, my_smp, lane);
+            __syncwarp();   // every lane's metadata is written (and my_smp read) before the arrival publishes it
             if (lane == 0) mbar_arrive(&full[ms]);
         }
         return;
     }
 
-#endif
     // ------------------------------- compute -------------------------------
     const int cw = warp - NBUF;
     const int set = cw / CHUNKS, chunk = cw % CHUNKS;
-    const int col4 = chunk * 32 + lane;   // this thread's LW-float column of every row
+    const int col4 = chunk * 32 + lane;   // this thread's float4 column of every row
     uint32_t done = 0;                    // producers that have published their last tile
-    // table-row ring of this warp (TDEPTH > 0): requests issued / taken so far
-    float* my_ring = tring + (size_t)cw * kRingDepth * 4 * CW;
-    uint64_t* my_tbar = tbar + cw * kRingDepth;
-    uint32_t ring_issued = 0, ring_taken = 0;
     for (uint32_t t = 0; done != (1u << NBUF) - 1u; ++t) {
         const uint32_t pi = t % NBUF, j = t / NBUF;
-        const uint32_t lb = kSharedLanding ? t % (uint32_t)NLAND : pi;
-        if ((done >> pi) & 1u) {
-            // shared landing buffers are handed on in tile order: a tile that never lands still takes its turn
-            if (kSharedLanding && lane == 0) mbar_arrive(&rows_free[lb]);
-            continue;
-        }
+        if ((done >> pi) & 1u) continue;
         const uint32_t ms = pi + (uint32_t)NBUF * (j & 1u);
         mbar_wait(&full[ms], (j >> 1) & 1u);
         const Meta* M = metas + ms;
         const uint32_t n_rows = M->n_rows;
         if (n_rows == 0) {
             done |= 1u << pi;
-            if (kSharedLanding && lane == 0) mbar_arrive(&rows_free[lb]);
             continue;
         }
         // accumulators of the set's voxels: landing buffer -> registers, then the buffer goes back to the producer
         f32x2_t acc_lo[kTileSlots], acc_hi[kTileSlots];
-        const float* land = rows_buf + (size_t)lb * G * C;
+        const ulonglong2* land = reinterpret_cast<const ulonglong2*>(rows_buf + (size_t)pi * G * C) + col4;
 #pragma unroll
         for (int s = 0; s < kTileSlots; ++s) {
             if ((uint32_t)(set * kTileSlots + s) < n_rows) {
-                ld_col_shared<LW>(land + (size_t)(set * kTileSlots + s) * C, col4, acc_lo[s], acc_hi[s]);
+                const ulonglong2 v = land[(size_t)(set * kTileSlots + s) * (C / 4)];
+                acc_lo[s] = v.x;
+                acc_hi[s] = v.y;
             } else {
                 acc_lo[s] = 0ull;
                 acc_hi[s] = 0ull;
@@ -2265,109 +2015,43 @@ feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, co
         }
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&rows_free[lb]);
+        if (lane == 0) mbar_arrive(&rows_free[pi]);
 
-#ifdef SAF_DBG_SKIP_COMPUTE
-        const uint32_t fm = M->fmask[set] & SAF_DBG_SKIP_COMPUTE;   // timing experiment only
-#else
         const uint32_t fm = M->fmask[set];
-#endif
         if (fm) {
+            // one update: the record (weights, a, b, rows, 1.0f) is two 16-byte broadcast loads
+            auto update = [&](int b, int s, const uint4& m0, const uint4& m1, const RowRegs& T) {
+                const float w0 = __uint_as_float(m0.x), w1 = __uint_as_float(m0.y), w2 = __uint_as_float(m0.z),
+                            w3 = __uint_as_float(m0.w), a = __uint_as_float(m1.x), bb = __uint_as_float(m1.y),
+                            one = __uint_as_float(m1.w);
+                const f32x2_t wp[4] = {pack2(w0, w0), pack2(w1, w1), pack2(w2, w2), pack2(w3, w3)};
+                const f32x2_t ap = pack2(a, a), bp = pack2(bb, bb), op = pack2(one, one);
+                acc_lo[s] = mix_blend2(T.lo, wp, ap, bp, op, acc_lo[s]);
+                acc_hi[s] = mix_blend2(T.hi, wp, ap, bp, op, acc_hi[s]);
+            };
             // one frame of the window: every voxel of the set that the frame sees, with the frame's rows in T
             auto frame_updates = [&](int b, RowRegs& T, uint32_t& cur_rows) {
                 const uint32_t vm = M->vmask[set][b];
+                const uint4* rec = reinterpret_cast<const uint4*>(&M->upd[set][b][0]);
                 if (M->uniform[set][b]) {
                     // every valid voxel of the set samples the prefetched rows: no per-voxel row check
-#if SAF_TILE_DENSE > 0
-                    if (__popc(vm) >= SAF_TILE_DENSE) {
 #pragma unroll
-                        for (int s = 0; s < kTileSlots; ++s) {
-                            const uint4 m0 = *reinterpret_cast<const uint4*>(&M->upd[set][b][s]);
-                            const uint4 m1 = *(reinterpret_cast<const uint4*>(&M->upd[set][b][s]) + 1);
-                            const float w0 = __uint_as_float(m0.x), w1 = __uint_as_float(m0.y), w2 = __uint_as_float(m0.z),
-                                        w3 = __uint_as_float(m0.w), a = __uint_as_float(m1.x), bb = __uint_as_float(m1.y),
-                                        one = __uint_as_float(m1.w);
-                            const f32x2_t wp[4] = {pack2(w0, w0), pack2(w1, w1), pack2(w2, w2), pack2(w3, w3)};
-                            const f32x2_t ap = pack2(a, a), bp = pack2(bb, bb), op = pack2(one, one);
-                            const uint32_t commit = (vm >> s) & 1u;
-                            acc_lo[s] = mix_blend2_if(T.lo, wp, ap, bp, op, acc_lo[s], commit);
-                            if constexpr (LW == 4) acc_hi[s] = mix_blend2_if(T.hi, wp, ap, bp, op, acc_hi[s], commit);
-                        }
-                        return;
-                    }
-#endif
-#pragma unroll
-                    for (int s = 0; s < kTileSlots; ++s) {
-                        if ((vm >> s) & 1u) {
-                            const uint4 m0 = *reinterpret_cast<const uint4*>(&M->upd[set][b][s]);
-                            const uint4 m1 = *(reinterpret_cast<const uint4*>(&M->upd[set][b][s]) + 1);
-                            const float w0 = __uint_as_float(m0.x), w1 = __uint_as_float(m0.y), w2 = __uint_as_float(m0.z),
-                                        w3 = __uint_as_float(m0.w), a = __uint_as_float(m1.x), bb = __uint_as_float(m1.y),
-                                        one = __uint_as_float(m1.w);
-                            const f32x2_t wp[4] = {pack2(w0, w0), pack2(w1, w1), pack2(w2, w2), pack2(w3, w3)};
-                            const f32x2_t ap = pack2(a, a), bp = pack2(bb, bb), op = pack2(one, one);
-                            acc_lo[s] = mix_blend2(T.lo, wp, ap, bp, op, acc_lo[s]);
-                            if constexpr (LW == 4) acc_hi[s] = mix_blend2(T.hi, wp, ap, bp, op, acc_hi[s]);
-                        }
-                    }
+                    for (int s = 0; s < kTileSlots; ++s)
+                        if ((vm >> s) & 1u) update(b, s, rec[2 * s], rec[2 * s + 1], T);
                     return;
                 }
 #pragma unroll
                 for (int s = 0; s < kTileSlots; ++s) {
                     if ((vm >> s) & 1u) {
-                        const uint4 m0 = *reinterpret_cast<const uint4*>(&M->upd[set][b][s]);
-                        const uint4 m1 = *(reinterpret_cast<const uint4*>(&M->upd[set][b][s]) + 1);
+                        const uint4 m0 = rec[2 * s], m1 = rec[2 * s + 1];
                         if (m1.z != cur_rows) {   // a voxel of the set straddles a table cell boundary: rare
                             cur_rows = m1.z;
-                            load_rows<LW>(T, wt.ptr[b], cur_rows, C, col4);
+                            load_rows(T, wt.ptr[b], cur_rows, C, col4);
                         }
-                        const float w0 = __uint_as_float(m0.x), w1 = __uint_as_float(m0.y), w2 = __uint_as_float(m0.z),
-                                    w3 = __uint_as_float(m0.w), a = __uint_as_float(m1.x), bb = __uint_as_float(m1.y),
-                                    one = __uint_as_float(m1.w);
-                        const f32x2_t wp[4] = {pack2(w0, w0), pack2(w1, w1), pack2(w2, w2), pack2(w3, w3)};
-                        const f32x2_t ap = pack2(a, a), bp = pack2(bb, bb), op = pack2(one, one);
-                        acc_lo[s] = mix_blend2(T.lo, wp, ap, bp, op, acc_lo[s]);
-                        if constexpr (LW == 4) acc_hi[s] = mix_blend2(T.hi, wp, ap, bp, op, acc_hi[s]);
+                        update(b, s, m0, m1, T);
                     }
                 }
             };
-            if constexpr (TDEPTH > 0) {
-                // frames of the set in order; the rows of frame i + TDEPTH are requested when frame i's have been
-                // taken to registers
-                uint32_t use_rest = fm, req_rest = fm;
-                auto request_next = [&]() {
-                    const int b = __ffs(req_rest) - 1;
-                    req_rest &= req_rest - 1u;
-                    const uint32_t slot = ring_issued % (uint32_t)kRingDepth;
-                    const uint32_t rows = M->prim_rows[set][b];
-                    if (lane == 0) mbar_arrive_expect_tx(&my_tbar[slot], 4u * CW * 4u);
-                    __syncwarp();
-                    if (lane < 4)
-                        tma_bulk_g2s(my_ring + ((size_t)slot * 4 + lane) * CW,
-                                     wt.ptr[b] + (size_t)((rows >> (8 * lane)) & 0xffu) * C + chunk * CW, CW * 4u,
-                                     &my_tbar[slot]);
-                    ++ring_issued;
-                };
-#pragma unroll
-                for (int i = 0; i < kRingDepth; ++i)
-                    if (req_rest) request_next();
-                RowRegs T;
-                while (use_rest) {
-                    const int b = __ffs(use_rest) - 1;
-                    use_rest &= use_rest - 1u;
-                    const uint32_t slot = ring_taken % (uint32_t)kRingDepth;
-                    mbar_wait(&my_tbar[slot], (ring_taken / (uint32_t)kRingDepth) & 1u);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        ld_col_shared<LW>(my_ring + ((size_t)slot * 4 + k) * CW, lane, T.lo[k], T.hi[k]);
-                    ++ring_taken;
-                    fence_proxy_async();
-                    __syncwarp();   // every lane has its slice before the slot is refilled
-                    if (req_rest) request_next();
-                    uint32_t cur_rows = M->prim_rows[set][b];
-                    frame_updates(b, T, cur_rows);
-                }
-            } else {
             uint32_t rest = fm;
             auto next_frame = [&]() {
                 const int b = rest ? __ffs(rest) - 1 : -1;
@@ -2377,7 +2061,7 @@ feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, co
             auto request = [&](int b, RowRegs& T, uint32_t& rows) {
                 if (b >= 0) {
                     rows = M->prim_rows[set][b];
-                    load_rows<LW>(T, wt.ptr[b], rows, C, col4);
+                    load_rows(T, wt.ptr[b], rows, C, col4);
                 }
             };
             // the next frame's rows are requested before a frame's arithmetic starts; two register sets take turns
@@ -2395,17 +2079,11 @@ feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, co
                 frame_updates(b1, T1, rows1);
                 if (b0 < 0) break;
             }
-            }
 #pragma unroll
             for (int s = 0; s < kTileSlots; ++s) {
                 if ((uint32_t)(set * kTileSlots + s) < n_rows) {
                     const uint32_t v = M->voxel[set * kTileSlots + s];
-                    if constexpr (LW == 4)
-                        st_stream_b64x2(reinterpret_cast<ulonglong2*>(p.vol.clip_feat + (size_t)v * C) + col4, acc_lo[s],
-                                        acc_hi[s]);
-                    else
-                        st_stream_b64(reinterpret_cast<unsigned long long*>(p.vol.clip_feat + (size_t)v * C) + col4,
-                                      acc_lo[s]);
+                    st_stream_b64x2(reinterpret_cast<ulonglong2*>(p.vol.clip_feat + (size_t)v * C) + col4, acc_lo[s], acc_hi[s]);
                 }
             }
         }
@@ -2858,18 +2536,16 @@ static int launch_k3w_fixed(const FusionParams& p, const WindowTables& wt, int s
     return 0;
 }
 
-template <int CHUNKS, int NSET, int NBUF, int NLAND = NBUF, int TDEPTH = 0, int LW = 4>
-static int launch_k3w_tile(const FusionParams& p, const WindowTables& wt, int sms, cudaStream_t st)
+template <int CHUNKS, int NSET, int NBUF>
+static int launch_k3w_tile(const FusionParams& p, const WindowTables& wt, int sms, cudaStream_t st, int stages)
 {
     constexpr int kThreads = (CHUNKS * NSET + NBUF) * 32;
-    constexpr size_t smem = (size_t)NLAND * NSET * kTileSlots * CHUNKS * 32 * LW * sizeof(float) +
+    constexpr size_t smem = (size_t)NBUF * NSET * kTileSlots * CHUNKS * 128 * sizeof(float) +
                             2 * (size_t)NBUF * sizeof(TileMeta<NSET>) +
                             (size_t)NBUF * NSET * kTileSlots * SAF_MAX_BATCH * sizeof(float4) +
-                            (size_t)CHUNKS * NSET * TDEPTH * 4 * 32 * LW * sizeof(float) +
-                            (4 * (size_t)NBUF + NLAND + (size_t)CHUNKS * NSET * TDEPTH) * sizeof(uint64_t);
+                            5 * (size_t)NBUF * sizeof(uint64_t);
     static_assert(smem <= 227 * 1024, "tile kernel shared memory");
-    static_assert(kThreads <= 1024, "tile kernel threads");
-    auto kern = feature_accumulate_window_tile_kernel<CHUNKS, NSET, NBUF, NLAND, TDEPTH, LW>;
+    auto kern = feature_accumulate_window_tile_kernel<CHUNKS, NSET, NBUF>;
     { int rc_ = ensure_dynamic_smem(kern, smem); if (rc_) return rc_; }
     // A shard of a grid (multi-GPU) has small windows: their cost is the chain of dependent launches, not
     // throughput.  K3W then leaves some SMs free (it holds one CTA per SM and fills every SM it is given), so that
@@ -2882,12 +2558,14 @@ static int launch_k3w_tile(const FusionParams& p, const WindowTables& wt, int sm
     const int reserve = reserve_env >= 0 ? reserve_env
                                          : (share < 0.75 ? (int)(sms * std::min(0.28, 0.035 / std::max(share, 1e-3))) : 0);
     const int grid = std::max(1, sms - std::min(reserve, sms - 1));
-    if (NSET == 2 && p.tile_meta_cap > 0) {
+    if ((stages & SAF_STAGE_TILE_SETUP) && NSET == 2 && p.tile_meta_cap > 0) {
         window_tile_setup_kernel<<<sms * 4, kK2TWarps * 32, 0, st>>>(p);
         SAF_CHECK_LAUNCH("window_tile_setup_kernel (K2T)", st);
     }
-    kern<<<grid, kThreads, smem, st>>>(p, wt);
-    SAF_CHECK_LAUNCH("feature_accumulate_window_tile_kernel (K3W)", st);
+    if (stages & SAF_STAGE_ACCUMULATE) {
+        kern<<<grid, kThreads, smem, st>>>(p, wt);
+        SAF_CHECK_LAUNCH("feature_accumulate_window_tile_kernel (K3W)", st);
+    }
     return 0;
 }
 
@@ -2903,7 +2581,7 @@ static int k3w_variant()
     return v;
 }
 
-static int launch_k3w(const FusionParams& p, int sms, cudaStream_t st)
+static int launch_k3w(const FusionParams& p, int sms, cudaStream_t st, int stages = SAF_STAGE_TILE_SETUP | SAF_STAGE_ACCUMULATE)
 {
     const int C = p.vol.feature_dim;
     WindowTables wt;
@@ -2921,14 +2599,13 @@ static int launch_k3w(const FusionParams& p, int sms, cudaStream_t st)
                                                                           : (p.frames[b].npy + 2) * (p.frames[b].npx + 2)) <= 256;
         if (k3w_variant() == 2 && small_tables) {
             switch (C) {
-                case 512: return launch_k3w_tile<4, 2, SAF_TILE_NBUF>(p, wt, sms, st);
-                case 768:
-                    return launch_k3w_tile<768 / (32 * SAF_TILE_LW), 2, SAF_TILE_NBUF, SAF_TILE_NLAND, SAF_TILE_TDEPTH,
-                                           SAF_TILE_LW>(p, wt, sms, st);
-                case 1024: return launch_k3w_tile<8, 2, 2>(p, wt, sms, st);
+                case 512: return launch_k3w_tile<4, 2, SAF_TILE_NBUF>(p, wt, sms, st, stages);
+                case 768: return launch_k3w_tile<6, 2, SAF_TILE_NBUF>(p, wt, sms, st, stages);
+                case 1024: return launch_k3w_tile<8, 2, 2>(p, wt, sms, st, stages);
                 default: break;
             }
         }
+        if (!(stages & SAF_STAGE_ACCUMULATE)) return 0;   // only the tile kernel has a setup stage
         if (k3w_variant() >= 1) {
             switch (C) {
                 case 512: return launch_k3w_pair<4, K3W2_WARPS>(p, wt, sms, st);
@@ -2944,6 +2621,7 @@ static int launch_k3w(const FusionParams& p, int sms, cudaStream_t st)
         }
         feature_accumulate_window_generic_kernel<4><<<sms * 2, kK3Threads, 0, st>>>(p, wt);
     } else {
+        if (!(stages & SAF_STAGE_ACCUMULATE)) return 0;
         feature_accumulate_window_generic_kernel<1><<<sms * 2, kK3Threads, 0, st>>>(p, wt);
     }
     SAF_CHECK_LAUNCH("feature_accumulate_window_generic_kernel (K3W)", st);
@@ -3089,6 +2767,15 @@ int saf_feature_accumulate_window(const saf_grid_desc* grid, const saf_volume* v
                                   int32_t batch, int32_t H, int32_t W, int32_t rgb_mode, const saf_workspace* ws,
                                   void* stream)
 {
+    return saf_feature_accumulate_window_stages(grid, vol, frames, batch, H, W, rgb_mode, ws,
+                                                SAF_STAGE_TILE_SETUP | SAF_STAGE_ACCUMULATE, stream);
+}
+
+int saf_feature_accumulate_window_stages(const saf_grid_desc* grid, const saf_volume* vol, const saf_frame* frames,
+                                         int32_t batch, int32_t H, int32_t W, int32_t rgb_mode, const saf_workspace* ws,
+                                         int32_t stages, void* stream)
+{
+    if (stages < 1 || stages > (SAF_STAGE_TILE_SETUP | SAF_STAGE_ACCUMULATE)) return SAF_ERR_UNSUPPORTED;
     int sms = 0;
     int rc = device_sm_count(&sms, nullptr);
     if (rc) return rc;
@@ -3100,10 +2787,12 @@ int saf_feature_accumulate_window(const saf_grid_desc* grid, const saf_volume* v
     if (rc) return rc;
     if ((rc = check_window_tables(vol, frames, batch, ws))) return rc;
     p.sequential = 1;
-    // saf_frustum_cull does not know the call is a window: repack the feature images here (K1's pack CTAs only)
-    frame_setup_kernel<<<64, kK1Threads, 0, (cudaStream_t)stream>>>(p, 0u);
-    SAF_CHECK_LAUNCH("frame_setup_kernel (table repack)", (cudaStream_t)stream);
-    return launch_k3w(p, sms, (cudaStream_t)stream);
+    if (stages & SAF_STAGE_TILE_SETUP) {
+        // saf_frustum_cull does not know the call is a window: repack the feature images here (K1's pack CTAs only)
+        frame_setup_kernel<<<64, kK1Threads, 0, (cudaStream_t)stream>>>(p, 0u);
+        SAF_CHECK_LAUNCH("frame_setup_kernel (table repack)", (cudaStream_t)stream);
+    }
+    return launch_k3w(p, sms, (cudaStream_t)stream, stages);
 }
 
 // K1 + K2 of one integrate() call on `st_geo`, then its K3 launches on `st_feat`.
@@ -3277,10 +2966,14 @@ int saf_integrate_sequence(const saf_grid_desc* grid, const saf_volume* vol, con
         n_frames = (int32_t)kept.size();
         if (n_frames == 0) return 0;
     }
+    // windows of (nearly) equal length: 100 frames are 7 windows of 14-15 frames, not 6 of 16 and one of 4 whose
+    // rows would be read and written for a quarter of the updates
     const int32_t n_calls = (n_frames + window - 1) / window;
+    const int32_t w_base = n_frames / n_calls, w_rem = n_frames % n_calls;
+    auto call_begin = [&](int32_t c) { return c * w_base + std::min(c, w_rem); };
     if (n_calls < 4) {
         for (int32_t c = 0; c < n_calls; ++c) {
-            const int32_t i0 = c * window, nb = std::min(window, n_frames - i0);
+            const int32_t i0 = call_begin(c), nb = call_begin(c + 1) - i0;
             rc = integrate_call(grid, vol, frames + i0, nb, H, W, trunc, rgb_mode, ws, 0, sms, smem_optin, st, st, nullptr,
                                 nullptr, true);
             if (rc) return rc;
@@ -3294,7 +2987,7 @@ int saf_integrate_sequence(const saf_grid_desc* grid, const saf_volume* vol, con
     SAF_CUDA_TRY(cudaStreamWaitEvent(ss->side, ss->fork, 0));
     for (int32_t c = 0; c < n_calls && rc == 0; ++c) {
         const uint32_t slot = (uint32_t)(c & 1);
-        const int32_t i0 = c * window, nb = std::min(window, n_frames - i0);
+        const int32_t i0 = call_begin(c), nb = call_begin(c + 1) - i0;
         // slot reuse: the feature kernel of call c-2 must have finished reading this slot's lists
         if (c >= 2) rc = (int)cudaStreamWaitEvent(ss->side, ss->feat_done[slot], 0);
         if (rc == 0)

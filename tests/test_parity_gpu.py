@@ -384,7 +384,7 @@ def test_depth_aware_block_culling_keeps_results():
     _check_against(vol, orc.tsdf, orc.weight, orc.tsdf_weight, orc.rgb, orc.clip_feat, orc.labels_one_hot, exact=True)
 
 
-# ---- window mode: saf_integrate_sequence fuses up to 8 consecutive frames per launch trio -----------------
+# ---- window mode: saf_integrate_sequence fuses up to 16 consecutive frames per K0/K1/K2/K2T/K3W launch set ----
 
 @pytest.mark.parametrize("name", ["seem_a", "fusion_a", "seem_edge"])
 def test_sequence_window_matches_reference_golden(name):
