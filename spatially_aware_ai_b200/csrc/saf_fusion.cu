@@ -1702,8 +1702,11 @@ struct __align__(128) TileMeta {
     uint32_t fmask[NSET];                           // frames in which any voxel of the set is valid
     uint32_t voxel[NSET * kTileSlots];
     uint32_t prim_rows[NSET][SAF_MAX_BATCH];        // rows of the set's first valid voxel in the frame
+    uint32_t alt_rows[NSET][SAF_MAX_BATCH];         // rows of its first valid voxel that samples other rows (uniform = 0)
     uint8_t vmask[NSET][SAF_MAX_BATCH];             // voxels of the set valid in the frame
     uint8_t uniform[NSET][SAF_MAX_BATCH];           // 1: every valid voxel of the set uses prim_rows in the frame
+    uint8_t pmask[NSET][SAF_MAX_BATCH];             // uniform = 0: valid voxels that use prim_rows,
+    uint8_t amask[NSET][SAF_MAX_BATCH];             //              and those that use alt_rows (the rest: a third cell)
     TileUpdate upd[NSET][SAF_MAX_BATCH][kTileSlots];
 };
 
@@ -1868,9 +1871,19 @@ __device__ __forceinline__ void fill_tile_meta(const FusionParams& p, const Tile
         const int first = group * 8 + (gb ? __ffs(gb) - 1 : 0);
         const uint32_t prim = __shfl_sync(0xffffffffu, cell_rows, first);
         const uint32_t mb = __ballot_sync(0xffffffffu, cell_valid && cell_rows != prim);
+        // a set that straddles a table cell boundary (~30 % of the frames on cfg2) nearly always sees just two cells:
+        // its voxels are grouped by cell so that the compute warps load each cell's rows once per frame
+        const uint32_t mg = (mb >> (group * 8)) & 0xffu;
+        const int first_alt = group * 8 + (mg ? __ffs(mg) - 1 : 0);
+        const uint32_t alt = __shfl_sync(0xffffffffu, cell_rows, first_alt);
+        const uint32_t ob = __ballot_sync(0xffffffffu, cell_valid && cell_rows != prim && cell_rows != alt);
         if (gb && lane == first) {
-            M->prim_rows[v / kTileSlots][b] = prim;
-            M->uniform[v / kTileSlots][b] = ((mb >> (group * 8)) & 0xffu) == 0u ? 1 : 0;
+            const int st = v / kTileSlots;
+            M->prim_rows[st][b] = prim;
+            M->uniform[st][b] = mg == 0u ? 1 : 0;
+            M->alt_rows[st][b] = alt;
+            M->pmask[st][b] = (uint8_t)(gb & ~mg);
+            M->amask[st][b] = (uint8_t)(mg & ~((ob >> (group * 8)) & 0xffu));
         }
     }
     __syncwarp();   // samples and update records of every cell are in shared memory
@@ -1895,8 +1908,22 @@ __device__ __forceinline__ void fill_tile_meta(const FusionParams& p, const Tile
     __syncwarp();   // every lane's metadata is written (and my_smp read) before the arrival publishes it
 }
 
+// Register budget.  The producers are one warpgroup (warps 0-3, the last one idle) that hands most of its registers to
+// the compute warpgroups right after start-up (setmaxnreg): with 12 compute warps at C = 768 that is 152 registers per
+// compute thread instead of 128, which pays for a third set of table-row registers - a frame's rows are requested
+// TWO frames ahead, so their L2 round trip is covered by two frames of arithmetic instead of one.
+constexpr int kTileProducerWarps = 4;
+constexpr int kTileProducerRegs = 56;
+template <int NCW>
+struct TileRegs {
+    static constexpr int kLaunch = 65536 / ((NCW + kTileProducerWarps) * 32) / 8 * 8;   // what __launch_bounds__ grants
+    static constexpr int kPool = (NCW + kTileProducerWarps) * 32 * kLaunch;
+    static constexpr int kRaw = (kPool - kTileProducerWarps * 32 * kTileProducerRegs) / (NCW * 32) / 8 * 8;
+    static constexpr int kCompute = kRaw > 232 ? 232 : kRaw;
+};
+
 template <int CHUNKS, int NSET, int NBUF>
-__global__ void __launch_bounds__((CHUNKS * NSET + NBUF) * 32, 1)
+__global__ void __launch_bounds__((CHUNKS * NSET + kTileProducerWarps) * 32, 1)
 feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, const __grid_constant__ WindowTables wt)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1904,6 +1931,7 @@ feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, co
     constexpr int G = NSET * kTileSlots;
     constexpr int NCW = CHUNKS * NSET;
     static_assert(G <= 32, "one producer lane per voxel of the tile");
+    static_assert(NBUF < kTileProducerWarps + 1 && NCW % 4 == 0, "warpgroups");
     using Meta = TileMeta<NSET>;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     SlotCounters* sc = &p.hdr->slot[p.slot];
@@ -1927,8 +1955,10 @@ feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, co
     }
     __syncthreads();
 
-    if (warp < NBUF) {
+    if (warp < kTileProducerWarps) {
         // ------------------------------- producer -------------------------------
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kTileProducerRegs));
+        if (warp >= NBUF) return;
         const uint32_t n_blocks = sc->n_blocks;
         float* my_rows = rows_buf + (size_t)warp * G * C;
         float4* my_smp = smp_buf + (size_t)warp * G * SAF_MAX_BATCH;   // [voxel][frame] rgb sample
@@ -1984,15 +2014,24 @@ feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, co
     }
 
     // ------------------------------- compute -------------------------------
-    const int cw = warp - NBUF;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TileRegs<NCW>::kCompute));
+    const int cw = warp - kTileProducerWarps;
     const int set = cw / CHUNKS, chunk = cw % CHUNKS;
     const int col4 = chunk * 32 + lane;   // this thread's float4 column of every row
     uint32_t done = 0;                    // producers that have published their last tile
+#ifdef SAF_TILE_TIMING
+    long long tm_wait = 0, tm_load = 0, tm_frames = 0, tm_store = 0, tm_c0 = clock64(), tm_c1;
+    uint32_t tm_tiles = 0, tm_nframes = 0, tm_upd = 0, tm_nonuni = 0;
+#define TM_MARK(acc) do { tm_c1 = clock64(); acc += tm_c1 - tm_c0; tm_c0 = tm_c1; } while (0)
+#else
+#define TM_MARK(acc) do { } while (0)
+#endif
     for (uint32_t t = 0; done != (1u << NBUF) - 1u; ++t) {
         const uint32_t pi = t % NBUF, j = t / NBUF;
         if ((done >> pi) & 1u) continue;
         const uint32_t ms = pi + (uint32_t)NBUF * (j & 1u);
         mbar_wait(&full[ms], (j >> 1) & 1u);
+        TM_MARK(tm_wait);
         const Meta* M = metas + ms;
         const uint32_t n_rows = M->n_rows;
         if (n_rows == 0) {
@@ -2016,8 +2055,18 @@ feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, co
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&rows_free[pi]);
+        TM_MARK(tm_load);
 
         const uint32_t fm = M->fmask[set];
+#ifdef SAF_TILE_TIMING
+        tm_tiles += 1;
+        tm_nframes += __popc(fm);
+        for (uint32_t q = fm; q; q &= q - 1u) {
+            const int b = __ffs(q) - 1;
+            tm_upd += __popc((uint32_t)M->vmask[set][b]);
+            tm_nonuni += M->uniform[set][b] ? 0 : 1;
+        }
+#endif
         if (fm) {
             // one update: the record (weights, a, b, rows, 1.0f) is two 16-byte broadcast loads
             auto update = [&](int b, int s, const uint4& m0, const uint4& m1, const RowRegs& T) {
@@ -2030,7 +2079,7 @@ feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, co
                 acc_hi[s] = mix_blend2(T.hi, wp, ap, bp, op, acc_hi[s]);
             };
             // one frame of the window: every voxel of the set that the frame sees, with the frame's rows in T
-            auto frame_updates = [&](int b, RowRegs& T, uint32_t& cur_rows) {
+            auto frame_updates = [&](int b, const RowRegs& T) {
                 const uint32_t vm = M->vmask[set][b];
                 const uint4* rec = reinterpret_cast<const uint4*>(&M->upd[set][b][0]);
                 if (M->uniform[set][b]) {
@@ -2040,15 +2089,30 @@ feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, co
                         if ((vm >> s) & 1u) update(b, s, rec[2 * s], rec[2 * s + 1], T);
                     return;
                 }
+                // the set straddles a table cell boundary: the second cell's rows are requested now and arrive while
+                // the voxels of the first cell are updated (the order of a frame's voxels does not matter)
+                const uint32_t pm = M->pmask[set][b], am = M->amask[set][b];
+                RowRegs TA;
+                uint32_t alt_rows = M->alt_rows[set][b];
+                load_rows(TA, wt.ptr[b], alt_rows, C, col4);
 #pragma unroll
-                for (int s = 0; s < kTileSlots; ++s) {
-                    if ((vm >> s) & 1u) {
-                        const uint4 m0 = rec[2 * s], m1 = rec[2 * s + 1];
-                        if (m1.z != cur_rows) {   // a voxel of the set straddles a table cell boundary: rare
-                            cur_rows = m1.z;
-                            load_rows(T, wt.ptr[b], cur_rows, C, col4);
+                for (int s = 0; s < kTileSlots; ++s)
+                    if ((pm >> s) & 1u) update(b, s, rec[2 * s], rec[2 * s + 1], T);
+#pragma unroll
+                for (int s = 0; s < kTileSlots; ++s)
+                    if ((am >> s) & 1u) update(b, s, rec[2 * s], rec[2 * s + 1], TA);
+                const uint32_t rest = vm & ~(pm | am);
+                if (rest) {   // a third (fourth) cell: rare
+#pragma unroll
+                    for (int s = 0; s < kTileSlots; ++s) {
+                        if ((rest >> s) & 1u) {
+                            const uint4 m0 = rec[2 * s], m1 = rec[2 * s + 1];
+                            if (m1.z != alt_rows) {
+                                alt_rows = m1.z;
+                                load_rows(TA, wt.ptr[b], alt_rows, C, col4);
+                            }
+                            update(b, s, m0, m1, TA);
                         }
-                        update(b, s, m0, m1, T);
                     }
                 }
             };
@@ -2058,27 +2122,29 @@ feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, co
                 rest &= rest - 1u;
                 return b;
             };
-            auto request = [&](int b, RowRegs& T, uint32_t& rows) {
-                if (b >= 0) {
-                    rows = M->prim_rows[set][b];
-                    load_rows(T, wt.ptr[b], rows, C, col4);
-                }
+            auto request = [&](int b, RowRegs& T) {
+                if (b >= 0) load_rows(T, wt.ptr[b], M->prim_rows[set][b], C, col4);
             };
-            // the next frame's rows are requested before a frame's arithmetic starts; two register sets take turns
-            RowRegs T0, T1;
-            uint32_t rows0 = 0, rows1 = 0;
-            int b0 = next_frame(), b1;
-            request(b0, T0, rows0);
+            // a frame's rows are requested two frames before its arithmetic starts; three register sets take turns
+            RowRegs T0, T1, T2;
+            int b0 = next_frame(), b1 = next_frame(), b2;
+            request(b0, T0);
+            request(b1, T1);
             for (;;) {
-                b1 = next_frame();
-                request(b1, T1, rows1);
-                frame_updates(b0, T0, rows0);
+                b2 = next_frame();
+                request(b2, T2);
+                frame_updates(b0, T0);
                 if (b1 < 0) break;
                 b0 = next_frame();
-                request(b0, T0, rows0);
-                frame_updates(b1, T1, rows1);
+                request(b0, T0);
+                frame_updates(b1, T1);
+                if (b2 < 0) break;
+                b1 = next_frame();
+                request(b1, T1);
+                frame_updates(b2, T2);
                 if (b0 < 0) break;
             }
+            TM_MARK(tm_frames);
 #pragma unroll
             for (int s = 0; s < kTileSlots; ++s) {
                 if ((uint32_t)(set * kTileSlots + s) < n_rows) {
@@ -2090,7 +2156,16 @@ feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, co
         fence_proxy_async();   // prepared tiles: the slot is refilled by a bulk copy
         __syncwarp();
         if (lane == 0) mbar_arrive(&meta_free[ms]);
+        TM_MARK(tm_store);
     }
+#ifdef SAF_TILE_TIMING
+    if (lane == 0 && (cw == 0 || cw == NCW - 1) && (blockIdx.x % 37) == 0)
+        printf("[k3w timing] cta %d warp %d: tiles %u frames %u updates %u non-uniform frames %u | cycles wait %lld load %lld "
+               "frames %lld store %lld | per update %.1f per frame %.1f\n", blockIdx.x, cw, tm_tiles, tm_nframes, tm_upd,
+               tm_nonuni, tm_wait, tm_load, tm_frames, tm_store, (double)tm_frames / max(1u, tm_upd),
+               (double)tm_frames / max(1u, tm_nframes));
+#endif
+#undef TM_MARK
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -2539,7 +2614,7 @@ static int launch_k3w_fixed(const FusionParams& p, const WindowTables& wt, int s
 template <int CHUNKS, int NSET, int NBUF>
 static int launch_k3w_tile(const FusionParams& p, const WindowTables& wt, int sms, cudaStream_t st, int stages)
 {
-    constexpr int kThreads = (CHUNKS * NSET + NBUF) * 32;
+    constexpr int kThreads = (CHUNKS * NSET + kTileProducerWarps) * 32;
     constexpr size_t smem = (size_t)NBUF * NSET * kTileSlots * CHUNKS * 128 * sizeof(float) +
                             2 * (size_t)NBUF * sizeof(TileMeta<NSET>) +
                             (size_t)NBUF * NSET * kTileSlots * SAF_MAX_BATCH * sizeof(float4) +
