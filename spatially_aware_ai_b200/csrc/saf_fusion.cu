@@ -69,6 +69,7 @@ struct FusionParams {
     WinEntry* ulist;           // window mode: [nblocks_total*512] voxels valid in any frame, rank r's start at r*512
     float2* wcoords;           // window mode: [nblocks_total][batch][512] (gx, gy) per (block rank, frame, local voxel)
     float* tables;
+    int32_t* w0_list;          // window mode: the union voxels' weights before the window (K2T -> K3W), indexed like ulist
     void* tile_meta;           // window mode: [tile_meta_cap] TileMeta<2> written by K2T for K3W's tiles (idle list regions)
     uint32_t tile_meta_cap;    // tiles of the union list K2T prepares; later tiles are prepared inside K3W
     uint8_t* valid_out;
@@ -1743,6 +1744,10 @@ struct TileLane {
     float rgb0[3];
 };
 
+// SMALL: the caller is K2T, which owns the window's small state: weight and rgb are read from the volume and the
+// weight before the window is left in w0_list for K3W's own producers (they run while K2T already works on the next
+// window and must not look at the volume's weights).
+template <bool SMALL>
 __device__ __forceinline__ TileLane load_tile_lane(const FusionParams& p, uint32_t n_blocks, uint32_t base, uint32_t cnt,
                                                    int lane)
 {
@@ -1762,16 +1767,22 @@ __device__ __forceinline__ TileLane load_tile_lane(const FusionParams& p, uint32
         const uint32_t i = base + lane;
         uint32_t r = lo;
         while (r + 1u < n_blocks && __ldg(off + r + 1u) <= i) ++r;   // the tile spans a few blocks at most
-        const WinEntry e = p.ulist[(uint64_t)r * kBlockVoxels + (i - __ldg(off + r))];
+        const uint64_t slot = (uint64_t)r * kBlockVoxels + (i - __ldg(off + r));
+        const WinEntry e = p.ulist[slot];
         L.voxel = e.voxel;
         L.mask = e.mask_local & 0xffffu;
         L.local = e.mask_local >> 16;
         L.rank = r;
-        L.w0 = p.vol.weight[L.voxel];
-        const float* src3 = p.vol.rgb + (size_t)L.voxel * 3;
-        L.rgb0[0] = src3[0];
-        L.rgb0[1] = src3[1];
-        L.rgb0[2] = src3[2];
+        if (SMALL) {
+            L.w0 = p.vol.weight[L.voxel];
+            p.w0_list[slot] = L.w0;
+            const float* src3 = p.vol.rgb + (size_t)L.voxel * 3;
+            L.rgb0[0] = src3[0];
+            L.rgb0[1] = src3[1];
+            L.rgb0[2] = src3[2];
+        } else {
+            L.w0 = p.w0_list[slot];
+        }
     }
     return L;
 }
@@ -1780,7 +1791,8 @@ __device__ __forceinline__ TileLane load_tile_lane(const FusionParams& p, uint32
 // producer prepares the tile itself, global memory when K2T prepares it ahead - and the tile's small state: rgb
 // running average, label counters, weight.  my_smp: G x SAF_MAX_BATCH float4 of shared-memory scratch of this warp.
 // The valid (voxel, frame) CELLS of the tile are spread over the 32 lanes and handled independently.
-template <int NSET>
+// META: write M (K2T skips it for tiles past its capacity).  SMALL: update the small state (K2T only).
+template <int NSET, bool META, bool SMALL>
 __device__ __forceinline__ void fill_tile_meta(const FusionParams& p, const TileLane& L, uint32_t cnt, TileMeta<NSET>* M,
                                                float4* my_smp, int lane)
 {
@@ -1794,7 +1806,7 @@ __device__ __forceinline__ void fill_tile_meta(const FusionParams& p, const Tile
         const uint32_t bal = __ballot_sync(0xffffffffu, (L.mask >> b) & 1u);
         if (lane == b) my_ballot = bal;
     }
-    if (lane < SAF_MAX_BATCH) {
+    if (META && lane < SAF_MAX_BATCH) {
 #pragma unroll
         for (int s = 0; s < NSET; ++s) M->vmask[s][lane] = (uint8_t)((my_ballot >> (s * kTileSlots)) & 0xffu);
     }
@@ -1802,10 +1814,10 @@ __device__ __forceinline__ void fill_tile_meta(const FusionParams& p, const Tile
     for (int s = 0; s < NSET; ++s) {
         const uint32_t fm = __ballot_sync(0xffffffffu, lane < SAF_MAX_BATCH &&
                                                            ((my_ballot >> (s * kTileSlots)) & 0xffu) != 0u);
-        if (lane == 0) M->fmask[s] = fm;
+        if (META && lane == 0) M->fmask[s] = fm;
     }
-    if (lane == 0) M->n_rows = cnt;
-    if (lane < cnt) M->voxel[lane] = L.voxel;
+    if (META && lane == 0) M->n_rows = cnt;
+    if (META && lane < cnt) M->voxel[lane] = L.voxel;
     // cells: c -> (frame c / G, voxel c % G).  Pass 1 requests every valid cell's image coordinates.
     float2 cg[kCellIters];
 #pragma unroll
@@ -1830,29 +1842,33 @@ __device__ __forceinline__ void fill_tile_meta(const FusionParams& p, const Tile
         if (cell_valid) {
             const saf_frame& f = p.frames[b];
             const float2 g = cg[it];
-            const int w = w0 + __popc(mv & ((1u << b) - 1u));   // single-frame calls before this one
-            const float a = __frcp_rn(__int2float_rn(w + 1));
-            const float bb = __fmul_rn(__int2float_rn(w), a);
-            Taps t;
-            feature_taps_padded(f, g.x, g.y, p.W, p.H, &p.hdr->error_flags, t);
-            const uint32_t rows = (uint32_t)t.idx[0] | ((uint32_t)t.idx[1] << 8) | ((uint32_t)t.idx[2] << 16) |
-                                  ((uint32_t)t.idx[3] << 24);
-            TileUpdate u;
-            u.w[0] = t.w[0];
-            u.w[1] = t.w[1];
-            u.w[2] = t.w[2];
-            u.w[3] = t.w[3];
-            u.a = a;
-            u.b = bb;
-            u.rows = rows;
-            u.one = 1.0f;
-            M->upd[v / kTileSlots][b][v % kTileSlots] = u;
-            cell_rows = rows;
+            if (META) {
+                const int w = w0 + __popc(mv & ((1u << b) - 1u));   // single-frame calls before this one
+                const float a = __frcp_rn(__int2float_rn(w + 1));
+                const float bb = __fmul_rn(__int2float_rn(w), a);
+                Taps t;
+                feature_taps_padded(f, g.x, g.y, p.W, p.H, &p.hdr->error_flags, t);
+                const uint32_t rows = (uint32_t)t.idx[0] | ((uint32_t)t.idx[1] << 8) | ((uint32_t)t.idx[2] << 16) |
+                                      ((uint32_t)t.idx[3] << 24);
+                TileUpdate u;
+                u.w[0] = t.w[0];
+                u.w[1] = t.w[1];
+                u.w[2] = t.w[2];
+                u.w[3] = t.w[3];
+                u.a = a;
+                u.b = bb;
+                u.rows = rows;
+                u.one = 1.0f;
+                M->upd[v / kTileSlots][b][v % kTileSlots] = u;
+                cell_rows = rows;
+            }
             const int px = nearest_index(g.x, p.W), py = nearest_index(g.y, p.H);
-            float smp[3];
-            sample_rgb(p, f, g.x, g.y, px, py, smp);
-            my_smp[v * SAF_MAX_BATCH + b] = make_float4(smp[0], smp[1], smp[2], 0.f);
-            if (p.vol.labels_one_hot && f.seg) {
+            float smp[3] = {0.f, 0.f, 0.f};
+            if (SMALL) {
+                sample_rgb(p, f, g.x, g.y, px, py, smp);
+                my_smp[v * SAF_MAX_BATCH + b] = make_float4(smp[0], smp[1], smp[2], 0.f);
+            }
+            if (SMALL && p.vol.labels_one_hot && f.seg) {
                 const float lf = (px >= 0 && py >= 0) ? load_class_id(f.seg, f.seg_dtype, py * p.W + px) : 0.0f;
                 const long long id = (long long)lf;
                 if (id >= 0 && id < p.vol.n_classes)
@@ -1877,7 +1893,7 @@ __device__ __forceinline__ void fill_tile_meta(const FusionParams& p, const Tile
         const int first_alt = group * 8 + (mg ? __ffs(mg) - 1 : 0);
         const uint32_t alt = __shfl_sync(0xffffffffu, cell_rows, first_alt);
         const uint32_t ob = __ballot_sync(0xffffffffu, cell_valid && cell_rows != prim && cell_rows != alt);
-        if (gb && lane == first) {
+        if (META && gb && lane == first) {
             const int st = v / kTileSlots;
             M->prim_rows[st][b] = prim;
             M->uniform[st][b] = mg == 0u ? 1 : 0;
@@ -1887,7 +1903,7 @@ __device__ __forceinline__ void fill_tile_meta(const FusionParams& p, const Tile
         }
     }
     __syncwarp();   // samples and update records of every cell are in shared memory
-    if (lane < cnt) {
+    if (SMALL && lane < cnt) {
         // the rgb running average walks the voxel's frames in order (clip_seem_fusion.py:808-813)
         float acc[3] = {L.rgb0[0], L.rgb0[1], L.rgb0[2]};
         int w = L.w0;
@@ -1940,8 +1956,7 @@ feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, co
 
     float* rows_buf = reinterpret_cast<float*>(smem_raw);                                   // [NBUF][G][C]
     Meta* metas = reinterpret_cast<Meta*>(smem_raw + (size_t)NBUF * G * C * sizeof(float));  // [2*NBUF]
-    float4* smp_buf = reinterpret_cast<float4*>(metas + 2 * NBUF);                           // [NBUF][G][16]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smp_buf + (size_t)NBUF * G * SAF_MAX_BATCH);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(metas + 2 * NBUF);
     uint64_t* full = bars;                    // [2*NBUF]
     uint64_t* meta_free = bars + 2 * NBUF;    // [2*NBUF]
     uint64_t* rows_free = bars + 4 * NBUF;    // [NBUF]
@@ -1961,7 +1976,6 @@ feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, co
         if (warp >= NBUF) return;
         const uint32_t n_blocks = sc->n_blocks;
         float* my_rows = rows_buf + (size_t)warp * G * C;
-        float4* my_smp = smp_buf + (size_t)warp * G * SAF_MAX_BATCH;   // [voxel][frame] rgb sample
         const Meta* prepared = reinterpret_cast<const Meta*>(p.tile_meta);
         for (uint32_t j = 0;; ++j) {
             uint32_t base = 0;
@@ -1996,8 +2010,8 @@ feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, co
                 if (lane == 0) mbar_arrive(&full[ms]);
                 continue;
             }
-            // a tile past K2T's capacity (or a build without it): prepared here, one tile at a time
-            const TileLane L = load_tile_lane(p, n_blocks, base, cnt, lane);
+            // a tile past K2T's capacity: its metadata is prepared here (the small state is always K2T's)
+            const TileLane L = load_tile_lane<false>(p, n_blocks, base, cnt, lane);
             // the landing buffer was handed back when the compute warps took its rows to registers
             mbar_wait(&rows_free[warp], (j & 1u) ^ 1u);
             if (lane == 0) mbar_expect_tx(&full[ms], cnt * (uint32_t)C * 4u);
@@ -2006,7 +2020,7 @@ feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, co
                 tma_bulk_g2s(my_rows + (size_t)lane * C, p.vol.clip_feat + (size_t)L.voxel * C, (uint32_t)C * 4u, &full[ms]);
             // the metadata slot was last read two of this producer's tiles ago
             mbar_wait(&meta_free[ms], ((j >> 1) & 1u) ^ 1u);
-            fill_tile_meta<NSET>(p, L, cnt, M, my_smp, lane);
+            fill_tile_meta<NSET, true, false>(p, L, cnt, M, nullptr, lane);
             __syncwarp();   // every lane's metadata is written (and my_smp read) before the arrival publishes it
             if (lane == 0) mbar_arrive(&full[ms]);
         }
@@ -2185,12 +2199,15 @@ __global__ void __launch_bounds__(kK2TWarps * 32) window_tile_setup_kernel(const
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const SlotCounters* sc = &p.hdr->slot[p.slot];
     const uint32_t n = sc->n_union, n_blocks = sc->n_blocks;
-    const uint32_t n_tiles = min((n + G - 1) / G, p.tile_meta_cap);
+    const uint32_t n_tiles = (n + G - 1) / G;
     TileMeta<NSET>* metas = reinterpret_cast<TileMeta<NSET>*>(p.tile_meta);
     for (uint32_t tile = blockIdx.x * kK2TWarps + warp; tile < n_tiles; tile += gridDim.x * kK2TWarps) {
         const uint32_t base = tile * G, cnt = min((uint32_t)G, n - base);
-        const TileLane L = load_tile_lane(p, n_blocks, base, cnt, lane);
-        fill_tile_meta<NSET>(p, L, cnt, metas + tile, s_smp[warp], lane);
+        const TileLane L = load_tile_lane<true>(p, n_blocks, base, cnt, lane);
+        if (tile < p.tile_meta_cap)
+            fill_tile_meta<NSET, true, true>(p, L, cnt, metas + tile, s_smp[warp], lane);
+        else   // no room for the metadata (K3W prepares it itself): the small state only
+            fill_tile_meta<NSET, false, true>(p, L, cnt, metas, s_smp[warp], lane);
         __syncwarp();   // s_smp is reused by the warp's next tile
     }
 }
@@ -2455,6 +2472,7 @@ static int build_params(const saf_grid_desc* grid, const saf_volume* vol, const 
     // window mode reuses the per-frame list regions: region 0 holds the union list, regions 1.. the coordinates
     p->ulist = (WinEntry*)p->lists;
     p->wcoords = (float2*)(p->lists + L.list_cap);
+    p->w0_list = (int32_t*)(p->ulist + L.list_cap);   // second half of list region 0
     p->tables = (float*)(sb + L.off_tables);
     // a window workspace's list regions past the coordinates are idle in window mode: K2T's tile metadata
     {
@@ -2612,13 +2630,11 @@ static int launch_k3w_fixed(const FusionParams& p, const WindowTables& wt, int s
 }
 
 template <int CHUNKS, int NSET, int NBUF>
-static int launch_k3w_tile(const FusionParams& p, const WindowTables& wt, int sms, cudaStream_t st, int stages)
+static int launch_k3w_tile(const FusionParams& p, const WindowTables& wt, int sms, cudaStream_t st)
 {
     constexpr int kThreads = (CHUNKS * NSET + kTileProducerWarps) * 32;
     constexpr size_t smem = (size_t)NBUF * NSET * kTileSlots * CHUNKS * 128 * sizeof(float) +
-                            2 * (size_t)NBUF * sizeof(TileMeta<NSET>) +
-                            (size_t)NBUF * NSET * kTileSlots * SAF_MAX_BATCH * sizeof(float4) +
-                            5 * (size_t)NBUF * sizeof(uint64_t);
+                            2 * (size_t)NBUF * sizeof(TileMeta<NSET>) + 5 * (size_t)NBUF * sizeof(uint64_t);
     static_assert(smem <= 227 * 1024, "tile kernel shared memory");
     auto kern = feature_accumulate_window_tile_kernel<CHUNKS, NSET, NBUF>;
     { int rc_ = ensure_dynamic_smem(kern, smem); if (rc_) return rc_; }
@@ -2627,20 +2643,15 @@ static int launch_k3w_tile(const FusionParams& p, const WindowTables& wt, int sm
     // K0 / K1 / K2 of the NEXT window - already queued on the side stream - run beside it instead of after it.
     // Whole grids keep all SMs: there both kernels are throughput-bound and sharing would only slow K3W.
     static const int reserve_env = getenv("SAF_K3W_RESERVE_SMS") ? atoi(getenv("SAF_K3W_RESERVE_SMS")) : -1;
-    // share of the grid this volume holds; measured on the cfg3 grid (one GPU running one rank's shard): a 1/8 shard
-    // is fastest with ~40 of 148 SMs left free (step -11 %), a 1/2 shard with ~10-18 (-4 %)
+    // share of the grid this volume holds.  Measured on the cfg3 grid (one GPU running one rank's shard, K2T on its
+    // own stream): a half grid is fastest with ~8 of 148 SMs left free (there K3W is most of the window), quarter and
+    // eighth shards with ~54 (K0 -> K1 -> K2 -> K2T of the next window take as long as K3W of this one, and the two
+    // chains run side by side: 1.75 -> 1.62 ms per 100 frames at 1/4, 1.30 -> 1.08 at 1/8 against 8 free SMs)
     const double share = (double)p.nslab / ((double)p.grid.nvox[0] * p.grid.nvox[1] * p.grid.nvox[2]);
-    const int reserve = reserve_env >= 0 ? reserve_env
-                                         : (share < 0.75 ? (int)(sms * std::min(0.28, 0.035 / std::max(share, 1e-3))) : 0);
+    const int reserve = reserve_env >= 0 ? reserve_env : (share >= 0.75 ? 0 : (share >= 0.4 ? (int)(sms * 0.055) : (int)(sms * 0.365)));
     const int grid = std::max(1, sms - std::min(reserve, sms - 1));
-    if ((stages & SAF_STAGE_TILE_SETUP) && NSET == 2 && p.tile_meta_cap > 0) {
-        window_tile_setup_kernel<<<sms * 4, kK2TWarps * 32, 0, st>>>(p);
-        SAF_CHECK_LAUNCH("window_tile_setup_kernel (K2T)", st);
-    }
-    if (stages & SAF_STAGE_ACCUMULATE) {
-        kern<<<grid, kThreads, smem, st>>>(p, wt);
-        SAF_CHECK_LAUNCH("feature_accumulate_window_tile_kernel (K3W)", st);
-    }
+    kern<<<grid, kThreads, smem, st>>>(p, wt);
+    SAF_CHECK_LAUNCH("feature_accumulate_window_tile_kernel (K3W)", st);
     return 0;
 }
 
@@ -2656,7 +2667,31 @@ static int k3w_variant()
     return v;
 }
 
-static int launch_k3w(const FusionParams& p, int sms, cudaStream_t st, int stages = SAF_STAGE_TILE_SETUP | SAF_STAGE_ACCUMULATE)
+// does this window take the tile kernel (and therefore K2T)?
+static bool k3w_uses_tiles(const FusionParams& p)
+{
+    const int C = p.vol.feature_dim;
+    if (k3w_variant() != 2 || (C != 512 && C != 768 && C != 1024)) return false;
+    if ((((uintptr_t)p.vol.clip_feat & 15u) != 0) || (p.table_slot_elems % 4 != 0)) return false;
+    // the tile kernel addresses table rows with one byte each
+    for (int b = 0; b < p.batch; ++b)
+        if ((p.frames[b].table_mode == SAF_TABLE_SEGMENTS ? p.frames[b].npx + 1
+                                                          : (p.frames[b].npy + 2) * (p.frames[b].npx + 2)) > 256)
+            return false;
+    return true;
+}
+
+// K2T: after K2 of the same window, on K2's stream - it touches rgb / weight / label counters, which K3W never
+// does, so it may run while K3W is still busy with the previous window
+static int launch_k2t(const FusionParams& p, int sms, cudaStream_t st)
+{
+    if (!k3w_uses_tiles(p)) return 0;   // the other window kernels update the small state themselves
+    window_tile_setup_kernel<<<sms * 4, kK2TWarps * 32, 0, st>>>(p);
+    SAF_CHECK_LAUNCH("window_tile_setup_kernel (K2T)", st);
+    return 0;
+}
+
+static int launch_k3w(const FusionParams& p, int sms, cudaStream_t st)
 {
     const int C = p.vol.feature_dim;
     WindowTables wt;
@@ -2666,21 +2701,14 @@ static int launch_k3w(const FusionParams& p, int sms, cudaStream_t st, int stage
         wt.ptr[b] = b < p.batch ? p.tables + (uint64_t)b * p.table_slot_elems : nullptr;
         wt.stride_r[b] = C;
     }
-    if (rows16) {
-        // the tile kernel addresses table rows with one byte each
-        bool small_tables = true;
-        for (int b = 0; b < p.batch; ++b)
-            small_tables &= (p.frames[b].table_mode == SAF_TABLE_SEGMENTS ? p.frames[b].npx + 1
-                                                                          : (p.frames[b].npy + 2) * (p.frames[b].npx + 2)) <= 256;
-        if (k3w_variant() == 2 && small_tables) {
-            switch (C) {
-                case 512: return launch_k3w_tile<4, 2, SAF_TILE_NBUF>(p, wt, sms, st, stages);
-                case 768: return launch_k3w_tile<6, 2, SAF_TILE_NBUF>(p, wt, sms, st, stages);
-                case 1024: return launch_k3w_tile<8, 2, 2>(p, wt, sms, st, stages);
-                default: break;
-            }
+    if (k3w_uses_tiles(p)) {
+        switch (C) {
+            case 512: return launch_k3w_tile<4, 2, SAF_TILE_NBUF>(p, wt, sms, st);
+            case 768: return launch_k3w_tile<6, 2, SAF_TILE_NBUF>(p, wt, sms, st);
+            default: return launch_k3w_tile<8, 2, 2>(p, wt, sms, st);
         }
-        if (!(stages & SAF_STAGE_ACCUMULATE)) return 0;   // only the tile kernel has a setup stage
+    }
+    if (rows16) {
         if (k3w_variant() >= 1) {
             switch (C) {
                 case 512: return launch_k3w_pair<4, K3W2_WARPS>(p, wt, sms, st);
@@ -2696,7 +2724,6 @@ static int launch_k3w(const FusionParams& p, int sms, cudaStream_t st, int stage
         }
         feature_accumulate_window_generic_kernel<4><<<sms * 2, kK3Threads, 0, st>>>(p, wt);
     } else {
-        if (!(stages & SAF_STAGE_ACCUMULATE)) return 0;
         feature_accumulate_window_generic_kernel<1><<<sms * 2, kK3Threads, 0, st>>>(p, wt);
     }
     SAF_CHECK_LAUNCH("feature_accumulate_window_generic_kernel (K3W)", st);
@@ -2866,15 +2893,17 @@ int saf_feature_accumulate_window_stages(const saf_grid_desc* grid, const saf_vo
         // saf_frustum_cull does not know the call is a window: repack the feature images here (K1's pack CTAs only)
         frame_setup_kernel<<<64, kK1Threads, 0, (cudaStream_t)stream>>>(p, 0u);
         SAF_CHECK_LAUNCH("frame_setup_kernel (table repack)", (cudaStream_t)stream);
+        if ((rc = launch_k2t(p, sms, (cudaStream_t)stream))) return rc;
     }
-    return launch_k3w(p, sms, (cudaStream_t)stream, stages);
+    return (stages & SAF_STAGE_ACCUMULATE) ? launch_k3w(p, sms, (cudaStream_t)stream) : 0;
 }
 
 // K1 + K2 of one integrate() call on `st_geo`, then its K3 launches on `st_feat`.
 static int integrate_call(const saf_grid_desc* grid, const saf_volume* vol, const saf_frame* frames, int32_t batch,
                           int32_t H, int32_t W, float trunc, int32_t rgb_mode, const saf_workspace* ws, uint32_t slot,
                           int sms, int smem_optin, cudaStream_t st_geo, cudaStream_t st_feat, cudaEvent_t geo_done,
-                          cudaEvent_t feat_done, bool sequential = false)
+                          cudaEvent_t feat_done, bool sequential = false, cudaStream_t st_tile = nullptr,
+                          cudaEvent_t tile_done = nullptr)
 {
     FusionParams p;
     int rc = build_params(grid, vol, frames, batch, H, W, trunc, rgb_mode, ws, &p, slot);
@@ -2886,9 +2915,17 @@ static int integrate_call(const saf_grid_desc* grid, const saf_volume* vol, cons
     // (the window's union list and coordinates live in list regions 0 and 1 .. ceil(batch / 2) <= batch - 1)
     if ((rc = launch_k1(p, st_geo))) return rc;
     if ((rc = launch_k2(p, sms, st_geo))) return rc;
-    if (geo_done) {
-        SAF_CUDA_TRY(cudaEventRecord(geo_done, st_geo));
-        SAF_CUDA_TRY(cudaStreamWaitEvent(st_feat, geo_done, 0));
+    if (geo_done) SAF_CUDA_TRY(cudaEventRecord(geo_done, st_geo));
+    if (p.sequential && st_tile && tile_done && geo_done) {
+        // K2T on its own stream: behind K2 of this window, beside K0 / K1 / K2 of the next one (st_geo) and beside
+        // K3W of the previous one (st_feat), which never touches the small state K2T updates
+        SAF_CUDA_TRY(cudaStreamWaitEvent(st_tile, geo_done, 0));
+        if ((rc = launch_k2t(p, sms, st_tile))) return rc;
+        SAF_CUDA_TRY(cudaEventRecord(tile_done, st_tile));
+        SAF_CUDA_TRY(cudaStreamWaitEvent(st_feat, tile_done, 0));
+    } else {
+        if (geo_done) SAF_CUDA_TRY(cudaStreamWaitEvent(st_feat, geo_done, 0));
+        if (p.sequential && (rc = launch_k2t(p, sms, st_feat))) return rc;
     }
     if (p.sequential) {
         if ((rc = launch_k3w(p, sms, st_feat))) return rc;
@@ -2948,8 +2985,9 @@ static bool frame_may_reach_slab_host(const saf_grid_desc& g, const float* pose,
 // Side stream and events of saf_integrate_sequence's two-slot overlap: created once per (host thread, device) and
 // kept (creating and destroying a stream and five events per call cost more than a window's kernels).
 struct SeqStreams {
-    cudaStream_t side = nullptr;
+    cudaStream_t side = nullptr, tile = nullptr;
     cudaEvent_t fork = nullptr, geo_done[2] = {nullptr, nullptr}, feat_done[2] = {nullptr, nullptr}, join = nullptr;
+    cudaEvent_t tile_done[2] = {nullptr, nullptr}, tile_join = nullptr;
     bool ok = false;
 };
 static int seq_streams(SeqStreams** out)
@@ -2961,11 +2999,14 @@ static int seq_streams(SeqStreams** out)
     SeqStreams& s = cache[dev];
     if (!s.ok) {
         SAF_CUDA_TRY(cudaStreamCreateWithFlags(&s.side, cudaStreamNonBlocking));
+        SAF_CUDA_TRY(cudaStreamCreateWithFlags(&s.tile, cudaStreamNonBlocking));
         SAF_CUDA_TRY(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
         SAF_CUDA_TRY(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
+        SAF_CUDA_TRY(cudaEventCreateWithFlags(&s.tile_join, cudaEventDisableTiming));
         for (int i = 0; i < 2; ++i) {
             SAF_CUDA_TRY(cudaEventCreateWithFlags(&s.geo_done[i], cudaEventDisableTiming));
             SAF_CUDA_TRY(cudaEventCreateWithFlags(&s.feat_done[i], cudaEventDisableTiming));
+            SAF_CUDA_TRY(cudaEventCreateWithFlags(&s.tile_done[i], cudaEventDisableTiming));
         }
         s.ok = true;
     }
@@ -3067,12 +3108,13 @@ int saf_integrate_sequence(const saf_grid_desc* grid, const saf_volume* vol, con
         if (c >= 2) rc = (int)cudaStreamWaitEvent(ss->side, ss->feat_done[slot], 0);
         if (rc == 0)
             rc = integrate_call(grid, vol, frames + i0, nb, H, W, trunc, rgb_mode, ws, slot, sms, smem_optin, ss->side, st,
-                                ss->geo_done[slot], ss->feat_done[slot], true);
+                                ss->geo_done[slot], ss->feat_done[slot], true, ss->tile, ss->tile_done[slot]);
     }
     // Whatever happened, the caller's stream must not run ahead of the kernels already queued on the side stream
     // (after an error the caller drops the frame tensors and the workspace; the last K2 is otherwise awaited
     // through geo_done).
     if (cudaEventRecord(ss->join, ss->side) == cudaSuccess) cudaStreamWaitEvent(st, ss->join, 0);
+    if (cudaEventRecord(ss->tile_join, ss->tile) == cudaSuccess) cudaStreamWaitEvent(st, ss->tile_join, 0);
     return rc;
 }
 
