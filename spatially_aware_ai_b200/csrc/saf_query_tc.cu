@@ -309,6 +309,248 @@ query_gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Persistent form of the kernel above (the default): one CTA per SM walks the row tiles blockIdx.x, blockIdx.x +
+// gridDim.x, ... with TWO TMEM accumulators, so nothing drains between tiles - the TMA warp keeps the k-block ring
+// full across tile boundaries, the MMA warp starts tile i+1 in the other accumulator while the epilogue warps read
+// tile i out of TMEM, and barrier set-up / TMEM allocation are paid once per SM instead of once per 128 rows.
+//   warp 0      TMA producer          warp 1      TMEM allocation + single-thread tcgen05.mma issue
+//   warps 2-5   row norms from the A tiles (handed to the epilogue through shared memory)
+//   warps 6-9   epilogue: tcgen05.ld -> scale -> (scores: 128-column halves parked in shared memory, coalesced
+//               stores | top-k: candidate filter), TMEM lane group = warp % 4
+// Measured with the one-tile-per-CTA kernel (12 M rows x 256 texts): neither HBM (47 %), L2 (35 %) nor the tensor
+// pipe (36 %) was busy - a tile cost ~20 us of which the overlapped main loop is ~9.
+// ---------------------------------------------------------------------------------------------
+constexpr int P_THREADS = 320;
+constexpr int P_PARK_COLS = 128;                 // columns of a tile parked at a time by the scores epilogue
+constexpr int P_PARK_PITCH = P_PARK_COLS + 4;    // floats; keeps the 128-bit shared stores conflict free
+
+template <bool FILTER>
+__global__ void __launch_bounds__(P_THREADS, 1)
+query_gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                                  int64_t M, int C, int n_pad, int t_valid, int t0, int norm_mode, float* __restrict__ out,
+                                  int64_t ldo, int64_t tile0, int64_t n_tiles, const FilterArgs fa, const int STAGES)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const uint32_t stage_bytes = A_BYTES + (uint32_t)n_pad * BK * 4;
+    unsigned char* after_ring = smem + (size_t)STAGES * stage_bytes;
+    float* park_all = reinterpret_cast<float*>(after_ring);                       // [4 warps][32][P_PARK_PITCH] (scores only)
+    float* snorm = reinterpret_cast<float*>(after_ring + (FILTER ? 0 : 4 * 32 * P_PARK_PITCH * 4));   // [2][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(snorm + 2 * BM);
+    uint64_t* full = bars;                      // [STAGES]
+    uint64_t* empty = full + STAGES;            // [STAGES]
+    uint64_t* tmem_full = empty + STAGES;       // [2]
+    uint64_t* tmem_empty = tmem_full + 2;       // [2]
+    uint64_t* norm_full = tmem_empty + 2;       // [2]
+    uint64_t* norm_empty = norm_full + 2;       // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(norm_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_k = (C + BK - 1) / BK;
+    const int64_t my_tiles = (int64_t)blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1 + 4);  // MMA commit + one arrive per norm warp
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tmem_full[b], 1);
+            mbar_init(&tmem_empty[b], 4);
+            mbar_init(&norm_full[b], 4);
+            mbar_init(&norm_empty[b], 4);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ---- TMA producer: one k-block stream across all of this CTA's tiles --------------------------
+        if (lane == 0) {
+            uint32_t g = 0;
+            for (int64_t i = 0; i < my_tiles; ++i) {
+                const int64_t m0 = (tile0 + blockIdx.x + i * gridDim.x) * BM;
+                for (int k = 0; k < num_k; ++k, ++g) {
+                    const uint32_t s = g % (uint32_t)STAGES, ph = (g / (uint32_t)STAGES) & 1u;
+                    mbar_wait(&empty[s], ph ^ 1u);
+                    unsigned char* a_dst = smem + (size_t)s * stage_bytes;
+                    mbar_arrive_expect_tx(&full[s], stage_bytes);
+                    tma_load_2d(a_dst, &map_a, k * BK, (int)m0, &full[s]);
+                    tma_load_2d(a_dst + A_BYTES, &map_b, k * BK, t0, &full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---- MMA issuer: tile i accumulates in TMEM columns [(i & 1) * 256, +n_pad) --------------------
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32((uint32_t)n_pad);
+            uint32_t g = 0;
+            for (int64_t i = 0; i < my_tiles; ++i) {
+                const uint32_t buf = (uint32_t)i & 1u, use = (uint32_t)(i >> 1);
+                mbar_wait(&tmem_empty[buf], (use & 1u) ^ 1u);   // the epilogue has read this accumulator's previous tile
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + buf * 256u;
+                for (int k = 0; k < num_k; ++k, ++g) {
+                    const uint32_t s = g % (uint32_t)STAGES, ph = (g / (uint32_t)STAGES) & 1u;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const unsigned char* a_src = smem + (size_t)s * stage_bytes;
+                    const uint64_t adesc = umma_desc(a_src), bdesc = umma_desc(a_src + A_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < BK / UMMA_K; ++kk)
+                        umma_tf32(tmem_d, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
+                                  (uint32_t)((k | kk) != 0));
+                    umma_commit(&empty[s]);   // frees the stage once these MMAs have read it
+                }
+                umma_commit(&tmem_full[buf]);   // accumulator complete
+            }
+        }
+    } else if (warp < 6) {
+        // ---- row norms, one tile ahead of the epilogue ---------------------------------------------
+        const int row = (warp - 2) * 32 + lane;
+        uint32_t g = 0;
+        for (int64_t i = 0; i < my_tiles; ++i) {
+            const uint32_t buf = (uint32_t)i & 1u, use = (uint32_t)(i >> 1);
+            float norm2 = 0.0f;
+            for (int k = 0; k < num_k; ++k, ++g) {
+                const uint32_t s = g % (uint32_t)STAGES, ph = (g / (uint32_t)STAGES) & 1u;
+                mbar_wait(&full[s], ph);
+                if (FILTER || norm_mode != SAF_NORM_NONE) {
+                    const float4* a4 = reinterpret_cast<const float4*>(smem + (size_t)s * stage_bytes) + row * 8;
+                    float n0 = 0.f, n1 = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 8; j += 2) {
+                        // the swizzle only permutes the eight 16-byte chunks inside the row: rotate the starting
+                        // chunk by the row so that a quarter-warp touches all 32 banks
+                        const float4 v = a4[(j + row) & 7], w = a4[(j + 1 + row) & 7];
+                        n0 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, n0))));
+                        n1 = fmaf(w.x, w.x, fmaf(w.y, w.y, fmaf(w.z, w.z, fmaf(w.w, w.w, n1))));
+                    }
+                    norm2 += n0 + n1;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s]);
+            }
+            mbar_wait(&norm_empty[buf], (use & 1u) ^ 1u);
+            snorm[buf * BM + row] = norm2;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&norm_full[buf]);
+        }
+    } else {
+        // ---- epilogue ------------------------------------------------------------------------------
+        const int q = warp & 3;                    // TMEM lane group of this warp
+        const int row = q * 32 + lane;
+        float* park = park_all + (size_t)q * 32 * P_PARK_PITCH;
+        for (int64_t i = 0; i < my_tiles; ++i) {
+            const uint32_t buf = (uint32_t)i & 1u, use = (uint32_t)(i >> 1);
+            const int64_t m0 = (tile0 + blockIdx.x + i * gridDim.x) * BM;
+            mbar_wait(&norm_full[buf], use & 1u);
+            const float norm2 = snorm[buf * BM + row];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&norm_empty[buf]);
+            const float scale = row_scale(norm2, norm_mode);
+            mbar_wait(&tmem_full[buf], use & 1u);
+            tc_fence_after();
+            const uint32_t lane_base = tmem_base + buf * 256u + ((uint32_t)(q * 32) << 16);
+            if (FILTER) {
+                // (see query_gemm_tf32_kernel for the error radius and the treatment of all-zero rows)
+                const float eps_row = 0.001953125f * sqrtf(norm2) * scale;
+                const int64_t m = m0 + row;
+                const bool zero_row = m < M && norm2 == 0.0f;
+                if (__any_sync(0xffffffffu, zero_row) && lane == 0) fa.flags[1] = 1u;
+                for (int c0 = 0; c0 < n_pad; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(lane_base + (uint32_t)c0, r);
+                    if (c0 + 32 >= n_pad) {   // the accumulator is in registers: hand it back to the MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+                    }
+                    if (m < M && !zero_row) {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            const int t = t0 + c0 + c;
+                            if (c0 + c < t_valid) {
+                                const float sc = __uint_as_float(r[c]) * scale;
+                                const float e = eps_row * __ldg(fa.xnorm + t) + 1e-6f;
+                                if (sc + e >= __ldg(fa.thr + t)) {
+                                    const uint32_t pos = atomicAdd(fa.counts + t, 1u);
+                                    if (pos < fa.cap) {
+                                        Candidate cd;
+                                        cd.score = sc;
+                                        cd.eps = e;
+                                        cd.row = (uint32_t)m;
+                                        cd.pad = 0;
+                                        fa.buckets[(size_t)t * fa.cap + pos] = cd;
+                                    } else {
+                                        atomicOr(fa.flags, 1u);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            } else {
+                const int64_t row0 = m0 + q * 32;
+                const bool vec_ok = ((ldo | (int64_t)t0) & 3) == 0 && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
+                for (int h0 = 0; h0 < n_pad; h0 += P_PARK_COLS) {
+                    const int hcols = min(P_PARK_COLS, n_pad - h0);
+                    for (int c0 = 0; c0 < hcols; c0 += 32) {
+                        uint32_t r[32];
+                        tmem_ld32(lane_base + (uint32_t)(h0 + c0), r);
+                        float4* dst = reinterpret_cast<float4*>(park + (size_t)lane * P_PARK_PITCH + c0);
+#pragma unroll
+                        for (int c = 0; c < 32; c += 4)
+                            if (c0 + c < hcols)
+                                dst[c >> 2] = make_float4(__uint_as_float(r[c]) * scale, __uint_as_float(r[c + 1]) * scale,
+                                                          __uint_as_float(r[c + 2]) * scale, __uint_as_float(r[c + 3]) * scale);
+                    }
+                    if (h0 + P_PARK_COLS >= n_pad) {   // last read of this accumulator: hand it back to the MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+                    }
+                    __syncwarp();
+                    const int hvalid = min(hcols, t_valid - h0);   // columns of this half that exist in `out`
+                    for (int rr = 0; rr < 32; ++rr) {
+                        const int64_t m = row0 + rr;
+                        if (m >= M || hvalid <= 0) break;
+                        const float* src = park + (size_t)rr * P_PARK_PITCH;
+                        float* dst = out + m * ldo + t0 + h0;
+                        if (vec_ok) {
+                            const int c = lane * 4;
+                            if (c < hvalid) {
+                                const float4 v = *reinterpret_cast<const float4*>(src + c);
+                                if (c + 3 < hvalid) {
+                                    *reinterpret_cast<float4*>(dst + c) = v;
+                                } else {
+                                    dst[c] = v.x;
+                                    if (c + 1 < hvalid) dst[c + 1] = v.y;
+                                    if (c + 2 < hvalid) dst[c + 2] = v.z;
+                                }
+                            }
+                        } else {
+                            for (int c = lane; c < hvalid; c += 32) dst[c] = src[c];
+                        }
+                    }
+                    __syncwarp();   // the park buffer is reused by the next half / tile
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -368,6 +610,31 @@ static int launch_gemm(bool filter, const float* feats, int64_t M, int32_t C, in
         rc = make_map(enc, &map_b, text, (uint64_t)T, (uint64_t)C, (uint64_t)C, (uint32_t)n_pad);
         if (rc) return rc;
         const size_t stage_bytes = A_BYTES + (size_t)n_pad * BK * 4;
+        // Persistent kernel (default): one CTA per SM over the tiles, two TMEM accumulators.  SAF_QUERY_PERSISTENT=0
+        // selects the one-tile-per-CTA kernel.
+        static const bool persistent = !(getenv("SAF_QUERY_PERSISTENT") && atoi(getenv("SAF_QUERY_PERSISTENT")) == 0);
+        if (persistent) {
+            int sms = 0;
+            if ((rc = device_sm_count(&sms, nullptr))) return rc;
+            const size_t extra = (filter ? 0 : (size_t)4 * 32 * P_PARK_PITCH * 4) + 2 * BM * 4 + 8 * 8 + 16;
+            int STAGES = MAX_STAGES;
+            while (STAGES > 2 && (size_t)STAGES * stage_bytes + 2 * STAGES * 8 + extra > 227 * 1024) --STAGES;
+            const size_t smem = (size_t)STAGES * stage_bytes + 2 * STAGES * 8 + extra;
+            const unsigned grid = (unsigned)std::min<int64_t>(tiles, sms);
+            if (filter) {
+                SAF_CUDA_TRY(cudaFuncSetAttribute(query_gemm_tf32_persistent_kernel<true>,
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                query_gemm_tf32_persistent_kernel<true><<<grid, P_THREADS, smem, st>>>(
+                    map_a, map_b, M, C, n_pad, t_valid, t0, norm_mode, out, (int64_t)T, tile0, tiles, fa, STAGES);
+            } else {
+                SAF_CUDA_TRY(cudaFuncSetAttribute(query_gemm_tf32_persistent_kernel<false>,
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                query_gemm_tf32_persistent_kernel<false><<<grid, P_THREADS, smem, st>>>(
+                    map_a, map_b, M, C, n_pad, t_valid, t0, norm_mode, out, (int64_t)T, tile0, tiles, fa, STAGES);
+            }
+            SAF_CHECK_LAUNCH("query_gemm_tf32_persistent_kernel", st);
+            continue;
+        }
         // The fused top-k kernel with more than 128 texts runs TWO CTAs per SM on a 2-deep ring each (2 x 96 KB of
         // shared memory, 2 x 256 TMEM columns): one CTA's filter epilogue overlaps the other's main loop.  The
         // scores kernel parks its output tile in the ring buffers and keeps 4 stages.  SAF_QUERY_STAGES overrides.
