@@ -322,8 +322,9 @@ query_gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
 // Measured with the one-tile-per-CTA kernel (12 M rows x 256 texts): neither HBM (47 %), L2 (35 %) nor the tensor
 // pipe (36 %) was busy - a tile cost ~20 us of which the overlapped main loop is ~9.
 // ---------------------------------------------------------------------------------------------
-constexpr int P_THREADS = 320;
-constexpr int P_PARK_COLS = 128;                 // columns of a tile parked at a time by the scores epilogue
+constexpr int P_EPI_WARPS = 8;                   // two per TMEM lane group, each takes half of the columns
+constexpr int P_THREADS = (6 + P_EPI_WARPS) * 32;
+constexpr int P_PARK_COLS = 64;                  // columns of a tile parked at a time by a scores-epilogue warp
 constexpr int P_PARK_PITCH = P_PARK_COLS + 4;    // floats; keeps the 128-bit shared stores conflict free
 
 template <bool FILTER>
@@ -335,8 +336,10 @@ query_gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap map_a, con
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t stage_bytes = A_BYTES + (uint32_t)n_pad * BK * 4;
     unsigned char* after_ring = smem + (size_t)STAGES * stage_bytes;
-    float* park_all = reinterpret_cast<float*>(after_ring);                       // [4 warps][32][P_PARK_PITCH] (scores only)
-    float* snorm = reinterpret_cast<float*>(after_ring + (FILTER ? 0 : 4 * 32 * P_PARK_PITCH * 4));   // [2][128]
+    // scores: [P_EPI_WARPS][32][P_PARK_PITCH] park buffers; top-k: [256] {threshold, |x|} per text of this pass
+    float* park_all = reinterpret_cast<float*>(after_ring);
+    float2* sthr = reinterpret_cast<float2*>(after_ring);
+    float* snorm = reinterpret_cast<float*>(after_ring + (FILTER ? 256 * 8 : P_EPI_WARPS * 32 * P_PARK_PITCH * 4));   // [2][128]
     uint64_t* bars = reinterpret_cast<uint64_t*>(snorm + 2 * BM);
     uint64_t* full = bars;                      // [STAGES]
     uint64_t* empty = full + STAGES;            // [STAGES]
@@ -357,11 +360,17 @@ query_gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap map_a, con
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tmem_full[b], 1);
-            mbar_init(&tmem_empty[b], 4);
+            mbar_init(&tmem_empty[b], P_EPI_WARPS);
             mbar_init(&norm_full[b], 4);
-            mbar_init(&norm_empty[b], 4);
+            mbar_init(&norm_empty[b], P_EPI_WARPS);
         }
         fence_mbar_init();
+    }
+    if (FILTER) {
+        // the thresholds are constants of a launch (they rise between waves): one copy per CTA instead of two global
+        // loads per score; a padding column can never be a candidate
+        for (int t = threadIdx.x; t < 256; t += P_THREADS)
+            sthr[t] = t < t_valid ? make_float2(__ldg(fa.thr + t0 + t), __ldg(fa.xnorm + t0 + t)) : make_float2(INFINITY, 0.f);
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
@@ -422,16 +431,14 @@ query_gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap map_a, con
                 mbar_wait(&full[s], ph);
                 if (FILTER || norm_mode != SAF_NORM_NONE) {
                     const float4* a4 = reinterpret_cast<const float4*>(smem + (size_t)s * stage_bytes) + row * 8;
-                    float n0 = 0.f, n1 = 0.f;
 #pragma unroll
-                    for (int j = 0; j < 8; j += 2) {
+                    for (int j = 0; j < 8; ++j) {
                         // the swizzle only permutes the eight 16-byte chunks inside the row: rotate the starting
-                        // chunk by the row so that a quarter-warp touches all 32 banks
-                        const float4 v = a4[(j + row) & 7], w = a4[(j + 1 + row) & 7];
-                        n0 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, n0))));
-                        n1 = fmaf(w.x, w.x, fmaf(w.y, w.y, fmaf(w.z, w.z, fmaf(w.w, w.w, n1))));
+                        // chunk by the row so that a quarter-warp touches all 32 banks.  (Same summation order as
+                        // the one-tile kernel: the norms, and with them the scores, are bit-identical.)
+                        const float4 v = a4[(j + row) & 7];
+                        norm2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, norm2))));
                     }
-                    norm2 += n0 + n1;
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[s]);
@@ -444,8 +451,11 @@ query_gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap map_a, con
     } else {
         // ---- epilogue ------------------------------------------------------------------------------
         const int q = warp & 3;                    // TMEM lane group of this warp
+        const int half = (warp - 6) >> 2;          // which half of the columns
+        const int n_half = ((n_pad / 2 + 31) / 32) * 32;
+        const int col_begin = half * n_half, col_end = min(n_pad, col_begin + n_half);
         const int row = q * 32 + lane;
-        float* park = park_all + (size_t)q * 32 * P_PARK_PITCH;
+        float* park = park_all + (size_t)(warp - 6) * 32 * P_PARK_PITCH;
         for (int64_t i = 0; i < my_tiles; ++i) {
             const uint32_t buf = (uint32_t)i & 1u, use = (uint32_t)(i >> 1);
             const int64_t m0 = (tile0 + blockIdx.x + i * gridDim.x) * BM;
@@ -457,39 +467,41 @@ query_gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap map_a, con
             mbar_wait(&tmem_full[buf], use & 1u);
             tc_fence_after();
             const uint32_t lane_base = tmem_base + buf * 256u + ((uint32_t)(q * 32) << 16);
+            bool released = false;
+            auto release = [&]() {   // this warp's part of the accumulator is in registers: hand it back to the MMA warp
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+                released = true;
+            };
             if (FILTER) {
                 // (see query_gemm_tf32_kernel for the error radius and the treatment of all-zero rows)
                 const float eps_row = 0.001953125f * sqrtf(norm2) * scale;
                 const int64_t m = m0 + row;
                 const bool zero_row = m < M && norm2 == 0.0f;
-                if (__any_sync(0xffffffffu, zero_row) && lane == 0) fa.flags[1] = 1u;
-                for (int c0 = 0; c0 < n_pad; c0 += 32) {
+                if (half == 0 && __any_sync(0xffffffffu, zero_row) && lane == 0) fa.flags[1] = 1u;
+                for (int c0 = col_begin; c0 < col_end; c0 += 32) {
                     uint32_t r[32];
                     tmem_ld32(lane_base + (uint32_t)c0, r);
-                    if (c0 + 32 >= n_pad) {   // the accumulator is in registers: hand it back to the MMA warp
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&tmem_empty[buf]);
-                    }
+                    if (c0 + 32 >= col_end) release();
                     if (m < M && !zero_row) {
 #pragma unroll
                         for (int c = 0; c < 32; ++c) {
-                            const int t = t0 + c0 + c;
-                            if (c0 + c < t_valid) {
-                                const float sc = __uint_as_float(r[c]) * scale;
-                                const float e = eps_row * __ldg(fa.xnorm + t) + 1e-6f;
-                                if (sc + e >= __ldg(fa.thr + t)) {
-                                    const uint32_t pos = atomicAdd(fa.counts + t, 1u);
-                                    if (pos < fa.cap) {
-                                        Candidate cd;
-                                        cd.score = sc;
-                                        cd.eps = e;
-                                        cd.row = (uint32_t)m;
-                                        cd.pad = 0;
-                                        fa.buckets[(size_t)t * fa.cap + pos] = cd;
-                                    } else {
-                                        atomicOr(fa.flags, 1u);
-                                    }
+                            const float2 tx = sthr[c0 + c];   // broadcast
+                            const float sc = __uint_as_float(r[c]) * scale;
+                            const float e = eps_row * tx.y + 1e-6f;
+                            if (sc + e >= tx.x) {
+                                const int t = t0 + c0 + c;
+                                const uint32_t pos = atomicAdd(fa.counts + t, 1u);
+                                if (pos < fa.cap) {
+                                    Candidate cd;
+                                    cd.score = sc;
+                                    cd.eps = e;
+                                    cd.row = (uint32_t)m;
+                                    cd.pad = 0;
+                                    fa.buckets[(size_t)t * fa.cap + pos] = cd;
+                                } else {
+                                    atomicOr(fa.flags, 1u);
                                 }
                             }
                         }
@@ -498,8 +510,8 @@ query_gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap map_a, con
             } else {
                 const int64_t row0 = m0 + q * 32;
                 const bool vec_ok = ((ldo | (int64_t)t0) & 3) == 0 && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
-                for (int h0 = 0; h0 < n_pad; h0 += P_PARK_COLS) {
-                    const int hcols = min(P_PARK_COLS, n_pad - h0);
+                for (int h0 = col_begin; h0 < col_end; h0 += P_PARK_COLS) {
+                    const int hcols = min(P_PARK_COLS, col_end - h0);
                     for (int c0 = 0; c0 < hcols; c0 += 32) {
                         uint32_t r[32];
                         tmem_ld32(lane_base + (uint32_t)(h0 + c0), r);
@@ -510,22 +522,18 @@ query_gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap map_a, con
                                 dst[c >> 2] = make_float4(__uint_as_float(r[c]) * scale, __uint_as_float(r[c + 1]) * scale,
                                                           __uint_as_float(r[c + 2]) * scale, __uint_as_float(r[c + 3]) * scale);
                     }
-                    if (h0 + P_PARK_COLS >= n_pad) {   // last read of this accumulator: hand it back to the MMA warp
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&tmem_empty[buf]);
-                    }
+                    if (h0 + P_PARK_COLS >= col_end) release();
                     __syncwarp();
-                    const int hvalid = min(hcols, t_valid - h0);   // columns of this half that exist in `out`
-                    for (int rr = 0; rr < 32; ++rr) {
-                        const int64_t m = row0 + rr;
-                        if (m >= M || hvalid <= 0) break;
-                        const float* src = park + (size_t)rr * P_PARK_PITCH;
-                        float* dst = out + m * ldo + t0 + h0;
+                    const int hvalid = min(hcols, t_valid - h0);   // columns of this part that exist in `out`
+                    if (hvalid > 0) {
                         if (vec_ok) {
-                            const int c = lane * 4;
-                            if (c < hvalid) {
-                                const float4 v = *reinterpret_cast<const float4*>(src + c);
+                            // two rows per pass: 16 lanes x 16 bytes cover the 64 parked columns of a row
+                            const int c = (lane & 15) * 4;
+                            for (int rr = lane >> 4; rr < 32; rr += 2) {
+                                const int64_t m = row0 + rr;
+                                if (m >= M || c >= hvalid) continue;
+                                const float4 v = *reinterpret_cast<const float4*>(park + (size_t)rr * P_PARK_PITCH + c);
+                                float* dst = out + m * ldo + t0 + h0;
                                 if (c + 3 < hvalid) {
                                     *reinterpret_cast<float4*>(dst + c) = v;
                                 } else {
@@ -535,12 +543,18 @@ query_gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap map_a, con
                                 }
                             }
                         } else {
-                            for (int c = lane; c < hvalid; c += 32) dst[c] = src[c];
+                            for (int rr = 0; rr < 32; ++rr) {
+                                const int64_t m = row0 + rr;
+                                if (m >= M) break;
+                                for (int c = lane; c < hvalid; c += 32)
+                                    out[m * ldo + t0 + h0 + c] = park[(size_t)rr * P_PARK_PITCH + c];
+                            }
                         }
                     }
-                    __syncwarp();   // the park buffer is reused by the next half / tile
+                    __syncwarp();   // the park buffer is reused by the next part / tile
                 }
             }
+            if (!released) release();   // a warp whose half of the columns is empty (few texts)
         }
     }
     tc_fence_before();
@@ -616,7 +630,7 @@ static int launch_gemm(bool filter, const float* feats, int64_t M, int32_t C, in
         if (persistent) {
             int sms = 0;
             if ((rc = device_sm_count(&sms, nullptr))) return rc;
-            const size_t extra = (filter ? 0 : (size_t)4 * 32 * P_PARK_PITCH * 4) + 2 * BM * 4 + 8 * 8 + 16;
+            const size_t extra = (filter ? (size_t)256 * 8 : (size_t)P_EPI_WARPS * 32 * P_PARK_PITCH * 4) + 2 * BM * 4 + 8 * 8 + 16;
             int STAGES = MAX_STAGES;
             while (STAGES > 2 && (size_t)STAGES * stage_bytes + 2 * STAGES * 8 + extra > 227 * 1024) --STAGES;
             const size_t smem = (size_t)STAGES * stage_bytes + 2 * STAGES * 8 + extra;
