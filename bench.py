@@ -694,6 +694,7 @@ def run_native_arm(args):
         k3_ms, k3_upd, k3_union, k1_ms, k2_ms, k2t_ms, timed = 0.0, 0, 0, 0.0, 0.0, 0.0, 0
         ea, eb, e0, et, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(5))
         probe = steps_arr[W_steps]
+        ws = vol._workspace(window, npy * npx * C)    # the e2e leg may have replaced the volume's workspace by a larger one
         for i in range(n_probe):
             fr = ctypes.cast(probe.ctypes.data + i * bw * ctypes.sizeof(_lib.Frame), ctypes.POINTER(_lib.Frame))
             sb = vol.stats()

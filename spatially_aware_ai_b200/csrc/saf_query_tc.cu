@@ -484,24 +484,35 @@ query_gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap map_a, con
                     uint32_t r[32];
                     tmem_ld32(lane_base + (uint32_t)c0, r);
                     if (c0 + 32 >= col_end) release();
-                    if (m < M && !zero_row) {
+                    const bool live = m < M && !zero_row;
+                    if (__any_sync(0xffffffffu, live)) {
 #pragma unroll
                         for (int c = 0; c < 32; ++c) {
                             const float2 tx = sthr[c0 + c];   // broadcast
                             const float sc = __uint_as_float(r[c]) * scale;
                             const float e = eps_row * tx.y + 1e-6f;
-                            if (sc + e >= tx.x) {
+                            const bool hit = live && sc + e >= tx.x;
+                            // one counter update per warp and text: while the thresholds are still -inf (first wave)
+                            // every row is a candidate and 32 same-address atomics per column would serialise
+                            const uint32_t bal = __ballot_sync(0xffffffffu, hit);
+                            if (bal) {
                                 const int t = t0 + c0 + c;
-                                const uint32_t pos = atomicAdd(fa.counts + t, 1u);
-                                if (pos < fa.cap) {
-                                    Candidate cd;
-                                    cd.score = sc;
-                                    cd.eps = e;
-                                    cd.row = (uint32_t)m;
-                                    cd.pad = 0;
-                                    fa.buckets[(size_t)t * fa.cap + pos] = cd;
-                                } else {
-                                    atomicOr(fa.flags, 1u);
+                                const int leader = __ffs(bal) - 1;
+                                uint32_t base = 0;
+                                if (lane == leader) base = atomicAdd(fa.counts + t, (uint32_t)__popc(bal));
+                                base = __shfl_sync(0xffffffffu, base, leader);
+                                if (hit) {
+                                    const uint32_t pos = base + (uint32_t)__popc(bal & ((1u << lane) - 1u));
+                                    if (pos < fa.cap) {
+                                        Candidate cd;
+                                        cd.score = sc;
+                                        cd.eps = e;
+                                        cd.row = (uint32_t)m;
+                                        cd.pad = 0;
+                                        fa.buckets[(size_t)t * fa.cap + pos] = cd;
+                                    } else {
+                                        atomicOr(fa.flags, 1u);
+                                    }
                                 }
                             }
                         }
