@@ -191,7 +191,7 @@ def test_size_independent_properties_at_cfg2_scale(mode, n_frames, step):
     """At a ScanNet-scale grid (2 cm, 640x480) the oracle is too slow for a full comparison; check
     invariants instead: counter sums equal the kernels' own valid counts, every histogram row sums
     to the voxel's weight, untouched voxels stay zero, and a sampled x-slab matches the oracle.
-    "frame": one integrate() per frame; "window": one integrate_sequence() call (2.5 windows of 8)."""
+    "frame": one integrate() per frame; "window": one integrate_sequence() call (two windows of 10)."""
     cfg = synth.baseline_config("cfg2", feature_dim=512, frames=n_frames, extent=(6.0, 6.0, 3.0))
     origin, nvox = cfg.grid()
     g = dict(cls="ClipSeemFusion", feature_dim=cfg.feature_dim, origin=origin, nvox=nvox,

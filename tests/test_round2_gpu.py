@@ -320,3 +320,89 @@ def test_fused_topk_on_a_mostly_unobserved_grid():
     ts2, ti2 = saf.query_topk(F2.cuda(), Xd, k, norm="nan_to_num", mode="dot", precision="tf32")
     s2 = _np(saf.query_scores(F2.cuda(), Xd, norm="nan_to_num", mode="dot"))
     assert np.array_equal(_np(ti2), O.topk_indices(s2, k))
+
+
+# ---- BASELINE configs 3 / 4 at full size ------------------------------------------------------------------
+
+def _free_gb():
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()      # the previous tests' volumes sit in torch's caching allocator
+    free, _ = torch.cuda.mem_get_info()
+    return free / 2 ** 30
+
+
+def test_sampled_slab_at_cfg3_scale_window16():
+    """BASELINE config 3 (8x8x3 m at 2 cm: 25.1 M voxels x 768-d) is far too large for the oracle; 32 frames of its
+    orbit are fused in two 16-frame windows (K0/K1/K2/K2T/K3W) and a 12-plane x-slab of the result must equal the
+    oracle bit for bit, next to the size-independent invariants."""
+    if _free_gb() < 130:
+        pytest.skip("needs ~110 GB of device memory")
+    cfg = synth.baseline_config("cfg3", frames=32)
+    origin, nvox = cfg.grid()
+    g = dict(cls="ClipSeemFusion", feature_dim=cfg.feature_dim, origin=origin, nvox=nvox,
+             voxel_size=cfg.voxel_size, trunc=cfg.trunc)
+    vol, clip, seg = Hh.make_gpu_volume(g)
+    frames = [synth.make_frame(cfg, i * 3, table_layout="hwc") for i in range(cfg.frames)]
+    clip.next_table = torch.stack([torch.from_numpy(np.ascontiguousarray(f["table"].transpose(1, 2, 0)))
+                                   for f in frames]).cuda().permute(0, 3, 1, 2)
+    seg.queue = [torch.from_numpy(f["seg"]).cuda() for f in frames]
+    vol.integrate_sequence(torch.stack([torch.from_numpy(f["depth"]) for f in frames]).cuda(),
+                           torch.stack([torch.from_numpy(f["rgb"]) for f in frames]).cuda(),
+                           torch.stack([torch.from_numpy(f["pose"]) for f in frames]),
+                           torch.stack([torch.from_numpy(f["K"]) for f in frames]))
+    # the 12 planes these frames update most (the oracle only computes that slab)
+    nx, ny, nz = (int(v) for v in nvox)
+    per_plane = vol.weight.view(nx, ny * nz).sum(dim=1, dtype=torch.int64)
+    win = torch.nn.functional.avg_pool1d(per_plane.double()[None, None], 12, 1)[0, 0]
+    xs0 = int(win.argmax())
+    xs1 = xs0 + 12
+    orc = O.OracleVolume(origin, cfg.voxel_size, nvox, cfg.trunc, cfg.feature_dim, x_begin=xs0, x_end=xs1, num_threads=0)
+    for fr in frames:
+        orc.integrate(fr["depth"][None], fr["rgb"][None], fr["pose"][None], fr["K"][None], fr["table"][None],
+                      fr["seg"][None], want_masks=False)
+    st = vol.stats()
+    assert st["total_frames"] == cfg.frames and st["total_calls"] == 2
+    assert int(vol.weight.sum(dtype=torch.int64)) == st["total_valid"] > 0
+    assert int(vol.tsdf_weight.sum(dtype=torch.int64)) == st["total_tsdf_valid"] >= st["total_valid"]
+    assert torch.equal(vol.labels_one_hot.sum(dim=1, dtype=torch.int32), vol.weight)
+    sl = slice(xs0 * ny * nz, xs1 * ny * nz)
+    assert orc.weight.sum() > 10000
+    assert np.array_equal(_np(vol.weight[sl]), orc.weight)
+    assert np.array_equal(_np(vol.tsdf_weight[sl]), orc.tsdf_weight)
+    assert np.array_equal(_np(vol.tsdf[sl]), orc.tsdf)
+    assert np.array_equal(_np(vol.rgb[sl]), orc.rgb)
+    assert np.array_equal(_np(vol.clip_feat[sl]), orc.clip_feat)
+    assert np.array_equal(_np(vol.labels_one_hot[sl]), orc.labels_one_hot)
+
+
+def test_fused_topk_at_cfg4_scale_equals_chunked_fp32_ranking():
+    """BASELINE config 4: 256 texts against 24 M feature rows x 768-d.  The fused tensor-core top-100 (persistent tf32
+    GEMM + candidate filter + fp32 rescoring, no [M,T] matrix) must return exactly the ranking of the fp32 scores,
+    here ranked chunk by chunk (1 M rows at a time) and merged."""
+    import spatially_aware_ai_b200 as saf
+    if _free_gb() < 100:
+        pytest.skip("needs ~80 GB of device memory")
+    M, C, T, k, chunk = 24_000_000, 768, 256, 100, 1_000_000
+    gen = torch.Generator(device="cuda").manual_seed(24)
+    F = torch.empty((M, C), device="cuda")
+    for r0 in range(0, M, chunk):                      # a fused grid: most rows unobserved (zero), the rest smooth-ish
+        blk = torch.randn((chunk, C), device="cuda", generator=gen)
+        keep = torch.rand((chunk, 1), device="cuda", generator=gen) < 0.3
+        F[r0:r0 + chunk] = blk * keep
+    X = torch.nn.functional.normalize(torch.randn((T, C), device="cuda", generator=gen), dim=-1)
+    ts, ti = saf.query_topk(F, X, k, norm="nan_to_num", mode="dot", precision="tf32")
+    best_s = torch.full((T, 0), 0.0, device="cuda")
+    best_i = torch.zeros((T, 0), dtype=torch.int64, device="cuda")
+    for r0 in range(0, M, chunk):
+        sc = saf.query_scores(F[r0:r0 + chunk], X, norm="nan_to_num", mode="dot", precision="fp32").T.contiguous()   # [T, chunk]
+        cs, ci = torch.topk(sc, k, dim=1)
+        best_s = torch.cat([best_s, cs], dim=1)
+        best_i = torch.cat([best_i, ci + r0], dim=1)
+        # keep the k best so far; ties broken by the lower row index, as the library does
+        order = torch.argsort(best_i, dim=1, stable=True)
+        best_s, best_i = torch.gather(best_s, 1, order), torch.gather(best_i, 1, order)
+        order = torch.argsort(best_s, dim=1, descending=True, stable=True)[:, :k]
+        best_s, best_i = torch.gather(best_s, 1, order), torch.gather(best_i, 1, order)
+    assert torch.equal(ts, best_s)
+    assert torch.equal(ti.to(torch.int64), best_i)
