@@ -466,24 +466,44 @@ __global__ void __launch_bounds__(kK1Threads) frame_setup_kernel(const FusionPar
         // repack channel-major feature images into [R,C] rows (only frames in pack_mask)
         const uint32_t pack_ctas = gridDim.x - cull_ctas;
         const int C = p.vol.feature_dim;
-        for (int b = 0; b < p.batch; ++b) {
-            const saf_frame& f = p.frames[b];
-            float* dst = p.tables + (uint64_t)b * p.table_slot_elems;
-            if (p.sequential) {
-                // window mode: [(npy+2)*(npx+2), C] rows with a zero border, so that the feature kernel's four
-                // taps are always in range (dropped taps land on a zero row: grid_sample's zeros padding)
+        if (p.sequential) {
+            // window mode: [(npy+2)*(npx+2), C] rows with a zero border, so that the feature kernel's four taps are
+            // always in range (dropped taps land on a zero row: grid_sample's zeros padding).  The (frame, row)
+            // pairs of the whole window are dealt over the pack CTAs, one 16-byte access per thread where the
+            // layout allows - a loop over the frames with scalar copies was K1's long pole (16 dependent passes).
+            int rp_max = 0;
+            for (int b = 0; b < p.batch; ++b) {
+                const saf_frame& f = p.frames[b];
+                rp_max = max(rp_max, f.table_mode == SAF_TABLE_SEGMENTS ? f.npx + 1 : (f.npy + 2) * (f.npx + 2));
+            }
+            for (int idx = (int)(blockIdx.x - cull_ctas); idx < p.batch * rp_max; idx += (int)pack_ctas) {
+                const int b = idx / rp_max, r = idx - b * rp_max;
+                const saf_frame& f = p.frames[b];
                 const bool segs = f.table_mode == SAF_TABLE_SEGMENTS;   // [zero row, one row per segment]
                 const int pw = f.npx + 2;
                 const int Rp = segs ? f.npx + 1 : (f.npy + 2) * pw;
-                for (int r = (int)(blockIdx.x - cull_ctas); r < Rp; r += (int)pack_ctas) {   // one padded row per CTA pass
-                    const int py = segs ? 0 : r / pw - 1, px = segs ? r - 1 : r % pw - 1;
-                    const bool in = py >= 0 && py < f.npy && px >= 0 && px < f.npx;
-                    const float* src = f.table + ((int64_t)py * f.npx + px) * f.table_stride_r;
+                if (r >= Rp) continue;
+                float* dst = p.tables + (uint64_t)b * p.table_slot_elems + (int64_t)r * C;
+                const int py = segs ? 0 : r / pw - 1, px = segs ? r - 1 : r % pw - 1;
+                const bool in = py >= 0 && py < f.npy && px >= 0 && px < f.npx;
+                const float* src = f.table + ((int64_t)py * f.npx + px) * f.table_stride_r;
+                const bool vec = f.table_stride_c == 1 && (C & 3) == 0 && (p.table_slot_elems & 3) == 0 &&
+                                 ((reinterpret_cast<uintptr_t>(p.tables) | reinterpret_cast<uintptr_t>(f.table)) & 15u) == 0 &&
+                                 (f.table_stride_r & 3) == 0;
+                if (vec) {
+                    for (int c = threadIdx.x; c < C / 4; c += kK1Threads)
+                        reinterpret_cast<float4*>(dst)[c] =
+                            in ? __ldg(reinterpret_cast<const float4*>(src) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                } else {
                     for (int c = threadIdx.x; c < C; c += kK1Threads)
-                        dst[(int64_t)r * C + c] = in ? src[(int64_t)c * f.table_stride_c] : 0.0f;
+                        dst[c] = in ? src[(int64_t)c * f.table_stride_c] : 0.0f;
                 }
-                continue;
             }
+            return;
+        }
+        for (int b = 0; b < p.batch; ++b) {
+            const saf_frame& f = p.frames[b];
+            float* dst = p.tables + (uint64_t)b * p.table_slot_elems;
             if (!((p.pack_mask >> b) & 1u)) continue;
             const int64_t R = (int64_t)f.npy * f.npx;
             for (int64_t e = (int64_t)(blockIdx.x - cull_ctas) * kK1Threads + threadIdx.x; e < R * C;
@@ -2139,24 +2159,41 @@ feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, co
             auto request = [&](int b, RowRegs& T) {
                 if (b >= 0) load_rows(T, wt.ptr[b], M->prim_rows[set][b], C, col4);
             };
-            // a frame's rows are requested two frames before its arithmetic starts; three register sets take turns
-            RowRegs T0, T1, T2;
-            int b0 = next_frame(), b1 = next_frame(), b2;
-            request(b0, T0);
-            request(b1, T1);
-            for (;;) {
-                b2 = next_frame();
-                request(b2, T2);
-                frame_updates(b0, T0);
-                if (b1 < 0) break;
-                b0 = next_frame();
+            if constexpr (TileRegs<NCW>::kCompute >= 144) {
+                // a frame's rows are requested two frames before its arithmetic starts; three register sets take turns
+                RowRegs T0, T1, T2;
+                int b0 = next_frame(), b1 = next_frame(), b2;
                 request(b0, T0);
-                frame_updates(b1, T1);
-                if (b2 < 0) break;
-                b1 = next_frame();
                 request(b1, T1);
-                frame_updates(b2, T2);
-                if (b0 < 0) break;
+                for (;;) {
+                    b2 = next_frame();
+                    request(b2, T2);
+                    frame_updates(b0, T0);
+                    if (b1 < 0) break;
+                    b0 = next_frame();
+                    request(b0, T0);
+                    frame_updates(b1, T1);
+                    if (b2 < 0) break;
+                    b1 = next_frame();
+                    request(b1, T1);
+                    frame_updates(b2, T2);
+                    if (b0 < 0) break;
+                }
+            } else {
+                // C = 1024 (16 compute warps, 104 registers each): one frame ahead, two register sets
+                RowRegs T0, T1;
+                int b0 = next_frame(), b1;
+                request(b0, T0);
+                for (;;) {
+                    b1 = next_frame();
+                    request(b1, T1);
+                    frame_updates(b0, T0);
+                    if (b1 < 0) break;
+                    b0 = next_frame();
+                    request(b0, T0);
+                    frame_updates(b1, T1);
+                    if (b0 < 0) break;
+                }
             }
             TM_MARK(tm_frames);
 #pragma unroll
@@ -2522,7 +2559,7 @@ static int check_window_tables(const saf_volume* vol, const saf_frame* frames, i
 
 static int launch_k1(const FusionParams& p, cudaStream_t st)
 {
-    const uint32_t pack_ctas = (p.pack_mask || p.sequential) ? 64u : 0u;
+    const uint32_t pack_ctas = p.sequential ? 256u : (p.pack_mask ? 64u : 0u);
     const int ntiles = p.ntx * p.nty;
     depth_tiles_kernel<<<(p.batch * ntiles + 7) / 8, 256, 0, st>>>(p);
     SAF_CHECK_LAUNCH("depth_tiles_kernel (K0)", st);
@@ -2891,7 +2928,7 @@ int saf_feature_accumulate_window_stages(const saf_grid_desc* grid, const saf_vo
     p.sequential = 1;
     if (stages & SAF_STAGE_TILE_SETUP) {
         // saf_frustum_cull does not know the call is a window: repack the feature images here (K1's pack CTAs only)
-        frame_setup_kernel<<<64, kK1Threads, 0, (cudaStream_t)stream>>>(p, 0u);
+        frame_setup_kernel<<<256, kK1Threads, 0, (cudaStream_t)stream>>>(p, 0u);
         SAF_CHECK_LAUNCH("frame_setup_kernel (table repack)", (cudaStream_t)stream);
         if ((rc = launch_k2t(p, sms, (cudaStream_t)stream))) return rc;
     }
