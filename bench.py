@@ -739,14 +739,22 @@ def run_native_arm(args):
         bytes_win = k3_union * 8 * C + k3_upd * 40 + timed * imgs    # per union row once per window
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "r02_k3w_traffic.json" if bw > 1 else "k3_traffic.json")
+        traffic_note = None
         if os.path.exists(tpath) and plan.mode == "single" and cfg.name == "cfg2" and C == 768:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            traffic = tj.get("dram_bytes_per_launch")
+            cap_upd = tj.get("updates_in_captured_launch")
+            if traffic and cap_upd and k3_upd:
+                # the ncu capture is one window of the same sequence with a different number of updates: scaled to
+                # this run's average launch (K3W's DRAM bytes go with its union rows, i.e. with its updates)
+                traffic = traffic * (k3_upd / timed) / cap_upd
+                traffic_note = "dram__bytes of %s, scaled by updates per launch (%d captured)" % (tj.get("source"), cap_upd)
         ach = bytes_win / (k3_ms * 1e-3) / 1e9 if k3_ms > 0 else 0.0
         ach8 = bytes_8d / (k3_ms * 1e-3) / 1e9 if k3_ms > 0 else 0.0
         roof = {"bound": "hbm",
                 "kernel": "feature_accumulate_window_tile_kernel (K3W, %d-frame window)" % bw if bw > 1 else
                           "feature_accumulate_kernel (K3)",
-                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_note": traffic_note,
                 "peak_source": peak_src, "launches_timed": timed, "avg_launch_us": k3_ms / timed * 1e3,
                 "k1_avg_us": k1_ms / timed * 1e3, "k2_avg_us": k2_ms / timed * 1e3, "k2t_avg_us": k2t_ms / timed * 1e3,
                 "avg_updates_per_launch": k3_upd / timed, "avg_union_rows_per_launch": k3_union / timed,
