@@ -406,3 +406,18 @@ def test_fused_topk_at_cfg4_scale_equals_chunked_fp32_ranking():
         best_s, best_i = torch.gather(best_s, 1, order), torch.gather(best_i, 1, order)
     assert torch.equal(ts, best_s)
     assert torch.equal(ti.to(torch.int64), best_i)
+
+
+def test_window_path_without_prepared_tiles():
+    """SAF_TILE_SETUP=0: K2T keeps the small state but leaves every tile's metadata to K3W's own producers (the
+    path taken by tiles past K2T's capacity).  The library reads the switch once per process, hence a subprocess."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, SAF_TILE_SETUP="0")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-m", "pytest", "tests/test_parity_gpu.py", "tests/test_round2_gpu.py", "-q", "-x", "-m", "gpu",
+                          "-k", "sequence_window_matches_oracle or window_kernels_every_width or segment_table_mode",
+                          "-p", "no:cacheprovider"], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-1000:]
+    assert " passed" in res.stdout
