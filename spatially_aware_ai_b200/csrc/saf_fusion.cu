@@ -2232,7 +2232,10 @@ feature_accumulate_window_tile_kernel(const __grid_constant__ FusionParams p, co
 // ---------------------------------------------------------------------------------------------
 constexpr int kK2TWarps = 8;
 
-__global__ void __launch_bounds__(kK2TWarps * 32) window_tile_setup_kernel(const __grid_constant__ FusionParams p)
+#ifndef SAF_K2T_MINBLOCKS
+#define SAF_K2T_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(kK2TWarps * 32, SAF_K2T_MINBLOCKS) window_tile_setup_kernel(const __grid_constant__ FusionParams p)
 {
     constexpr int NSET = 2, G = NSET * kTileSlots;
     __shared__ float4 s_smp[kK2TWarps][G * SAF_MAX_BATCH];
@@ -2726,7 +2729,7 @@ static bool k3w_uses_tiles(const FusionParams& p)
 static int launch_k2t(const FusionParams& p, int sms, cudaStream_t st)
 {
     if (!k3w_uses_tiles(p)) return 0;   // the other window kernels update the small state themselves
-    window_tile_setup_kernel<<<sms * 4, kK2TWarps * 32, 0, st>>>(p);
+    window_tile_setup_kernel<<<sms * SAF_K2T_MINBLOCKS, kK2TWarps * 32, 0, st>>>(p);
     SAF_CHECK_LAUNCH("window_tile_setup_kernel (K2T)", st);
     return 0;
 }
