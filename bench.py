@@ -595,6 +595,32 @@ def run_native_arm(args):
     whole_bytes = 16 * tv + upd * (8 * C + 40) + img_bytes
     whole_bytes_window = 16 * tv + union * 8 * C + upd * 40 + img_bytes
 
+    # ---- the same frames one integrate() at a time (what a caller of the reference's per-frame API gets): the first
+    # 48 frames of the next step through saf_integrate, K0/K1/K2/K3 per frame, no window -----------------------------
+    frame_by_frame = None
+    if world == 1 and window > 1:
+        arr = step_structs(W_steps + K_steps)
+        n_fb = min(48, F)
+        s_a = vol.stats()
+        fa, fb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fptr = arr.ctypes.data
+        for rep in range(2):                 # the first pass warms the single-frame kernels up
+            fa.record()
+            for i in range(n_fb):
+                _lib.check(lib.saf_integrate(ctypes.byref(grid_d), ctypes.byref(vol_d),
+                                             ctypes.cast(fptr + i * ctypes.sizeof(_lib.Frame), ctypes.POINTER(_lib.Frame)), 1,
+                                             H, Wd, trunc, _lib.SAF_RGB_BILINEAR, ctypes.byref(ws), stream), "saf_integrate")
+            fb.record()
+            torch.cuda.synchronize(dev)
+            if rep == 0:
+                s_a = vol.stats()
+        s_b = vol.stats()
+        fb_ms = fa.elapsed_time(fb)
+        frame_by_frame = {"value": (s_b["total_valid"] - s_a["total_valid"]) / (fb_ms * 1e-3), "unit": UNIT,
+                          "frames": n_fb, "frames_per_s": n_fb / (fb_ms * 1e-3),
+                          "note": "saf_integrate, one frame per call (K0/K1/K2/K3), inputs resident; the CPU arm's frames are "
+                                  "integrated the same way (ClipSeemFusion.integrate per frame)"}
+
     # ---- e2e: public API, host buffers, H2D inside the timed region ---------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -842,7 +868,8 @@ def run_native_arm(args):
             # rank 0's count: K0 + K1 + K2 + K2T + K3W per window the library launched (its own counter)
             "gpu_launches": (5 if window > 1 else 4) * calls,
             "timed_region_attempts_ms": attempts,
-            "clocks": clocks, "e2e": e2e, "roofline": roof, "query": query, "cpu_baseline": cpu,
+            "clocks": clocks, "e2e": e2e, "frame_by_frame": frame_by_frame, "roofline": roof, "query": query,
+            "cpu_baseline": cpu,
         }
         line = json.dumps(out) + "\n"
         if json_fd is not None:
