@@ -16,9 +16,12 @@
 //                              bilinear sample of the frame's [R,C] table (TMA-staged in shared memory) and
 //                              streamed back with 128-bit stores; rgb, label counter and weight one lane per
 //                              voxel
-//   K3W feature_accumulate_window_*  window mode: each listed row is read once, every valid frame's update is
-//                              applied in frame order in registers, and it is written once (two neighbouring
-//                              voxels per warp pass share their table-row loads)
+//   K2T window_tile_setup_kernel  window mode: per 16-voxel tile of the union list the update records of every valid
+//                              (voxel, frame) (bilinear weights, a, b, table rows) for K3W, and the window's rgb /
+//                              weight / label-counter updates; one warp per tile over the whole GPU
+//   K3W feature_accumulate_window_tile_kernel  window mode: each listed row is read once, every valid frame's
+//                              update is applied in frame order in registers, and it is written once; a set of 8
+//                              voxels shares the table-row loads of a frame (older variants: pair / per-voxel)
 // The lists are deterministic and spatially ordered (ascending block, then voxel): warps work on runs of
 // neighbouring voxels, which keeps their feature rows close together in DRAM, lets the per-voxel 4-byte
 // accesses (weight, rgb, label counter) of the lanes share sectors and keeps the table rows in L1.
