@@ -16,6 +16,7 @@ SAF_MAX_BATCH = 16
 
 SAF_SEG_NONE, SAF_SEG_U8, SAF_SEG_I16, SAF_SEG_I32, SAF_SEG_I64, SAF_SEG_F32 = range(6)
 SAF_RGB_NEAREST, SAF_RGB_BILINEAR = 0, 1
+SAF_STAGE_TILE_SETUP, SAF_STAGE_ACCUMULATE = 1, 2     # saf_feature_accumulate_window_stages
 SAF_DEPTH_F32, SAF_DEPTH_U16_MM = 0, 1
 SAF_RGB_F32, SAF_RGB_U8 = 0, 1
 SAF_TABLE_PATCH_GRID, SAF_TABLE_SEGMENTS = 0, 1

@@ -158,3 +158,24 @@ def test_build_scene_knowledge_matches_reference_golden():
     first = next(iter(uo.values()))
     assert all(g["voxel_obj_ids"][v] == first["object_index"] for v in first["voxels"])
     assert set(know) >= {"unique_objects", "object_counts", "unchanged_objects", "new_objects", "missing_objects"}
+
+
+def test_ctypes_signatures_have_the_header_arity():
+    """Every prototype of include/saf_b200.h takes as many parameters as its ctypes signature in _lib.py."""
+    text = open(os.path.join(ROOT, "include", "saf_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = re.findall(r"\b(saf_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S)
+    assert len(protos) >= 28
+    for name, params in protos:
+        params = " ".join(params.split())
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(_lib.SIGNATURES[name][1]), (name, n, len(_lib.SIGNATURES[name][1]))
+
+
+def test_window_stage_argument_checks(lib):
+    """saf_feature_accumulate_window_stages refuses stage masks it does not know before touching the device."""
+    g, v, ws, f = _lib.GridDesc(), _lib.Volume(), _lib.Workspace(), (_lib.Frame * 2)()
+    for stages in (0, 4, -1):
+        rc = lib.saf_feature_accumulate_window_stages(ctypes.byref(g), ctypes.byref(v), f, 2, 48, 64, _lib.SAF_RGB_BILINEAR,
+                                                      ctypes.byref(ws), stages, None)
+        assert rc == -8, (stages, rc)      # SAF_ERR_UNSUPPORTED
